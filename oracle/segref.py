@@ -1,0 +1,401 @@
+"""CPU/torch ORACLE for the SegmenTron dense hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a functional restatement (plain ``torch.nn.functional`` calls over a flat
+parameter dict) of the reference's forward pass for the hot path of SURVEY.md section 8.
+It is NOT the product: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it, and only as the checker or the
+timed CPU baseline.  Nothing under ``segmentron_b200/`` imports it.
+
+Pinning: the reference ships no golden vectors.  The oracle is pinned by
+``tests/golden/make_golden.py``, which imports the real reference from /root/reference in the
+build container, loads the SAME parameter dict into the reference ``nn.Module`` tree
+(``load_state_dict(strict=True)`` => names and shapes are the reference's) and checks that
+reference and oracle agree, then commits the reference's outputs as fixtures under
+``tests/golden/``.  ``tests/test_oracle_golden.py`` re-checks the oracle against those
+fixtures everywhere (no /root/reference needed).
+
+Parameter dicts use the reference's ``state_dict`` key names.  A ``Params`` object creates
+missing entries lazily from a seeded CPU generator, so running a forward once on a tiny input
+yields a complete, reproducible state dict.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------
+# parameter store
+# ----------------------------------------------------------------------------------------
+class Params:
+    """Flat ``name -> tensor`` store with lazy, seeded creation.
+
+    BatchNorm buffers are randomised (NOT the identity default of nn.BatchNorm2d) so that a
+    folded-BN bug cannot hide (SURVEY.md 8c "non-vacuous oracle").  Gains are chosen so the
+    activation scale neither collapses nor explodes through ~70 layers.
+    """
+
+    def __init__(self, seed: int = 0, tensors: Optional[Dict[str, torch.Tensor]] = None,
+                 device: str = "cpu", dtype: torch.dtype = torch.float32):
+        self.t: Dict[str, torch.Tensor] = dict(tensors) if tensors else {}
+        self.g = torch.Generator(device="cpu")
+        self.g.manual_seed(seed)
+        self.device, self.dtype = device, dtype
+        self.frozen = tensors is not None
+
+    # -- creation helpers (always drawn on CPU in fp32, then moved) ----------------------
+    def _new(self, name, make):
+        if name not in self.t:
+            if self.frozen:
+                raise KeyError(f"oracle parameter '{name}' missing from the supplied state dict")
+            self.t[name] = make().to(torch.float32)
+        v = self.t[name]
+        if v.is_floating_point():
+            v = v.to(device=self.device, dtype=self.dtype)
+        else:
+            v = v.to(device=self.device)
+        return v
+
+    def conv_w(self, name, cout, cin_g, k, gain=1.0):
+        fan_in = cin_g * k * k
+        std = gain / math.sqrt(fan_in)
+        return self._new(name, lambda: torch.randn(cout, cin_g, k, k, generator=self.g) * std)
+
+    def vec(self, name, n, kind):
+        def make():
+            if kind == "gamma":
+                return 0.75 + 0.5 * torch.rand(n, generator=self.g)
+            if kind == "var":
+                return 0.6 + 0.8 * torch.rand(n, generator=self.g)
+            if kind in ("beta", "mean", "bias"):
+                return 0.1 * torch.randn(n, generator=self.g)
+            raise ValueError(kind)
+        return self._new(name, make)
+
+    def scalar(self, name, value):
+        return self._new(name, lambda: torch.full((1,), float(value)))
+
+    def count(self, name):
+        return self._new(name, lambda: torch.zeros((), dtype=torch.long).float()).long()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for k, v in self.t.items():
+            out[k] = v.long() if k.endswith("num_batches_tracked") else v
+        return out
+
+    def to(self, device=None, dtype=None) -> "Params":
+        p = Params(tensors=self.t)
+        p.device = device or self.device
+        p.dtype = dtype or self.dtype
+        return p
+
+
+# ----------------------------------------------------------------------------------------
+# leaf ops  (Appendix D semantics)
+# ----------------------------------------------------------------------------------------
+def conv2d(P: Params, x, name, cout, k=1, stride=1, padding=0, dilation=1, groups=1,
+           bias=False, gain=1.0):
+    """nn.Conv2d, OIHW cross-correlation, zero padding (torch semantics)."""
+    cin = x.shape[1]
+    w = P.conv_w(name + ".weight", cout, cin // groups, k, gain)
+    b = P.vec(name + ".bias", cout, "bias") if bias else None
+    return F.conv2d(x, w, b, stride, padding, dilation, groups)
+
+
+def batchnorm(P: Params, x, name, eps=1e-5):
+    """nn.BatchNorm2d in eval mode: (x-mean)/sqrt(var+eps)*weight+bias  (batch_norm.py:126)."""
+    c = x.shape[1]
+    g = P.vec(name + ".weight", c, "gamma")
+    b = P.vec(name + ".bias", c, "beta")
+    m = P.vec(name + ".running_mean", c, "mean")
+    v = P.vec(name + ".running_var", c, "var")
+    P.count(name + ".num_batches_tracked")
+    return F.batch_norm(x, m, v, g, b, False, 0.0, eps)
+
+
+def conv_bn_act(P, x, prefix, cout, k, stride=1, padding=0, dilation=1, groups=1, act="relu",
+                eps=1e-5, conv="conv", bn="bn"):
+    """_ConvBNReLU / _ConvBN  (modules/basic.py:65-77, :95-105)."""
+    gain = math.sqrt(2.0)
+    x = conv2d(P, x, f"{prefix}.{conv}" if conv else prefix, cout, k, stride, padding, dilation,
+               groups, gain=gain)
+    x = batchnorm(P, x, f"{prefix}.{bn}", eps)
+    if act == "relu":
+        x = F.relu(x)
+    elif act == "relu6":
+        x = F.relu6(x)
+    return x
+
+
+def separable_conv2d(P, x, prefix, planes, stride=1, dilation=1, relu_first=True, eps=1e-5,
+                     pw_gain=1.0):
+    """SeparableConv2d (modules/basic.py:34-62).
+
+    relu_first=True : ReLU -> dw3x3(pad=dil) -> BN -> pw1x1 -> BN
+    relu_first=False: dw3x3 -> BN -> ReLU -> pw1x1 -> BN -> ReLU
+    """
+    c = x.shape[1]
+    p = prefix + ".block"
+    if relu_first:
+        x = F.relu(x)                                   # not in place: input re-used by the skip
+    x = conv2d(P, x, p + ".depthwise", c, 3, stride, dilation, dilation, groups=c,
+               gain=math.sqrt(2.0) if relu_first else 1.0)
+    x = batchnorm(P, x, p + ".bn_depth", eps)
+    if not relu_first:
+        x = F.relu(x)
+    x = conv2d(P, x, p + ".pointwise", planes, 1,
+               gain=pw_gain * (math.sqrt(2.0) if not relu_first else 1.0))
+    x = batchnorm(P, x, p + ".bn_point", eps)
+    if not relu_first:
+        x = F.relu(x)
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# Xception65  (models/backbones/xception.py)
+# ----------------------------------------------------------------------------------------
+def xception_block(P, x, prefix, chans, stride=1, dilation=1, skip="conv", relu_first=True,
+                   low_feat=False, eps=1e-5):
+    """XceptionBlock (xception.py:10-51): 3 separable convs + {conv|sum|none} skip, no ReLU
+    after the add."""
+    sc1 = separable_conv2d(P, x, prefix + ".sep_conv1", chans[1], 1, dilation, relu_first, eps)
+    sc2 = separable_conv2d(P, sc1, prefix + ".sep_conv2", chans[2], 1, dilation, relu_first, eps)
+    # (synthetic-weight gain only: keeps the 16 'sum' blocks from doubling the variance each)
+    res = separable_conv2d(P, sc2, prefix + ".sep_conv3", chans[3], stride, dilation, relu_first, eps,
+                           pw_gain=0.35 if skip == "sum" else 1.0)
+    if skip == "conv":
+        s = conv2d(P, x, prefix + ".conv", chans[3], 1, stride)       # xception.py:21,38
+        s = batchnorm(P, s, prefix + ".bn", eps)                      # :22,39
+        out = res + s                                                 # :40
+    elif skip == "sum":
+        out = res + x                                                 # :42
+    else:
+        out = res                                                     # :44
+    return (out, sc2) if low_feat else out
+
+
+def xception65(P, x, prefix="encoder", output_stride=16, eps=1e-5):
+    """Xception65.forward (xception.py:129-165); stride/dilation table :57-74."""
+    if output_stride == 32:
+        b3s, mid_d, exit_d, exit_s = 2, 1, (1, 1), 2
+    elif output_stride == 16:
+        b3s, mid_d, exit_d, exit_s = 2, 1, (1, 2), 1
+    elif output_stride == 8:
+        b3s, mid_d, exit_d, exit_s = 1, 2, (2, 4), 1
+    else:
+        raise NotImplementedError(output_stride)
+    p = prefix
+    x = conv2d(P, x, p + ".conv1", 32, 3, 2, 1, gain=math.sqrt(2.0))  # :131
+    x = F.relu(batchnorm(P, x, p + ".bn1", eps))
+    x = conv2d(P, x, p + ".conv2", 64, 3, 1, 1, gain=math.sqrt(2.0))  # :135
+    x = F.relu(batchnorm(P, x, p + ".bn2", eps))
+    x = xception_block(P, x, p + ".block1", [64, 128, 128, 128], 2, eps=eps)
+    x, c1 = xception_block(P, x, p + ".block2", [128, 256, 256, 256], 2, low_feat=True, eps=eps)
+    x, c2 = xception_block(P, x, p + ".block3", [256, 728, 728, 728], b3s, low_feat=True, eps=eps)
+    for i in range(4, 20):                                            # middle flow :144-159
+        x = xception_block(P, x, f"{p}.block{i}", [728] * 4, 1, mid_d, skip="sum", eps=eps)
+    c3 = x
+    x = xception_block(P, c3, p + ".block20", [728, 728, 1024, 1024], exit_s, exit_d[0], eps=eps)
+    c4 = xception_block(P, x, p + ".block21", [1024, 1536, 1536, 2048], 1, exit_d[1],
+                        skip="none", relu_first=False, eps=eps)
+    return c1, c2, c3, c4
+
+
+# ----------------------------------------------------------------------------------------
+# MobileNetV2  (models/backbones/mobilenet.py:55-143, modules/basic.py:139-163)
+# ----------------------------------------------------------------------------------------
+def inverted_residual(P, x, prefix, cout, stride, expand, dilation=1, eps=1e-5):
+    """InvertedResidual (basic.py:139-163): [pw+BN+ReLU6] -> dw(stride,dil)+BN+ReLU6 -> pw+BN."""
+    cin = x.shape[1]
+    inter = int(round(cin * expand))
+    y, i = x, 0
+    if expand != 1:
+        y = conv_bn_act(P, y, f"{prefix}.conv.{i}", inter, 1, act="relu6", eps=eps)
+        i += 1
+    y = conv_bn_act(P, y, f"{prefix}.conv.{i}", inter, 3, stride, dilation, dilation, groups=inter,
+                    act="relu6", eps=eps)
+    i += 1
+    y = conv2d(P, y, f"{prefix}.conv.{i}", cout, 1)
+    y = batchnorm(P, y, f"{prefix}.conv.{i + 1}", eps)
+    return x + y if (stride == 1 and cin == cout) else y
+
+
+def mobilenet_v2(P, x, prefix="encoder", output_stride=16, eps=1e-5):
+    """MobileNetV2.forward (mobilenet.py:131-143).  Quirk kept: inside a dilated stage only the
+    FIRST block of each (t,c,n,s) group gets the dilation (mobilenet.py:125 vs :128)."""
+    dil = {32: (1, 1), 16: (1, 2), 8: (2, 4)}[output_stride]
+    setting = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1],
+               [6, 160, 3, 2], [6, 320, 1, 1]]
+    x = conv_bn_act(P, x, prefix + ".conv1", 32, 3, 2, 1, act="relu6", eps=eps)
+
+    def layer(x, name, rows, dilation=1):
+        j = 0
+        for t, c, n, s in rows:
+            stride = s if dilation == 1 else 1
+            x = inverted_residual(P, x, f"{prefix}.{name}.{j}", c, stride, t, dilation, eps); j += 1
+            for _ in range(n - 1):
+                x = inverted_residual(P, x, f"{prefix}.{name}.{j}", c, 1, t, 1, eps); j += 1
+        return x
+
+    x = layer(x, "block1", setting[0:1])
+    c1 = layer(x, "block2", setting[1:2])
+    c2 = layer(c1, "block3", setting[2:3])
+    c3 = layer(c2, "block4", setting[3:5], dil[0])
+    c4 = layer(c3, "block5", setting[5:], dil[1])
+    return c1, c2, c3, c4
+
+
+# ----------------------------------------------------------------------------------------
+# heads
+# ----------------------------------------------------------------------------------------
+def aspp(P, x, prefix="head.aspp", out_ch=256, output_stride=16):
+    """_ASPP.forward (modules/module.py:62-77).  Concat order [pool, aspp0..3] (:70).  Always
+    nn.BatchNorm2d with default eps (:46,54,58).  Dropout2d is identity in eval."""
+    d = {16: (6, 12, 18), 8: (12, 24, 36), 32: (6, 12, 18)}[output_stride]
+    size = x.shape[2:]
+    pool = F.adaptive_avg_pool2d(x, 1)                                                # :52
+    pool = conv_bn_act(P, pool, prefix + ".image_pooling", out_ch, 1)                  # :53-55
+    pool = F.interpolate(pool, size=size, mode="bilinear", align_corners=True)        # :64
+    x0 = conv_bn_act(P, x, prefix + ".aspp0", out_ch, 1)
+    x1 = separable_conv2d(P, x, prefix + ".aspp1", out_ch, 1, d[0], relu_first=False)
+    x2 = separable_conv2d(P, x, prefix + ".aspp2", out_ch, 1, d[1], relu_first=False)
+    x3 = separable_conv2d(P, x, prefix + ".aspp3", out_ch, 1, d[2], relu_first=False)
+    y = torch.cat((pool, x0, x1, x2, x3), dim=1)
+    return conv_bn_act(P, y, prefix, out_ch, 1)                                       # :72-74
+
+
+def deeplab_head(P, c4, c1, nclass, prefix="head", use_aspp=True, use_decoder=True,
+                 output_stride=16):
+    """_DeepLabHead.forward (models/deeplabv3_plus.py:66-75)."""
+    x = c4
+    if use_aspp:
+        x = aspp(P, x, prefix + ".aspp", 256, output_stride)
+    if use_decoder:
+        x = F.interpolate(x, c1.shape[2:], mode="bilinear", align_corners=True)       # :71
+        c1 = conv_bn_act(P, c1, prefix + ".c1_block", 48, 1)                          # :72
+        x = torch.cat([x, c1], dim=1)                                                 # :73
+    x = separable_conv2d(P, x, prefix + ".block.0", 256, relu_first=False)            # :62
+    x = separable_conv2d(P, x, prefix + ".block.1", 256, relu_first=False)            # :63
+    return conv2d(P, x, prefix + ".block.2", nclass, 1, bias=True, gain=4.0)          # :64
+
+
+def deeplabv3plus(P, x, backbone="xception65", nclass=19, output_stride=16, eps_encoder=1e-5,
+                  use_aspp=True, use_decoder=True, return_lowres=False):
+    """DeepLabV3Plus.forward (models/deeplabv3_plus.py:33-46), aux head off (SOLVER.AUX False).
+
+    ``eps_encoder`` mirrors cfg.MODEL.BN_EPS_FOR_ENCODER applied by tools/eval.py:50-53
+    (1e-3 for the Xception65 YAML)."""
+    size = x.shape[2:]
+    if backbone == "xception65":
+        c1, _, _, c4 = xception65(P, x, "encoder", output_stride, eps_encoder)
+    elif backbone == "mobilenet_v2":
+        c1, _, _, c4 = mobilenet_v2(P, x, "encoder", output_stride, eps_encoder)
+    else:
+        raise NotImplementedError(backbone)
+    y = deeplab_head(P, c4, c1, nclass, "head", use_aspp, use_decoder, output_stride)
+    out = F.interpolate(y, size, mode="bilinear", align_corners=True)                 # :39
+    return (out, y) if return_lowres else out
+
+
+def pyramid_pooling(P, x, prefix, sizes=(1, 2, 3, 6)):
+    """PyramidPooling.forward (modules/module.py:92-97): cat[x, up(conv(pool_s(x)))...]."""
+    c = x.shape[1]
+    size = x.shape[2:]
+    feats = [x]
+    for i, s in enumerate(sizes):
+        y = F.adaptive_avg_pool2d(x, s)
+        y = conv_bn_act(P, y, f"{prefix}.convs.{i}", c // 4, 1)
+        feats.append(F.interpolate(y, size, mode="bilinear", align_corners=True))
+    return torch.cat(feats, dim=1)
+
+
+def pam(P, x, prefix, gamma=0.5):
+    """PAM_Module.forward (modules/module.py:112-131): softmax(Q^T K) (no 1/sqrt(d)), V A^T,
+    gamma*out + x.  q/k/v 1x1 convs carry bias (:106-108).  ``gamma`` non-zero on creation so
+    the branch is not vacuous (reference default 0, :109)."""
+    b, c, h, w = x.shape
+    q = conv2d(P, x, prefix + ".query_conv", c // 8, 1, bias=True).view(b, -1, h * w).permute(0, 2, 1)
+    k = conv2d(P, x, prefix + ".key_conv", c // 8, 1, bias=True).view(b, -1, h * w)
+    v = conv2d(P, x, prefix + ".value_conv", c, 1, bias=True).view(b, -1, h * w)
+    g = P.scalar(prefix + ".gamma", gamma)
+    att = torch.softmax(torch.bmm(q, k), dim=-1)
+    out = torch.bmm(v, att.permute(0, 2, 1)).view(b, c, h, w)
+    return g * out + x
+
+
+def cam(P, x, prefix, gamma=0.5):
+    """CAM_Module.forward (modules/module.py:142-162): E = X X^T, softmax(rowmax(E) - E), A X."""
+    b, c, h, w = x.shape
+    q = x.view(b, c, -1)
+    e = torch.bmm(q, q.permute(0, 2, 1))
+    e = torch.max(e, -1, keepdim=True)[0].expand_as(e) - e
+    att = torch.softmax(e, dim=-1)
+    out = torch.bmm(att, q).view(b, c, h, w)
+    return P.scalar(prefix + ".gamma", gamma) * out + x
+
+
+def ca_weight(t, f):
+    """_C.ca_forward (csrc/criss_cross_attention/ca_cuda.cu:8-36): energies over the criss-cross
+    neighbourhood.  Output channel z<W: same row, column z (self included); z>=W: same column,
+    row j = i<y ? i : i+1 with i=z-W (self excluded)."""
+    n, c, h, w = t.shape
+    row = torch.einsum("nchw,nchv->nvhw", t, f)          # [n, W(key col v), h, w]
+    col = torch.einsum("nchw,ncjw->njhw", t, f)          # [n, H(key row j), h, w]
+    out = t.new_zeros(n, h + w - 1, h, w)
+    out[:, :w] = row
+    for y in range(h):
+        js = [j for j in range(h) if j != y]
+        out[:, w:, y, :] = col[:, js, y, :]
+    return out
+
+
+def ca_map(wgt, g):
+    """_C.ca_map_forward (ca_cuda.cu:94-120): aggregate values with the same index map."""
+    n, c, h, w = g.shape
+    out = torch.einsum("nvhw,nchv->nchw", wgt[:, :w], g)
+    for y in range(h):
+        js = [j for j in range(h) if j != y]
+        out[:, :, y, :] += torch.einsum("njw,ncjw->ncw", wgt[:, w:, y, :], g[:, :, js, :])
+    return out
+
+
+def criss_cross_attention(P, x, prefix, gamma=0.5):
+    """CrissCrossAttention.forward (modules/cc_attention.py:62-72): softmax over H+W-1 (dim 1)."""
+    c = x.shape[1]
+    q = conv2d(P, x, prefix + ".query_conv", c // 8, 1, bias=True)
+    k = conv2d(P, x, prefix + ".key_conv", c // 8, 1, bias=True)
+    v = conv2d(P, x, prefix + ".value_conv", c, 1, bias=True)
+    att = torch.softmax(ca_weight(q, k), dim=1)
+    return P.scalar(prefix + ".gamma", gamma) * ca_map(att, v) + x
+
+
+# ----------------------------------------------------------------------------------------
+# convenience
+# ----------------------------------------------------------------------------------------
+MODELS = {
+    # name: (forward kwargs)  -- BASELINE.json configs
+    "deeplabv3plus_xception65": dict(backbone="xception65", eps_encoder=1e-3, use_aspp=True,
+                                     use_decoder=True),
+    "deeplabv3plus_mobilenet_v2": dict(backbone="mobilenet_v2", eps_encoder=1e-5, use_aspp=False,
+                                       use_decoder=False),
+}
+
+
+def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
+    """Create the full reference-named parameter dict for ``model`` by tracing one tiny forward."""
+    P = Params(seed)
+    with torch.no_grad():
+        deeplabv3plus(P, torch.zeros(1, 3, 33, 33), nclass=nclass, **MODELS[model])
+    P.frozen = True
+    return P
+
+
+def forward(model: str, P: Params, x, nclass: int = 19, **kw):
+    with torch.no_grad():
+        return deeplabv3plus(P, x, nclass=nclass, **MODELS[model], **kw)
