@@ -1,0 +1,134 @@
+/* segb200 -- C ABI of the B200-native compute engine for SegmenTron's dense hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own for
+ * this path other than the pybind module `segmentron._C` (segmentron/modules/csrc/vision.cpp:6-11)
+ * and, for everything else, `torch.nn.functional` calls made from its nn.Module classes.  Each entry
+ * point below names the reference call site(s) it replaces.  INTEGRATION.md shows the Python/ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions (segmentron/modules/csrc/criss_cross_attention/ca.h:25-72 is the model):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - activations are NHWC ("channels_last"), element type `dtype` (SEGB200_BF16 / SEGB200_F16),
+ *     channel pitch `*_ld` in elements so a tensor may be a channel slice of a wider buffer
+ *     (this is how torch.cat on the hot path is eliminated); pitches and channel counts are
+ *     multiples of 8 elements (16 bytes) unless stated otherwise;
+ *   - every function enqueues work on `stream` (a cudaStream_t) and returns immediately:
+ *     0 = ok, negative = argument error, positive = cudaError_t.  No function synchronises,
+ *     allocates device memory or throws.  `segb200_last_error()` returns a thread-local message.
+ *   - re-entrant; no global mutable state besides the lazily resolved driver entry point.
+ */
+#ifndef SEGB200_H_
+#define SEGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGB200_VERSION 100
+
+enum { SEGB200_BF16 = 0, SEGB200_F16 = 1, SEGB200_F32 = 2 };
+enum { SEGB200_ACT_NONE = 0, SEGB200_ACT_RELU = 1, SEGB200_ACT_RELU6 = 2 };
+
+int segb200_version(void);
+const char* segb200_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense convolution as an implicit GEMM on tcgen05 tensor cores, with the following
+ * BatchNorm (folded to per-channel scale/shift), residual add and activation fused in the epilogue:
+ *     y = act( conv(x, w) * scale[c] + shift[c] + residual )
+ * Replaces: F.conv2d + F.batch_norm + F.relu sequences of `_ConvBNReLU` / `_ConvBN`
+ * (modules/basic.py:65-77, :95-105), the pointwise half of `SeparableConv2d` (basic.py:42-43),
+ * the 1x1 shortcut + add of `XceptionBlock` (backbones/xception.py:37-42), ResNet bottleneck
+ * convs (backbones/resnet.py:50-58,78-79), ASPP / classifier 1x1 convs (modules/module.py:45-59,
+ * models/deeplabv3_plus.py:62-64).
+ *
+ * wgt: packed [cout][kh*kw][cin_pad] (K-major), element type `dtype`, cin_pad = cin rounded up to a
+ *      multiple of the K block (64, or 32/16 when cin < 64); build it with segb200_conv_kblock().
+ * Output spatial size (ho, wo) and the top/left padding are explicit so that asymmetric cases
+ * (space-to-depth stems) are expressible: tap (ky,kx) reads x[ho*stride + ky*dilation - pad_t, ...].
+ */
+typedef struct segb200_conv_args {
+  const void* x;        /* [n][h][w][x_ld] */
+  const void* wgt;      /* packed weights */
+  const float* scale;   /* [cout] or NULL (1.0) */
+  const float* shift;   /* [cout] or NULL (0.0) */
+  const void* residual; /* [n][ho][wo][res_ld] or NULL */
+  void* y;              /* [n][ho][wo][y_ld] */
+  int32_t n, h, w, cin, x_ld;
+  int32_t ho, wo, cout, y_ld, res_ld;
+  int32_t kh, kw, stride, dilation, pad_t, pad_l;
+  int32_t act;          /* SEGB200_ACT_* */
+  int32_t dtype;        /* SEGB200_BF16 | SEGB200_F16 */
+  int32_t max_ctas;     /* 0 = number of SMs */
+} segb200_conv_args;
+
+int segb200_conv_kblock(int cin);                 /* K block (elements) the kernel will use for `cin` */
+int segb200_conv_gemm(const segb200_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Depthwise 3x3 convolution (groups = C, padding = dilation) with optional leading ReLU and the
+ * following BatchNorm (+ ReLU/ReLU6) fused:  y = act( dw3x3(pre_relu ? relu(x) : x) + shift[c] )
+ * The BN scale is folded into the fp32 weights by the caller.
+ * Replaces: the depthwise half of `SeparableConv2d` (modules/basic.py:38-41,45-59) and the
+ * depthwise `_ConvBNReLU` of `InvertedResidual` (basic.py:152-154).
+ * wgt: fp32 [9][c] (tap-major: tap = ky*3+kx).
+ */
+typedef struct segb200_dwconv_args {
+  const void* x;        /* [n][h][w][x_ld] */
+  const float* wgt;     /* [9][c] */
+  const float* shift;   /* [c] or NULL */
+  void* y;              /* [n][ho][wo][y_ld] */
+  int32_t n, h, w, c, x_ld, y_ld;
+  int32_t ho, wo, stride, dilation;
+  int32_t pre_relu, act;
+  int32_t dtype;
+} segb200_dwconv_args;
+
+int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input packing for stride-2 stems: NCHW image (fp32 / bf16 / fp16) -> space-to-depth NHWC
+ *   out[n][i][j][(dy*2+dx)*c + ch] = x[n][ch][2i+dy][2j+dx]   (zero beyond the image; channels
+ *   4c..ld-1 zero), so that a kxk stride-2 conv becomes a ceil((k+1)/2)^2 stride-1 conv on the
+ *   tensor cores.  Replaces the first conv's input read (backbones/xception.py:131,
+ *   mobilenet.py:79, resnet.py:116).   hs = ceil(h/2), ws = ceil(w/2).
+ */
+int segb200_pack_s2d(const void* x_nchw, int x_dtype, void* out, int out_dtype, int n, int c, int h, int w,
+                     int out_ld, void* stream);
+
+/* Global average pool over H*W: x [n][h][w][x_ld] -> out [n][c] (dtype), fp32 accumulation.
+ * `workspace`: n*c floats, zeroed by the call.  Replaces nn.AdaptiveAvgPool2d((1,1)) (module.py:52). */
+int segb200_global_avgpool(const void* x, void* out, float* workspace, int n, int h, int w, int c, int x_ld,
+                           int dtype, void* stream);
+
+/* Adaptive average pool to s x s bins (torch bin rule floor/ceil): out [n][s][s][out_ld].
+ * Replaces nn.AdaptiveAvgPool2d(s) of PyramidPooling (module.py:89). */
+int segb200_adaptive_avgpool(const void* x, void* out, int n, int h, int w, int c, int x_ld, int s, int out_ld,
+                             int dtype, void* stream);
+
+/* Bilinear resize NHWC -> NHWC channel slice.  align_corners as F.interpolate.  From a 1x1 source
+ * this is the ASPP image-pooling broadcast (module.py:64).  Replaces F.interpolate at
+ * module.py:64,96, deeplabv3_plus.py:71, hrnet_seg.py:57-59. */
+int segb200_bilinear_nhwc(const void* x, void* y, int n, int hi, int wi, int c, int x_ld, int ho, int wo,
+                          int y_ld, int align_corners, int dtype, void* stream);
+
+/* Final logits upsample: NHWC [n][hi][wi][x_ld] (first c channels) -> NCHW [n][c][ho][wo] contiguous,
+ * `out_dtype` may be the input dtype or SEGB200_F32.  Replaces F.interpolate at deeplabv3_plus.py:39,
+ * danet.py:32-34.  If `argmax_out` is non-NULL also writes the per-pixel argmax class (uint8,
+ * first-max tie-break like torch.argmax) -- the fused metric path of SURVEY.md 8(f1). */
+int segb200_bilinear_nchw_out(const void* x, void* y, uint8_t* argmax_out, int n, int hi, int wi, int c,
+                              int x_ld, int ho, int wo, int align_corners, int dtype, int out_dtype,
+                              void* stream);
+
+/* Layout converters at the module boundary: logical-NCHW contiguous <-> NHWC (channel pitch ld). */
+int segb200_nchw_to_nhwc(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w, int y_ld,
+                         void* stream);
+int segb200_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w, int x_ld,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGB200_H_ */

@@ -1,0 +1,440 @@
+// segb200 -- dense convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * W[cout, tap, cin]
+//   y = act(D * scale + shift + residual)
+//
+// One persistent CTA per SM, 6 warps, warp-specialised:
+//   warp 0      : TMA producer. A tiles are 4-D boxes {K-block channels, BW, BH, 1} of the NHWC
+//                 activation (BW*BH = 128 output pixels); the tap shift is a coordinate offset and the
+//                 conv zero padding is TMA out-of-bounds zero fill.  Stride-2 convs read one of up
+//                 to four parity views (doubled strides) of the same tensor.  B tiles are 2-D boxes
+//                 {K-block, BN} of the packed K-major weights.  Both land in 128B/64B/32B-swizzled smem.
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N<=256, K=16 per instr),
+//                 fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns) so the epilogue
+//                 of tile i overlaps the main loop of tile i+1.
+//   warps 2..5  : epilogue. tcgen05.ld 32 columns at a time -> scale/shift (+residual) -> activation
+//                 -> bf16/fp16 -> 128B-swizzled smem staging -> TMA store (which clips the M and N tails
+//                 and writes straight into a channel slice of the consumer's buffer).
+// smem ring: num_stages x {A 128 x bk_bytes, B bn x bk_bytes} in the first 192 KB, 2 x 16 KB store
+// staging, then the control block (mbarriers, TMEM base, scale/shift of the current N tile).
+#include "common.cuh"
+#include "../../include/segb200.h"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace segb200 {
+
+constexpr int kStageRegion = 196608;          // bytes for the A/B ring
+constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
+constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
+constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct Control {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  float scale[256];
+  float shift[256];
+};
+static_assert(sizeof(Control) <= 2304, "control block too large");
+
+struct ConvGemmParams {
+  int n_img, ho, wo;
+  int bw, bh, wtiles, htiles;
+  int n_tiles, total_tiles;
+  int cout, bn;
+  int cblocks, ntaps, bk_bytes, num_stages;
+  int a_stage_bytes, b_stage_bytes;
+  int act;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  long long res_ld;
+  uint32_t taps[64];   // map id (bits 0..1) | (off_w + 128) << 8 | (off_h + 128) << 16
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Control* ctl = reinterpret_cast<Control*>(smem + kCtlOffset);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int num_kb = p.ntaps * p.cblocks;
+  const int bk_elems = p.bk_bytes >> 1;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("segb200: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      const CUtensorMap* amaps[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(128 * p.bk_bytes + p.bn * p.bk_bytes);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
+        const int hb = m_tile % p.htiles;
+        const int img = m_tile / p.htiles;
+        const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = n_tile * p.bn;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const uint32_t t = p.taps[tap];
+          const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          mbar_expect_tx(&ctl->full[stage], tx);
+          uint8_t* sa = smem + stage * stage_bytes;
+          tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img);
+          tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, kb * bk_elems, n0);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      const int kmma = p.bk_bytes >> 5;          // K=16 elements (32 B) per instruction
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int n0 = n_tile * p.bn;
+        int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+        const uint32_t umma_n = (uint32_t)((nvalid + 15) & ~15);
+        const uint32_t idesc = make_idesc(kBF16, umma_n);
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
+          const uint64_t bdesc = make_kmajor_desc(sa + (uint32_t)p.a_stage_bytes, (uint32_t)p.bk_bytes);
+          for (int k = 0; k < kmma; ++k)
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(&ctl->empty[stage]);           // frees the smem slot when these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&ctl->tmem_full[acc]);            // accumulator ready for the epilogue
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    using H = Half2<kBF16>;
+    const int et = threadIdx.x - 64;                 // 0..127
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;                   // tile row == TMEM lane
+    uint8_t* epi = smem + kStageRegion;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
+      const int hb = m_tile % p.htiles;
+      const int img = m_tile / p.htiles;
+      const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = n_tile * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      const int nchunks = (nvalid + 63) >> 6;
+
+      named_bar_sync(1, 128);                        // previous tile's readers of scale/shift are done
+      for (int i = et; i < p.bn; i += 128) {
+        const int c = n0 + i;
+        ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
+        ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
+      }
+      // residual row pointer (pixel of this thread's row), or null if the row is outside the image
+      const int ph = h0 + row / p.bw, pw = w0 + row % p.bw;
+      const bool row_ok = ph < p.ho && pw < p.wo;
+      const typename H::T* res_row = nullptr;
+      if (p.residual != nullptr && row_ok)
+        res_row = reinterpret_cast<const typename H::T*>(p.residual) +
+                  ((long long)(img * p.ho + ph) * p.wo + pw) * p.res_ld + n0;
+
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+      for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
+        uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
+        if (et == 0) tma_store_wait_read<1>();       // the store that last used `buf` has drained it
+        named_bar_sync(1, 128);                      // (also publishes scale/shift on the first chunk)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col0 = ch * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = col0 + g * 8 + j;
+              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), ctl->scale[c], ctl->shift[c]);
+            }
+            if (res_row != nullptr && (col0 + g * 8) < nvalid) {
+              const uint4 r = ldg_nc_v4(res_row + col0 + g * 8);
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t2 = H::unpack(rr[j]);
+                f[2 * j] += t2.x; f[2 * j + 1] += t2.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              packed[g * 4 + j] = H::pack(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
+          }
+          // 128B-swizzled staging row: 16 B chunk c lives at chunk (c ^ (row & 7))
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk16 = (half * 4 + g) ^ (row & 7);
+            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) =
+                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl->tmem_empty[acc]);             // 128 arrivals release the accumulator stage
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, int dtype, int rank, const void* base, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(m, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(-11, "cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+                     what, (int)r, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+                     (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0), b[0],
+                     rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0);
+  return 0;
+}
+
+static int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
+  const int p = ((o % 2) + 2) % 2;
+  *parity = p;
+  return (o - p) / 2;
+}
+
+}  // namespace segb200
+
+using namespace segb200;
+
+extern "C" int segb200_conv_kblock(int cin) { return cin >= 64 ? 64 : (cin >= 32 ? 32 : 16); }
+
+extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->x || !a->wgt || !a->y) return set_error(-1, "conv_gemm: null pointer argument");
+  if (a->dtype != DT_BF16 && a->dtype != DT_F16) return set_error(-2, "conv_gemm: dtype must be bf16 or f16");
+  if (a->stride != 1 && a->stride != 2) return set_error(-3, "conv_gemm: stride must be 1 or 2");
+  if ((a->x_ld & 7) || (a->y_ld & 7) || (a->cin & 7) || (a->cout & 7) || a->cin > a->x_ld || a->cout > a->y_ld)
+    return set_error(-4, "conv_gemm: channel counts/pitches must be multiples of 8 (cin %d x_ld %d cout %d y_ld %d)",
+                     a->cin, a->x_ld, a->cout, a->y_ld);
+  if (a->residual && ((a->res_ld & 7) || a->res_ld < a->cout)) return set_error(-4, "conv_gemm: bad res_ld");
+  const int ntaps = a->kh * a->kw;
+  if (ntaps < 1 || ntaps > 64) return set_error(-5, "conv_gemm: unsupported kernel %dx%d", a->kh, a->kw);
+  if (a->n < 1 || a->ho < 1 || a->wo < 1) return set_error(-6, "conv_gemm: empty output");
+  if (((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15) || ((uintptr_t)a->wgt & 15) || ((uintptr_t)a->residual & 15))
+    return set_error(-7, "conv_gemm: pointers must be 16-byte aligned");
+
+  const int bk = segb200_conv_kblock(a->cin);
+  const int bk_bytes = bk * 2;
+  const int cblocks = (a->cin + bk - 1) / bk;
+  const int cin_pad = cblocks * bk;
+  const long long ktot = (long long)ntaps * cin_pad;
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- M tiling: flattened pixels for contiguous 1x1 stride-1, else a BW x BH patch per image ----
+  const bool flat = (ntaps == 1 && a->stride == 1 && a->pad_t == 0 && a->pad_l == 0 && a->ho == a->h && a->wo == a->w);
+  long long Wv_out, Hv_out, Nv_out;   // output extents as seen by the C map
+  if (flat) {
+    Wv_out = (long long)a->n * a->h * a->w; Hv_out = 1; Nv_out = 1;
+    p.bw = 128; p.bh = 1;
+  } else {
+    Wv_out = a->wo; Hv_out = a->ho; Nv_out = a->n;
+    long long best = -1;
+    const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
+    for (int i = 0; i < 5; ++i) {
+      const long long t = (long long)((a->wo + cand[i][0] - 1) / cand[i][0]) * ((a->ho + cand[i][1] - 1) / cand[i][1]);
+      if (best < 0 || t < best) { best = t; p.bw = cand[i][0]; p.bh = cand[i][1]; }
+    }
+  }
+  p.n_img = (int)Nv_out; p.ho = (int)Hv_out; p.wo = (int)Wv_out;
+  if (Wv_out > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many pixels");
+  p.wtiles = (int)((Wv_out + p.bw - 1) / p.bw);
+  p.htiles = (int)((Hv_out + p.bh - 1) / p.bh);
+  // ---- N tiling ----
+  p.cout = a->cout;
+  p.bn = a->cout >= 256 ? 256 : ((a->cout + 15) & ~15);
+  p.n_tiles = (a->cout + p.bn - 1) / p.bn;
+  const long long total = (long long)p.wtiles * p.htiles * p.n_img * p.n_tiles;
+  if (total > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many tiles");
+  p.total_tiles = (int)total;
+  p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
+  p.a_stage_bytes = 128 * bk_bytes;
+  p.b_stage_bytes = ((p.bn * bk_bytes) + 1023) & ~1023;
+  p.num_stages = kStageRegion / (p.a_stage_bytes + p.b_stage_bytes);
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
+
+  // ---- A maps (parity views for stride 2) and the tap table ----
+  CUtensorMap tmA[4], tmB, tmC;
+  memset(tmA, 0, sizeof(tmA));
+  bool used[4] = {false, false, false, false};
+  for (int ky = 0; ky < a->kh; ++ky)
+    for (int kx = 0; kx < a->kw; ++kx) {
+      const int oh = ky * a->dilation - a->pad_t, ow = kx * a->dilation - a->pad_l;
+      int ph = 0, pw = 0, ah = oh, aw = ow;
+      if (a->stride == 2) { ah = floordiv2(oh, &ph); aw = floordiv2(ow, &pw); }
+      if (ah < -128 || ah > 127 || aw < -128 || aw > 127) return set_error(-9, "conv_gemm: tap offset out of range");
+      const int mid = ph * 2 + pw;
+      used[mid] = true;
+      p.taps[ky * a->kw + kx] = (uint32_t)mid | ((uint32_t)(aw + 128) << 8) | ((uint32_t)(ah + 128) << 16);
+    }
+  const char* xb = reinterpret_cast<const char*>(a->x);
+  const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+  for (int mid = 0; mid < 4; ++mid) {
+    if (!used[mid]) continue;
+    int rc;
+    if (flat) {
+      const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)Wv_out, 1, 1};
+      const uint64_t str[3] = {(uint64_t)a->x_ld * 2, (uint64_t)a->x_ld * 2 * (uint64_t)Wv_out,
+                               (uint64_t)a->x_ld * 2 * (uint64_t)Wv_out};
+      rc = encode_map(&tmA[mid], a->dtype, 4, xb, dims, str, boxA, bk_bytes, "A/flat");
+    } else {
+      const int s = a->stride, ph = mid >> 1, pw = mid & 1;
+      if (ph >= a->h || pw >= a->w) {   // degenerate parity view: point at pixel 0 with zero extent impossible -> 1x1 view never hit
+        return set_error(-9, "conv_gemm: input too small for stride-2 parity view");
+      }
+      const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)((a->w - pw + s - 1) / s), (uint64_t)((a->h - ph + s - 1) / s),
+                                (uint64_t)a->n};
+      const uint64_t str[3] = {(uint64_t)a->x_ld * 2 * s, (uint64_t)a->x_ld * 2 * a->w * s,
+                               (uint64_t)a->x_ld * 2 * a->w * a->h};
+      rc = encode_map(&tmA[mid], a->dtype, 4, xb + ((long long)ph * a->w + pw) * a->x_ld * 2, dims, str, boxA, bk_bytes,
+                      "A/patch");
+    }
+    if (rc) return rc;
+  }
+  for (int mid = 0; mid < 4; ++mid)
+    if (!used[mid]) for (int j = 0; j < 4; ++j) if (used[j]) { tmA[mid] = tmA[j]; break; }
+  {
+    const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
+    const uint64_t str[1] = {(uint64_t)ktot * 2};
+    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)p.bn};
+    int rc = encode_map(&tmB, a->dtype, 2, a->wgt, dims, str, box, bk_bytes, "B");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)Wv_out, (uint64_t)Hv_out, (uint64_t)Nv_out};
+    const uint64_t str[3] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 2 * (uint64_t)Wv_out,
+                             (uint64_t)a->y_ld * 2 * (uint64_t)Wv_out * (uint64_t)Hv_out};
+    const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+    int rc = encode_map(&tmC, a->dtype, 4, a->y, dims, str, box, 128, "C");
+    if (rc) return rc;
+  }
+
+  int grid = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  });
+  if (a->dtype == DT_BF16)
+    conv_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, p);
+  else
+    conv_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, p);
+  return check_launch("conv_gemm");
+}

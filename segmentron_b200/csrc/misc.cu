@@ -1,0 +1,369 @@
+// segb200 -- memory-bound glue kernels (NHWC, 128-bit vectors, fp32 math): stem packing, pooling,
+// bilinear resize, layout converters.  All are HBM-roofline kernels (no data reuse beyond L1/L2).
+#include "common.cuh"
+#include "../../include/segb200.h"
+
+namespace segb200 {
+
+__device__ __forceinline__ float load_any(const void* p, long long i, int dtype) {
+  if (dtype == DT_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void store_any(void* p, long long i, float v, int dtype) {
+  if (dtype == DT_F32) reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+__device__ __forceinline__ uint32_t pack_any(float a, float b, int dtype) {
+  return dtype == DT_BF16 ? Half2<true>::pack(a, b) : Half2<false>::pack(a, b);
+}
+__device__ __forceinline__ float2 unpack_any(uint32_t u, int dtype) {
+  return dtype == DT_BF16 ? Half2<true>::unpack(u) : Half2<false>::unpack(u);
+}
+__device__ __forceinline__ float round_any(float v, int dtype) {
+  if (dtype == DT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (dtype == DT_F16) return __half2float(__float2half_rn(v));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, int dtype, float (&f)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = unpack_any(u[j], dtype); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int dtype) {
+  return make_uint4(pack_any(f[0], f[1], dtype), pack_any(f[2], f[3], dtype), pack_any(f[4], f[5], dtype),
+                    pack_any(f[6], f[7], dtype));
+}
+
+static inline int grid_for(long long total, int block) {
+  long long b = (total + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+// -------------------------------------------------------------------------------------------
+// space-to-depth stem packing
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_s2d_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ out, int out_dtype, int n, int c, int h,
+                int w, int hs, int ws, int out_ld) {
+  const int groups = out_ld / 8;
+  const long long total = (long long)n * hs * ws * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    long long r = idx / groups;
+    const int j = (int)(r % ws); r /= ws;
+    const int i = (int)(r % hs);
+    const int b = (int)(r / hs);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch4 = g * 8 + k;
+      float v = 0.f;
+      if (ch4 < 4 * c) {
+        const int par = ch4 / c, ch = ch4 - par * c;
+        const int yy = 2 * i + (par >> 1), xx = 2 * j + (par & 1);
+        if (yy < h && xx < w) v = load_any(x, (((long long)b * c + ch) * h + yy) * w + xx, x_dtype);
+      }
+      f[k] = v;
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (((long long)b * hs + i) * ws + j) * out_ld * 2 + g * 16) =
+        pack8(f, out_dtype);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// global average pool
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gap_partial_kernel(const void* __restrict__ x, float* __restrict__ ws, int hw, int c, int x_ld, int dtype, int lanes_c,
+                   int lanes_p, int splits) {
+  const int n = blockIdx.y;
+  const int lc = threadIdx.x % lanes_c, lp = threadIdx.x / lanes_c;
+  if (lp >= lanes_p) return;
+  const int cvn = c / 8;
+  const int per = (hw + splits - 1) / splits;
+  const int p0 = blockIdx.x * per;
+  const int p1 = min(hw, p0 + per);
+  const char* base = reinterpret_cast<const char*>(x) + (long long)n * hw * x_ld * 2;
+  for (int cv = lc; cv < cvn; cv += lanes_c) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = p0 + lp; p < p1; p += lanes_p) {
+      float f[8];
+      unpack8(ldg_nc_v4(base + ((long long)p * x_ld + cv * 8) * 2), dtype, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(ws + (long long)n * c + cv * 8 + j, acc[j]);
+  }
+}
+__global__ void gap_finalize_kernel(const float* __restrict__ ws, void* __restrict__ out, int total, float inv,
+                                    int dtype) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) store_any(out, i, ws[i] * inv, dtype);
+}
+
+// -------------------------------------------------------------------------------------------
+// adaptive average pool to s x s
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+adaptive_pool_kernel(const void* __restrict__ x, void* __restrict__ out, int n, int h, int w, int c, int x_ld, int s,
+                     int out_ld, int dtype) {
+  const int cvn = c / 8;
+  const long long total = (long long)n * s * s * cvn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    long long r = idx / cvn;
+    const int bj = (int)(r % s); r /= s;
+    const int bi = (int)(r % s);
+    const int b = (int)(r / s);
+    const int h0 = (bi * h) / s, h1 = ((bi + 1) * h + s - 1) / s;
+    const int w0 = (bj * w) / s, w1 = ((bj + 1) * w + s - 1) / s;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int yy = h0; yy < h1; ++yy)
+      for (int xx = w0; xx < w1; ++xx) {
+        float f[8];
+        unpack8(ldg_nc_v4(reinterpret_cast<const char*>(x) + ((((long long)b * h + yy) * w + xx) * x_ld + cv * 8) * 2),
+                dtype, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + ((((long long)b * s + bi) * s + bj) * out_ld + cv * 8) * 2) =
+        pack8(acc, dtype);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// bilinear resize (torch upsample_bilinear2d index rules, fp32 math)
+// -------------------------------------------------------------------------------------------
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out, int align) {
+  float src;
+  if (align) {
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = scale * (float)dst;
+  } else {
+    const float scale = (float)in / (float)out;
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  Lerp r;
+  r.i0 = (int)src;
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int hi, int wi, int c, int x_ld, int ho,
+                     int wo, int y_ld, int align, int dtype) {
+  const int cvn = c / 8;
+  const long long total = (long long)n * ho * wo * cvn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    long long r = idx / cvn;
+    const int ox = (int)(r % wo); r /= wo;
+    const int oy = (int)(r % ho);
+    const int b = (int)(r / ho);
+    const Lerp ly = lerp_coord(oy, hi, ho, align), lx = lerp_coord(ox, wi, wo, align);
+    const char* base = reinterpret_cast<const char*>(x) + ((long long)b * hi * wi * x_ld + cv * 8) * 2;
+    float f00[8], f01[8], f10[8], f11[8], o[8];
+    unpack8(ldg_v4(base + ((long long)ly.i0 * wi + lx.i0) * x_ld * 2), dtype, f00);
+    unpack8(ldg_v4(base + ((long long)ly.i0 * wi + lx.i1) * x_ld * 2), dtype, f01);
+    unpack8(ldg_v4(base + ((long long)ly.i1 * wi + lx.i0) * x_ld * 2), dtype, f10);
+    unpack8(ldg_v4(base + ((long long)ly.i1 * wi + lx.i1) * x_ld * 2), dtype, f11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = ly.l0 * (lx.l0 * f00[j] + lx.l1 * f01[j]) + ly.l1 * (lx.l0 * f10[j] + lx.l1 * f11[j]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + ((((long long)b * ho + oy) * wo + ox) * y_ld + cv * 8) * 2) =
+        pack8(o, dtype);
+  }
+}
+
+// NHWC low-res logits -> NCHW full-res (+ optional fused argmax). One thread per output pixel.
+template <int kMaxC>
+__global__ void __launch_bounds__(256)
+bilinear_nchw_out_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ amax, int n, int hi,
+                         int wi, int c, int x_ld, int ho, int wo, int align, int dtype, int out_dtype) {
+  const long long total = (long long)n * ho * wo;
+  const long long plane = (long long)ho * wo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % wo);
+    long long r = idx / wo;
+    const int oy = (int)(r % ho);
+    const int b = (int)(r / ho);
+    const Lerp ly = lerp_coord(oy, hi, ho, align), lx = lerp_coord(ox, wi, wo, align);
+    const char* base = reinterpret_cast<const char*>(x) + (long long)b * hi * wi * x_ld * 2;
+    const char* p00 = base + ((long long)ly.i0 * wi + lx.i0) * x_ld * 2;
+    const char* p01 = base + ((long long)ly.i0 * wi + lx.i1) * x_ld * 2;
+    const char* p10 = base + ((long long)ly.i1 * wi + lx.i0) * x_ld * 2;
+    const char* p11 = base + ((long long)ly.i1 * wi + lx.i1) * x_ld * 2;
+    float best = -INFINITY; int besti = 0;
+    char* yb = reinterpret_cast<char*>(y);
+#pragma unroll
+    for (int cv = 0; cv < kMaxC / 8; ++cv) {
+      if (cv * 8 >= c) break;
+      float f00[8], f01[8], f10[8], f11[8];
+      unpack8(ldg_v4(p00 + cv * 16), dtype, f00);
+      unpack8(ldg_v4(p01 + cv * 16), dtype, f01);
+      unpack8(ldg_v4(p10 + cv * 16), dtype, f10);
+      unpack8(ldg_v4(p11 + cv * 16), dtype, f11);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = cv * 8 + j;
+        if (ch < c) {
+          float o = ly.l0 * (lx.l0 * f00[j] + lx.l1 * f01[j]) + ly.l1 * (lx.l0 * f10[j] + lx.l1 * f11[j]);
+          o = round_any(o, out_dtype);
+          const long long oi = ((long long)b * c + ch) * plane + (long long)oy * wo + ox;
+          if (out_dtype == DT_F32) reinterpret_cast<float*>(yb)[oi] = o;
+          else if (out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(yb)[oi] = __float2bfloat16_rn(o);
+          else reinterpret_cast<__half*>(yb)[oi] = __float2half_rn(o);
+          if (o > best) { best = o; besti = ch; }
+        }
+      }
+    }
+    if (amax != nullptr) amax[idx] = (uint8_t)besti;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// layout converters: [n][c][hw] <-> [n][hw][ld]   (32x32 smem tile transpose)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ y, int y_dtype, int c, long long hw,
+                    int y_ld) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int ch = c0 + k; const long long p = p0 + tx;
+    tile[k][tx] = (ch < c && p < hw) ? load_any(x, ((long long)n * c + ch) * hw + p, x_dtype) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const long long p = p0 + k; const int ch = c0 + tx;
+    if (p < hw && ch < c) store_any(y, ((long long)n * hw + p) * y_ld + ch, tile[tx][k], y_dtype);
+  }
+}
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ y, int y_dtype, int c, long long hw,
+                    int x_ld) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const long long p = p0 + k; const int ch = c0 + tx;
+    tile[k][tx] = (p < hw && ch < c) ? load_any(x, ((long long)n * hw + p) * x_ld + ch, x_dtype) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int ch = c0 + k; const long long p = p0 + tx;
+    if (ch < c && p < hw) store_any(y, ((long long)n * c + ch) * hw + p, tile[tx][k], y_dtype);
+  }
+}
+
+}  // namespace segb200
+
+using namespace segb200;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+static inline bool half_dt(int d) { return d == DT_BF16 || d == DT_F16; }
+
+extern "C" int segb200_pack_s2d(const void* x, int x_dtype, void* out, int out_dtype, int n, int c, int h, int w,
+                                int out_ld, void* stream) {
+  if (!x || !out) return set_error(-1, "pack_s2d: null pointer");
+  if (!half_dt(out_dtype) || x_dtype < 0 || x_dtype > 2) return set_error(-2, "pack_s2d: bad dtype");
+  if ((out_ld & 7) || out_ld < 4 * c) return set_error(-4, "pack_s2d: out_ld must be a multiple of 8 and >= 4*c");
+  const int hs = (h + 1) / 2, ws = (w + 1) / 2;
+  const long long total = (long long)n * hs * ws * (out_ld / 8);
+  pack_s2d_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, x_dtype, out, out_dtype, n, c, h, w, hs, ws, out_ld);
+  return check_launch("pack_s2d");
+}
+
+extern "C" int segb200_global_avgpool(const void* x, void* out, float* workspace, int n, int h, int w, int c, int x_ld,
+                                      int dtype, void* stream) {
+  if (!x || !out || !workspace) return set_error(-1, "global_avgpool: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "global_avgpool: bad dtype");
+  if ((c & 7) || (x_ld & 7)) return set_error(-4, "global_avgpool: c and x_ld must be multiples of 8");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)n * c, STREAM(stream));
+  if (e != cudaSuccess) return set_error((int)e, "global_avgpool: memset: %s", cudaGetErrorString(e));
+  const int cvn = c / 8;
+  int lanes_c = 1; while (lanes_c < cvn && lanes_c < 256) lanes_c <<= 1;
+  const int lanes_p = 256 / lanes_c;
+  const int hw = h * w;
+  int splits = (hw + lanes_p * 8 - 1) / (lanes_p * 8);
+  if (splits > 592) splits = 592;
+  if (splits < 1) splits = 1;
+  gap_partial_kernel<<<dim3(splits, n), 256, 0, STREAM(stream)>>>(x, workspace, hw, c, x_ld, dtype, lanes_c, lanes_p, splits);
+  gap_finalize_kernel<<<(n * c + 255) / 256, 256, 0, STREAM(stream)>>>(workspace, out, n * c, 1.f / (float)hw, dtype);
+  return check_launch("global_avgpool");
+}
+
+extern "C" int segb200_adaptive_avgpool(const void* x, void* out, int n, int h, int w, int c, int x_ld, int s, int out_ld,
+                                        int dtype, void* stream) {
+  if (!x || !out) return set_error(-1, "adaptive_avgpool: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "adaptive_avgpool: bad dtype");
+  if ((c & 7) || (x_ld & 7) || (out_ld & 7) || s < 1) return set_error(-4, "adaptive_avgpool: bad sizes");
+  const long long total = (long long)n * s * s * (c / 8);
+  adaptive_pool_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(x, out, n, h, w, c, x_ld, s, out_ld, dtype);
+  return check_launch("adaptive_avgpool");
+}
+
+extern "C" int segb200_bilinear_nhwc(const void* x, void* y, int n, int hi, int wi, int c, int x_ld, int ho, int wo,
+                                     int y_ld, int align_corners, int dtype, void* stream) {
+  if (!x || !y) return set_error(-1, "bilinear_nhwc: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "bilinear_nhwc: bad dtype");
+  if ((c & 7) || (x_ld & 7) || (y_ld & 7)) return set_error(-4, "bilinear_nhwc: c/pitches must be multiples of 8");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, n, hi, wi, c, x_ld, ho, wo, y_ld,
+                                                                         align_corners, dtype);
+  return check_launch("bilinear_nhwc");
+}
+
+extern "C" int segb200_bilinear_nchw_out(const void* x, void* y, uint8_t* argmax_out, int n, int hi, int wi, int c,
+                                         int x_ld, int ho, int wo, int align_corners, int dtype, int out_dtype,
+                                         void* stream) {
+  if (!x || !y) return set_error(-1, "bilinear_nchw_out: null pointer");
+  if (!half_dt(dtype) || out_dtype < 0 || out_dtype > 2) return set_error(-2, "bilinear_nchw_out: bad dtype");
+  if ((x_ld & 7) || c < 1 || c > 256 || ((c + 7) & ~7) > x_ld) return set_error(-4, "bilinear_nchw_out: bad c/x_ld");
+  const long long total = (long long)n * ho * wo;
+  const int g = grid_for(total, 256);
+  if (c <= 32)
+    bilinear_nchw_out_kernel<32><<<g, 256, 0, STREAM(stream)>>>(x, y, argmax_out, n, hi, wi, c, x_ld, ho, wo,
+                                                                align_corners, dtype, out_dtype);
+  else
+    bilinear_nchw_out_kernel<256><<<g, 256, 0, STREAM(stream)>>>(x, y, argmax_out, n, hi, wi, c, x_ld, ho, wo,
+                                                                 align_corners, dtype, out_dtype);
+  return check_launch("bilinear_nchw_out");
+}
+
+extern "C" int segb200_nchw_to_nhwc(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w,
+                                    int y_ld, void* stream) {
+  if (!x || !y) return set_error(-1, "nchw_to_nhwc: null pointer");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, x_dtype, y, y_dtype, c, hw, y_ld);
+  return check_launch("nchw_to_nhwc");
+}
+extern "C" int segb200_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w,
+                                    int x_ld, void* stream) {
+  if (!x || !y) return set_error(-1, "nhwc_to_nchw: null pointer");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, x_dtype, y, y_dtype, c, hw, x_ld);
+  return check_launch("nhwc_to_nchw");
+}

@@ -1,0 +1,74 @@
+"""ctypes binding of the C-ABI engine library (include/segb200.h).
+
+There is NO fallback: if ``libsegb200.so`` is missing or a call fails, a RuntimeError is raised
+(the reference's own convention for its native op: ``AT_ERROR("Not implemented on the CPU")``,
+segmentron/modules/csrc/criss_cross_attention/ca.h:34).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegb200.so")
+
+BF16, F16, F32 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6}
+
+i32 = C.c_int32
+vp = C.c_void_p
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", vp), ("wgt", vp), ("scale", vp), ("shift", vp), ("residual", vp), ("y", vp),
+                ("n", i32), ("h", i32), ("w", i32), ("cin", i32), ("x_ld", i32),
+                ("ho", i32), ("wo", i32), ("cout", i32), ("y_ld", i32), ("res_ld", i32),
+                ("kh", i32), ("kw", i32), ("stride", i32), ("dilation", i32), ("pad_t", i32), ("pad_l", i32),
+                ("act", i32), ("dtype", i32), ("max_ctas", i32)]
+
+
+class DwArgs(C.Structure):
+    _fields_ = [("x", vp), ("wgt", vp), ("shift", vp), ("y", vp),
+                ("n", i32), ("h", i32), ("w", i32), ("c", i32), ("x_ld", i32), ("y_ld", i32),
+                ("ho", i32), ("wo", i32), ("stride", i32), ("dilation", i32),
+                ("pre_relu", i32), ("act", i32), ("dtype", i32)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
+SYMBOLS = {
+    "segb200_version": (C.c_int, []),
+    "segb200_last_error": (C.c_char_p, []),
+    "segb200_conv_kblock": (C.c_int, [C.c_int]),
+    "segb200_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), vp]),
+    "segb200_dwconv3x3": (C.c_int, [C.POINTER(DwArgs), vp]),
+    "segb200_pack_s2d": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
+    "segb200_global_avgpool": (C.c_int, [vp, vp, vp] + [C.c_int] * 6 + [vp]),
+    "segb200_adaptive_avgpool": (C.c_int, [vp, vp] + [C.c_int] * 8 + [vp]),
+    "segb200_bilinear_nhwc": (C.c_int, [vp, vp] + [C.c_int] * 10 + [vp]),
+    "segb200_bilinear_nchw_out": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
+    "segb200_nchw_to_nhwc": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
+    "segb200_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the engine library; raises RuntimeError (never falls back) if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"segb200: native engine library not found at {LIB_PATH}; build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU/PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().segb200_last_error().decode(errors="replace")
+        raise RuntimeError(f"segb200 {what} failed (code {rc}): {msg}")

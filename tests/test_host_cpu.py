@@ -1,0 +1,100 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/segb200.h declares, host-side
+weight packing is exact, and the product refuses to run without CUDA (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from segmentron_b200 import lib
+    return lib
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "segb200.h")).read()
+    declared = set(re.findall(r"\b(segb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = built.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/segb200.h but not exported"
+    assert declared == set(built.SYMBOLS), declared ^ set(built.SYMBOLS)
+    assert lib.segb200_version() == 100
+    assert [lib.segb200_conv_kblock(c) for c in (16, 24, 32, 48, 64, 728)] == [16, 16, 32, 32, 64, 64]
+
+
+def test_argument_errors_without_gpu(built):
+    import ctypes as C
+    lib = built.load()
+    assert lib.segb200_conv_gemm(None, None) < 0
+    assert b"null" in lib.segb200_last_error()
+    a = built.DwArgs()
+    a.x = a.wgt = a.y = 16
+    a.c, a.x_ld, a.y_ld, a.dtype = 60, 60, 60, 0
+    assert lib.segb200_dwconv3x3(C.byref(a), None) == -4
+
+
+def test_no_cpu_fallback(built):
+    from segmentron_b200 import ops
+    from segmentron_b200.engine import DeepLabV3PlusB200
+    x = torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.dwconv3x3(x, x, x)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            DeepLabV3PlusB200({})
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "segmentron_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_bn_fold_and_weight_packing():
+    from segmentron_b200 import fold
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 24, 5, 7, generator=g)
+    w, b, m = torch.rand(24, generator=g) + 0.5, torch.randn(24, generator=g), torch.randn(24, generator=g)
+    v = torch.rand(24, generator=g) + 0.5
+    s, t = fold.bn_fold(w, b, m, v, 1e-3)
+    ref = F.batch_norm(x, m, v, w, b, False, 0.0, 1e-3)
+    assert torch.allclose(x * s[None, :, None, None] + t[None, :, None, None], ref, atol=1e-5)
+    wt = torch.randn(19, 40, 3, 3, generator=g)
+    pk = fold.pack_conv_weight(wt, torch.float32)
+    assert pk.shape == (24, 9, 64)
+    assert torch.equal(pk[:19, 4, :40], wt[:, :, 1, 1]) and float(pk[19:].abs().sum()) == 0 and float(pk[:, :, 40:].abs().sum()) == 0
+    dw = torch.randn(16, 1, 3, 3, generator=g)
+    pdw = fold.pack_dw_weight(dw, torch.full((16,), 2.0))
+    assert torch.allclose(pdw[5], dw[:, 0, 1, 2] * 2)
+
+
+@pytest.mark.parametrize("k,pad", [(3, 1), (7, 3), (5, 2)])
+def test_stem_space_to_depth_is_exact(k, pad):
+    """stride-2 kxk conv == stride-1 TxT conv over the space-to-depth tensor (what pack_s2d + conv_gemm run)."""
+    from segmentron_b200 import fold
+    g = torch.Generator().manual_seed(1)
+    n, c, h, w = 2, 3, 13, 18
+    x = torch.randn(n, c, h, w, generator=g, dtype=torch.float64)
+    wt = torch.randn(8, c, k, k, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, wt, None, 2, pad)
+    pk, T, pad2, ld = fold.pack_stem_s2d(wt, pad, torch.float64)
+    hs, ws = (h + 1) // 2, (w + 1) // 2
+    xp = F.pad(x, (0, 2 * ws - w, 0, 2 * hs - h))
+    s2d = torch.zeros(n, ld, hs, ws, dtype=torch.float64)
+    for py in range(2):
+        for px in range(2):
+            s2d[:, (py * 2 + px) * c:(py * 2 + px + 1) * c] = xp[:, :, py::2, px::2]
+    w2 = pk.reshape(8, T, T, ld).permute(0, 3, 1, 2)
+    ho, wo = ref.shape[2:]
+    full = F.conv2d(F.pad(s2d, (pad2, T, pad2, T)), w2)
+    assert torch.allclose(full[:, :, :ho, :wo], ref, atol=1e-5)   # packing goes through fp32

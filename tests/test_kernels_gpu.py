@@ -1,0 +1,201 @@
+"""Per-kernel parity on the B200: every C-ABI kernel against the same op in plain PyTorch fp32
+(inputs/weights rounded to the kernel's 16-bit dtype first, so the only differences are the output
+rounding and summation order).  Tolerance: |err| <= 2^-7 * |ref| + 2^-7 * rms(ref)   (bf16 has 8 bits of
+mantissa; fp16 results are held to the same bound and are in practice ~8x tighter)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _close(got, ref, what, tol=2.0 ** -7):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    rms = float(ref.pow(2).mean().sqrt()) + 1e-12
+    err = (got - ref).abs()
+    bound = tol * ref.abs() + tol * rms
+    bad = err > bound
+    if bad.any():
+        idx = bad.nonzero()[0].tolist()
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; first at {idx}: "
+                             f"got {float(got[tuple(idx)])} ref {float(ref[tuple(idx)])}; max err {float(err.max())}, "
+                             f"rms {rms}, rel-L2 {float((got - ref).norm() / ref.norm())}")
+
+
+def _rand(*shape, dtype, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _to_nchw(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # name, n,h,w, cin,cout, k, stride, dil, pad, act, residual, out slice (ld, off)
+    ("pw_flat_64_128", 1, 25, 40, 64, 128, 1, 1, 1, 0, "relu", False, None),
+    ("pw_flat_728_728_res", 2, 33, 65, 728, 728, 1, 1, 1, 0, None, True, None),
+    ("pw_flat_304_256", 1, 33, 65, 304, 256, 1, 1, 1, 0, "relu", False, None),
+    ("pw_flat_2048_256_slice", 1, 17, 33, 2048, 256, 1, 1, 1, 0, "relu", False, (1280, 512)),
+    ("pw_flat_256_48_slice", 1, 33, 65, 256, 48, 1, 1, 1, 0, "relu", False, (304, 256)),
+    ("pw_flat_256_24_cls", 1, 33, 65, 256, 24, 1, 1, 1, 0, None, False, (32, 0)),
+    ("pw_flat_tinyM", 8, 1, 1, 2048, 256, 1, 1, 1, 0, "relu", False, None),
+    ("pw_flat_1536_2048", 1, 17, 33, 1536, 2048, 1, 1, 1, 0, "relu", False, None),
+    ("pw_s2_64_128", 2, 33, 65, 64, 128, 1, 2, 1, 0, None, False, None),
+    ("pw_s2_256_728_even", 1, 34, 66, 256, 728, 1, 2, 1, 0, None, False, None),
+    ("c3_32_64", 2, 37, 53, 32, 64, 3, 1, 1, 1, "relu", False, None),
+    ("c3_64_64_d2", 1, 33, 65, 64, 64, 3, 1, 2, 2, "relu", True, None),
+    ("c3_128_128_d4", 1, 33, 65, 128, 128, 3, 1, 4, 4, "relu", False, None),
+    ("c3_64_128_s2", 2, 33, 65, 64, 128, 3, 2, 1, 1, "relu", False, None),
+    ("c3_16_32", 1, 20, 24, 16, 32, 3, 1, 1, 1, "relu6", False, None),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm(case, dtype):
+    from segmentron_b200 import fold, ops
+    name, n, h, w, cin, cout, k, stride, dil, pad, act, use_res, sl = case
+    x = _rand(n, h, w, cin, dtype=dtype, seed=1)
+    wt = _rand(cout, cin, k, k, dtype=dtype, seed=2, scale=1.0 / math.sqrt(cin * k * k))
+    scale = (0.5 + torch.rand(cout, generator=torch.Generator().manual_seed(3))).cuda()
+    shift = (0.2 * torch.randn(cout, generator=torch.Generator().manual_seed(4))).cuda()
+    ho = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    wo = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    res = _rand(n, ho, wo, cout, dtype=dtype, seed=5) if use_res else None
+    if sl is None:
+        buf = torch.full((n, ho, wo, cout), float("nan"), dtype=dtype, device="cuda")
+        y = buf
+    else:
+        ld, off = sl
+        buf = torch.full((n, ho, wo, ld), 7.0, dtype=dtype, device="cuda")
+        y = buf[..., off:off + cout]
+    wpk = fold.pack_conv_weight(wt, dtype)
+    ops.conv_gemm(x, wpk, y, cin=cin, cout=cout, kh=k, kw=k, stride=stride, dilation=dil, pad_t=pad, pad_l=pad,
+                  scale=scale, shift=shift, act=act, residual=res)
+    torch.cuda.synchronize()
+    ref = F.conv2d(_to_nchw(x), wt.float(), None, stride, pad, dil)
+    ref = ref * scale[None, :, None, None] + shift[None, :, None, None]
+    if use_res:
+        ref = ref + _to_nchw(res)
+    ref = F.relu(ref) if act == "relu" else (F.relu6(ref) if act == "relu6" else ref)
+    _close(_to_nchw(y), ref, name)
+    if sl is not None:                      # bytes outside the slice untouched
+        ld, off = sl
+        mask = torch.ones(ld, dtype=torch.bool); mask[off:off + cout] = False
+        assert (buf[..., mask.cuda()] == 7.0).all(), f"{name}: wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("k,pad,cout", [(3, 1, 32), (7, 3, 64)])
+def test_stem_s2d(k, pad, cout):
+    from segmentron_b200 import fold, ops
+    dtype = torch.bfloat16
+    n, h, w = 2, 65, 129
+    x = _rand(n, 3, h, w, dtype=torch.float32, seed=1)
+    wt = _rand(cout, 3, k, k, dtype=dtype, seed=2, scale=0.3)
+    wpk, T, pad2, ld = fold.pack_stem_s2d(wt, pad, dtype)
+    hs, ws = (h + 1) // 2, (w + 1) // 2
+    s2d = torch.empty(n, hs, ws, ld, dtype=dtype, device="cuda")
+    ops.pack_s2d(x, s2d)
+    ho, wo = (h + 2 * pad - k) // 2 + 1, (w + 2 * pad - k) // 2 + 1
+    y = torch.empty(n, ho, wo, cout, dtype=dtype, device="cuda")
+    ops.conv_gemm(s2d, wpk, y, cin=ld, cout=cout, kh=T, kw=T, pad_t=pad2, pad_l=pad2, act="relu")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.to(dtype).float(), wt.float(), None, 2, pad))
+    _close(_to_nchw(y), ref, f"stem{k}")
+
+
+DW_CASES = [(2, 33, 65, 728, 1, 1, True, None), (1, 33, 65, 128, 2, 1, True, None), (1, 34, 66, 256, 2, 1, True, None),
+            (1, 33, 65, 2048, 1, 6, False, "relu"), (1, 33, 65, 256, 1, 18, False, "relu"),
+            (2, 17, 19, 304, 1, 1, False, "relu"), (1, 16, 32, 96, 1, 2, False, "relu6"), (1, 9, 9, 8, 1, 12, False, None)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", DW_CASES, ids=[f"dw{i}" for i in range(len(DW_CASES))])
+def test_dwconv(case, dtype):
+    from segmentron_b200 import fold, ops
+    n, h, w, c, stride, dil, pre_relu, act = case
+    x = _rand(n, h, w, c, dtype=dtype, seed=1)
+    wt = _rand(c, 1, 3, 3, dtype=torch.float32, seed=2, scale=0.4)
+    scale = (0.5 + torch.rand(c, generator=torch.Generator().manual_seed(3))).cuda()
+    shift = (0.2 * torch.randn(c, generator=torch.Generator().manual_seed(4))).cuda()
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.full((n, ho, wo, c), float("nan"), dtype=dtype, device="cuda")
+    ops.dwconv3x3(x, fold.pack_dw_weight(wt, scale), y, stride=stride, dilation=dil, shift=shift, pre_relu=pre_relu, act=act)
+    torch.cuda.synchronize()
+    xin = _to_nchw(x)
+    if pre_relu:
+        xin = F.relu(xin)
+    ref = F.conv2d(xin, wt, None, stride, dil, dil, groups=c) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = F.relu(ref) if act == "relu" else (F.relu6(ref) if act == "relu6" else ref)
+    _close(_to_nchw(y), ref, "dwconv")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_pool_and_resize(dtype):
+    from segmentron_b200 import ops
+    n, h, w, c = 2, 33, 65, 256
+    x = _rand(n, h, w, c, dtype=dtype, seed=1)
+    xn = _to_nchw(x)
+    # global average pool
+    out = torch.empty(n, 1, 1, c, dtype=dtype, device="cuda")
+    ws = torch.empty(n * c, dtype=torch.float32, device="cuda")
+    ops.global_avgpool(x, out, ws)
+    _close(_to_nchw(out), F.adaptive_avg_pool2d(xn, 1), "gap")
+    # adaptive pools (PSP sizes)
+    for s in (1, 2, 3, 6):
+        o = torch.empty(n, s, s, c, dtype=dtype, device="cuda")
+        ops.adaptive_avgpool(x, o, s)
+        _close(_to_nchw(o), F.adaptive_avg_pool2d(xn, s), f"adaptive{s}")
+    # bilinear, both corner modes, up and from 1x1, into a channel slice
+    for align in (True, False):
+        buf = torch.zeros(n, 129, 257, c + 48, dtype=dtype, device="cuda")
+        ops.bilinear_nhwc(x, buf[..., :c], align_corners=align)
+        _close(_to_nchw(buf[..., :c]), F.interpolate(xn, (129, 257), mode="bilinear", align_corners=align), f"bilinear{align}")
+        assert (buf[..., c:] == 0).all()
+    y1 = torch.empty(n, 17, 33, c, dtype=dtype, device="cuda")
+    ops.bilinear_nhwc(out, y1, align_corners=True)
+    _close(_to_nchw(y1), F.interpolate(_to_nchw(out), (17, 33), mode="bilinear", align_corners=True), "broadcast")
+    # final logits upsample to NCHW + fused argmax
+    lg = _rand(n, h, w, 32, dtype=dtype, seed=9)
+    for od in (dtype, torch.float32):
+        yo = torch.empty(n, 19, 4 * h - 3, 4 * w - 3, dtype=od, device="cuda")
+        am = torch.empty(n, 4 * h - 3, 4 * w - 3, dtype=torch.uint8, device="cuda")
+        ops.bilinear_nchw_out(lg, yo, 19, True, am)
+        ref = F.interpolate(_to_nchw(lg)[:, :19], (4 * h - 3, 4 * w - 3), mode="bilinear", align_corners=True)
+        _close(yo, ref, "logits_up")
+        assert (am.long() == yo.float().argmax(1)).all(), "fused argmax != torch.argmax of the same output"
+
+
+def test_layout_converters():
+    from segmentron_b200 import ops
+    x = _rand(2, 19, 37, 41, dtype=torch.float32, seed=3)
+    y = torch.zeros(2, 37, 41, 24, dtype=torch.bfloat16, device="cuda")
+    ops.nchw_to_nhwc(x, y[..., :19])
+    assert torch.equal(y[..., :19].permute(0, 3, 1, 2), x.to(torch.bfloat16))
+    z = torch.empty(2, 19, 37, 41, dtype=torch.float32, device="cuda")
+    ops.nhwc_to_nchw(y[..., :19], z)
+    assert torch.equal(z, x.to(torch.bfloat16).float())
+
+
+def test_errors_are_loud():
+    from segmentron_b200 import ops
+    x = torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16)          # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.dwconv3x3(x, x, x)
+    xc = torch.zeros(1, 4, 4, 60, dtype=torch.bfloat16, device="cuda")   # 60 channels: not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops.dwconv3x3(xc, torch.zeros(9, 60, device="cuda"), torch.empty_like(xc))
