@@ -53,7 +53,13 @@ class Plan:
         self.keep.append(wpk)
         a = ops.make_conv_args(x, wpk, y, **kw)
         fn = self.lib.segb200_conv_gemm
-        self.steps.append(lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "conv_gemm"))
+        pix = a.n * a.ho * a.wo
+        taps = a.kh * a.kw
+        meta = dict(kind="conv_gemm", flops=2.0 * pix * a.cout * a.cin * taps,
+                    bytes=2.0 * (a.n * a.h * a.w * a.cin + pix * a.cout * (2 if kw.get("residual") is not None else 1)
+                                 + a.cout * a.cin * taps),
+                    desc=f"{a.kh}x{a.kw}s{a.stride}d{a.dilation} {a.cin}->{a.cout} @{a.n}x{a.ho}x{a.wo}")
+        self.steps.append((lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "conv_gemm"), meta))
         self.n_launch += 1
         return y
 
@@ -63,19 +69,35 @@ class Plan:
             self.keep.append(kw["shift"])
         a = ops.make_dw_args(x, wdw, y, **kw)
         fn = self.lib.segb200_dwconv3x3
-        self.steps.append(lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "dwconv3x3"))
+        meta = dict(kind="dwconv3x3", flops=2.0 * 9 * a.n * a.ho * a.wo * a.c,
+                    bytes=2.0 * (a.n * a.h * a.w * a.c + a.n * a.ho * a.wo * a.c),
+                    desc=f"dw3x3 s{a.stride}d{a.dilation} c{a.c} @{a.n}x{a.ho}x{a.wo}")
+        self.steps.append((lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "dwconv3x3"), meta))
         self.n_launch += 1
         return y
 
-    def call(self, name, *args, launches=1):
+    def call(self, name, *args, launches=1, nbytes=0.0):
         fn = getattr(self.lib, name)
-        self.steps.append(lambda s, fn=fn, args=args, name=name: L.check(fn(*args, s), name))
+        meta = dict(kind=name.replace("segb200_", ""), flops=0.0, bytes=float(nbytes), desc=name)
+        self.steps.append((lambda s, fn=fn, args=args, name=name: L.check(fn(*args, s), name), meta))
         self.n_launch += launches
 
     def run(self):
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for f in self.steps:
+        for f, _ in self.steps:
             f(s)
+
+    def run_timed(self):
+        """Direct (non-graph) replay with a CUDA event pair around every step on the launching stream.
+        Returns [(meta, milliseconds)] -- used by bench.py for the per-kernel roofline numbers."""
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.steps) + 1)]
+        evs[0].record()
+        for i, (f, _) in enumerate(self.steps):
+            f(s)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return [(m, evs[i].elapsed_time(evs[i + 1])) for i, (_, m) in enumerate(self.steps)]
 
     # ---- composite layers -----------------------------------------------------------------
     def conv_bn_act(self, x, prefix, cout, k=1, stride=1, dilation=1, pad=0, act="relu", eps=1e-5, out=None,
@@ -122,7 +144,8 @@ class Plan:
         wpk, T, pad2, ld = fold.pack_stem_s2d(self.w(prefix_conv + ".weight"), pad, self.dtype)
         hs, ws = (h + 1) // 2, (w_ + 1) // 2
         s2d = self.new(n, hs, ws, ld)
-        self.steps.append(lambda s, holder=x_holder, s2d=s2d: ops.pack_s2d(holder["x"], s2d))
+        meta = dict(kind="pack_s2d", flops=0.0, bytes=float(n * cin * h * w_ * 4 + n * hs * ws * ld * 2), desc="pack_s2d")
+        self.steps.append((lambda s, holder=x_holder, s2d=s2d: ops.pack_s2d(holder["x"], s2d), meta))
         self.n_launch += 1
         ho = (h + 2 * pad - k) // 2 + 1
         wo = (w_ + 2 * pad - k) // 2 + 1

@@ -1,0 +1,347 @@
+"""Drop-in ``nn.Module`` replacements for the reference's L1 building blocks.
+
+Same constructor signatures, same sub-module names, hence the same ``state_dict`` keys as
+``segmentron/modules/basic.py`` and ``segmentron/modules/module.py``; parameters stay ordinary
+``nn.Parameter``s owned by the module (optimizer param groups, ``load_state_dict``, ``convert_sync_batchnorm``
+and the post-construction ``eps`` mutation of tools/eval.py:50-53 keep working).  ``forward`` takes and returns
+logical-NCHW tensors; physically the engine works in NHWC, so a ``channels_last`` 16-bit input crosses the
+boundary with zero copies and the output is returned as a ``channels_last`` view.
+
+Folded BatchNorm / packed weights are caches keyed on parameter versions and ``eps``; they are rebuilt
+lazily at the next forward after any change.
+
+No CPU implementation and no PyTorch fallback: a non-CUDA input raises RuntimeError, like the reference's
+native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training-mode forward
+(batch-statistics BN + backward) is not part of this round and raises as well.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import fold, ops
+
+_COMPUTE_DTYPE = torch.bfloat16
+
+
+def set_compute_dtype(dtype):
+    """16-bit dtype used when a module receives fp32 activations (default bf16)."""
+    global _COMPUTE_DTYPE
+    assert dtype in (torch.bfloat16, torch.float16)
+    _COMPUTE_DTYPE = dtype
+
+
+# ------------------------------------------------------------------------------------------------
+# boundary helpers
+# ------------------------------------------------------------------------------------------------
+def _enter(x, module):
+    """logical NCHW tensor -> (NHWC 16-bit tensor, original dtype)."""
+    if not x.is_cuda:
+        raise RuntimeError(f"segb200: {type(module).__name__} is not implemented on the CPU (input must be a CUDA tensor)")
+    if module.training:
+        raise RuntimeError(f"segb200: training-mode forward of {type(module).__name__} is not implemented in this "
+                           "round (inference engine); call .eval()")
+    if x.dim() != 4:
+        raise RuntimeError("segb200: expected a 4-D NCHW tensor")
+    dt = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else _COMPUTE_DTYPE
+    n, c, h, w = x.shape
+    if x.dtype == dt and c % 8 == 0 and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1), x.dtype                      # zero-copy: already channels_last
+    buf = torch.empty(n, h, w, fold.round_up(c, 8), dtype=dt, device=x.device)
+    if buf.shape[3] != c:
+        buf.zero_()
+    ops.nchw_to_nhwc(x, buf[..., :c])
+    return (buf[..., :c] if buf.shape[3] != c else buf), x.dtype
+
+
+def _leave(y_nhwc, out_dtype):
+    """NHWC tensor -> logical NCHW (channels_last view); converts back if the caller's dtype was fp32."""
+    y = y_nhwc.permute(0, 3, 1, 2)
+    return y if y.dtype == out_dtype else y.to(out_dtype)
+
+
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+class _Cache:
+    """Lazily rebuilt derived tensors (folded BN, packed weights)."""
+
+    def __init__(self):
+        self.key, self.val = None, None
+
+    def get(self, key, build):
+        if self.key != key:
+            self.val, self.key = build(), key
+        return self.val
+
+
+def _bn_tensors(bn):
+    if not isinstance(bn, nn.modules.batchnorm._BatchNorm) and not hasattr(bn, "running_var"):
+        raise RuntimeError(f"segb200: unsupported norm layer {type(bn).__name__}")
+    return bn.weight, bn.bias, bn.running_mean, bn.running_var
+
+
+def _fold(bn):
+    w, b, m, v = _bn_tensors(bn)
+    return fold.bn_fold(w.detach(), b.detach(), m, v, bn.eps)
+
+
+def _out_hw(h, w, k, stride, pad, dil):
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _run_conv_bn_act(x, conv, bn, act, cache, dt, out=None, residual=None):
+    """conv (dense, or depthwise 3x3) + optional BN + activation on an NHWC tensor."""
+    n, h, w, cin = x.shape
+    k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+    ho, wo = _out_hw(h, w, k, s, p, d)
+    cout = conv.out_channels
+    bn_t = _bn_tensors(bn) if bn is not None else ()
+    key = (dt, bn.eps if bn is not None else None) + _versions(conv.weight, conv.bias, *bn_t)
+    if conv.groups == 1:
+        def build():
+            cop = fold.round_up(cout, 8)
+            if bn is not None:
+                sc, sh = _fold(bn)
+                if conv.bias is not None:
+                    sh = sh + conv.bias.detach().float() * sc
+                sc, sh = fold.pad_vec(sc, cop, 1.0), fold.pad_vec(sh, cop)
+            else:
+                sc, sh = None, (fold.pad_vec(conv.bias.detach(), cop) if conv.bias is not None else None)
+            return fold.pack_conv_weight(conv.weight.detach(), dt, cop), sc, sh, cop
+        wpk, sc, sh, cop = cache.get(key, build)
+        if out is None:
+            buf = torch.empty(n, ho, wo, cop, dtype=dt, device=x.device)
+            out = buf
+        ops.conv_gemm(x, wpk, out, cin=cin, cout=cop, kh=k, kw=k, stride=s, dilation=d, pad_t=p, pad_l=p, scale=sc, shift=sh,
+                      act=act, residual=residual)
+        return out[..., :cout] if out.shape[3] != cout else out
+    if conv.groups == cin == cout and k == 3 and p == d:
+        def build():
+            if bn is not None:
+                sc, sh = _fold(bn)
+            else:
+                sc, sh = torch.ones(cout, device=x.device), torch.zeros(cout, device=x.device)
+            if conv.bias is not None:
+                sh = sh + conv.bias.detach().float() * sc
+            return fold.pack_dw_weight(conv.weight.detach(), sc), sh.contiguous()
+        wdw, sh = cache.get(key, build)
+        if out is None:
+            out = torch.empty(n, ho, wo, cout, dtype=dt, device=x.device)
+        return ops.dwconv3x3(x, wdw, out, stride=s, dilation=d, shift=sh, pre_relu=False, act=act)
+    raise RuntimeError(f"segb200: no kernel for Conv2d(groups={conv.groups}, k={k}) yet")
+
+
+# ------------------------------------------------------------------------------------------------
+# modules/basic.py replacements
+# ------------------------------------------------------------------------------------------------
+class SeparableConv2d(nn.Module):
+    """Replaces segmentron.modules.basic.SeparableConv2d (basic.py:34-62): one depthwise kernel (pre-ReLU, BN_depth,
+    ReLU fused) + one tcgen05 GEMM (BN_point, ReLU fused)."""
+
+    def __init__(self, inplanes, planes, kernel_size=3, stride=1, dilation=1, relu_first=True, bias=False,
+                 norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        depthwise = nn.Conv2d(inplanes, inplanes, kernel_size, stride=stride, padding=dilation, dilation=dilation,
+                              groups=inplanes, bias=bias)
+        bn_depth = norm_layer(inplanes)
+        pointwise = nn.Conv2d(inplanes, planes, 1, bias=bias)
+        bn_point = norm_layer(planes)
+        self.relu_first = relu_first
+        if relu_first:
+            layers = [("relu", nn.ReLU()), ("depthwise", depthwise), ("bn_depth", bn_depth), ("pointwise", pointwise),
+                      ("bn_point", bn_point)]
+        else:
+            layers = [("depthwise", depthwise), ("bn_depth", bn_depth), ("relu1", nn.ReLU(inplace=True)),
+                      ("pointwise", pointwise), ("bn_point", bn_point), ("relu2", nn.ReLU(inplace=True))]
+        self.block = nn.Sequential(OrderedDict(layers))
+        self._c_dw, self._c_pw = _Cache(), _Cache()
+
+    def forward_nhwc(self, x, out=None, residual=None):
+        b = self.block
+        dt = x.dtype
+        n, h, w, c = x.shape
+        dwc = b.depthwise
+        s, d = dwc.stride[0], dwc.dilation[0]
+        key = (b.bn_depth.eps,) + _versions(dwc.weight, dwc.bias, *_bn_tensors(b.bn_depth))
+
+        def build():
+            sc, sh = _fold(b.bn_depth)
+            if dwc.bias is not None:
+                sh = sh + dwc.bias.detach().float() * sc
+            return fold.pack_dw_weight(dwc.weight.detach(), sc), sh.contiguous()
+        wdw, sh = self._c_dw.get(key, build)
+        ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+        tmp = torch.empty(n, ho, wo, c, dtype=dt, device=x.device)
+        ops.dwconv3x3(x, wdw, tmp, stride=s, dilation=d, shift=sh, pre_relu=self.relu_first,
+                      act=None if self.relu_first else "relu")
+        return _run_conv_bn_act(tmp, b.pointwise, b.bn_point, None if self.relu_first else "relu", self._c_pw, dt, out=out,
+                                residual=residual)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class _ConvBNReLU(nn.Module):
+    """Replaces segmentron.modules.basic._ConvBNReLU (basic.py:65-77): conv + BN + ReLU/ReLU6 in one kernel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, relu6=False,
+                 norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias=False)
+        self.bn = norm_layer(out_channels)
+        self.relu = nn.ReLU6(True) if relu6 else nn.ReLU(True)
+        self._act = "relu6" if relu6 else "relu"
+        self._cache = _Cache()
+
+    def forward_nhwc(self, x, out=None):
+        return _run_conv_bn_act(x, self.conv, self.bn, self._act, self._cache, x.dtype, out=out)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class _ConvBN(nn.Module):
+    """Replaces segmentron.modules.basic._ConvBN (basic.py:95-105)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 norm_layer=nn.BatchNorm2d, **kwargs):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias=False)
+        self.bn = norm_layer(out_channels)
+        self._cache = _Cache()
+
+    def forward_nhwc(self, x, out=None):
+        return _run_conv_bn_act(x, self.conv, self.bn, None, self._cache, x.dtype, out=out)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class InvertedResidual(nn.Module):
+    """Replaces segmentron.modules.basic.InvertedResidual (basic.py:139-163); the residual add is fused into the
+    pw-linear GEMM epilogue."""
+
+    def __init__(self, in_channels, out_channels, stride, expand_ratio, dilation=1, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        assert stride in [1, 2]
+        self.use_res_connect = stride == 1 and in_channels == out_channels
+        layers = []
+        inter = int(round(in_channels * expand_ratio))
+        if expand_ratio != 1:
+            layers.append(_ConvBNReLU(in_channels, inter, 1, relu6=True, norm_layer=norm_layer))
+        layers.extend([_ConvBNReLU(inter, inter, 3, stride, dilation, dilation, groups=inter, relu6=True,
+                                   norm_layer=norm_layer),
+                       nn.Conv2d(inter, out_channels, 1, bias=False), norm_layer(out_channels)])
+        self.conv = nn.Sequential(*layers)
+        self._cache = _Cache()
+
+    def forward_nhwc(self, x):
+        y = x
+        mods = list(self.conv)
+        for m in mods[:-2]:
+            y = m.forward_nhwc(y)
+        return _run_conv_bn_act(y, mods[-2], mods[-1], None, self._cache, x.dtype,
+                                residual=x if self.use_res_connect else None)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+# ------------------------------------------------------------------------------------------------
+# modules/module.py replacements
+# ------------------------------------------------------------------------------------------------
+class _ASPP(nn.Module):
+    """Replaces segmentron.modules.module._ASPP (module.py:32-77).  ``output_stride`` comes from the reference's
+    global cfg when it is importable (module.py:35), else from the keyword.  Every branch writes its 256-channel
+    slice of one 1280-channel NHWC buffer (no torch.cat); the image-pooling branch is GAP -> GEMM -> broadcast."""
+
+    def __init__(self, in_channels=2048, out_channels=256, output_stride=None):
+        super().__init__()
+        if output_stride is None:
+            try:
+                from segmentron.config import cfg          # the reference's global config (module.py:8,35)
+                output_stride = cfg.MODEL.OUTPUT_STRIDE
+            except Exception:
+                output_stride = 16
+        dilations = {16: [6, 12, 18], 8: [12, 24, 36], 32: [6, 12, 18]}.get(output_stride)
+        if dilations is None:
+            raise NotImplementedError
+        self.aspp0 = nn.Sequential(OrderedDict([("conv", nn.Conv2d(in_channels, out_channels, 1, bias=False)),
+                                                ("bn", nn.BatchNorm2d(out_channels)), ("relu", nn.ReLU(inplace=True))]))
+        self.aspp1 = SeparableConv2d(in_channels, out_channels, dilation=dilations[0], relu_first=False)
+        self.aspp2 = SeparableConv2d(in_channels, out_channels, dilation=dilations[1], relu_first=False)
+        self.aspp3 = SeparableConv2d(in_channels, out_channels, dilation=dilations[2], relu_first=False)
+        self.image_pooling = nn.Sequential(OrderedDict([("gap", nn.AdaptiveAvgPool2d((1, 1))),
+                                                        ("conv", nn.Conv2d(in_channels, out_channels, 1, bias=False)),
+                                                        ("bn", nn.BatchNorm2d(out_channels)),
+                                                        ("relu", nn.ReLU(inplace=True))]))
+        self.conv = nn.Conv2d(out_channels * 5, out_channels, 1, bias=False)
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.dropout = nn.Dropout2d(p=0.1)
+        self._c0, self._cp, self._cproj = _Cache(), _Cache(), _Cache()
+
+    def forward_nhwc(self, x):
+        n, h, w, c = x.shape
+        dt = x.dtype
+        oc = self.conv.out_channels
+        cat = torch.empty(n, h, w, 5 * oc, dtype=dt, device=x.device)
+        pooled = torch.empty(n, 1, 1, c, dtype=dt, device=x.device)
+        ops.global_avgpool(x, pooled, torch.empty(n * c, dtype=torch.float32, device=x.device))
+        pf = _run_conv_bn_act(pooled, self.image_pooling.conv, self.image_pooling.bn, "relu", self._cp, dt)
+        ops.bilinear_nhwc(pf, cat[..., 0:oc], align_corners=True)
+        _run_conv_bn_act(x, self.aspp0.conv, self.aspp0.bn, "relu", self._c0, dt, out=cat[..., oc:2 * oc])
+        for i, m in enumerate((self.aspp1, self.aspp2, self.aspp3)):
+            m.forward_nhwc(x, out=cat[..., (2 + i) * oc:(3 + i) * oc])
+        return _run_conv_bn_act(cat, self.conv, self.bn, "relu", self._cproj, dt)     # Dropout2d: identity in eval
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class PyramidPooling(nn.Module):
+    """Replaces segmentron.modules.module.PyramidPooling (module.py:82-97): adaptive pools, 1x1 conv+BN+ReLU GEMMs and
+    bilinear up-samples all write channel slices of the 2C output buffer (no torch.cat)."""
+
+    def __init__(self, in_channels, sizes=(1, 2, 3, 6), norm_layer=nn.BatchNorm2d, **kwargs):
+        super().__init__()
+        out_channels = int(in_channels / 4)
+        self.sizes = tuple(sizes)
+        self.avgpools = nn.ModuleList()
+        self.convs = nn.ModuleList()
+        for size in sizes:
+            self.avgpools.append(nn.AdaptiveAvgPool2d(size))
+            self.convs.append(_ConvBNReLU(in_channels, out_channels, 1, norm_layer=norm_layer, **kwargs))
+
+    def forward_nhwc(self, x):
+        n, h, w, c = x.shape
+        oc = c // 4
+        out = torch.empty(n, h, w, c + oc * len(self.sizes), dtype=x.dtype, device=x.device)
+        out[..., :c].copy_(x)
+        for i, (s, conv) in enumerate(zip(self.sizes, self.convs)):
+            p = torch.empty(n, s, s, c, dtype=x.dtype, device=x.device)
+            ops.adaptive_avgpool(x, p, s)
+            f = conv.forward_nhwc(p)
+            ops.bilinear_nhwc(f, out[..., c + i * oc:c + (i + 1) * oc], align_corners=True)
+        return out
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+REPLACEMENTS = {
+    "SeparableConv2d": SeparableConv2d,
+    "_ConvBNReLU": _ConvBNReLU,
+    "_ConvBN": _ConvBN,
+    "InvertedResidual": InvertedResidual,
+    "_ASPP": _ASPP,
+    "PyramidPooling": PyramidPooling,
+}
