@@ -55,10 +55,10 @@ class Params:
                 raise KeyError(f"oracle parameter '{name}' missing from the supplied state dict")
             self.t[name] = make().to(torch.float32)
         v = self.t[name]
-        if v.is_floating_point():
+        if name.endswith("num_batches_tracked"):
+            return v
+        if v.device != torch.device(self.device) or v.dtype != self.dtype:
             v = v.to(device=self.device, dtype=self.dtype)
-        else:
-            v = v.to(device=self.device)
         return v
 
     def conv_w(self, name, cout, cin_g, k, gain=1.0):
@@ -81,7 +81,7 @@ class Params:
         return self._new(name, lambda: torch.full((1,), float(value)))
 
     def count(self, name):
-        return self._new(name, lambda: torch.zeros((), dtype=torch.long).float()).long()
+        return self._new(name, lambda: torch.zeros(()))
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {}
@@ -90,9 +90,12 @@ class Params:
         return out
 
     def to(self, device=None, dtype=None) -> "Params":
-        p = Params(tensors=self.t)
-        p.device = device or self.device
-        p.dtype = dtype or self.dtype
+        """Materialised copy on ``device`` / in ``dtype`` (like ``model.to(...)``: converted once, not per use)."""
+        device, dtype = device or self.device, dtype or self.dtype
+        conv = {k: (v.to(device=device, dtype=dtype) if not k.endswith("num_batches_tracked") else v.to(device))
+                for k, v in self.t.items()}
+        p = Params(tensors=conv)
+        p.device, p.dtype = device, dtype
         return p
 
 

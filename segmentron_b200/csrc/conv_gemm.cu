@@ -28,6 +28,7 @@ namespace segb200 {
 constexpr int kStageRegion = 196608;          // bytes for the A/B ring
 constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
 constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
+constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
 constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
@@ -37,6 +38,7 @@ struct Control {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
   float scale[256];
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                 const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Control* ctl = reinterpret_cast<Control*>(smem + kCtlOffset);
   const int warp = threadIdx.x >> 5;
@@ -83,7 +85,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); mbar_init(&ctl->res_full[i], 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -158,8 +162,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int et = threadIdx.x - 64;                 // 0..127
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                   // tile row == TMEM lane
-    uint8_t* epi = smem + kStageRegion;
+    uint8_t* epi = smem + kStageRegion;              // 2 store-staging buffers
+    uint8_t* resb = smem + kStageRegion - kResRegion;  // 2 residual buffers (ring is shortened by the host)
+    const bool has_res = p.residual != nullptr;
     int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
+
+    // residual prefetch cursor (leader only): runs exactly one chunk ahead of the consumer
+    int pf_tile = blockIdx.x, pf_ch = 0;
+    auto pf_issue = [&](uint32_t idx) {
+      // issue the TMA load of the residual chunk (pf_tile, pf_ch) into resb[idx & 1], then advance the cursor
+      if (pf_tile >= p.total_tiles) return;
+      const int n_tile = pf_tile % p.n_tiles;
+      int m_tile = pf_tile / p.n_tiles;
+      const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
+      const int hb = m_tile % p.htiles;
+      const int img = m_tile / p.htiles;
+      const int n0 = n_tile * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      mbar_expect_tx(&ctl->res_full[idx & 1], (uint32_t)kEpiBufBytes);
+      tma_load_4d(&tmR, &ctl->res_full[idx & 1], resb + (idx & 1) * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += gridDim.x; }
+    };
+    if (has_res && et == 0) pf_issue(0);
+
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
@@ -176,21 +201,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
         ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
       }
-      // residual row pointer (pixel of this thread's row), or null if the row is outside the image
-      const int ph = h0 + row / p.bw, pw = w0 + row % p.bw;
-      const bool row_ok = ph < p.ho && pw < p.wo;
-      const typename H::T* res_row = nullptr;
-      if (p.residual != nullptr && row_ok)
-        res_row = reinterpret_cast<const typename H::T*>(p.residual) +
-                  ((long long)(img * p.ho + ph) * p.wo + pw) * p.res_ld + n0;
 
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
         uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
-        if (et == 0) tma_store_wait_read<1>();       // the store that last used `buf` has drained it
+        const uint8_t* rbuf = resb + (chunk_ctr & 1) * kEpiBufBytes;
+        if (et == 0) {
+          tma_store_wait_read<1>();                  // the store that last used `buf` has drained it
+          if (has_res) pf_issue(chunk_ctr + 1);      // resb[(ctr+1)&1] was last read before the previous chunk's barrier
+        }
         named_bar_sync(1, 128);                      // (also publishes scale/shift on the first chunk)
+        if (has_res) mbar_wait(&ctl->res_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col0 = ch * 64 + half * 32;
@@ -200,14 +223,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint32_t packed[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
+            const int chunk16 = (half * 4 + g) ^ (row & 7);   // 128B swizzle: 16 B chunk c lives at c ^ (row & 7)
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int c = col0 + g * 8 + j;
               f[j] = fmaf(__uint_as_float(v[g * 8 + j]), ctl->scale[c], ctl->shift[c]);
             }
-            if (res_row != nullptr && (col0 + g * 8) < nvalid) {
-              const uint4 r = ldg_nc_v4(res_row + col0 + g * 8);
+            if (has_res) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + chunk16 * 16);
               const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -218,11 +242,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               packed[g * 4 + j] = H::pack(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
-          }
-          // 128B-swizzled staging row: 16 B chunk c lives at chunk (c ^ (row & 7))
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk16 = (half * 4 + g) ^ (row & 7);
             *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) =
                 make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
           }
@@ -365,12 +384,12 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
   p.a_stage_bytes = 128 * bk_bytes;
   p.b_stage_bytes = ((p.bn * bk_bytes) + 1023) & ~1023;
-  p.num_stages = kStageRegion / (p.a_stage_bytes + p.b_stage_bytes);
+  p.num_stages = (kStageRegion - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
 
   // ---- A maps (parity views for stride 2) and the tap table ----
-  CUtensorMap tmA[4], tmB, tmC;
+  CUtensorMap tmA[4], tmB, tmC, tmR;
   memset(tmA, 0, sizeof(tmA));
   bool used[4] = {false, false, false, false};
   for (int ky = 0; ky < a->kh; ++ky)
@@ -423,6 +442,13 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
     int rc = encode_map(&tmC, a->dtype, 4, a->y, dims, str, box, 128, "C");
     if (rc) return rc;
+    tmR = tmC;
+    if (a->residual) {
+      const uint64_t rstr[3] = {(uint64_t)a->res_ld * 2, (uint64_t)a->res_ld * 2 * (uint64_t)Wv_out,
+                                (uint64_t)a->res_ld * 2 * (uint64_t)Wv_out * (uint64_t)Hv_out};
+      rc = encode_map(&tmR, a->dtype, 4, a->residual, dims, rstr, box, 128, "R");
+      if (rc) return rc;
+    }
   }
 
   int grid = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -433,8 +459,8 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
   if (a->dtype == DT_BF16)
-    conv_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, p);
+    conv_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
   else
-    conv_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, p);
+    conv_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
   return check_launch("conv_gemm");
 }

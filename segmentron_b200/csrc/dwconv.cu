@@ -1,11 +1,16 @@
-// segb200 -- depthwise 3x3 convolution, NHWC, HBM/L2-bound (sm_100a).
+// segb200 -- depthwise 3x3 convolution, NHWC, HBM-bound (sm_100a).
 //
 //   y[n,ho,wo,c] = act( sum_{ky,kx} wgt[ky*3+kx][c] * pre(x[n, ho*s + (ky-1)*d, wo*s + (kx-1)*d, c]) + shift[c] )
 //
-// One thread owns 8 consecutive channels (one 16-byte vector) of kPix horizontally adjacent output
-// pixels; the lanes of a warp cover consecutive channel vectors first (fully coalesced 128-bit
-// loads/stores), then pixels.  Pixels are enumerated in 8-row x 16-column tiles so the 3x3 halo is
-// re-used out of L1/L2.  BN scale is pre-folded into the fp32 weights; fp32 accumulation.
+// Row-streaming design: a thread owns one output column `wo` and 8 consecutive channels (one 16-byte vector)
+// and walks DOWN the image.  For every input row it touches it loads the three horizontal taps once
+// (3 x 128-bit loads), converts them to fp32 once and forms the three per-kernel-row partial sums
+//        s_ky(r) = sum_kx w[ky][kx] * x[r][wo*s + (kx-1)*d]
+// so that  y[h] = s_0(h*s - d) + s_1(h*s) + s_2(h*s + d)  is assembled from two rolling accumulators:
+// each input element is loaded 3x (from L1: the 16x8 thread block shares its horizontal halo) instead of
+// 9x, and converted once.  The 72 folded weights of the thread's 8 channels live in registers for the whole
+// walk.  Dilation d>1 (stride 1) is handled as d interleaved row chains (rows h0, h0+d, h0+2d, ...).
+// Math is packed fp32x2 FMA (fma.rn.f32x2), fp32 accumulation, BN scale pre-folded into the weights.
 #include "common.cuh"
 #include "../../include/segb200.h"
 
@@ -14,81 +19,170 @@ namespace segb200 {
 struct DwParams {
   const void* x; const float* wgt; const float* shift; void* y;
   int n, h, w, c, x_ld, y_ld, ho, wo, stride, dil, pre_relu, act;
-  int cv;             // channel vectors (c / 8)
-  int tiles_w, tiles_h;
-  long long total;    // threads of work: n * tiles_h * tiles_w * (8*16/kPix) * cv
+  int cv;              // channel vectors (c / 8)
+  int lc;              // channel-vector lanes per block (8 or 16); 128 / lc column lanes
+  int cblocks;         // ceil(cv / lc)
+  int rows_per_block;  // output rows per blockIdx.y segment
 };
 
-constexpr int kTileH = 8, kTileW = 16, kPix = 2;
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 
 template <bool kBF16>
-__global__ void __launch_bounds__(256)
+struct RowSums {
+  float2 s[3][4];   // [ky][channel pair]
+};
+
+// partial sums of one input row for the thread's column; xrow = &x[n][r][0][c0] or nullptr for a padded row
+template <bool kBF16>
+__device__ __forceinline__ void row_sums(const typename Half2<kBF16>::T* xrow, int wi0, int wstep, int w, int x_ld,
+                                         bool pre_relu, const float2 (&wt)[9][4], float2 (&s)[3][4]) {
+  using H = Half2<kBF16>;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[ky][j] = make_float2(0.f, 0.f);
+  if (xrow == nullptr) return;
+  uint4 v[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const int wi = wi0 + kx * wstep;
+    v[kx] = (wi >= 0 && wi < w) ? ldg_v4(xrow + (long long)wi * x_ld) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const uint32_t u[4] = {v[kx].x, v[kx].y, v[kx].z, v[kx].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = H::unpack(u[j]);
+      if (pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], s[ky][j]);
+    }
+  }
+}
+
+template <bool kBF16>
+__device__ __forceinline__ void store_out(typename Half2<kBF16>::T* dst, const float2 (&o)[4], int act) {
+  using H = Half2<kBF16>;
+  uint4 r;
+  r.x = H::pack(apply_act(o[0].x, act), apply_act(o[0].y, act));
+  r.y = H::pack(apply_act(o[1].x, act), apply_act(o[1].y, act));
+  r.z = H::pack(apply_act(o[2].x, act), apply_act(o[2].y, act));
+  r.w = H::pack(apply_act(o[3].x, act), apply_act(o[3].y, act));
+  *reinterpret_cast<uint4*>(dst) = r;
+}
+
+template <bool kBF16, int kStride>
+__global__ void __launch_bounds__(128, 4)
 dwconv3x3_kernel(const DwParams p) {
   using H = Half2<kBF16>;
   using T = typename H::T;
-  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
-  T* __restrict__ y = reinterpret_cast<T*>(p.y);
-  constexpr int kSlots = kTileH * kTileW / kPix;     // work items per tile per channel vector
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % p.cv);
-    long long r = idx / p.cv;
-    const int slot = (int)(r % kSlots); r /= kSlots;
-    const int tw = (int)(r % p.tiles_w); r /= p.tiles_w;
-    const int th = (int)(r % p.tiles_h);
-    const int n = (int)(r / p.tiles_h);
-    const int ho = th * kTileH + slot / (kTileW / kPix);
-    const int wo0 = tw * kTileW + (slot % (kTileW / kPix)) * kPix;
-    if (ho >= p.ho || wo0 >= p.wo) continue;
-    const int c0 = cv * 8;
+  const int lc = threadIdx.x % p.lc, lw = threadIdx.x / p.lc;
+  const int cblk = blockIdx.x % p.cblocks, wblk = blockIdx.x / p.cblocks;
+  const int cv = cblk * p.lc + lc;
+  const int wo = wblk * (128 / p.lc) + lw;
+  if (cv >= p.cv || wo >= p.wo) return;
+  const int c0 = cv * 8;
+  const int n = blockIdx.z;
+  const int h_begin = blockIdx.y * p.rows_per_block;
+  int h_end = h_begin + p.rows_per_block; if (h_end > p.ho) h_end = p.ho;
 
-    float acc[kPix][8];
+  float2 wt[9][4];
 #pragma unroll
-    for (int q = 0; q < kPix; ++q)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0 + 4));
+    wt[t][0] = make_float2(a.x, a.y); wt[t][1] = make_float2(a.z, a.w);
+    wt[t][2] = make_float2(b.x, b.y); wt[t][3] = make_float2(b.z, b.w);
+  }
+  float2 sh[4];
+  if (p.shift != nullptr) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    sh[0] = make_float2(a.x, a.y); sh[1] = make_float2(a.z, a.w); sh[2] = make_float2(b.x, b.y); sh[3] = make_float2(b.z, b.w);
+  } else {
+    sh[0] = sh[1] = sh[2] = sh[3] = make_float2(0.f, 0.f);
+  }
+  const T* xn = reinterpret_cast<const T*>(p.x) + (long long)n * p.h * p.w * p.x_ld + c0;
+  T* yn = reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + wo) * p.y_ld + c0;
+  const int d = p.dil;
+  const int wi0 = wo * kStride - d;
+  const bool relu = p.pre_relu != 0;
+  const long long xrow_stride = (long long)p.w * p.x_ld;
+  const long long yrow_stride = (long long)p.wo * p.y_ld;
 
+  if (kStride == 1) {
+    // d interleaved chains: chain `ch` produces output rows h0, h0+d, ... from input rows r_k = h0 + (k-1)*d.
+    // Before step k:  acc1 = shift + s0(r-2d) + s1(r-d)  (pending out(r-d)),  acc0 = shift + s0(r-d)  (pending out(r)).
+    const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
+    for (int ch = 0; ch < nchains; ++ch) {
+      const int h0 = h_begin + ch;
+      const int n_out = (h_end - h0 + d - 1) / d;
+      float2 acc0[4], acc1[4];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int hi = ho * p.stride + (ky - 1) * p.dil;
-      if (hi < 0 || hi >= p.h) continue;
-      const T* xrow = x + ((long long)n * p.h + hi) * p.w * p.x_ld + c0;
+      for (int j = 0; j < 4; ++j) { acc0[j] = sh[j]; acc1[j] = sh[j]; }
+      for (int k = 0; k < n_out + 2; ++k) {
+        const int r = h0 + (k - 1) * d;
+        float2 s[3][4];
+        row_sums<kBF16>((r >= 0 && r < p.h) ? xn + r * xrow_stride : nullptr, wi0, d, p.w, p.x_ld, relu, wt, s);
+        if (k >= 2) {
+          float2 o[4];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wgt + (ky * 3 + kx) * p.c + c0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wgt + (ky * 3 + kx) * p.c + c0 + 4));
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int q = 0; q < kPix; ++q) {
-          const int wi = (wo0 + q) * p.stride + (kx - 1) * p.dil;
-          if (wi < 0 || wi >= p.w || wo0 + q >= p.wo) continue;
-          const uint4 v = ldg_v4(xrow + (long long)wi * p.x_ld);
-          const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = H::unpack(vv[j]);
-            if (p.pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-            acc[q][2 * j] = fmaf(f.x, wv[2 * j], acc[q][2 * j]);
-            acc[q][2 * j + 1] = fmaf(f.y, wv[2 * j + 1], acc[q][2 * j + 1]);
-          }
+          for (int j = 0; j < 4; ++j) o[j] = fadd2(acc1[j], s[2][j]);
+          store_out<kBF16>(yn + (r - d) * yrow_stride, o, p.act);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc1[j] = fadd2(acc0[j], s[1][j]); acc0[j] = fadd2(sh[j], s[0][j]); }
       }
     }
-    float sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (p.shift != nullptr) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-      sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-    }
+  } else if (d == 1) {
+    // stride 2, dilation 1: out(ho) = s0(2ho-1) + s1(2ho) + s2(2ho+1); row 2ho+1 is shared with out(ho+1)
+    float2 acc0[4];
+    {
+      const int r = 2 * h_begin - 1;
+      float2 s[3][4];
+      row_sums<kBF16>((r >= 0 && r < p.h) ? xn + r * xrow_stride : nullptr, wi0, 1, p.w, p.x_ld, relu, wt, s);
 #pragma unroll
-    for (int q = 0; q < kPix; ++q) {
-      if (wo0 + q >= p.wo) continue;
-      uint4 o;
-      o.x = H::pack(apply_act(acc[q][0] + sh[0], p.act), apply_act(acc[q][1] + sh[1], p.act));
-      o.y = H::pack(apply_act(acc[q][2] + sh[2], p.act), apply_act(acc[q][3] + sh[3], p.act));
-      o.z = H::pack(apply_act(acc[q][4] + sh[4], p.act), apply_act(acc[q][5] + sh[5], p.act));
-      o.w = H::pack(apply_act(acc[q][6] + sh[6], p.act), apply_act(acc[q][7] + sh[7], p.act));
-      *reinterpret_cast<uint4*>(y + (((long long)n * p.ho + ho) * p.wo + wo0 + q) * p.y_ld + c0) = o;
+      for (int j = 0; j < 4; ++j) acc0[j] = fadd2(sh[j], s[0][j]);
+    }
+    for (int ho = h_begin; ho < h_end; ++ho) {
+      float2 sa[3][4], sb[3][4];
+      const int r0 = 2 * ho, r1 = 2 * ho + 1;
+      row_sums<kBF16>((r0 < p.h) ? xn + r0 * xrow_stride : nullptr, wi0, 1, p.w, p.x_ld, relu, wt, sa);
+      row_sums<kBF16>((r1 < p.h) ? xn + r1 * xrow_stride : nullptr, wi0, 1, p.w, p.x_ld, relu, wt, sb);
+      float2 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = fadd2(fadd2(acc0[j], sa[1][j]), sb[2][j]);
+        acc0[j] = fadd2(sh[j], sb[0][j]);
+      }
+      store_out<kBF16>(yn + ho * yrow_stride, o, p.act);
+    }
+  } else {
+    // stride 2 with dilation > 1 (not used by the zoo's hot path): no row sharing
+    for (int ho = h_begin; ho < h_end; ++ho) {
+      float2 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = sh[j];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int r = ho * 2 + (ky - 1) * d;
+        if (r < 0 || r >= p.h) continue;
+        float2 s[3][4];
+        row_sums<kBF16>(xn + r * xrow_stride, wi0, d, p.w, p.x_ld, relu, wt, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fadd2(o[j], s[ky][j]);
+      }
+      store_out<kBF16>(yn + ho * yrow_stride, o, p.act);
     }
   }
 }
@@ -106,19 +200,32 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   if (a->stride < 1 || a->stride > 2 || a->dilation < 1) return set_error(-3, "dwconv3x3: bad stride/dilation");
   if (((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15) || ((uintptr_t)a->wgt & 15) || ((uintptr_t)a->shift & 15))
     return set_error(-7, "dwconv3x3: pointers must be 16-byte aligned");
+  if (a->n < 1 || a->ho < 1 || a->wo < 1) return set_error(-6, "dwconv3x3: empty");
+  if (a->n > 65535) return set_error(-6, "dwconv3x3: batch too large");
   DwParams p;
   p.x = a->x; p.wgt = a->wgt; p.shift = a->shift; p.y = a->y;
   p.n = a->n; p.h = a->h; p.w = a->w; p.c = a->c; p.x_ld = a->x_ld; p.y_ld = a->y_ld;
   p.ho = a->ho; p.wo = a->wo; p.stride = a->stride; p.dil = a->dilation; p.pre_relu = a->pre_relu; p.act = a->act;
   p.cv = a->c / 8;
-  p.tiles_w = (a->wo + kTileW - 1) / kTileW;
-  p.tiles_h = (a->ho + kTileH - 1) / kTileH;
-  p.total = (long long)a->n * p.tiles_h * p.tiles_w * (kTileH * kTileW / kPix) * p.cv;
-  if (p.total <= 0) return set_error(-6, "dwconv3x3: empty");
-  long long blocks = (p.total + 255) / 256;
-  const long long cap = 148LL * 8 * 4;
-  if (blocks > cap) blocks = cap;
-  if (a->dtype == DT_BF16) dwconv3x3_kernel<true><<<(int)blocks, 256, 0, stream>>>(p);
-  else dwconv3x3_kernel<false><<<(int)blocks, 256, 0, stream>>>(p);
+  p.lc = p.cv <= 8 ? 8 : 16;
+  p.cblocks = (p.cv + p.lc - 1) / p.lc;
+  const int lw = 128 / p.lc;
+  const int wblocks = (a->wo + lw - 1) / lw;
+  // rows per block: long enough to amortise the 2-row halo of each chain, short enough to fill the GPU
+  int rows = a->stride == 1 ? 16 * a->dilation : 16;
+  if (rows > a->ho) rows = a->ho;
+  long long blocks_xy = (long long)p.cblocks * wblocks * a->n;
+  while (rows > 4 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 8) rows = (rows + 1) / 2;
+  if (a->stride == 1 && rows < a->ho) rows = ((rows + a->dilation - 1) / a->dilation) * a->dilation;   // whole chains
+  p.rows_per_block = rows;
+  dim3 grid((unsigned)(p.cblocks * wblocks), (unsigned)((a->ho + rows - 1) / rows), (unsigned)a->n);
+  if (grid.y > 65535) return set_error(-6, "dwconv3x3: too many row segments");
+  if (a->dtype == DT_BF16) {
+    if (a->stride == 1) dwconv3x3_kernel<true, 1><<<grid, 128, 0, stream>>>(p);
+    else dwconv3x3_kernel<true, 2><<<grid, 128, 0, stream>>>(p);
+  } else {
+    if (a->stride == 1) dwconv3x3_kernel<false, 1><<<grid, 128, 0, stream>>>(p);
+    else dwconv3x3_kernel<false, 2><<<grid, 128, 0, stream>>>(p);
+  }
   return check_launch("dwconv3x3");
 }
