@@ -98,10 +98,9 @@ int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream);
 int segb200_pack_s2d(const void* x_nchw, int x_dtype, void* out, int out_dtype, int n, int c, int h, int w,
                      int out_ld, void* stream);
 
-/* Global average pool over H*W: x [n][h][w][x_ld] -> out [n][c] (dtype), fp32 accumulation.
- * `workspace`: n*c floats, zeroed by the call.  Replaces nn.AdaptiveAvgPool2d((1,1)) (module.py:52). */
-int segb200_global_avgpool(const void* x, void* out, float* workspace, int n, int h, int w, int c, int x_ld,
-                           int dtype, void* stream);
+/* Global average pool over H*W: x [n][h][w][x_ld] -> out [n][c] (dtype), fp32 accumulation in a fixed
+ * order (bit-reproducible, no atomics).  Replaces nn.AdaptiveAvgPool2d((1,1)) (module.py:52). */
+int segb200_global_avgpool(const void* x, void* out, int n, int h, int w, int c, int x_ld, int dtype, void* stream);
 
 /* Adaptive average pool to s x s bins (torch bin rule floor/ceil): out [n][s][s][out_ld].
  * Replaces nn.AdaptiveAvgPool2d(s) of PyramidPooling (module.py:89). */

@@ -16,6 +16,11 @@ namespace segb200 {
 // ---------------------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda);
+// dtype is DT_BF16/DT_F16, strides in bytes for dims 1..rank-1, swizzle_bytes in {0,32,64,128}
+int encode_map(CUtensorMap* m, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes, const char* what);
+int num_sms();
 
 enum : int { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };

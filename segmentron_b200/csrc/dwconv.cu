@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "../../include/segb200.h"
 
+#include <mutex>
+
 namespace segb200 {
 
 struct DwParams {
@@ -187,6 +189,178 @@ dwconv3x3_kernel(const DwParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA-ring variant (C >= 64): one producer warp streams input rows (box = 64 channels x (tile width + halo)
+// columns x 1 row; conv zero padding = TMA out-of-bounds zero fill) into a shared-memory ring guarded by
+// full/empty mbarriers; 8 consumer warps read their three horizontal taps with conflict-free LDS.128 and
+// run the same rolling partial-sum recurrence as above.  Many rows are in flight per SM without holding
+// registers, which is what an HBM-bound stencil needs (Little's law: ~26 KB/SM at 6.5 TB/s).
+// ---------------------------------------------------------------------------------------------
+struct DwRingParams {
+  DwParams b;
+  int twin;          // input columns per ring slot
+  int slot_bytes;    // twin * 128
+  int nslots;
+};
+
+constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = t >> 3); +1 producer warp = 256 threads
+constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
+
+template <bool kBF16>
+__device__ __forceinline__ void ring_row_sums(const uint8_t* row, int col0, int d, bool pre_relu, const float2 (&wt)[9][4],
+                                              float2 (&s)[3][4], uint64_t* empty_bar, int c8) {
+  using H = Half2<kBF16>;
+  uint4 v[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) v[kx] = *reinterpret_cast<const uint4*>(row + (col0 + kx * d) * 128 + c8 * 16);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(empty_bar);     // slot may be refilled once all 8 warps have read it
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[ky][j] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const uint32_t u[4] = {v[kx].x, v[kx].y, v[kx].z, v[kx].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = H::unpack(u[j]);
+      if (pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], s[ky][j]);
+    }
+  }
+}
+
+template <bool kBF16, int kStride>
+__global__ void __launch_bounds__(kDwConsumers + 32, 2)
+dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
+  using H = Half2<kBF16>;
+  using T = typename H::T;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const DwParams& p = rp.b;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + rp.nslots * rp.slot_bytes);
+  uint64_t* empty = full + rp.nslots;
+  const int warp = threadIdx.x >> 5;
+  const int cblk = blockIdx.x % p.cblocks, wblk = blockIdx.x / p.cblocks;
+  const int n = blockIdx.z;
+  const int h_begin = blockIdx.y * p.rows_per_block;
+  int h_end = h_begin + p.rows_per_block; if (h_end > p.ho) h_end = p.ho;
+  const int d = p.dil;
+  const int w0 = wblk * kDwTW;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kDwConsumers / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // the row sequence is identical for producer and consumers:
+  //   stride 1: for each chain ch: rows h_begin + ch + (k-1)*d, k = 0 .. n_out+1
+  //   stride 2 (d == 1): rows 2*h_begin-1 .. 2*(h_end-1)+1
+  if (warp == kDwConsumers / 32) {
+    if ((threadIdx.x & 31) == 0) {
+      int slot = 0; uint32_t phase = 0;
+      auto issue = [&](int r) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_expect_tx(&full[slot], (uint32_t)rp.slot_bytes);
+        tma_load_4d(&tmX, &full[slot], dsm + slot * rp.slot_bytes, cblk * 64, w0 * kStride - d, r, n);
+        if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      };
+      if (kStride == 1) {
+        const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
+        for (int ch = 0; ch < nchains; ++ch) {
+          const int h0 = h_begin + ch;
+          const int n_out = (h_end - h0 + d - 1) / d;
+          for (int k = 0; k < n_out + 2; ++k) issue(h0 + (k - 1) * d);
+        }
+      } else {
+        for (int r = 2 * h_begin - 1; r <= 2 * (h_end - 1) + 1; ++r) issue(r);
+      }
+    }
+    return;
+  }
+
+  const int c8 = threadIdx.x & 7, wl = threadIdx.x >> 3;
+  const int cv = cblk * 8 + c8;
+  const int wo = w0 + wl;
+  const bool active = cv < p.cv && wo < p.wo;
+  const int c0 = (cv < p.cv ? cv : 0) * 8;
+  float2 wt[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0 + 4));
+    wt[t][0] = make_float2(a.x, a.y); wt[t][1] = make_float2(a.z, a.w);
+    wt[t][2] = make_float2(b.x, b.y); wt[t][3] = make_float2(b.z, b.w);
+  }
+  float2 sh[4];
+  if (p.shift != nullptr) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    sh[0] = make_float2(a.x, a.y); sh[1] = make_float2(a.z, a.w); sh[2] = make_float2(b.x, b.y); sh[3] = make_float2(b.z, b.w);
+  } else {
+    sh[0] = sh[1] = sh[2] = sh[3] = make_float2(0.f, 0.f);
+  }
+  T* yn = reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0;
+  const long long yrow_stride = (long long)p.wo * p.y_ld;
+  const bool relu = p.pre_relu != 0;
+  const int col0 = wl * kStride;            // slot column of the left tap (slot starts at input column w0*s - d)
+  int slot = 0; uint32_t phase = 0;
+
+  if (kStride == 1) {
+    const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
+    for (int ch = 0; ch < nchains; ++ch) {
+      const int h0 = h_begin + ch;
+      const int n_out = (h_end - h0 + d - 1) / d;
+      float2 acc0[4], acc1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc0[j] = sh[j]; acc1[j] = sh[j]; }
+      for (int k = 0; k < n_out + 2; ++k) {
+        const int r = h0 + (k - 1) * d;
+        float2 s[3][4];
+        mbar_wait(&full[slot], phase);
+        ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, d, relu, wt, s, &empty[slot], c8);
+        if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+        if (k >= 2 && active) {
+          float2 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fadd2(acc1[j], s[2][j]);
+          store_out<kBF16>(yn + (r - d) * yrow_stride, o, p.act);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc1[j] = fadd2(acc0[j], s[1][j]); acc0[j] = fadd2(sh[j], s[0][j]); }
+      }
+    }
+  } else {
+    float2 acc0[4];
+    {
+      float2 s[3][4];
+      mbar_wait(&full[slot], phase);
+      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, s, &empty[slot], c8);
+      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc0[j] = fadd2(sh[j], s[0][j]);
+    }
+    for (int ho = h_begin; ho < h_end; ++ho) {
+      float2 sa[3][4], sb[3][4];
+      mbar_wait(&full[slot], phase);
+      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, sa, &empty[slot], c8);
+      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      mbar_wait(&full[slot], phase);
+      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, sb, &empty[slot], c8);
+      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      float2 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = fadd2(fadd2(acc0[j], sa[1][j]), sb[2][j]);
+        acc0[j] = fadd2(sh[j], sb[0][j]);
+      }
+      if (active) store_out<kBF16>(yn + ho * yrow_stride, o, p.act);
+    }
+  }
+}
+
 }  // namespace segb200
 
 using namespace segb200;
@@ -207,12 +381,13 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   p.n = a->n; p.h = a->h; p.w = a->w; p.c = a->c; p.x_ld = a->x_ld; p.y_ld = a->y_ld;
   p.ho = a->ho; p.wo = a->wo; p.stride = a->stride; p.dil = a->dilation; p.pre_relu = a->pre_relu; p.act = a->act;
   p.cv = a->c / 8;
-  p.lc = p.cv <= 8 ? 8 : 16;
-  p.cblocks = (p.cv + p.lc - 1) / p.lc;
-  const int lw = 128 / p.lc;
+  const bool ring = a->c >= 64 && (a->stride == 1 || a->dilation == 1) && a->dilation <= 64;
+  int lw;
+  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = kDwTW; }
+  else { p.lc = p.cv <= 8 ? 8 : 16; p.cblocks = (p.cv + p.lc - 1) / p.lc; lw = 128 / p.lc; }
   const int wblocks = (a->wo + lw - 1) / lw;
   // rows per block: long enough to amortise the 2-row halo of each chain, short enough to fill the GPU
-  int rows = a->stride == 1 ? 16 * a->dilation : 16;
+  int rows = a->stride == 1 ? (ring ? 32 : 16) * a->dilation : (ring ? 32 : 16);
   if (rows > a->ho) rows = a->ho;
   long long blocks_xy = (long long)p.cblocks * wblocks * a->n;
   while (rows > 4 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 8) rows = (rows + 1) / 2;
@@ -220,6 +395,38 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   p.rows_per_block = rows;
   dim3 grid((unsigned)(p.cblocks * wblocks), (unsigned)((a->ho + rows - 1) / rows), (unsigned)a->n);
   if (grid.y > 65535) return set_error(-6, "dwconv3x3: too many row segments");
+  if (ring) {
+    DwRingParams rp;
+    rp.b = p;
+    rp.twin = (kDwTW - 1) * a->stride + 2 * a->dilation + 1;
+    rp.slot_bytes = rp.twin * 128;
+    rp.nslots = 49152 / rp.slot_bytes;
+    if (rp.nslots > 12) rp.nslots = 12;
+    if (rp.nslots < 3) rp.nslots = 3;
+    const int smem = rp.nslots * rp.slot_bytes + 2 * rp.nslots * 8;
+    CUtensorMap tmX;
+    const uint64_t dims[4] = {(uint64_t)a->c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    const uint64_t str[3] = {(uint64_t)a->x_ld * 2, (uint64_t)a->x_ld * 2 * a->w, (uint64_t)a->x_ld * 2 * a->w * a->h};
+    const uint32_t box[4] = {64u, (uint32_t)rp.twin, 1u, 1u};
+    int rc = encode_map(&tmX, a->dtype, 4, a->x, dims, str, box, 0, "dw/X");
+    if (rc) return rc;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(dwconv3x3_ring_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(dwconv3x3_ring_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(dwconv3x3_ring_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(dwconv3x3_ring_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    });
+    const int threads = kDwConsumers + 32;
+    if (a->dtype == DT_BF16) {
+      if (a->stride == 1) dwconv3x3_ring_kernel<true, 1><<<grid, threads, smem, stream>>>(tmX, rp);
+      else dwconv3x3_ring_kernel<true, 2><<<grid, threads, smem, stream>>>(tmX, rp);
+    } else {
+      if (a->stride == 1) dwconv3x3_ring_kernel<false, 1><<<grid, threads, smem, stream>>>(tmX, rp);
+      else dwconv3x3_ring_kernel<false, 2><<<grid, threads, smem, stream>>>(tmX, rp);
+    }
+    return check_launch("dwconv3x3(ring)");
+  }
   if (a->dtype == DT_BF16) {
     if (a->stride == 1) dwconv3x3_kernel<true, 1><<<grid, 128, 0, stream>>>(p);
     else dwconv3x3_kernel<true, 2><<<grid, 128, 0, stream>>>(p);

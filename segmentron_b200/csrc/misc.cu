@@ -75,35 +75,51 @@ pack_s2d_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ out,
 }
 
 // -------------------------------------------------------------------------------------------
-// global average pool
+// global average pool: one block per (image, 16 channel vectors); 16 pixel lanes x 16 channel lanes,
+// fixed-order accumulation and a fixed-order shared-memory reduction => bit-reproducible (no atomics)
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gap_partial_kernel(const void* __restrict__ x, float* __restrict__ ws, int hw, int c, int x_ld, int dtype, int lanes_c,
-                   int lanes_p, int splits) {
+gap_kernel(const void* __restrict__ x, void* __restrict__ out, int hw, int c, int x_ld, int dtype) {
+  __shared__ float red[16][16][8];
   const int n = blockIdx.y;
-  const int lc = threadIdx.x % lanes_c, lp = threadIdx.x / lanes_c;
-  if (lp >= lanes_p) return;
+  const int lc = threadIdx.x & 15, lp = threadIdx.x >> 4;
+  const int cv = blockIdx.x * 16 + lc;
   const int cvn = c / 8;
-  const int per = (hw + splits - 1) / splits;
-  const int p0 = blockIdx.x * per;
-  const int p1 = min(hw, p0 + per);
-  const char* base = reinterpret_cast<const char*>(x) + (long long)n * hw * x_ld * 2;
-  for (int cv = lc; cv < cvn; cv += lanes_c) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int p = p0 + lp; p < p1; p += lanes_p) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cv < cvn) {
+    const char* base = reinterpret_cast<const char*>(x) + ((long long)n * hw * x_ld + cv * 8) * 2;
+    int p = lp;
+    for (; p + 48 < hw; p += 64) {                   // 4 independent 128-bit loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(ldg_nc_v4(base + (long long)p * x_ld * 2), dtype, f0);
+      unpack8(ldg_nc_v4(base + (long long)(p + 16) * x_ld * 2), dtype, f1);
+      unpack8(ldg_nc_v4(base + (long long)(p + 32) * x_ld * 2), dtype, f2);
+      unpack8(ldg_nc_v4(base + (long long)(p + 48) * x_ld * 2), dtype, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; p < hw; p += 16) {
       float f[8];
-      unpack8(ldg_nc_v4(base + ((long long)p * x_ld + cv * 8) * 2), dtype, f);
+      unpack8(ldg_nc_v4(base + (long long)p * x_ld * 2), dtype, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(ws + (long long)n * c + cv * 8 + j, acc[j]);
   }
-}
-__global__ void gap_finalize_kernel(const float* __restrict__ ws, void* __restrict__ out, int total, float inv,
-                                    int dtype) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) store_any(out, i, ws[i] * inv, dtype);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lp][lc][j] = acc[j];
+  __syncthreads();
+  if (lp == 0 && cv < cvn) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = 0.f;
+    for (int q = 0; q < 16; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] += red[q][lc][j];
+    const float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] *= inv;
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + ((long long)n * c + cv * 8) * 2) = pack8(t, dtype);
+  }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -294,22 +310,13 @@ extern "C" int segb200_pack_s2d(const void* x, int x_dtype, void* out, int out_d
   return check_launch("pack_s2d");
 }
 
-extern "C" int segb200_global_avgpool(const void* x, void* out, float* workspace, int n, int h, int w, int c, int x_ld,
-                                      int dtype, void* stream) {
-  if (!x || !out || !workspace) return set_error(-1, "global_avgpool: null pointer");
+extern "C" int segb200_global_avgpool(const void* x, void* out, int n, int h, int w, int c, int x_ld, int dtype,
+                                      void* stream) {
+  if (!x || !out) return set_error(-1, "global_avgpool: null pointer");
   if (!half_dt(dtype)) return set_error(-2, "global_avgpool: bad dtype");
   if ((c & 7) || (x_ld & 7)) return set_error(-4, "global_avgpool: c and x_ld must be multiples of 8");
-  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)n * c, STREAM(stream));
-  if (e != cudaSuccess) return set_error((int)e, "global_avgpool: memset: %s", cudaGetErrorString(e));
-  const int cvn = c / 8;
-  int lanes_c = 1; while (lanes_c < cvn && lanes_c < 256) lanes_c <<= 1;
-  const int lanes_p = 256 / lanes_c;
-  const int hw = h * w;
-  int splits = (hw + lanes_p * 8 - 1) / (lanes_p * 8);
-  if (splits > 592) splits = 592;
-  if (splits < 1) splits = 1;
-  gap_partial_kernel<<<dim3(splits, n), 256, 0, STREAM(stream)>>>(x, workspace, hw, c, x_ld, dtype, lanes_c, lanes_p, splits);
-  gap_finalize_kernel<<<(n * c + 255) / 256, 256, 0, STREAM(stream)>>>(workspace, out, n * c, 1.f / (float)hw, dtype);
+  if (((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return set_error(-7, "global_avgpool: pointers must be 16-byte aligned");
+  gap_kernel<<<dim3((c / 8 + 15) / 16, n), 256, 0, STREAM(stream)>>>(x, out, h * w, c, x_ld, dtype);
   return check_launch("global_avgpool");
 }
 

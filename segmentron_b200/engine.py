@@ -244,10 +244,7 @@ def _aspp(pl, x, prefix, output_stride):
     cat = pl.new(n, h, w_, 1280)
     # image pooling branch: GAP -> 1x1 conv+BN+ReLU on n "pixels" -> broadcast (bilinear from 1x1)
     pooled = pl.new(n, 1, 1, c)
-    ws = torch.empty(n * c, dtype=torch.float32, device=pl.device)
-    pl.keep.append(ws)
-    pl.call("segb200_global_avgpool", ops._ptr(x), ops._ptr(pooled), ops._ptr(ws), n, h, w_, c, x.stride(2),
-            ops.dt_code(pl.dtype), launches=3)
+    pl.call("segb200_global_avgpool", ops._ptr(x), ops._ptr(pooled), n, h, w_, c, x.stride(2), ops.dt_code(pl.dtype))
     pf = pl.conv_bn_act(pooled, prefix + ".image_pooling", 256, 1, act="relu")
     pl.call("segb200_bilinear_nhwc", ops._ptr(pf), ops._ptr(cat[..., 0:256]), n, 1, 1, 256, pf.stride(2), h, w_,
             cat.stride(2), 1, ops.dt_code(pl.dtype))

@@ -293,7 +293,7 @@ class _ASPP(nn.Module):
         oc = self.conv.out_channels
         cat = torch.empty(n, h, w, 5 * oc, dtype=dt, device=x.device)
         pooled = torch.empty(n, 1, 1, c, dtype=dt, device=x.device)
-        ops.global_avgpool(x, pooled, torch.empty(n * c, dtype=torch.float32, device=x.device))
+        ops.global_avgpool(x, pooled)
         pf = _run_conv_bn_act(pooled, self.image_pooling.conv, self.image_pooling.bn, "relu", self._cp, dt)
         ops.bilinear_nhwc(pf, cat[..., 0:oc], align_corners=True)
         _run_conv_bn_act(x, self.aspp0.conv, self.aspp0.bn, "relu", self._c0, dt, out=cat[..., oc:2 * oc])

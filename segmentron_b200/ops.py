@@ -101,10 +101,10 @@ def pack_s2d(x_nchw, out):
     return out
 
 
-def global_avgpool(x, out, workspace):
+def global_avgpool(x, out):
     n, h, w, c, ld = _nhwc(x, "x")
-    L.check(L.load().segb200_global_avgpool(_ptr(x), _ptr(out), _ptr(workspace), n, h, w, c, ld, dt_code(x.dtype),
-                                            _stream()), "global_avgpool")
+    L.check(L.load().segb200_global_avgpool(_ptr(x), _ptr(out), n, h, w, c, ld, dt_code(x.dtype), _stream()),
+            "global_avgpool")
     return out
 
 
