@@ -46,9 +46,13 @@ template <> struct Half2<true> {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {      // 2 ALU ops: bf16 is the top half of an fp32
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
+  static __device__ __forceinline__ uint32_t relu2(uint32_t u) {     // packed max(x, 0)
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(v);
+    v = __hmax2(v, __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
   }
   static __device__ __forceinline__ float to_f(T v) { return __bfloat162float(v); }
   static __device__ __forceinline__ T from_f(float v) { return __float2bfloat16_rn(v); }
@@ -63,6 +67,11 @@ template <> struct Half2<false> {
   static __device__ __forceinline__ float2 unpack(uint32_t u) {
     __half2 v = *reinterpret_cast<__half2*>(&u);
     return __half22float2(v);
+  }
+  static __device__ __forceinline__ uint32_t relu2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    v = __hmax2(v, __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
   }
   static __device__ __forceinline__ float to_f(T v) { return __half2float(v); }
   static __device__ __forceinline__ T from_f(float v) { return __float2half_rn(v); }
@@ -112,6 +121,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// lean spin (no watchdog) for the innermost loops of memory-bound kernels
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}"
+      ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------

