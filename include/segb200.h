@@ -33,6 +33,15 @@ enum { SEGB200_ACT_NONE = 0, SEGB200_ACT_RELU = 1, SEGB200_ACT_RELU6 = 2 };
 
 int segb200_version(void);
 const char* segb200_last_error(void);
+/* Diagnostics: point subsequent segb200_conv_gemm launches at 16 device uint64 counters that accumulate, over all
+ * CTAs, the clock cycles each role spent waiting ([0] producer:ring slot free, [1] MMA:accumulator free, [2] MMA:operands
+ * landed, [3]/[4] epilogue group 0/1:accumulator ready, [5]/[6] epilogue group 0/1:store drained, [7] total CTA cycles, [8..11] epilogue group-0 leader: entry barrier, residual wait,
+ * TMEM load + math + staging stores, fence + exit barrier).
+ * NULL disables (default).  Not thread-safe; for profiling only. */
+int segb200_debug_set_counters(void* dev_ptr_16_u64);
+/* Diagnostics: ablate parts of the conv_gemm epilogue (results become WRONG): bit0 skip scale/shift loads, bit1 skip
+ * TMEM loads, bit2 skip staging stores.  0 = normal (default). */
+int segb200_debug_set_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Dense convolution as an implicit GEMM on tcgen05 tensor cores, with the following
@@ -106,6 +115,10 @@ int segb200_global_avgpool(const void* x, void* out, int n, int h, int w, int c,
  * Replaces nn.AdaptiveAvgPool2d(s) of PyramidPooling (module.py:89). */
 int segb200_adaptive_avgpool(const void* x, void* out, int n, int h, int w, int c, int x_ld, int s, int out_ld,
                              int dtype, void* stream);
+
+/* MaxPool2d(3, 2, 1) (-inf padding): x [n][h][w][x_ld] -> y [n][(h-1)/2+1][(w-1)/2+1][y_ld].
+ * Replaces nn.MaxPool2d(3, 2, 1) of the ResNet stem (backbones/resnet.py:119). */
+int segb200_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, int x_ld, int y_ld, int dtype, void* stream);
 
 /* Bilinear resize NHWC -> NHWC channel slice.  align_corners as F.interpolate.  From a 1x1 source
  * this is the ASPP image-pooling broadcast (module.py:64).  Replaces F.interpolate at

@@ -254,6 +254,57 @@ def mobilenet_v2(P, x, prefix="encoder", output_stride=16, eps=1e-5):
     return c1, c2, c3, c4
 
 
+
+# ----------------------------------------------------------------------------------------
+# ResNetV1 / BottleneckV1b  (models/backbones/resnet.py:44-199)
+# ----------------------------------------------------------------------------------------
+def bottleneck_v1b(P, x, prefix, planes, stride=1, dilation=1, downsample=False, eps=1e-5, last_gain=0.5):
+    """BottleneckV1b.forward (resnet.py:60-81): 1x1 -> 3x3(stride, pad=dil, dil) -> 1x1, + identity, ReLU."""
+    g = math.sqrt(2.0)
+    out = F.relu(batchnorm(P, conv2d(P, x, prefix + ".conv1", planes, 1, gain=g), prefix + ".bn1", eps))
+    out = F.relu(batchnorm(P, conv2d(P, out, prefix + ".conv2", planes, 3, stride, dilation, dilation, gain=g),
+                           prefix + ".bn2", eps))
+    out = batchnorm(P, conv2d(P, out, prefix + ".conv3", planes * 4, 1, gain=g * last_gain), prefix + ".bn3", eps)
+    identity = x
+    if downsample:                                                    # resnet.py:142-147
+        identity = batchnorm(P, conv2d(P, x, prefix + ".downsample.0", planes * 4, 1, stride, gain=g),
+                             prefix + ".downsample.1", eps)
+    return F.relu(out + identity)                                     # :78-79
+
+
+def resnet_v1(P, x, prefix="encoder", layers=(3, 4, 23, 3), output_stride=16, multi_grid=False,
+              multi_dilation=None, eps=1e-5):
+    """ResNetV1.forward (resnet.py:183-199), non-deep-stem (resnet50/101/152).  Dilation/stride table :90-100,
+    first-block dilation rule and DANet multi-grid :149-179."""
+    dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
+    x = conv2d(P, x, prefix + ".conv1", 64, 7, 2, 3, gain=math.sqrt(2.0))        # :116
+    x = F.relu(batchnorm(P, x, prefix + ".bn1", eps))
+    x = F.max_pool2d(x, 3, 2, 1)                                                  # :119
+    inplanes = 64
+
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1, mg=False):
+        nonlocal inplanes
+        ds = stride != 1 or inplanes != planes * 4
+        if not mg:
+            first_d = 1 if dilation in (1, 2) else 2                               # :151-159
+        else:
+            first_d = multi_dilation[0]                                            # :161
+        x = bottleneck_v1b(P, x, f"{prefix}.{name}.0", planes, stride, first_d, ds, eps)
+        inplanes = planes * 4
+        for i in range(1, blocks):
+            d = multi_dilation[i % len(multi_dilation)] if mg else dilation        # :166-175
+            x = bottleneck_v1b(P, x, f"{prefix}.{name}.{i}", planes, 1, d, False, eps)
+        return x
+
+    c1 = make_layer(x, "layer1", 64, layers[0])
+    c2 = make_layer(c1, "layer2", 128, layers[1], 2)
+    c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], multi_grid)
+    # the (unused) classifier exists in the reference state_dict: resnet.py:129-131
+    P._new(prefix + ".fc.weight", lambda: torch.zeros(1000, 2048))
+    P._new(prefix + ".fc.bias", lambda: torch.zeros(1000))
+    return c1, c2, c3, c4
+
 # ----------------------------------------------------------------------------------------
 # heads
 # ----------------------------------------------------------------------------------------
@@ -299,6 +350,8 @@ def deeplabv3plus(P, x, backbone="xception65", nclass=19, output_stride=16, eps_
         c1, _, _, c4 = xception65(P, x, "encoder", output_stride, eps_encoder)
     elif backbone == "mobilenet_v2":
         c1, _, _, c4 = mobilenet_v2(P, x, "encoder", output_stride, eps_encoder)
+    elif backbone == "resnet101":
+        c1, _, _, c4 = resnet_v1(P, x, "encoder", (3, 4, 23, 3), output_stride, eps=eps_encoder)
     else:
         raise NotImplementedError(backbone)
     y = deeplab_head(P, c4, c1, nclass, "head", use_aspp, use_decoder, output_stride)
@@ -387,6 +440,7 @@ MODELS = {
                                      use_decoder=True),
     "deeplabv3plus_mobilenet_v2": dict(backbone="mobilenet_v2", eps_encoder=1e-5, use_aspp=False,
                                        use_decoder=False),
+    "deeplabv3plus_resnet101": dict(backbone="resnet101", eps_encoder=1e-5, use_aspp=True, use_decoder=True),
 }
 
 

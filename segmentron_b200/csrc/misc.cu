@@ -156,6 +156,50 @@ adaptive_pool_kernel(const void* __restrict__ x, void* __restrict__ out, int n, 
   }
 }
 
+
+// -------------------------------------------------------------------------------------------
+// max pool 3x3, stride 2, padding 1 (-inf padding), NHWC
+// -------------------------------------------------------------------------------------------
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w, int c, int x_ld, int ho, int wo,
+                    int y_ld) {
+  using H = Half2<kBF16>;
+  const int cvn = c / 8;
+  const long long total = (long long)n * ho * wo * cvn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    long long r = idx / cvn;
+    const int ox = (int)(r % wo); r /= wo;
+    const int oy = (int)(r % ho);
+    const int b = (int)(r / ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = ldg_v4(reinterpret_cast<const char*>(x) + ((((long long)b * h + iy) * w + ix) * x_ld + cv * 8) * 2);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = H::unpack(u[j]);
+          m[2 * j] = fmaxf(m[2 * j], f.x); m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+        }
+      }
+    }
+    uint4 o;
+    o.x = H::pack(m[0], m[1]); o.y = H::pack(m[2], m[3]); o.z = H::pack(m[4], m[5]); o.w = H::pack(m[6], m[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + ((((long long)b * ho + oy) * wo + ox) * y_ld + cv * 8) * 2) = o;
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // bilinear resize (torch upsample_bilinear2d index rules, fp32 math)
 // -------------------------------------------------------------------------------------------
@@ -328,6 +372,20 @@ extern "C" int segb200_adaptive_avgpool(const void* x, void* out, int n, int h, 
   const long long total = (long long)n * s * s * (c / 8);
   adaptive_pool_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(x, out, n, h, w, c, x_ld, s, out_ld, dtype);
   return check_launch("adaptive_avgpool");
+}
+
+extern "C" int segb200_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, int x_ld, int y_ld, int dtype,
+                                   void* stream) {
+  if (!x || !y) return set_error(-1, "maxpool3x3s2: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "maxpool3x3s2: bad dtype");
+  if ((c & 7) || (x_ld & 7) || (y_ld & 7)) return set_error(-4, "maxpool3x3s2: c/pitches must be multiples of 8");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  if (dtype == DT_BF16)
+    maxpool3x3s2_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, n, h, w, c, x_ld, ho, wo, y_ld);
+  else
+    maxpool3x3s2_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, n, h, w, c, x_ld, ho, wo, y_ld);
+  return check_launch("maxpool3x3s2");
 }
 
 extern "C" int segb200_bilinear_nhwc(const void* x, void* y, int n, int hi, int wi, int c, int x_ld, int ho, int wo,

@@ -237,6 +237,49 @@ def _mobilenet_v2(pl, x_shape, holder, output_stride, eps):
     return c1, c2, c3, c4
 
 
+def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, eps):
+    """BottleneckV1b.forward (backbones/resnet.py:60-81): three GEMMs; the identity / downsample branch is the
+    residual operand of the third GEMM's epilogue, followed by the fused ReLU (out += identity; relu)."""
+    y = pl.conv_bn_act(x, prefix, planes, 1, act="relu", eps=eps, conv="conv1", bn="bn1")
+    y = pl.conv_bn_act(y, prefix, planes, 3, stride=stride, dilation=dilation, pad=dilation, act="relu", eps=eps,
+                       conv="conv2", bn="bn2")
+    if downsample:
+        idn = pl.conv_bn_act(x, prefix + ".downsample", planes * 4, 1, stride=stride, act=None, eps=eps, conv="0", bn="1")
+    else:
+        idn = x
+    return pl.conv_bn_act(y, prefix, planes * 4, 1, act="relu", eps=eps, conv="conv3", bn="bn3", residual=idn)
+
+
+def _resnet(pl, x_shape, holder, layers, output_stride, eps, multi_grid=False, multi_dilation=None):
+    """ResNetV1.forward (backbones/resnet.py:183-199): 7x7/2 stem (space-to-depth -> 4x4 tensor-core conv) + BN + ReLU,
+    MaxPool(3,2,1), four bottleneck stages with the reference's stride/dilation table (:90-100, :149-179)."""
+    dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
+    p = "encoder"
+    x = pl.stem_s2d(x_shape, holder, p + ".conv1", p + ".bn1", 64, 7, 3, "relu", eps)
+    n, h, w_, c = x.shape
+    y = pl.new(n, (h - 1) // 2 + 1, (w_ - 1) // 2 + 1, c)
+    pl.call("segb200_maxpool3x3s2", ops._ptr(x), ops._ptr(y), n, h, w_, c, x.stride(2), y.stride(2), ops.dt_code(pl.dtype),
+            nbytes=2.0 * (x.numel() + y.numel()))
+    x = y
+    inplanes = [64]
+
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1, mg=False):
+        ds = stride != 1 or inplanes[0] != planes * 4
+        first_d = (1 if dilation in (1, 2) else 2) if not mg else multi_dilation[0]
+        x = _bottleneck(pl, x, f"{p}.{name}.0", planes, stride, first_d, ds, eps)
+        inplanes[0] = planes * 4
+        for i in range(1, blocks):
+            d = multi_dilation[i % len(multi_dilation)] if mg else dilation
+            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, d, False, eps)
+        return x
+
+    c1 = make_layer(x, "layer1", 64, layers[0])
+    c2 = make_layer(c1, "layer2", 128, layers[1], 2)
+    c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], multi_grid)
+    return c1, c2, c3, c4
+
+
 def _aspp(pl, x, prefix, output_stride):
     """_ASPP.forward (modules/module.py:62-77); concat order [pool, aspp0, aspp1, aspp2, aspp3]."""
     d = {16: (6, 12, 18), 8: (12, 24, 36), 32: (6, 12, 18)}[output_stride]
@@ -262,6 +305,9 @@ def build_deeplabv3plus(pl, x_shape, holder, backbone, nclass, output_stride, ep
         c1, _, _, c4 = _xception65(pl, x_shape, holder, output_stride, eps_encoder)
     elif backbone == "mobilenet_v2":
         c1, _, _, c4 = _mobilenet_v2(pl, x_shape, holder, output_stride, eps_encoder)
+    elif backbone in ("resnet50", "resnet101", "resnet152"):
+        layers = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}[backbone]
+        c1, _, _, c4 = _resnet(pl, x_shape, holder, layers, output_stride, eps_encoder)
     else:
         raise RuntimeError(f"segb200: backbone '{backbone}' has no B200 plan yet")
     x = c4

@@ -37,12 +37,15 @@ class DwArgs(C.Structure):
 SYMBOLS = {
     "segb200_version": (C.c_int, []),
     "segb200_last_error": (C.c_char_p, []),
+    "segb200_debug_set_counters": (C.c_int, [vp]),
+    "segb200_debug_set_mode": (C.c_int, [C.c_int]),
     "segb200_conv_kblock": (C.c_int, [C.c_int]),
     "segb200_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "segb200_dwconv3x3": (C.c_int, [C.POINTER(DwArgs), vp]),
     "segb200_pack_s2d": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
     "segb200_global_avgpool": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),
     "segb200_adaptive_avgpool": (C.c_int, [vp, vp] + [C.c_int] * 8 + [vp]),
+    "segb200_maxpool3x3s2": (C.c_int, [vp, vp] + [C.c_int] * 7 + [vp]),
     "segb200_bilinear_nhwc": (C.c_int, [vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_bilinear_nchw_out": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_nchw_to_nhwc": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),

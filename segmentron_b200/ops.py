@@ -116,6 +116,15 @@ def adaptive_avgpool(x, out, s):
     return out
 
 
+def maxpool3x3s2(x, y):
+    n, h, w, c, x_ld = _nhwc(x, "x")
+    _, ho, wo, cy, y_ld = _nhwc(y, "y")
+    assert cy == c and ho == (h - 1) // 2 + 1 and wo == (w - 1) // 2 + 1
+    L.check(L.load().segb200_maxpool3x3s2(_ptr(x), _ptr(y), n, h, w, c, x_ld, y_ld, dt_code(x.dtype), _stream()),
+            "maxpool3x3s2")
+    return y
+
+
 def bilinear_nhwc(x, y, align_corners=True):
     n, hi, wi, c, x_ld = _nhwc(x, "x")
     _, ho, wo, cy, y_ld = _nhwc(y, "y")

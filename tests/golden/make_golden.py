@@ -24,6 +24,7 @@ MODEL_CASES = {
     "dlv3p_xception65_65x129": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (1, 3, 65, 129), 0),
     "dlv3p_xception65_97x161_b2": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (2, 3, 97, 161), 1),
     "dlv3p_mobilenetv2_64x128": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (1, 3, 64, 128), 2),
+    "dlv3p_resnet101_65x129": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (1, 3, 65, 129), 4),
 }
 
 

@@ -179,6 +179,16 @@ def test_pool_and_resize(dtype):
         assert (am.long() == yo.float().argmax(1)).all(), "fused argmax != torch.argmax of the same output"
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_maxpool(dtype):
+    from segmentron_b200 import ops
+    for (n, h, w, c) in [(2, 33, 65, 64), (1, 34, 66, 128)]:
+        x = _rand(n, h, w, c, dtype=dtype, seed=1)
+        y = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=dtype, device="cuda")
+        ops.maxpool3x3s2(x, y)
+        assert torch.equal(_to_nchw(y), F.max_pool2d(_to_nchw(x), 3, 2, 1))
+
+
 def test_layout_converters():
     from segmentron_b200 import ops
     x = _rand(2, 19, 37, 41, dtype=torch.float32, seed=3)

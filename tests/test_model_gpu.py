@@ -61,7 +61,8 @@ def _check(model, P, x, y32, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)], ids=["f16", "bf16"])
-@pytest.mark.parametrize("case", ["dlv3p_xception65_65x129", "dlv3p_xception65_97x161_b2", "dlv3p_mobilenetv2_64x128"])
+@pytest.mark.parametrize("case", ["dlv3p_xception65_65x129", "dlv3p_xception65_97x161_b2", "dlv3p_mobilenetv2_64x128",
+                                  "dlv3p_resnet101_65x129"])
 def test_engine_vs_reference_fixture(case, dtype, tol):
     fx = torch.load(os.path.join(G, case + ".pt"))
     P = R.build_params(fx["model"], fx["seed"])
