@@ -30,7 +30,7 @@ constexpr int kStageRegion = 196608;          // bytes for the A/B ring
 constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
 constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
 constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
-constexpr int kSmemBytes = kCtlOffset + 1024;  // 230400 <= 232448
+constexpr int kSmemBytes = kCtlOffset + 3072;  // 232448 = the 227 KB maximum
 constexpr int kMaxStages = 32;
 constexpr int kEpiGroups = 1;                 // 4-warp epilogue groups taking the 64-column chunks round-robin (measured: 2 groups
                                               // gain 4% on HBM-bound layers but lose 5-10% on tensor-bound ones -> 1)
@@ -44,8 +44,10 @@ struct Control {
   uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
+  float scale[256];    // folded-BN scale/shift of the current N tile (global loads would miss: with 227 KB of smem the
+  float shift[256];    // L1 has no capacity left, every __ldg is an L2 round trip)
 };
-static_assert(sizeof(Control) <= 1024, "control block too large");
+static_assert(sizeof(Control) <= 3072, "control block too large");
 
 struct ConvGemmParams {
   int n_img, ho, wo;
@@ -185,7 +187,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint8_t* const rbuf0 = smem + kStageRegion - kResRegion + (kEpiGroups == 2 ? grp * kEpiBufBytes : 0);   // ring is shortened by the host
     const bool has_res = p.residual != nullptr;
     const int bar_id = 1 + grp;
-    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0; uint32_t my_uses = 0;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0; uint32_t my_uses = 0; int staged_n_tile = -1;
+    static_assert(kEpiGroups == 1, "scale/shift staging assumes a single epilogue group");
 
     // residual prefetch cursor (group leader only): points at this group's NEXT chunk in the global sequence
     int pf_tile = blockIdx.x, pf_ch = 0;
@@ -224,6 +227,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       const int nchunks = (nvalid + 63) >> 6;
 
+      if (n_tile != staged_n_tile) {                   // (re)stage scale/shift: only when the N tile changes
+        named_bar_sync(bar_id, 128);                   // previous readers are done
+        if (grp == 0) {
+          for (int i = et; i < p.bn; i += 128) {
+            const int c = n0 + i;
+            ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
+            ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
+          }
+        }
+        staged_n_tile = n_tile;                        // published by the first barrier of the chunk loop
+      }
       if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3 + grp); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
@@ -262,28 +276,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
             const int chunk16 = (half * 4 + g) ^ (row & 7);   // 128B swizzle: 16 B chunk c lives at c ^ (row & 7)
-            const int c = n0 + col0 + g * 8;         // first of 8 output channels (cout is a multiple of 8)
+            const int cl = col0 + g * 8;             // tile-local column of the first of 8 output channels
             float sc[8], sf[8];
-            if (c < p.cout && !(p.dbg_mode & 1)) {
-              if (p.scale != nullptr) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
-                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sc[j] = 1.f;
-              }
-              if (p.shift != nullptr) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
-                sf[0] = a.x; sf[1] = a.y; sf[2] = a.z; sf[3] = a.w; sf[4] = b.x; sf[5] = b.y; sf[6] = b.z; sf[7] = b.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sf[j] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sf[j] = 0.f; }
+            {
+              const float4 a0 = *reinterpret_cast<const float4*>(&ctl->scale[cl]);
+              const float4 a1 = *reinterpret_cast<const float4*>(&ctl->scale[cl + 4]);
+              const float4 b0 = *reinterpret_cast<const float4*>(&ctl->shift[cl]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&ctl->shift[cl + 4]);
+              sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+              sf[0] = b0.x; sf[1] = b0.y; sf[2] = b0.z; sf[3] = b0.w; sf[4] = b1.x; sf[5] = b1.y; sf[6] = b1.z; sf[7] = b1.w;
             }
             float f[8];
 #pragma unroll

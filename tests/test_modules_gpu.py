@@ -1,0 +1,92 @@
+"""Drop-in nn.Modules (segmentron_b200/modules.py) on the B200 against the oracle's functional restatement of the same
+reference modules, with the oracle's reference-named parameters loaded through load_state_dict(strict=True)."""
+import pytest
+import torch
+
+from oracle import segref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _load(mod, P, prefix):
+    sd = {k[len(prefix) + 1:]: v for k, v in P.state_dict().items() if k.startswith(prefix + ".")}
+    mod.load_state_dict(sd, strict=True)
+    return mod.cuda().eval()
+
+
+def _cmp(y, ref, tol):
+    rel = float((y.float().cpu() - ref).norm() / ref.norm())
+    assert rel < tol, rel
+    return rel
+
+
+def _x(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1.5e-3), (torch.bfloat16, 1e-2)], ids=["f16", "bf16"])
+def test_dropin_modules(dtype, tol):
+    from segmentron_b200 import modules as M
+    with torch.no_grad():
+        # SeparableConv2d, both orderings, stride/dilation
+        for relu_first, stride, dil in [(True, 1, 1), (True, 2, 1), (False, 1, 2), (False, 1, 12)]:
+            P = R.Params(1)
+            x = _x(2, 64, 33, 41, seed=3)
+            ref = R.separable_conv2d(P, x, "m", 128, stride, dil, relu_first, 1e-3)
+            m = M.SeparableConv2d(64, 128, stride=stride, dilation=dil, relu_first=relu_first)
+            for bn in (m.block.bn_depth, m.block.bn_point):
+                bn.eps = 1e-3                                  # mutated after construction, like tools/eval.py:50-53
+            m = _load(m, P, "m")
+            y = m(x.cuda().to(dtype))
+            assert y.shape == ref.shape and y.dtype == dtype
+            _cmp(y, ref, tol)
+            y32 = m(x.cuda())                                  # fp32 in -> bf16 compute -> fp32 out
+            assert y32.dtype == torch.float32
+        # _ConvBNReLU 3x3 dilated + relu6 1x1
+        P = R.Params(2)
+        x = _x(1, 64, 19, 23, seed=4)
+        ref = R.conv_bn_act(P, x, "c", 96, 3, 1, 2, 2)
+        _cmp(_load(M._ConvBNReLU(64, 96, 3, 1, 2, 2), P, "c")(x.cuda().to(dtype)), ref, tol)
+        # InvertedResidual with and without the skip
+        for cin, cout, stride, t in [(32, 32, 1, 6), (32, 64, 2, 6), (16, 24, 1, 1)]:
+            P = R.Params(5)
+            x = _x(1, cin, 20, 28, seed=6)
+            ref = R.inverted_residual(P, x, "ir", cout, stride, t)
+            _cmp(_load(M.InvertedResidual(cin, cout, stride, t), P, "ir")(x.cuda().to(dtype)), ref, tol)
+        # _ASPP (output stride 16) and PyramidPooling
+        P = R.Params(7)
+        x = _x(2, 256, 17, 33, seed=8)
+        ref = R.aspp(P, x, "aspp", 256, 16)
+        _cmp(_load(M._ASPP(256, 256, output_stride=16), P, "aspp")(x.cuda().to(dtype)), ref, 2 * tol)
+        P = R.Params(9)
+        x = _x(1, 64, 17, 33, seed=10)
+        ref = R.pyramid_pooling(P, x, "psp")
+        _cmp(_load(M.PyramidPooling(64), P, "psp")(x.cuda().to(dtype)), ref, tol)
+
+
+def test_dropin_errors_and_cache_invalidation():
+    from segmentron_b200 import modules as M
+    m = M.SeparableConv2d(64, 64).cuda().eval()
+    x = _x(1, 64, 9, 9).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m.block.bn_point.eps = 0.5                             # eps change must invalidate the folded-BN cache
+        y1 = m(x).clone()
+        assert not torch.equal(y0, y1)
+        m.block.pointwise.weight.mul_(2.0)                     # in-place parameter update bumps the version
+        y2 = m(x)
+        assert not torch.equal(y1, y2)
+    with pytest.raises(RuntimeError):
+        m(x.cpu())
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(x)
