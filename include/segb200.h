@@ -33,15 +33,11 @@ enum { SEGB200_ACT_NONE = 0, SEGB200_ACT_RELU = 1, SEGB200_ACT_RELU6 = 2 };
 
 int segb200_version(void);
 const char* segb200_last_error(void);
-/* Diagnostics: point subsequent segb200_conv_gemm launches at 16 device uint64 counters that accumulate, over all
- * CTAs, the clock cycles each role spent waiting ([0] producer:ring slot free, [1] MMA:accumulator free, [2] MMA:operands
- * landed, [3]/[4] epilogue group 0/1:accumulator ready, [5]/[6] epilogue group 0/1:store drained, [7] total CTA cycles, [8..11] epilogue group-0 leader: entry barrier, residual wait,
- * TMEM load + math + staging stores, fence + exit barrier).
- * NULL disables (default).  Not thread-safe; for profiling only. */
+/* Diagnostics (only in a library built with -DSEGB200_DBG; otherwise returns -20): point subsequent
+ * segb200_conv_gemm launches at 16 device uint64 counters that accumulate, over all CTAs, the clock cycles each role
+ * spent waiting: [0] producer: ring slot free, [1] MMA: accumulator free, [2] MMA: operands landed, [3] epilogue:
+ * accumulator ready.  NULL disables.  Not thread-safe; profiling only (tools/gemm_waits.py). */
 int segb200_debug_set_counters(void* dev_ptr_16_u64);
-/* Diagnostics: ablate parts of the conv_gemm epilogue (results become WRONG): bit0 skip scale/shift loads, bit1 skip
- * TMEM loads, bit2 skip staging stores.  0 = normal (default). */
-int segb200_debug_set_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Dense convolution as an implicit GEMM on tcgen05 tensor cores, with the following

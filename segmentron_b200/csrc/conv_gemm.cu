@@ -12,12 +12,11 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N<=256, K=16 per instr),
 //                 fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns) so the epilogue
 //                 of tile i overlaps the main loop of tile i+1.
-//   warps 2..9  : epilogue (two groups of four warps alternating over 64-column chunks). tcgen05.ld 32 columns at a time -> scale/shift (+residual) -> activation
+//   warps 2..5  : epilogue. tcgen05.ld 32 columns at a time -> scale/shift (+residual) -> activation
 //                 -> bf16/fp16 -> 128B-swizzled smem staging -> TMA store (which clips the M and N tails
 //                 and writes straight into a channel slice of the consumer's buffer).
-// smem ring: num_stages x {A 128 x bk_bytes, B bn x bk_bytes} in the first 192 KB (its top 32 KB hold the two
-// residual tiles when a residual is fused), 2 x 16 KB store staging (one per epilogue group), then the control
-// block (mbarriers, TMEM base).
+// smem ring: num_stages x {A 128 x bk_bytes, B bn x bk_bytes} in the first 192 KB, 2 x 16 KB store
+// staging, then the control block (mbarriers, TMEM base, scale/shift of the current N tile).
 #include "common.cuh"
 #include "../../include/segb200.h"
 
@@ -30,11 +29,9 @@ constexpr int kStageRegion = 196608;          // bytes for the A/B ring
 constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
 constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
 constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
-constexpr int kSmemBytes = kCtlOffset + 3072;  // 232448 = the 227 KB maximum
-constexpr int kMaxStages = 32;
-constexpr int kEpiGroups = 1;                 // 4-warp epilogue groups taking the 64-column chunks round-robin (measured: 2 groups
-                                              // gain 4% on HBM-bound layers but lose 5-10% on tensor-bound ones -> 1)
-constexpr int kThreads = 64 + 128 * kEpiGroups;
+constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
 
 struct Control {
   uint64_t full[kMaxStages];
@@ -44,10 +41,10 @@ struct Control {
   uint64_t res_full[2];
   uint32_t tmem_base;
   uint32_t pad[3];
-  float scale[256];    // folded-BN scale/shift of the current N tile (global loads would miss: with 227 KB of smem the
-  float shift[256];    // L1 has no capacity left, every __ldg is an L2 round trip)
+  float scale[256];
+  float shift[256];
 };
-static_assert(sizeof(Control) <= 3072, "control block too large");
+static_assert(sizeof(Control) <= 2304, "control block too large");
 
 struct ConvGemmParams {
   int n_img, ho, wo;
@@ -61,12 +58,12 @@ struct ConvGemmParams {
   const float* shift;
   const void* residual;
   long long res_ld;
-  int dbg_mode;              // diagnostics: bit0 skip scale/shift loads, bit1 skip TMEM loads, bit2 skip staging stores
-  unsigned long long* dbg;   // optional: per-role wait-cycle counters (segb200_debug_set_counters)
+  unsigned long long* dbg;   // only used when compiled with -DSEGB200_DBG
   uint32_t taps[64];   // map id (bits 0..1) | (off_w + 128) << 8 | (off_h + 128) << 16
 };
 
-// wait on an mbarrier and, when debugging counters are enabled, add the cycles spent to dbg[slot]
+// Diagnostics build (-DSEGB200_DBG): per-role wait-cycle counters, see segb200_debug_set_counters in the header.
+#ifdef SEGB200_DBG
 #define TIMED_WAIT(bar, parity, slot)                                             \
   do {                                                                            \
     if (p.dbg != nullptr) {                                                       \
@@ -77,6 +74,9 @@ struct ConvGemmParams {
       mbar_wait(bar, parity);                                                     \
     }                                                                             \
   } while (0)
+#else
+#define TIMED_WAIT(bar, parity, slot) mbar_wait(bar, parity)
+#endif
 
 template <bool kBF16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -91,7 +91,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int num_kb = p.ntaps * p.cblocks;
   const int bk_elems = p.bk_bytes >> 1;
-  const long long t_start_ = clock64();
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("segb200: dynamic smem base not 1024B aligned\n");
@@ -104,7 +103,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128 * kEpiGroups); mbar_init(&ctl->res_full[i], 1);
+        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); mbar_init(&ctl->res_full[i], 1);
       }
       fence_mbar_init();
     }
@@ -175,47 +174,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (warps 2..9, two groups of 4) ------------------------------
-    // Both groups walk the same (tile, 64-column chunk) sequence; group g owns the chunks with index == g (mod 2),
-    // its own 16 KB store-staging buffer, residual buffer, named barrier and bulk-store group.
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
     using H = Half2<kBF16>;
-    const int grp = (warp - 2) >> 2;                 // 0 or 1
-    const int et = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int et = threadIdx.x - 64;                 // 0..127
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                   // tile row == TMEM lane
-    uint8_t* const buf0 = smem + kStageRegion + (kEpiGroups == 2 ? grp * kEpiBufBytes : 0);
-    const uint8_t* const rbuf0 = smem + kStageRegion - kResRegion + (kEpiGroups == 2 ? grp * kEpiBufBytes : 0);   // ring is shortened by the host
+    uint8_t* epi = smem + kStageRegion;              // 2 store-staging buffers
+    uint8_t* resb = smem + kStageRegion - kResRegion;  // 2 residual buffers (ring is shortened by the host)
     const bool has_res = p.residual != nullptr;
-    const int bar_id = 1 + grp;
-    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0; uint32_t my_uses = 0; int staged_n_tile = -1;
-    static_assert(kEpiGroups == 1, "scale/shift staging assumes a single epilogue group");
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
 
-    // residual prefetch cursor (group leader only): points at this group's NEXT chunk in the global sequence
+    // residual prefetch cursor (leader only): runs exactly one chunk ahead of the consumer
     int pf_tile = blockIdx.x, pf_ch = 0;
-    auto pf_nchunks = [&](int tile) {
-      const int n0 = (tile % p.n_tiles) * p.bn;
-      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
-      return (nvalid + 63) >> 6;
-    };
-    auto pf_advance = [&]() {
-      if (pf_tile >= p.total_tiles) return;
-      if (++pf_ch >= pf_nchunks(pf_tile)) { pf_ch = 0; pf_tile += gridDim.x; }
-    };
-    auto pf_issue = [&](uint32_t bi) {               // bi: residual buffer / barrier index
+    auto pf_issue = [&](uint32_t idx) {
+      // issue the TMA load of the residual chunk (pf_tile, pf_ch) into resb[idx & 1], then advance the cursor
       if (pf_tile >= p.total_tiles) return;
       const int n_tile = pf_tile % p.n_tiles;
       int m_tile = pf_tile / p.n_tiles;
       const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
       const int hb = m_tile % p.htiles;
       const int img = m_tile / p.htiles;
-      uint8_t* dst = const_cast<uint8_t*>(rbuf0) + (kEpiGroups == 1 ? bi * kEpiBufBytes : 0);
-      mbar_expect_tx(&ctl->res_full[bi], (uint32_t)kEpiBufBytes);
-      tma_load_4d(&tmR, &ctl->res_full[bi], dst, n_tile * p.bn + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      const int n0 = n_tile * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      mbar_expect_tx(&ctl->res_full[idx & 1], (uint32_t)kEpiBufBytes);
+      tma_load_4d(&tmR, &ctl->res_full[idx & 1], resb + (idx & 1) * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += gridDim.x; }
     };
-    if (has_res && et == 0) {
-      for (int i = 0; i < grp; ++i) pf_advance();
-      pf_issue(kEpiGroups == 1 ? 0u : (uint32_t)grp);
-    }
+    if (has_res && et == 0) pf_issue(0);
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -227,68 +212,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       const int nchunks = (nvalid + 63) >> 6;
 
-      if (n_tile != staged_n_tile) {                   // (re)stage scale/shift: only when the N tile changes
-        named_bar_sync(bar_id, 128);                   // previous readers are done
-        if (grp == 0) {
-          for (int i = et; i < p.bn; i += 128) {
-            const int c = n0 + i;
-            ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
-            ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
-          }
-        }
-        staged_n_tile = n_tile;                        // published by the first barrier of the chunk loop
+      named_bar_sync(1, 128);                        // previous tile's readers of scale/shift are done
+      for (int i = et; i < p.bn; i += 128) {
+        const int c = n0 + i;
+        ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
+        ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
       }
-      if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3 + grp); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
+
+      if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
-        if ((int)(chunk_ctr % kEpiGroups) != grp) continue;
-        uint8_t* const buf = buf0 + (kEpiGroups == 1 ? (my_uses & 1) * kEpiBufBytes : 0);
+        uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
+        const uint8_t* rbuf = resb + (chunk_ctr & 1) * kEpiBufBytes;
         if (et == 0) {
-          const long long t0_ = p.dbg ? clock64() : 0;
-          if (kEpiGroups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>();   // the store that last used `buf` has drained it
-          if (p.dbg) atomicAdd(p.dbg + 5 + grp, (unsigned long long)(clock64() - t0_));
-          // one group: prefetch the NEXT chunk's residual into the other buffer (last read before the previous chunk's exit barrier)
-          if (kEpiGroups == 1 && has_res) { pf_advance(); pf_issue((my_uses + 1) & 1); }
+          tma_store_wait_read<1>();                  // the store that last used `buf` has drained it
+          if (has_res) pf_issue(chunk_ctr + 1);      // resb[(ctr+1)&1] was last read before the previous chunk's barrier
         }
-        const uint8_t* const rbuf = rbuf0 + (kEpiGroups == 1 ? (my_uses & 1) * kEpiBufBytes : 0);
-        const uint32_t rbi = kEpiGroups == 1 ? (my_uses & 1) : (uint32_t)grp;
-        const uint32_t rpar = kEpiGroups == 1 ? ((my_uses >> 1) & 1) : (my_uses & 1);
-        long long tA_ = 0;
-        const bool tim_ = (p.dbg != nullptr) && et == 0 && grp == 0;
-        if (tim_) tA_ = clock64();
-        named_bar_sync(bar_id, 128);
-        if (tim_) { const long long t_ = clock64(); atomicAdd(p.dbg + 8, (unsigned long long)(t_ - tA_)); tA_ = t_; }
-        if (has_res) mbar_wait(&ctl->res_full[rbi], rpar);
-        ++my_uses;
-        if (tim_) { const long long t_ = clock64(); atomicAdd(p.dbg + 9, (unsigned long long)(t_ - tA_)); tA_ = t_; }
+        named_bar_sync(1, 128);                      // (also publishes scale/shift on the first chunk)
+        if (has_res) mbar_wait(&ctl->res_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col0 = ch * 64 + half * 32;
           uint32_t v[32];
-          if (!(p.dbg_mode & 2)) {
-            tmem_ld_32x32(t_acc + (uint32_t)col0, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u + (uint32_t)(col0 + j + row);
-          }
+          tmem_ld_32x32(t_acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
             const int chunk16 = (half * 4 + g) ^ (row & 7);   // 128B swizzle: 16 B chunk c lives at c ^ (row & 7)
-            const int cl = col0 + g * 8;             // tile-local column of the first of 8 output channels
-            float sc[8], sf[8];
-            {
-              const float4 a0 = *reinterpret_cast<const float4*>(&ctl->scale[cl]);
-              const float4 a1 = *reinterpret_cast<const float4*>(&ctl->scale[cl + 4]);
-              const float4 b0 = *reinterpret_cast<const float4*>(&ctl->shift[cl]);
-              const float4 b1 = *reinterpret_cast<const float4*>(&ctl->shift[cl + 4]);
-              sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
-              sf[0] = b0.x; sf[1] = b0.y; sf[2] = b0.z; sf[3] = b0.w; sf[4] = b1.x; sf[5] = b1.y; sf[6] = b1.z; sf[7] = b1.w;
-            }
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sf[j]);
+            for (int j = 0; j < 8; ++j) {
+              const int c = col0 + g * 8 + j;
+              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), ctl->scale[c], ctl->shift[c]);
+            }
             if (has_res) {
               const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + chunk16 * 16);
               const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -298,36 +256,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 f[2 * j] += t2.x; f[2 * j + 1] += t2.y;
               }
             }
-            uint4 o;
-            o.x = H::pack(apply_act(f[0], p.act), apply_act(f[1], p.act));
-            o.y = H::pack(apply_act(f[2], p.act), apply_act(f[3], p.act));
-            o.z = H::pack(apply_act(f[4], p.act), apply_act(f[5], p.act));
-            o.w = H::pack(apply_act(f[6], p.act), apply_act(f[7], p.act));
-            if (!(p.dbg_mode & 4)) *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) = o;
-            else if (o.x == 0x12345678u) *reinterpret_cast<uint4*>(buf) = o;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              packed[g * 4 + j] = H::pack(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
+            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) =
+                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
           }
         }
-        if (tim_) { const long long t_ = clock64(); atomicAdd(p.dbg + 10, (unsigned long long)(t_ - tA_)); tA_ = t_; }
         fence_proxy_async();
-        named_bar_sync(bar_id, 128);
-        if (tim_) { const long long t_ = clock64(); atomicAdd(p.dbg + 11, (unsigned long long)(t_ - tA_)); tA_ = t_; }
+        named_bar_sync(1, 128);
         if (et == 0) {
           tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
           tma_store_commit();
-          if (kEpiGroups == 2 && has_res) {        // rbuf was last read before the barrier above
-            pf_advance(); pf_advance();
-            pf_issue((uint32_t)grp);
-          }
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctl->tmem_empty[acc]);             // 256 arrivals release the accumulator stage
+      mbar_arrive(&ctl->tmem_empty[acc]);             // 128 arrivals release the accumulator stage
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();
   }
 
-  if (p.dbg != nullptr && threadIdx.x == 0) atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - t_start_));
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -350,11 +299,14 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 using namespace segb200;
 
 static unsigned long long* g_dbg_counters = nullptr;
-static int g_dbg_mode = 0;
-extern "C" int segb200_debug_set_mode(int mode) { g_dbg_mode = mode; return 0; }
-extern "C" int segb200_debug_set_counters(void* dev_ptr_8_u64) {
-  g_dbg_counters = reinterpret_cast<unsigned long long*>(dev_ptr_8_u64);
+extern "C" int segb200_debug_set_counters(void* dev_ptr_16_u64) {
+#ifdef SEGB200_DBG
+  g_dbg_counters = reinterpret_cast<unsigned long long*>(dev_ptr_16_u64);
   return 0;
+#else
+  (void)dev_ptr_16_u64;
+  return set_error(-20, "segb200_debug_set_counters: library was built without -DSEGB200_DBG");
+#endif
 }
 
 extern "C" int segb200_conv_kblock(int cin) { return cin >= 64 ? 64 : (cin >= 32 ? 32 : 16); }
@@ -414,7 +366,6 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.num_stages = (kStageRegion - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
-  p.dbg_mode = g_dbg_mode;
   p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
 
   // ---- A maps (parity views for stride 2) and the tap table ----

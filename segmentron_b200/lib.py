@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsegb200.so")
+LIB_PATH = os.environ.get("SEGB200_LIB", os.path.join(_HERE, "libsegb200.so"))   # override: A/B builds only
 
 BF16, F16, F32 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
@@ -38,7 +38,6 @@ SYMBOLS = {
     "segb200_version": (C.c_int, []),
     "segb200_last_error": (C.c_char_p, []),
     "segb200_debug_set_counters": (C.c_int, [vp]),
-    "segb200_debug_set_mode": (C.c_int, [C.c_int]),
     "segb200_conv_kblock": (C.c_int, [C.c_int]),
     "segb200_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "segb200_dwconv3x3": (C.c_int, [C.POINTER(DwArgs), vp]),
@@ -65,7 +64,12 @@ def load():
                 "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU/PyTorch fallback)")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
-            fn = getattr(lib, name)
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if "SEGB200_LIB" in os.environ:      # A/B builds of older sources may lack newer diagnostics
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib

@@ -11,6 +11,12 @@ from segmentron_b200 import fold, lib, ops  # noqa: E402
 
 dt = torch.bfloat16
 L = lib.load()
+HAS_DBG = hasattr(L, "segb200_debug_set_counters") and "segb200_debug_set_counters" in dir(L) or False
+try:
+    L.segb200_debug_set_counters
+    HAS_DBG = True
+except AttributeError:
+    HAS_DBG = False
 cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
 NAMES = ["prod:slot_free", "mma:acc_free", "mma:operands", "epi0:acc_ready", "epi1:acc_ready", "epi0:store", "epi1:store", "total"]
 
@@ -31,10 +37,11 @@ def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 5 * 1e3
     cnt.zero_()
-    L.segb200_debug_set_counters(C.c_void_p(cnt.data_ptr()))
-    ops.conv_gemm(x, wt, y, **kw)
-    torch.cuda.synchronize()
-    L.segb200_debug_set_counters(None)
+    if HAS_DBG:
+        L.segb200_debug_set_counters(C.c_void_p(cnt.data_ptr()))
+        ops.conv_gemm(x, wt, y, **kw)
+        torch.cuda.synchronize()
+        L.segb200_debug_set_counters(None)
     c = cnt.tolist()
     ctas = min(148, 10 ** 9)
     tot = c[7] / 148.0
@@ -49,7 +56,8 @@ def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
 modes = [int(m) for m in sys.argv[1:]] or [0]
 for mode in modes:
     print(f"##### debug mode {mode}")
-    L.segb200_debug_set_mode(mode)
+    if HAS_DBG:
+        L.segb200_debug_set_mode(mode)
     run("pw 128->128 @8x513x1025", 8, 513, 1025, 128, 128)
     run("pw 728->728 @8x65x129", 8, 65, 129, 728, 728)
     run("pw 1536->2048", 8, 65, 129, 1536, 2048)
@@ -57,4 +65,5 @@ for mode in modes:
         run("pw 64->128 @8x513x1025", 8, 513, 1025, 64, 128)
         run("pw 728->728 +res", 8, 65, 129, 728, 728, res=True)
         run("c3 32->64 @8x513x1025", 8, 513, 1025, 32, 64, k=3, pad=1)
-L.segb200_debug_set_mode(0)
+if HAS_DBG:
+    L.segb200_debug_set_mode(0)
