@@ -246,6 +246,8 @@ def main():
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):
             traffic = json.load(open(tj)).get(top_desc)
+            if isinstance(traffic, dict):
+                traffic = traffic.get("dram_bytes_per_launch")
         roofline = {"kernel": "conv_gemm_kernel<bf16> (tcgen05 implicit GEMM)", "shape": top_desc, "bound": "tensor",
                     "achieved": ach, "peak": pk["tc"], "unit": "TFLOP/s", "frac": ach / pk["tc"], "traffic": traffic,
                     "algorithmic_flop_per_launch": top["flops"] / top["n"], "algorithmic_bytes_per_launch": top["bytes"] / top["n"],

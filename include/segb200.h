@@ -61,12 +61,13 @@ typedef struct segb200_conv_args {
   const float* shift;   /* [cout] or NULL (0.0) */
   const void* residual; /* [n][ho][wo][res_ld] or NULL */
   void* y;              /* [n][ho][wo][y_ld] */
-  int32_t n, h, w, cin, x_ld;
+  int32_t n, h, w, cin, x_ld;            /* cin, x_ld, y_ld, res_ld: multiples of 8 elements; cout: any >= 1 */
   int32_t ho, wo, cout, y_ld, res_ld;
   int32_t kh, kw, stride, dilation, pad_t, pad_l;
   int32_t act;          /* SEGB200_ACT_* */
   int32_t dtype;        /* SEGB200_BF16 | SEGB200_F16 */
   int32_t max_ctas;     /* 0 = number of SMs */
+  int32_t y_f32;        /* 1: y is fp32 [n][ho][wo][y_ld floats] (y_ld % 4 == 0), residual must be NULL */
 } segb200_conv_args;
 
 int segb200_conv_kblock(int cin);                 /* K block (elements) the kernel will use for `cin` */
@@ -130,11 +131,42 @@ int segb200_bilinear_nchw_out(const void* x, void* y, uint8_t* argmax_out, int n
                               int x_ld, int ho, int wo, int align_corners, int dtype, int out_dtype,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Position attention (PAM_Module.forward, modules/module.py:112-131: two torch.bmm + nn.Softmax over an N x N matrix)
+ * as a tiled softmax(Q K^T) V kernel on tcgen05 -- the N x N attention is never materialised (two exact passes:
+ * row max / row sum, then P V).   y[b][i][:] = gamma * (sum_j softmax_j(q_i . k_j) v_j + bias_v) + x[b][i][:]
+ *   q, k : [batch][n_tok][q_ld|k_ld], depth 64 (= in_dim/8 for DANet's 512 channels), outputs of the 1x1 convs incl. bias
+ *   vt   : V transposed, [batch][dv][vt_ld] (vt_ld >= n_tok), WITHOUT the conv bias (pass it as bias_v; rows of the
+ *          attention sum to 1);  dv % 256 == 0
+ *   stat_m, stat_l : workspace, batch*n_tok floats each.   gamma: device pointer to one float. */
+int segb200_pam_attention(const void* q, const void* k, const void* vt, const float* bias_v, const float* gamma,
+                          const void* x, void* y, float* stat_m, float* stat_l, int batch, int n_tok, int dv, int q_ld,
+                          int k_ld, int vt_ld, int x_ld, int y_ld, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Channel attention (CAM_Module, modules/module.py:142-162).  The two matrix products run on segb200_conv_gemm
+ * (E = X^T X with y_f32 = 1 on a [C][N] transposed copy; y = gamma*(A X) + x with scale = gamma, residual = x);
+ * this entry point is the softmax in between:  att[r][j] = softmax_j(rowmax_r(E) - E[r][j])  (fp32 in, dtype out). */
+int segb200_cam_softmax(const float* energy, void* att, int rows, int c, int e_ld, int att_ld, int dtype, void* stream);
+
+/* Criss-cross attention (CrissCrossAttention, modules/cc_attention.py:62-72; replaces _C.ca_forward + F.softmax and
+ * _C.ca_map_forward + gamma*out + x of csrc/criss_cross_attention/ca_cuda.cu:8-36,94-120).
+ *   att [n][h][w][att_ld] fp32 (att_ld >= h+w-1): channels [0,w) = same-row keys (self included), [w,h+w-1) = same-column
+ *   keys with the pixel's own row skipped (j = i<y ? i : i+1), softmax over those h+w-1 entries.
+ *   y = gamma * sum_z att[p][z] v[key(p,z)] + x   (gamma: device pointer to one float, the module's nn.Parameter). */
+int segb200_cca_weight_softmax(const void* q, const void* k, float* att, int n, int h, int w, int c, int q_ld, int k_ld,
+                               int att_ld, int dtype, void* stream);
+int segb200_cca_map(const float* att, const void* v, const void* x, void* y, const float* gamma, int n, int h, int w, int c,
+                    int att_ld, int v_ld, int x_ld, int y_ld, int dtype, void* stream);
+
 /* Layout converters at the module boundary: logical-NCHW contiguous <-> NHWC (channel pitch ld). */
 int segb200_nchw_to_nhwc(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w, int y_ld,
                          void* stream);
 int segb200_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_dtype, int n, int c, int h, int w, int x_ld,
                          void* stream);
+/* Same transpose with a padded pixel pitch: y[n][c][pitch] (pitch >= h*w; the tail is NOT written).  Produces the
+ * K-major [C][N] operand of CAM's Gram matrix. */
+int segb200_nhwc_to_cn(const void* x, void* y, int n, int c, int hw, int x_ld, int pitch, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,7 @@ struct ConvGemmParams {
   int cblocks, ntaps, bk_bytes, num_stages;
   int a_stage_bytes, b_stage_bytes;
   int act;
+  int out_f32;          // 1: y is fp32 (32-column TMA store units), no residual
   const float* scale;
   const float* shift;
   const void* residual;
@@ -222,6 +223,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+      if (p.out_f32) {
+        // fp32 output (attention energies etc.): one 32-column x 128-row unit (128 B rows) per staging buffer / TMA store
+        const int nunits = (nvalid + 31) >> 5;
+        for (int un = 0; un < nunits; ++un, ++chunk_ctr) {
+          uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          const int col0 = un * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {                // 8 groups of 4 floats = one 16 B vector each
+            float f[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = col0 + g * 4 + j;
+              f[j] = apply_act(fmaf(__uint_as_float(v[g * 4 + j]), ctl->scale[c], ctl->shift[c]), p.act);
+            }
+            *reinterpret_cast<float4*>(buf + row * 128 + ((g ^ (row & 7)) * 16)) = make_float4(f[0], f[1], f[2], f[3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            tma_store_4d(&tmC, buf, n0 + col0, w0, h0, img);
+            tma_store_commit();
+          }
+        }
+      } else
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
         uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
         const uint8_t* rbuf = resb + (chunk_ctr & 1) * kEpiBufBytes;
@@ -316,10 +346,11 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   if (!a || !a->x || !a->wgt || !a->y) return set_error(-1, "conv_gemm: null pointer argument");
   if (a->dtype != DT_BF16 && a->dtype != DT_F16) return set_error(-2, "conv_gemm: dtype must be bf16 or f16");
   if (a->stride != 1 && a->stride != 2) return set_error(-3, "conv_gemm: stride must be 1 or 2");
-  if ((a->x_ld & 7) || (a->y_ld & 7) || (a->cin & 7) || (a->cout & 7) || a->cin > a->x_ld || a->cout > a->y_ld)
-    return set_error(-4, "conv_gemm: channel counts/pitches must be multiples of 8 (cin %d x_ld %d cout %d y_ld %d)",
+  if ((a->x_ld & 7) || (a->y_ld & (a->y_f32 ? 3 : 7)) || (a->cin & 7) || a->cout < 1 || a->cin > a->x_ld || a->cout > a->y_ld)
+    return set_error(-4, "conv_gemm: cin and the pitches must be multiples of 8 elements (cin %d x_ld %d cout %d y_ld %d)",
                      a->cin, a->x_ld, a->cout, a->y_ld);
   if (a->residual && ((a->res_ld & 7) || a->res_ld < a->cout)) return set_error(-4, "conv_gemm: bad res_ld");
+  if (a->y_f32 && a->residual) return set_error(-4, "conv_gemm: fp32 output does not take a residual");
   const int ntaps = a->kh * a->kw;
   if (ntaps < 1 || ntaps > 64) return set_error(-5, "conv_gemm: unsupported kernel %dx%d", a->kh, a->kw);
   if (a->n < 1 || a->ho < 1 || a->wo < 1) return set_error(-6, "conv_gemm: empty output");
@@ -366,6 +397,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.num_stages = (kStageRegion - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
+  p.out_f32 = a->y_f32 ? 1 : 0;
   p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
 
   // ---- A maps (parity views for stride 2) and the tap table ----
@@ -417,10 +449,11 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   }
   {
     const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)Wv_out, (uint64_t)Hv_out, (uint64_t)Nv_out};
-    const uint64_t str[3] = {(uint64_t)a->y_ld * 2, (uint64_t)a->y_ld * 2 * (uint64_t)Wv_out,
-                             (uint64_t)a->y_ld * 2 * (uint64_t)Wv_out * (uint64_t)Hv_out};
-    const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
-    int rc = encode_map(&tmC, a->dtype, 4, a->y, dims, str, box, 128, "C");
+    const uint64_t esz = a->y_f32 ? 4 : 2;
+    const uint64_t str[3] = {(uint64_t)a->y_ld * esz, (uint64_t)a->y_ld * esz * (uint64_t)Wv_out,
+                             (uint64_t)a->y_ld * esz * (uint64_t)Wv_out * (uint64_t)Hv_out};
+    const uint32_t box[4] = {a->y_f32 ? 32u : 64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+    int rc = encode_map(&tmC, a->y_f32 ? (int)DT_F32 : a->dtype, 4, a->y, dims, str, box, 128, "C");
     if (rc) return rc;
     tmR = tmC;
     if (a->residual) {

@@ -218,6 +218,8 @@ constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs
 template <bool kBF16>
 __device__ __forceinline__ void ring_row_sums(uint32_t row_addr, uint32_t tap_step, bool pre_relu, const float2 (&wt)[9][4],
                                               float2 (&s)[3][4], uint32_t empty_bar) {
+  // On entry s[ky] holds the SEED of kernel row ky's FMA chain (the rolling accumulator it is added to), on exit
+  // seed + sum_kx w[ky][kx] * x[kx]: the accumulator updates cost no extra add instructions.
   using H = Half2<kBF16>;
   uint4 v[3];
 #pragma unroll
@@ -232,8 +234,7 @@ __device__ __forceinline__ void ring_row_sums(uint32_t row_addr, uint32_t tap_st
       if (pre_relu) u[j] = H::relu2(u[j]);
       const float2 f = H::unpack(u[j]);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-        s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], kx == 0 ? make_float2(0.f, 0.f) : s[ky][j]);
+      for (int ky = 0; ky < 3; ++ky) s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], s[ky][j]);
     }
   }
 }
@@ -331,36 +332,35 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
       for (int k = 0; k < n_out + 2; ++k) {
         const int r = h0 + (k - 1) * d;
         float2 s[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[2][j] = acc1[j]; s[1][j] = acc0[j]; s[0][j] = sh[j]; }   // chain seeds
         DW_ROW(s);
-        if (k >= 2 && active) {
-          float2 o[4];
+        if (k >= 2 && active) store_out<kBF16>(yn + (r - d) * yrow_stride, s[2], p.act);         // acc1 + s2(r)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fadd2(acc1[j], s[2][j]);
-          store_out<kBF16>(yn + (r - d) * yrow_stride, o, p.act);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { acc1[j] = fadd2(acc0[j], s[1][j]); acc0[j] = fadd2(sh[j], s[0][j]); }
+        for (int j = 0; j < 4; ++j) { acc1[j] = s[1][j]; acc0[j] = s[0][j]; }
       }
     }
   } else {
     float2 acc0[4];
     {
       float2 s[3][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[0][j] = sh[j]; s[1][j] = sh[j]; s[2][j] = sh[j]; }
       DW_ROW(s);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc0[j] = fadd2(sh[j], s[0][j]);
+      for (int j = 0; j < 4; ++j) acc0[j] = s[0][j];
     }
     for (int ho = h_begin; ho < h_end; ++ho) {
       float2 sa[3][4], sb[3][4];
-      DW_ROW(sa);
-      DW_ROW(sb);
-      float2 o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = fadd2(fadd2(acc0[j], sa[1][j]), sb[2][j]);
-        acc0[j] = fadd2(sh[j], sb[0][j]);
-      }
-      if (active) store_out<kBF16>(yn + ho * yrow_stride, o, p.act);
+      for (int j = 0; j < 4; ++j) { sa[1][j] = acc0[j]; sa[0][j] = sh[j]; sa[2][j] = sh[j]; }   // only sa[1] is used
+      DW_ROW(sa);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sb[2][j] = sa[1][j]; sb[0][j] = sh[j]; sb[1][j] = sh[j]; }   // sb[2] = out, sb[0] = next acc0
+      DW_ROW(sb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc0[j] = sb[0][j];
+      if (active) store_out<kBF16>(yn + ho * yrow_stride, sb[2], p.act);
     }
   }
 }

@@ -320,7 +320,7 @@ nchw_to_nhwc_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ 
 }
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ y, int y_dtype, int c, long long hw,
-                    int x_ld) {
+                    int x_ld, long long pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -333,7 +333,7 @@ nhwc_to_nchw_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ 
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
     const int ch = c0 + k; const long long p = p0 + tx;
-    if (ch < c && p < hw) store_any(y, ((long long)n * c + ch) * hw + p, tile[tx][k], y_dtype);
+    if (ch < c && p < hw) store_any(y, ((long long)n * c + ch) * pitch + p, tile[tx][k], y_dtype);
   }
 }
 
@@ -429,6 +429,13 @@ extern "C" int segb200_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_d
   if (!x || !y) return set_error(-1, "nhwc_to_nchw: null pointer");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, x_dtype, y, y_dtype, c, hw, x_ld);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, x_dtype, y, y_dtype, c, hw, x_ld, hw);
   return check_launch("nhwc_to_nchw");
+}
+extern "C" int segb200_nhwc_to_cn(const void* x, void* y, int n, int c, int hw, int x_ld, int pitch, int dtype, void* stream) {
+  if (!x || !y) return set_error(-1, "nhwc_to_cn: null pointer");
+  if (!half_dt(dtype) || pitch < hw) return set_error(-4, "nhwc_to_cn: bad dtype/pitch");
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, dtype, y, dtype, c, hw, x_ld, pitch);
+  return check_launch("nhwc_to_cn");
 }

@@ -1,0 +1,295 @@
+// segb200 -- position attention (DANet PAM_Module, modules/module.py:100-131) as a tiled softmax(Q K^T) V kernel on
+// tcgen05 tensor cores.  The N x N attention matrix (N = H*W = 32768 at 1024x2048 / OS8: 4.3 GB in fp32 per image in the
+// reference) is never materialised.
+//
+//   energy = Q K^T (no 1/sqrt(d) scaling), attention = softmax over keys, out = attention V, y = gamma*out + x
+//
+// Exact two-pass softmax (no running rescale of the output accumulator):
+//   pass 1 (kPass = 1): per 128-query tile, S = Q K^T tile by tile -> row max m_i and l_i = sum_j exp(s_ij - m_i)
+//   pass 2 (kPass = 2): per (128-query tile, 256-column half of d_v): S again, P = exp(S - m_i) / l_i in bf16/fp16
+//                       -> shared memory (A operand), O[128 x 256] += P V accumulates in TMEM over all key tiles,
+//                       epilogue y = gamma * (O + b_v) + x.
+// Warp roles (192 threads): warp 0 = TMA producer (Q tile once; K tile [64 keys x 64] and V^T tile [256 x 64 keys] per
+// key tile), warp 1 = tcgen05.mma issuer (S_j is issued before P_{j-1} V_{j-1} so the softmax of tile j overlaps the
+// PV MMAs of tile j-1), warps 2..5 = softmax / epilogue (one query row per thread = one TMEM lane).
+// TMEM: O = columns [0,256), S double buffer = columns [256,384).  Smem: Q 16 KB, K 2 x 8 KB, P 2 x 16 KB, V 3 x 32 KB.
+// V is consumed as V^T [d_v][N] (K-major along keys); the caller produces it with the same GEMM kernel (roles swapped),
+// the value bias b_v is added in the epilogue (sum_j attention_ij = 1).
+#include "common.cuh"
+#include "../../include/segb200.h"
+
+#include <mutex>
+
+namespace segb200 {
+
+constexpr int kPamQ = 128, kPamK = 64, kPamD = 64, kPamDV = 256;
+constexpr int kPamSmemQ = 0, kPamSmemK = 16384, kPamSmemP = 32768, kPamSmemV = 65536, kPamSmemCtl = 65536 + 3 * 32768;
+constexpr int kPamSmemBytes = kPamSmemCtl + 256;
+
+struct PamCtl {
+  uint64_t q_full, o_full;
+  uint64_t k_full[2], k_empty[2], s_full[2], s_empty[2], p_full[2], p_empty[2];
+  uint64_t v_full[3], v_empty[3];
+  uint32_t tmem_base;
+};
+
+struct PamParams {
+  int n_tok;            // N = H*W
+  int ktiles;           // ceil(N / 64)
+  float* stat_m;        // [B][N]
+  float* stat_l;        // [B][N]
+  const float* bias_v;  // [dv_total] or null
+  const float* gamma;   // 1 float (device)
+  const void* x;        // residual [B][N][x_ld]
+  void* y;              // [B][N][y_ld]
+  long long x_ld, y_ld;
+};
+
+template <bool kBF16, int kPass>
+__global__ void __launch_bounds__(192, 1)
+pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+           const __grid_constant__ CUtensorMap tmV, const PamParams p) {
+  using H = Half2<kBF16>;
+  using T = typename H::T;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  PamCtl* ctl = reinterpret_cast<PamCtl*>(smem + kPamSmemCtl);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kPamQ;
+  const int half = kPass == 2 ? blockIdx.y : 0;
+  const int b = blockIdx.z;
+  const int T_ = p.ktiles;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&ctl->q_full, 1); mbar_init(&ctl->o_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&ctl->k_full[i], 1); mbar_init(&ctl->k_empty[i], 1);
+        mbar_init(&ctl->s_full[i], 1); mbar_init(&ctl->s_empty[i], 128);
+        mbar_init(&ctl->p_full[i], 128); mbar_init(&ctl->p_empty[i], 1);
+      }
+      for (int i = 0; i < 3; ++i) { mbar_init(&ctl->v_full[i], 1); mbar_init(&ctl->v_empty[i], 1); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(&ctl->q_full, kPamQ * kPamD * 2);
+      tma_load_3d(&tmQ, &ctl->q_full, smem + kPamSmemQ, 0, q0, b);
+      for (int j = 0; j < T_; ++j) {
+        const int kb = j & 1; const uint32_t kph = (j >> 1) & 1;
+        mbar_wait(&ctl->k_empty[kb], kph ^ 1);
+        mbar_expect_tx(&ctl->k_full[kb], kPamK * kPamD * 2);
+        tma_load_3d(&tmK, &ctl->k_full[kb], smem + kPamSmemK + kb * 8192, 0, j * kPamK, b);
+        if (kPass == 2) {
+          const int vb = j % 3; const uint32_t vph = (j / 3) & 1;
+          mbar_wait(&ctl->v_empty[vb], vph ^ 1);
+          mbar_expect_tx(&ctl->v_full[vb], kPamDV * kPamK * 2);
+          tma_load_3d(&tmV, &ctl->v_full[vb], smem + kPamSmemV + vb * 32768, j * kPamK, half * kPamDV, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(kBF16, kPamK);
+      const uint32_t idesc_o = make_idesc(kBF16, kPamDV);
+      const uint64_t qdesc = make_kmajor_desc(smem_u32(smem + kPamSmemQ), 128);
+      auto do_pv = [&](int t) {
+        const int pb = t & 1; const uint32_t pph = (t >> 1) & 1;
+        const int vb = t % 3; const uint32_t vph = (t / 3) & 1;
+        mbar_wait(&ctl->p_full[pb], pph);
+        mbar_wait(&ctl->v_full[vb], vph);
+        tc_fence_after();
+        const uint64_t pdesc = make_kmajor_desc(smem_u32(smem + kPamSmemP + pb * 16384), 128);
+        const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + kPamSmemV + vb * 32768), 128);
+#pragma unroll
+        for (int k = 0; k < kPamK / 16; ++k)
+          umma_f16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (uint32_t)((t | k) != 0));
+        umma_commit(&ctl->p_empty[pb]);
+        umma_commit(&ctl->v_empty[vb]);
+      };
+      mbar_wait(&ctl->q_full, 0);
+      for (int j = 0; j < T_; ++j) {
+        const int kb = j & 1; const uint32_t kph = (j >> 1) & 1;
+        mbar_wait(&ctl->k_full[kb], kph);
+        mbar_wait(&ctl->s_empty[kb], kph ^ 1);
+        tc_fence_after();
+        const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + kPamSmemK + kb * 8192), 128);
+#pragma unroll
+        for (int k = 0; k < kPamD / 16; ++k)
+          umma_f16(tmem_s + (uint32_t)(kb * kPamK), qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+        umma_commit(&ctl->s_full[kb]);
+        umma_commit(&ctl->k_empty[kb]);
+        if (kPass == 2 && j >= 1) do_pv(j - 1);
+      }
+      if (kPass == 2) { do_pv(T_ - 1); umma_commit(&ctl->o_full); }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ softmax / epilogue warps ------------------------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int qi = q0 + row;
+    const bool row_ok = qi < p.n_tok;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = kPass == 2 ? 0.f : -INFINITY, l = 0.f, inv_l = 0.f;
+    if (kPass == 2 && row_ok) {
+      m = p.stat_m[(long long)b * p.n_tok + qi];
+      inv_l = 1.f / p.stat_l[(long long)b * p.n_tok + qi];
+    }
+    const float m2 = m * kLog2e;
+    for (int j = 0; j < T_; ++j) {
+      const int sb = j & 1; const uint32_t sph = (j >> 1) & 1;
+      mbar_wait(&ctl->s_full[sb], sph);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_s + (uint32_t)(sb * kPamK) + lane_off, v0);
+      tmem_ld_32x32(tmem_s + (uint32_t)(sb * kPamK + 32) + lane_off, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&ctl->s_empty[sb]);
+      const int nkeys = p.n_tok - j * kPamK;        // keys >= nkeys in this tile are padding (zero-filled by TMA)
+      if (kPass == 1) {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nkeys) tmax = fmaxf(tmax, __uint_as_float(v0[c]));
+          if (c + 32 < nkeys) tmax = fmaxf(tmax, __uint_as_float(v1[c]));
+        }
+        const float m_new = fmaxf(m, tmax);
+        float sum = 0.f;
+        const float mn2 = m_new * kLog2e;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nkeys) sum += exp2f(fmaf(__uint_as_float(v0[c]), kLog2e, -mn2));
+          if (c + 32 < nkeys) sum += exp2f(fmaf(__uint_as_float(v1[c]), kLog2e, -mn2));
+        }
+        l = l * exp2f((m - m_new) * kLog2e) + sum;
+        m = m_new;
+      } else {
+        mbar_wait(&ctl->p_empty[sb], sph ^ 1);
+        uint8_t* pbuf = smem + kPamSmemP + sb * 16384 + row * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {              // 8 x 16 B = 64 keys of this row, 128B-swizzled (A operand, K-major)
+          uint32_t pk[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int c = g * 8 + jj * 2;
+            const float s0 = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
+            const float s1 = __uint_as_float(c + 1 < 32 ? v0[(c + 1) & 31] : v1[(c + 1) & 31]);
+            const float p0 = c < nkeys ? exp2f(fmaf(s0, kLog2e, -m2)) * inv_l : 0.f;
+            const float p1 = c + 1 < nkeys ? exp2f(fmaf(s1, kLog2e, -m2)) * inv_l : 0.f;
+            pk[jj] = H::pack(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(pbuf + ((g ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&ctl->p_full[sb]);
+      }
+    }
+    if (kPass == 1) {
+      if (row_ok) {
+        p.stat_m[(long long)b * p.n_tok + qi] = m;
+        p.stat_l[(long long)b * p.n_tok + qi] = l;
+      }
+    } else {
+      mbar_wait(&ctl->o_full, 0);
+      tc_fence_after();
+      const float gamma = __ldg(p.gamma);
+      const T* xr = reinterpret_cast<const T*>(p.x) + ((long long)b * p.n_tok + qi) * p.x_ld + half * kPamDV;
+      T* yr = reinterpret_cast<T*>(p.y) + ((long long)b * p.n_tok + qi) * p.y_ld + half * kPamDV;
+      for (int c0 = 0; c0 < kPamDV; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_o + (uint32_t)c0 + lane_off, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 xv = ldg_nc_v4(xr + c0 + g * 8);
+            const uint32_t ux[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int c = c0 + g * 8 + jj * 2;
+              const float b0 = p.bias_v ? __ldg(p.bias_v + half * kPamDV + c) : 0.f;
+              const float b1 = p.bias_v ? __ldg(p.bias_v + half * kPamDV + c + 1) : 0.f;
+              const float2 xf = H::unpack(ux[jj]);
+              pk[jj] = H::pack(fmaf(gamma, __uint_as_float(o[g * 8 + jj * 2]) + b0, xf.x),
+                               fmaf(gamma, __uint_as_float(o[g * 8 + jj * 2 + 1]) + b1, xf.y));
+            }
+            *reinterpret_cast<uint4*>(yr + c0 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace segb200
+
+using namespace segb200;
+
+extern "C" int segb200_pam_attention(const void* q, const void* k, const void* vt, const float* bias_v, const float* gamma,
+                                     const void* x, void* y, float* stat_m, float* stat_l, int batch, int n_tok, int dv,
+                                     int q_ld, int k_ld, int vt_ld, int x_ld, int y_ld, int dtype, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !vt || !gamma || !x || !y || !stat_m || !stat_l) return set_error(-1, "pam_attention: null pointer");
+  if (dtype != DT_BF16 && dtype != DT_F16) return set_error(-2, "pam_attention: dtype must be bf16 or f16");
+  if (dv % kPamDV != 0 || dv < kPamDV) return set_error(-4, "pam_attention: d_v must be a multiple of 256");
+  if (q_ld < kPamD || k_ld < kPamD || (q_ld & 7) || (k_ld & 7) || (vt_ld & 7) || vt_ld < n_tok || (x_ld & 7) || (y_ld & 7))
+    return set_error(-4, "pam_attention: bad pitches (query/key depth is fixed at 64)");
+  if (batch < 1 || n_tok < 1) return set_error(-6, "pam_attention: empty");
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    const uint64_t dims[3] = {(uint64_t)kPamD, (uint64_t)n_tok, (uint64_t)batch};
+    const uint64_t sq[2] = {(uint64_t)q_ld * 2, (uint64_t)q_ld * 2 * n_tok};
+    const uint64_t sk[2] = {(uint64_t)k_ld * 2, (uint64_t)k_ld * 2 * n_tok};
+    const uint32_t bq[3] = {(uint32_t)kPamD, (uint32_t)kPamQ, 1u}, bk[3] = {(uint32_t)kPamD, (uint32_t)kPamK, 1u};
+    int rc = encode_map(&tmQ, dtype, 3, q, dims, sq, bq, 128, "pam/Q");
+    if (rc) return rc;
+    rc = encode_map(&tmK, dtype, 3, k, dims, sk, bk, 128, "pam/K");
+    if (rc) return rc;
+    const uint64_t dv_[3] = {(uint64_t)n_tok, (uint64_t)dv, (uint64_t)batch};
+    const uint64_t sv[2] = {(uint64_t)vt_ld * 2, (uint64_t)vt_ld * 2 * dv};
+    const uint32_t bv[3] = {(uint32_t)kPamK, (uint32_t)kPamDV, 1u};
+    rc = encode_map(&tmV, dtype, 3, vt, dv_, sv, bv, 128, "pam/Vt");
+    if (rc) return rc;
+  }
+  PamParams p;
+  p.n_tok = n_tok; p.ktiles = (n_tok + kPamK - 1) / kPamK;
+  p.stat_m = stat_m; p.stat_l = stat_l; p.bias_v = bias_v; p.gamma = gamma; p.x = x; p.y = y; p.x_ld = x_ld; p.y_ld = y_ld;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(pam_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPamSmemBytes);
+    cudaFuncSetAttribute(pam_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPamSmemBytes);
+    cudaFuncSetAttribute(pam_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPamSmemBytes);
+    cudaFuncSetAttribute(pam_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPamSmemBytes);
+  });
+  const int qtiles = (n_tok + kPamQ - 1) / kPamQ;
+  dim3 g1((unsigned)qtiles, 1, (unsigned)batch), g2((unsigned)qtiles, (unsigned)(dv / kPamDV), (unsigned)batch);
+  if (dtype == DT_BF16) {
+    pam_kernel<true, 1><<<g1, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<true, 2><<<g2, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    pam_kernel<false, 1><<<g1, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<false, 2><<<g2, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  }
+  return check_launch("pam_attention");
+}

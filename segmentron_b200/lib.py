@@ -23,7 +23,7 @@ class ConvArgs(C.Structure):
                 ("n", i32), ("h", i32), ("w", i32), ("cin", i32), ("x_ld", i32),
                 ("ho", i32), ("wo", i32), ("cout", i32), ("y_ld", i32), ("res_ld", i32),
                 ("kh", i32), ("kw", i32), ("stride", i32), ("dilation", i32), ("pad_t", i32), ("pad_l", i32),
-                ("act", i32), ("dtype", i32), ("max_ctas", i32)]
+                ("act", i32), ("dtype", i32), ("max_ctas", i32), ("y_f32", i32)]
 
 
 class DwArgs(C.Structure):
@@ -47,6 +47,11 @@ SYMBOLS = {
     "segb200_maxpool3x3s2": (C.c_int, [vp, vp] + [C.c_int] * 7 + [vp]),
     "segb200_bilinear_nhwc": (C.c_int, [vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_bilinear_nchw_out": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
+    "segb200_pam_attention": (C.c_int, [vp] * 9 + [C.c_int] * 9 + [vp]),
+    "segb200_cam_softmax": (C.c_int, [vp, vp] + [C.c_int] * 5 + [vp]),
+    "segb200_cca_weight_softmax": (C.c_int, [vp, vp, vp] + [C.c_int] * 8 + [vp]),
+    "segb200_cca_map": (C.c_int, [vp, vp, vp, vp, vp] + [C.c_int] * 9 + [vp]),
+    "segb200_nhwc_to_cn": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),
     "segb200_nchw_to_nhwc": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
     "segb200_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
 }

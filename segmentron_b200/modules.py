@@ -337,6 +337,87 @@ class PyramidPooling(nn.Module):
         return _leave(self.forward_nhwc(xh), odt)
 
 
+class PAM_Module(nn.Module):
+    """Replaces segmentron.modules.module.PAM_Module (module.py:100-131): q/k 1x1 convs and V^T as tcgen05 GEMMs, then the
+    tiled softmax(Q K^T) V kernel (csrc/pam.cu) with gamma*out + x in its epilogue."""
+
+    def __init__(self, in_dim):
+        super().__init__()
+        self.chanel_in = in_dim
+        self.query_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim // 8, kernel_size=1)
+        self.key_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim // 8, kernel_size=1)
+        self.value_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim, kernel_size=1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.softmax = nn.Softmax(dim=-1)
+        self._cache = _Cache()
+
+    def forward_nhwc(self, x):
+        from .attention import pam_nhwc
+        dt = x.dtype
+        convs = (self.query_conv, self.key_conv, self.value_conv)
+        key = (dt,) + _versions(*[t for cv in convs for t in (cv.weight, cv.bias)])
+
+        def build():
+            return tuple(t for cv in convs for t in (fold.pack_conv_weight(cv.weight.detach(), dt),
+                                                     cv.bias.detach().float().contiguous()))
+        wq, bq, wk, bk, wv, bv = self._cache.get(key, build)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        return pam_nhwc(x, wq, bq, wk, bk, wv, bv, self.gamma)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class CAM_Module(nn.Module):
+    """Replaces segmentron.modules.module.CAM_Module (module.py:134-162): Gram matrix and A.X on the tensor cores (fp32
+    energies), softmax(rowmax - E) in between; gamma*out + x fused into the second GEMM's epilogue."""
+
+    def __init__(self, in_dim):
+        super().__init__()
+        self.chanel_in = in_dim
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.softmax = nn.Softmax(dim=-1)
+
+    def forward_nhwc(self, x):
+        from .attention import cam_nhwc
+        return cam_nhwc(x, self.gamma)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
+class CrissCrossAttention(nn.Module):
+    """Replaces segmentron.modules.cc_attention.CrissCrossAttention (cc_attention.py:52-72) and the four
+    segmentron._C.ca_* functions it calls (csrc/vision.cpp:6-11)."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.query_conv = nn.Conv2d(in_channels, in_channels // 8, 1)
+        self.key_conv = nn.Conv2d(in_channels, in_channels // 8, 1)
+        self.value_conv = nn.Conv2d(in_channels, in_channels, 1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self._cache = _Cache()
+
+    def forward_nhwc(self, x):
+        from .attention import cca_nhwc
+        dt = x.dtype
+        convs = (self.query_conv, self.key_conv, self.value_conv)
+        key = (dt,) + _versions(*[t for cv in convs for t in (cv.weight, cv.bias)])
+
+        def build():
+            return tuple(t for cv in convs for t in (fold.pack_conv_weight(cv.weight.detach(), dt),
+                                                     cv.bias.detach().float().contiguous()))
+        wq, bq, wk, bk, wv, bv = self._cache.get(key, build)
+        return cca_nhwc(x, wq, bq, wk, bk, wv, bv, self.gamma)
+
+    def forward(self, x):
+        xh, odt = _enter(x, self)
+        return _leave(self.forward_nhwc(xh), odt)
+
+
 REPLACEMENTS = {
     "SeparableConv2d": SeparableConv2d,
     "_ConvBNReLU": _ConvBNReLU,
@@ -344,4 +425,7 @@ REPLACEMENTS = {
     "InvertedResidual": InvertedResidual,
     "_ASPP": _ASPP,
     "PyramidPooling": PyramidPooling,
+    "PAM_Module": PAM_Module,
+    "CAM_Module": CAM_Module,
+    "CrissCrossAttention": CrissCrossAttention,
 }

@@ -47,7 +47,7 @@ def make_conv_args(x, wgt, y, *, cin, cout, kh=1, kw=1, stride=1, dilation=1, pa
                    scale=None, shift=None, act=None, residual=None, max_ctas=0):
     n, h, w, cx, x_ld = _nhwc(x, "x")
     ny, ho, wo, cy, y_ld = _nhwc(y, "y")
-    if cx < cin or cy < cout or ny != n:
+    if cx < cin or cy < cout:
         raise RuntimeError("segb200 conv: shape mismatch")
     a = L.ConvArgs()
     a.x, a.wgt, a.y = _ptr(x), _ptr(wgt), _ptr(y)
@@ -60,6 +60,7 @@ def make_conv_args(x, wgt, y, *, cin, cout, kh=1, kw=1, stride=1, dilation=1, pa
     a.act = L.ACT[act]
     a.dtype = dt_code(x.dtype)
     a.max_ctas = max_ctas
+    a.y_f32 = 1 if y.dtype == torch.float32 else 0
     return a
 
 

@@ -24,7 +24,9 @@ def install(verbose=False):
     """Rebind the reference class names to the drop-in classes in all loaded ``segmentron.*`` namespaces."""
     if "segmentron" not in sys.modules:
         import segmentron  # noqa: F401  (the reference must be importable: PYTHONPATH=/path/to/SegmenTron)
-    ref_mods = sys.modules["segmentron.modules.basic"], sys.modules["segmentron.modules.module"]
+    ref_mods = [sys.modules["segmentron.modules.basic"], sys.modules["segmentron.modules.module"]]
+    if "segmentron.modules.cc_attention" in sys.modules:      # only importable with a segmentron._C (SURVEY App. B5)
+        ref_mods.append(sys.modules["segmentron.modules.cc_attention"])
     originals = {}
     for name in M.REPLACEMENTS:
         for rm in ref_mods:
@@ -65,6 +67,8 @@ def _adopt(cls, ref):
         new._cache = M._Cache()
     elif name == "_ASPP":
         new._c0, new._cp, new._cproj = M._Cache(), M._Cache(), M._Cache()
+    elif name in ("CrissCrossAttention", "PAM_Module"):
+        new._cache = M._Cache()
     elif name == "PyramidPooling":
         def _size(p):
             s = p.output_size

@@ -99,6 +99,19 @@ def test_conv_gemm(case, dtype):
         assert (buf[..., mask.cuda()] == 7.0).all(), f"{name}: wrote outside its channel slice"
 
 
+def test_conv_gemm_fp32_out():
+    """fp32 epilogue (attention energies): K = 4096 accumulation, y_f32 store path."""
+    from segmentron_b200 import fold, ops
+    dtype = torch.bfloat16
+    x = _rand(1, 1, 200, 4096, dtype=dtype, seed=1)
+    wt = _rand(136, 4096, 1, 1, dtype=dtype, seed=2)
+    y = torch.full((1, 1, 200, 136), float("nan"), dtype=torch.float32, device="cuda")
+    ops.conv_gemm(x, fold.pack_conv_weight(wt, dtype), y, cin=4096, cout=136)
+    torch.cuda.synchronize()
+    ref = x.float().view(200, 4096) @ wt.float().view(136, 4096).t()
+    assert torch.allclose(y.view(200, 136), ref, rtol=1e-4, atol=1e-2), float((y.view(200, 136) - ref).abs().max())
+
+
 @pytest.mark.parametrize("k,pad,cout", [(3, 1, 32), (7, 3, 64)])
 def test_stem_s2d(k, pad, cout):
     from segmentron_b200 import fold, ops

@@ -73,6 +73,29 @@ def test_dropin_modules(dtype, tol):
         _cmp(_load(M.PyramidPooling(64), P, "psp")(x.cuda().to(dtype)), ref, tol)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.2e-2)], ids=["f16", "bf16"])
+def test_attention_modules(dtype, tol):
+    """CAM_Module and CrissCrossAttention against the oracle (which is pinned to the reference classes / to a scalar
+    transcription of ca_cuda.cu in tests/golden/make_golden.py)."""
+    from segmentron_b200 import modules as M
+    with torch.no_grad():
+        for (n, c, h, w, s) in [(2, 64, 12, 20, 0.2), (1, 512, 17, 33, 0.05)]:
+            P = R.Params(21)
+            x = _x(n, c, h, w, seed=22) * s
+            ref = R.cam(P, x, "cam", gamma=0.7)
+            _cmp(_load(M.CAM_Module(c), P, "cam")(x.cuda().to(dtype)), ref, tol)
+        for (n, c, h, w) in [(2, 512, 12, 20), (1, 512, 32, 40)]:       # N = 240 (ragged key tile) and 1280
+            P = R.Params(25)
+            x = _x(n, c, h, w, seed=26) * 0.5
+            ref = R.pam(P, x, "pam", gamma=0.8)
+            _cmp(_load(M.PAM_Module(c), P, "pam")(x.cuda().to(dtype)), ref, tol)
+        for (n, c, h, w) in [(2, 64, 9, 13), (1, 512, 16, 24)]:
+            P = R.Params(23)
+            x = _x(n, c, h, w, seed=24)
+            ref = R.criss_cross_attention(P, x, "cca", gamma=0.6)
+            _cmp(_load(M.CrissCrossAttention(c), P, "cca")(x.cuda().to(dtype)), ref, tol)
+
+
 def test_dropin_errors_and_cache_invalidation():
     from segmentron_b200 import modules as M
     m = M.SeparableConv2d(64, 64).cuda().eval()
