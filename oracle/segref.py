@@ -431,6 +431,45 @@ def criss_cross_attention(P, x, prefix, gamma=0.5):
     return P.scalar(prefix + ".gamma", gamma) * ca_map(att, v) + x
 
 
+def ccnet(P, x, nclass=19, output_stride=16, recurrence=2):
+    """CCNet.forward (models/ccnet.py:27-40) with _CCHead / _RCCAModule (:43-82): conva -> CCA x recurrence (shared
+    weights, cfg.MODEL.CCNET.RECURRENCE = 2, config/settings.py:171) -> convb -> cat[x, out] -> bottleneck (3x3 + BN, no
+    ReLU; Dropout2d identity in eval) -> 1x1 classifier -> bilinear(align_corners=True)."""
+    size = x.shape[2:]
+    _, _, _, c4 = resnet_v1(P, x, "encoder", (3, 4, 23, 3), output_stride)
+    out = conv_bn_act(P, c4, "head.rcca.conva", 512, 3, 1, 1, conv="0", bn="1")
+    for _ in range(recurrence):
+        out = criss_cross_attention(P, out, "head.rcca.cca")
+    out = conv_bn_act(P, out, "head.rcca.convb", 512, 3, 1, 1, conv="0", bn="1")
+    out = torch.cat([c4, out], dim=1)                                               # ccnet.py:79
+    out = conv_bn_act(P, out, "head.rcca.bottleneck", 512, 3, 1, 1, act=None, conv="0", bn="1")
+    out = conv2d(P, out, "head.out", nclass, 1, bias=True, gain=4.0)
+    return F.interpolate(out, size, mode="bilinear", align_corners=True)
+
+
+def danet_head(P, x, nclass, prefix="head"):
+    """DANetHead.forward (models/danet.py:70-88).  Dropout2d is identity in eval."""
+    def cbr(x, name):                                  # nn.Sequential(conv3x3(pad 1, no bias), BN, ReLU)  danet.py:48-61
+        return conv_bn_act(P, x, f"{prefix}.{name}", 512, 3, 1, 1, conv="0", bn="1")
+    feat1 = cbr(x, "conv5a")
+    sa_conv = cbr(pam(P, feat1, prefix + ".sa"), "conv51")
+    sa_output = conv2d(P, sa_conv, prefix + ".conv6.1", nclass, 1, bias=True, gain=4.0)
+    feat2 = cbr(x, "conv5c")
+    sc_conv = cbr(cam(P, feat2, prefix + ".sc"), "conv52")
+    sc_output = conv2d(P, sc_conv, prefix + ".conv7.1", nclass, 1, bias=True, gain=4.0)
+    sasc_output = conv2d(P, sa_conv + sc_conv, prefix + ".conv8.1", nclass, 1, bias=True, gain=4.0)
+    return sasc_output, sa_output, sc_output
+
+
+def danet(P, x, nclass=19, output_stride=8, multi_grid=True, multi_dilation=(4, 8, 16)):
+    """DANet.forward (models/danet.py:26-41): ResNet101 (OS8, multi-grid 4/8/16) + DANetHead, three logit maps, each
+    bilinearly upsampled (align_corners=True) to the input size."""
+    size = x.shape[2:]
+    _, _, _, c4 = resnet_v1(P, x, "encoder", (3, 4, 23, 3), output_stride, multi_grid, list(multi_dilation))
+    outs = danet_head(P, c4, nclass)
+    return tuple(F.interpolate(o, size, mode="bilinear", align_corners=True) for o in outs)
+
+
 # ----------------------------------------------------------------------------------------
 # convenience
 # ----------------------------------------------------------------------------------------
@@ -448,11 +487,22 @@ def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
     """Create the full reference-named parameter dict for ``model`` by tracing one tiny forward."""
     P = Params(seed)
     with torch.no_grad():
-        deeplabv3plus(P, torch.zeros(1, 3, 33, 33), nclass=nclass, **MODELS[model])
+        if model == "danet_resnet101":
+            danet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
+        elif model == "ccnet_resnet101":
+            ccnet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
+        else:
+            deeplabv3plus(P, torch.zeros(1, 3, 33, 33), nclass=nclass, **MODELS[model])
     P.frozen = True
     return P
 
 
 def forward(model: str, P: Params, x, nclass: int = 19, **kw):
+    """-> logits [N, nclass, H, W] (for DANet: the first of its three outputs unless all=True)."""
     with torch.no_grad():
+        if model == "danet_resnet101":
+            outs = danet(P, x, nclass=nclass)
+            return outs if kw.get("all") else outs[0]
+        if model == "ccnet_resnet101":
+            return ccnet(P, x, nclass=nclass)
         return deeplabv3plus(P, x, nclass=nclass, **MODELS[model], **kw)

@@ -12,7 +12,7 @@ import torch
 from . import fold, lib as L, ops
 
 
-def cam_nhwc(x, gamma):
+def cam_nhwc(x, gamma, out=None):
     """x [n,h,w,c] (16-bit, c % 8 == 0), gamma: 1-element fp32 CUDA tensor -> gamma * CAM(x) + x."""
     n, h, w, c, x_ld = ops._nhwc(x, "x")
     dt = x.dtype
@@ -20,7 +20,8 @@ def cam_nhwc(x, gamma):
     pitch = fold.round_up(hw, 64)
     lib = L.load()
     st = ops._stream
-    out = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+    if out is None:
+        out = torch.empty(n, h, w, c, dtype=dt, device=x.device)
     gvec = gamma.detach().float().reshape(1).expand(c).contiguous()
     for b in range(n):
         xb = x[b:b + 1]
@@ -35,7 +36,7 @@ def cam_nhwc(x, gamma):
     return out
 
 
-def cca_nhwc(x, wq, bq, wk, bk, wv, bv, gamma):
+def cca_nhwc(x, wq, bq, wk, bk, wv, bv, gamma, out=None):
     """One criss-cross attention step.  wq/wk/wv: packed 1x1 weights (fold.pack_conv_weight), b*: fp32 bias vectors."""
     n, h, w, c, x_ld = ops._nhwc(x, "x")
     dt = x.dtype
@@ -51,14 +52,14 @@ def cca_nhwc(x, wq, bq, wk, bk, wv, bv, gamma):
     att = torch.empty(n, h, w, att_ld, dtype=torch.float32, device=x.device)
     L.check(lib.segb200_cca_weight_softmax(ops._ptr(q), ops._ptr(k), ops._ptr(att), n, h, w, cq, cq, cq, att_ld,
                                            ops.dt_code(dt), ops._stream()), "cca_weight_softmax")
-    y = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+    y = out if out is not None else torch.empty(n, h, w, c, dtype=dt, device=x.device)
     g = gamma.detach().float().reshape(1).contiguous()
     L.check(lib.segb200_cca_map(ops._ptr(att), ops._ptr(v), ops._ptr(x), ops._ptr(y), ops._ptr(g), n, h, w, c, att_ld, c, x_ld,
                                 c, ops.dt_code(dt), ops._stream()), "cca_map")
     return y
 
 
-def pam_nhwc(x, wq, bq, wk, bk, wv, bv, gamma):
+def pam_nhwc(x, wq, bq, wk, bk, wv, bv, gamma, out=None):
     """PAM_Module on NHWC x [n,h,w,c] (c % 64 == 0, contiguous).  wq/wk: packed [c/8 = 64][1][c], wv: packed [c][1][c]
     (fold.pack_conv_weight); bq/bk/bv fp32 bias vectors; gamma 1-element tensor."""
     n, h, w, c, x_ld = ops._nhwc(x, "x")
@@ -81,7 +82,7 @@ def pam_nhwc(x, wq, bq, wk, bk, wv, bv, gamma):
     wv_as_x = wv.view(1, 1, dv, wv.shape[-1])
     for b in range(n):
         ops.conv_gemm(wv_as_x, x[b], vt[b].view(1, 1, dv, pitch)[..., :ntok], cin=c, cout=ntok)
-    y = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+    y = out if out is not None else torch.empty(n, h, w, c, dtype=dt, device=x.device)
     sm = torch.empty(n * ntok, dtype=torch.float32, device=x.device)
     sl = torch.empty(n * ntok, dtype=torch.float32, device=x.device)
     g = gamma.detach().float().reshape(1).contiguous()

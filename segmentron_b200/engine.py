@@ -237,7 +237,7 @@ def _mobilenet_v2(pl, x_shape, holder, output_stride, eps):
     return c1, c2, c3, c4
 
 
-def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, eps):
+def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, eps, out=None):
     """BottleneckV1b.forward (backbones/resnet.py:60-81): three GEMMs; the identity / downsample branch is the
     residual operand of the third GEMM's epilogue, followed by the fused ReLU (out += identity; relu)."""
     y = pl.conv_bn_act(x, prefix, planes, 1, act="relu", eps=eps, conv="conv1", bn="bn1")
@@ -247,10 +247,10 @@ def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, eps):
         idn = pl.conv_bn_act(x, prefix + ".downsample", planes * 4, 1, stride=stride, act=None, eps=eps, conv="0", bn="1")
     else:
         idn = x
-    return pl.conv_bn_act(y, prefix, planes * 4, 1, act="relu", eps=eps, conv="conv3", bn="bn3", residual=idn)
+    return pl.conv_bn_act(y, prefix, planes * 4, 1, act="relu", eps=eps, conv="conv3", bn="bn3", residual=idn, out=out)
 
 
-def _resnet(pl, x_shape, holder, layers, output_stride, eps, multi_grid=False, multi_dilation=None):
+def _resnet(pl, x_shape, holder, layers, output_stride, eps, multi_grid=False, multi_dilation=None, c4_out=None):
     """ResNetV1.forward (backbones/resnet.py:183-199): 7x7/2 stem (space-to-depth -> 4x4 tensor-core conv) + BN + ReLU,
     MaxPool(3,2,1), four bottleneck stages with the reference's stride/dilation table (:90-100, :149-179)."""
     dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
@@ -263,20 +263,20 @@ def _resnet(pl, x_shape, holder, layers, output_stride, eps, multi_grid=False, m
     x = y
     inplanes = [64]
 
-    def make_layer(x, name, planes, blocks, stride=1, dilation=1, mg=False):
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1, mg=False, last_out=None):
         ds = stride != 1 or inplanes[0] != planes * 4
         first_d = (1 if dilation in (1, 2) else 2) if not mg else multi_dilation[0]
         x = _bottleneck(pl, x, f"{p}.{name}.0", planes, stride, first_d, ds, eps)
         inplanes[0] = planes * 4
         for i in range(1, blocks):
             d = multi_dilation[i % len(multi_dilation)] if mg else dilation
-            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, d, False, eps)
+            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, d, False, eps, out=last_out if i == blocks - 1 else None)
         return x
 
     c1 = make_layer(x, "layer1", 64, layers[0])
     c2 = make_layer(c1, "layer2", 128, layers[1], 2)
     c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
-    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], multi_grid)
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], multi_grid, last_out=c4_out)
     return c1, c2, c3, c4
 
 
@@ -330,6 +330,105 @@ def build_deeplabv3plus(pl, x_shape, holder, backbone, nclass, output_stride, ep
             logits.shape[2], nclass, logits.stride(2), H, W, 1, ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
     pl.keep += [out] + ([amax] if amax is not None else [])
     return out, amax, logits
+
+
+def build_danet(pl, x_shape, holder, nclass, output_stride, multi_grid, multi_dilation, out_dtype, want_argmax):
+    """DANet.forward (models/danet.py:26-41) + DANetHead.forward (:70-88).  conv8(sa_conv + sc_conv) is evaluated as
+    conv8(sa_conv) + conv8(sc_conv) (linear), the second GEMM taking the first as its residual operand."""
+    from . import attention as A
+    n, _, H, W = x_shape
+    _, _, _, c4 = _resnet(pl, x_shape, holder, (3, 4, 23, 3), output_stride, 1e-5, multi_grid, multi_dilation)
+    hp = "head"
+
+    def cbr(x, name):
+        return pl.conv_bn_act(x, f"{hp}.{name}", 512, 3, pad=1, act="relu", conv="0", bn="1")
+
+    def qkv(prefix):
+        ws = []
+        for nm in ("query_conv", "key_conv", "value_conv"):
+            ws += [fold.pack_conv_weight(pl.w(f"{prefix}.{nm}.weight"), pl.dtype), pl.w(f"{prefix}.{nm}.bias").float().contiguous()]
+        return ws
+
+    feat1 = cbr(c4, "conv5a")
+    sa_feat = pl.new(*feat1.shape)
+    wq, bq, wk, bk, wv, bv = qkv(hp + ".sa")
+    g_sa = pl.w(hp + ".sa.gamma").float()
+    pl.keep += [wq, bq, wk, bk, wv, bv, g_sa]
+    ntok = feat1.shape[1] * feat1.shape[2]
+    pl.steps.append((lambda s: A.pam_nhwc(feat1, wq, bq, wk, bk, wv, bv, g_sa, out=sa_feat),
+                     dict(kind="pam", flops=2.0 * n * ntok * ntok * (64 + 512), bytes=2.0 * n * ntok * (512 * 3 + 128),
+                          desc=f"PAM N={ntok} d=64 dv=512 b={n}")))
+    pl.n_launch += 4 + n
+    sa_conv = cbr(sa_feat, "conv51")
+    feat2 = cbr(c4, "conv5c")
+    sc_feat = pl.new(*feat2.shape)
+    g_sc = pl.w(hp + ".sc.gamma").float()
+    pl.keep.append(g_sc)
+    pl.steps.append((lambda s: A.cam_nhwc(feat2, g_sc, out=sc_feat),
+                     dict(kind="cam", flops=2.0 * 2 * n * ntok * 512 * 512, bytes=2.0 * n * ntok * 512 * 3, desc=f"CAM C=512 N={ntok} b={n}")))
+    pl.n_launch += 4 * n
+    sc_conv = cbr(sc_feat, "conv52")
+
+    def classifier(x, name, residual=None, bias=True):
+        lg = pl.new(n, x.shape[1], x.shape[2], fold.round_up(nclass, 8), ld=32)
+        cop = fold.round_up(nclass, 8)
+        wpk = fold.pack_conv_weight(pl.w(f"{hp}.{name}.1.weight"), pl.dtype, cop)
+        shift = fold.pad_vec(pl.w(f"{hp}.{name}.1.bias"), cop) if bias else None
+        return pl.conv(x, wpk, lg, cin=512, cout=cop, shift=shift, residual=residual)
+
+    sa_out = classifier(sa_conv, "conv6")
+    sc_out = classifier(sc_conv, "conv7")
+    t = classifier(sa_conv, "conv8", bias=False)
+    sasc_out = classifier(sc_conv, "conv8", residual=t)
+    outs = []
+    for lg in (sasc_out, sa_out, sc_out):
+        o = torch.empty(n, nclass, H, W, dtype=out_dtype, device=pl.device)
+        am = torch.empty(n, H, W, dtype=torch.uint8, device=pl.device) if (want_argmax and lg is sasc_out) else None
+        pl.call("segb200_bilinear_nchw_out", ops._ptr(lg), ops._ptr(o), ops._ptr(am), n, lg.shape[1], lg.shape[2], nclass,
+                lg.stride(2), H, W, 1, ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
+        pl.keep += [o] + ([am] if am is not None else [])
+        outs.append((o, am))
+    return outs
+
+
+def build_ccnet(pl, x_shape, holder, nclass, output_stride, recurrence, out_dtype, want_argmax):
+    """CCNet.forward + _RCCAModule.forward (models/ccnet.py:27-40, :73-82).  The backbone's last block and convb write
+    their channel slices of one 2560-channel buffer (no torch.cat); the recurrent criss-cross attention shares weights."""
+    from . import attention as A
+    n, _, H, W = x_shape
+    # the concat buffer must exist before the backbone is planned: c4 is produced straight into cat[..., :2048]
+    ho = wo = None
+    hh, ww = H, W
+    for s in ([2, 2, 2] + ([2] if output_stride >= 16 else []) + ([2] if output_stride == 32 else [])):
+        hh, ww = (hh - 1) // s + 1, (ww - 1) // s + 1
+    cat = pl.new(n, hh, ww, 2048 + 512)
+    _, _, _, c4 = _resnet(pl, x_shape, holder, (3, 4, 23, 3), output_stride, 1e-5, c4_out=cat[..., :2048])
+    assert tuple(c4.shape[1:3]) == (hh, ww), (c4.shape, hh, ww)
+    hp = "head.rcca"
+    out = pl.conv_bn_act(c4, hp + ".conva", 512, 3, pad=1, act="relu", conv="0", bn="1")
+    ws = []
+    for nm in ("query_conv", "key_conv", "value_conv"):
+        ws += [fold.pack_conv_weight(pl.w(f"{hp}.cca.{nm}.weight"), pl.dtype), pl.w(f"{hp}.cca.{nm}.bias").float().contiguous()]
+    g = pl.w(hp + ".cca.gamma").float()
+    pl.keep += ws + [g]
+    bufs = [pl.new(*out.shape) for _ in range(recurrence)]
+    cur = out
+    for i in range(recurrence):
+        pl.steps.append((lambda s, src=cur, dst=bufs[i]: A.cca_nhwc(src, *ws, g, out=dst),
+                         dict(kind="cca", flops=2.0 * n * hh * ww * (hh + ww - 1) * (64 + 512), bytes=2.0 * n * hh * ww * 512 * 4,
+                              desc=f"CCA {hh}x{ww} c512 b={n}")))
+        pl.n_launch += 5
+        cur = bufs[i]
+    pl.conv_bn_act(cur, hp + ".convb", 512, 3, pad=1, act="relu", conv="0", bn="1", out=cat[..., 2048:2560])
+    y = pl.conv_bn_act(cat, hp + ".bottleneck", 512, 3, pad=1, act=None, conv="0", bn="1")
+    logits = pl.new(n, hh, ww, fold.round_up(nclass, 8), ld=32)
+    pl.conv_bn_act(y, "head.out", nclass, 1, act=None, conv=None, bn=None, bias=True, out=logits)
+    o = torch.empty(n, nclass, H, W, dtype=out_dtype, device=pl.device)
+    am = torch.empty(n, H, W, dtype=torch.uint8, device=pl.device) if want_argmax else None
+    pl.call("segb200_bilinear_nchw_out", ops._ptr(logits), ops._ptr(o), ops._ptr(am), n, hh, ww, nclass, logits.stride(2), H, W, 1,
+            ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
+    pl.keep += [o] + ([am] if am is not None else [])
+    return [(o, am)]
 
 
 class DeepLabV3PlusB200:
@@ -394,3 +493,55 @@ class DeepLabV3PlusB200:
             raise RuntimeError("segb200: engine was built without want_argmax=True")
         self(x)
         return st["amax"]
+
+
+class DANetB200(DeepLabV3PlusB200):
+    """``engine(x) -> sasc logits`` (``DANet.forward(x)[0]``, models/danet.py:26-41); ``engine.outputs(x)`` returns all three
+    maps (sasc, sa, sc).  ResNet101 backbone at output stride 8 with multi-grid dilations, PAM/CAM on the tensor cores."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=8, multi_grid=True, multi_dilation=(4, 8, 16), dtype=torch.bfloat16,
+                 out_dtype=None, device="cuda", cuda_graph=False, want_argmax=False):
+        super().__init__(state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride, dtype=dtype,
+                         out_dtype=out_dtype, device=device, cuda_graph=cuda_graph, want_argmax=want_argmax)
+        self.mg = (multi_grid, list(multi_dilation))
+
+    def _build(self, shape, in_dtype):
+        holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
+        pl = Plan(self.sd, self.dtype, self.device)
+        outs = build_danet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.mg[0], self.mg[1],
+                           self.out_dtype, self.want_argmax)
+        graph = None
+        if self.cuda_graph:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                pl.run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                pl.run()
+        return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=graph, logits=None)
+
+    def outputs(self, x):
+        self(x)
+        return tuple(self.plan_for(x)["all"])
+
+
+class CCNetB200(DANetB200):
+    """``engine(x) -> logits`` (``CCNet.forward(x)[0]``, models/ccnet.py:27-40): ResNet101 OS16 + recurrent criss-cross
+    attention (RECURRENCE = 2)."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=16, recurrence=2, dtype=torch.bfloat16, out_dtype=None,
+                 device="cuda", cuda_graph=False, want_argmax=False):
+        DeepLabV3PlusB200.__init__(self, state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride,
+                                   dtype=dtype, out_dtype=out_dtype, device=device, cuda_graph=cuda_graph, want_argmax=want_argmax)
+        self.recurrence = recurrence
+
+    def _build(self, shape, in_dtype):
+        holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
+        pl = Plan(self.sd, self.dtype, self.device)
+        outs = build_ccnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.recurrence, self.out_dtype,
+                           self.want_argmax)
+        return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)

@@ -25,6 +25,8 @@ MODEL_CASES = {
     "dlv3p_xception65_97x161_b2": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (2, 3, 97, 161), 1),
     "dlv3p_mobilenetv2_64x128": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (1, 3, 64, 128), 2),
     "dlv3p_resnet101_65x129": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (1, 3, 65, 129), 4),
+    "danet_resnet101_64x96": ("danet_resnet101", "cityscapes_danet_resnet.yaml", (1, 3, 64, 96), 5),
+    "ccnet_resnet101_65x97": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (1, 3, 65, 97), 6),
 }
 
 
@@ -35,9 +37,22 @@ def run_model_case(case):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, REF)
     from oracle import segref as R
+    name, yaml_file, shape, seed = MODEL_CASES[case]
+    if name == "ccnet_resnet101":
+        # The reference's CCNet needs the pybind module `segmentron._C`, which cannot be built (THC headers, App. B5) and
+        # is commented out of models/__init__.py.  Provide a stand-in whose two forward functions are the oracle's
+        # ca_weight / ca_map (themselves pinned to a scalar transcription of ca_cuda.cu in run_module_cases), so the
+        # fixture pins the reference's MODEL structure (_RCCAModule, recurrence, cat order, bottleneck) around them.
+        import types
+        import segmentron
+        fake = types.ModuleType("segmentron._C")
+        fake.ca_forward = lambda t, f: R.ca_weight(t, f)
+        fake.ca_map_forward = lambda w, g: R.ca_map(w, g)
+        sys.modules["segmentron._C"] = fake
+        segmentron._C = fake
+        import segmentron.models.ccnet  # noqa: F401  (registers "CCNet")
     from segmentron.config import cfg
     from segmentron.models.model_zoo import get_segmentation_model
-    name, yaml_file, shape, seed = MODEL_CASES[case]
     cfg.update_from_file(os.path.join(REF, "configs", yaml_file))
     cfg.PHASE = "test"
     cfg.check_and_freeze()
@@ -49,6 +64,13 @@ def run_model_case(case):
                 m.eps = cfg.MODEL.BN_EPS_FOR_ENCODER
     P = R.build_params(name, seed)
     missing = model.load_state_dict(P.state_dict(), strict=True)
+    if name == "danet_resnet101":                       # three outputs (sasc, sa, sc): check all, store the first
+        g_ = torch.Generator().manual_seed(1000 + seed)
+        x_ = torch.randn(*shape, generator=g_)
+        with torch.no_grad():
+            yr, yo = model(x_), R.forward(name, P, x_, all=True)
+        for a_, b_ in zip(yr, yo):
+            assert float((a_ - b_).abs().max() / a_.abs().max()) < 1e-5
     g = torch.Generator().manual_seed(1000 + seed)
     x = torch.randn(*shape, generator=g)
     with torch.no_grad():

@@ -34,7 +34,11 @@ def _rel(a, b):
 
 
 def _engine(model, P, dtype, **kw):
-    from segmentron_b200.engine import DeepLabV3PlusB200
+    from segmentron_b200.engine import CCNetB200, DANetB200, DeepLabV3PlusB200
+    if model == "danet_resnet101":
+        return DANetB200(P.state_dict(), dtype=dtype, **kw)
+    if model == "ccnet_resnet101":
+        return CCNetB200(P.state_dict(), dtype=dtype, **kw)
     cfg = R.MODELS[model]
     return DeepLabV3PlusB200(P.state_dict(), backbone=cfg["backbone"], eps_encoder=cfg["eps_encoder"],
                              use_aspp=cfg["use_aspp"], use_decoder=cfg["use_decoder"], dtype=dtype, **kw)
@@ -62,7 +66,7 @@ def _check(model, P, x, y32, dtype, tol):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)], ids=["f16", "bf16"])
 @pytest.mark.parametrize("case", ["dlv3p_xception65_65x129", "dlv3p_xception65_97x161_b2", "dlv3p_mobilenetv2_64x128",
-                                  "dlv3p_resnet101_65x129"])
+                                  "dlv3p_resnet101_65x129", "danet_resnet101_64x96", "ccnet_resnet101_65x97"])
 def test_engine_vs_reference_fixture(case, dtype, tol):
     fx = torch.load(os.path.join(G, case + ".pt"))
     P = R.build_params(fx["model"], fx["seed"])
