@@ -117,6 +117,12 @@ int segb200_adaptive_avgpool(const void* x, void* out, int n, int h, int w, int 
  * Replaces nn.MaxPool2d(3, 2, 1) of the ResNet stem (backbones/resnet.py:119). */
 int segb200_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, int x_ld, int y_ld, int dtype, void* stream);
 
+/* HRNet fuse step: y = act(a + nearest_upsample(z, 2^k)), a/y [n][h][w][*], z [n][h>>k][w>>k][*]; k = 0 is a plain add.
+ * Replaces nn.Upsample(scale_factor=2^k, 'nearest') + the running sum + ReLU of HighResolutionModule.forward
+ * (backbones/hrnet.py:178-186, :215-232). */
+int segb200_upsample_add(const void* a, const void* z, void* y, int n, int h, int w, int c, int a_ld, int z_ld, int y_ld,
+                         int k, int act, int dtype, void* stream);
+
 /* Bilinear resize NHWC -> NHWC channel slice.  align_corners as F.interpolate.  From a 1x1 source
  * this is the ASPP image-pooling broadcast (module.py:64).  Replaces F.interpolate at
  * module.py:64,96, deeplabv3_plus.py:71, hrnet_seg.py:57-59. */

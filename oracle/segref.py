@@ -305,6 +305,112 @@ def resnet_v1(P, x, prefix="encoder", layers=(3, 4, 23, 3), output_stride=16, mu
     P._new(prefix + ".fc.bias", lambda: torch.zeros(1000))
     return c1, c2, c3, c4
 
+
+# ----------------------------------------------------------------------------------------
+# HRNet  (models/backbones/hrnet.py, models/hrnet_seg.py)
+# ----------------------------------------------------------------------------------------
+HRNET_W18_SMALL_V1 = dict(                     # configs/cityscapes_hrnet_w18_small_v1.yaml:23-64
+    stage1=dict(block="BOTTLENECK", blocks=[1], channels=[32]),
+    stage2=dict(modules=1, block="BASIC", blocks=[2, 2], channels=[16, 32]),
+    stage3=dict(modules=1, block="BASIC", blocks=[2, 2, 2], channels=[16, 32, 64]),
+    stage4=dict(modules=1, block="BASIC", blocks=[2, 2, 2, 2], channels=[16, 32, 64, 128]),
+    final_conv_kernel=1)
+
+
+def hr_basic_block(P, x, prefix, planes):
+    """BasicBlock.forward (hrnet.py:38-55): conv3x3-BN-ReLU-conv3x3-BN, + x, ReLU (no downsample inside HR modules)."""
+    g = math.sqrt(2.0)
+    out = F.relu(batchnorm(P, conv2d(P, x, prefix + ".conv1", planes, 3, 1, 1, gain=g), prefix + ".bn1"))
+    out = batchnorm(P, conv2d(P, out, prefix + ".conv2", planes, 3, 1, 1, gain=g * 0.5), prefix + ".bn2")
+    return F.relu(out + x)
+
+
+def hr_module(P, xs, prefix, blocks, channels):
+    """HighResolutionModule.forward (hrnet.py:215-232) with the fuse layers of _make_fuse_layers (:165-209)."""
+    nb = len(xs)
+    xs = list(xs)
+    for i in range(nb):
+        for b in range(blocks[i]):
+            xs[i] = hr_basic_block(P, xs[i], f"{prefix}.branches.{i}.{b}", channels[i])
+    if nb == 1:
+        return xs
+    outs = []
+    for i in range(nb):
+        y = None
+        for j in range(nb):
+            if j == i:
+                t = xs[j]
+            elif j > i:                                                               # 1x1 conv + BN + nearest up 2^(j-i)
+                t = batchnorm(P, conv2d(P, xs[j], f"{prefix}.fuse_layers.{i}.{j}.0", channels[i], 1),
+                              f"{prefix}.fuse_layers.{i}.{j}.1")
+                t = F.interpolate(t, scale_factor=2 ** (j - i), mode="nearest")
+            else:                                                                     # chain of 3x3 stride-2 convs
+                t = xs[j]
+                for k in range(i - j):
+                    last = k == i - j - 1
+                    co = channels[i] if last else channels[j]
+                    t = batchnorm(P, conv2d(P, t, f"{prefix}.fuse_layers.{i}.{j}.{k}.0", co, 3, 2, 1, gain=math.sqrt(2.0)),
+                                  f"{prefix}.fuse_layers.{i}.{j}.{k}.1")
+                    if not last:
+                        t = F.relu(t)
+            y = t if y is None else y + t
+        outs.append(F.relu(y))
+    return outs
+
+
+def hrnet_backbone(P, x, prefix="encoder", hcfg=None):
+    """HighResolutionNet.forward (hrnet.py:429-479)."""
+    hcfg = hcfg or HRNET_W18_SMALL_V1
+    g = math.sqrt(2.0)
+    x = F.relu(batchnorm(P, conv2d(P, x, prefix + ".conv1", 64, 3, 2, 1, gain=g), prefix + ".bn1"))
+    x = F.relu(batchnorm(P, conv2d(P, x, prefix + ".conv2", 64, 3, 2, 1, gain=g), prefix + ".bn2"))
+    # layer1: Bottleneck blocks (hrnet.py:58-94, _make_layer :383-399)
+    planes = hcfg["stage1"]["channels"][0]
+    inpl = 64
+    for b in range(hcfg["stage1"]["blocks"][0]):
+        ds = inpl != planes * 4
+        x = bottleneck_v1b(P, x, f"{prefix}.layer1.{b}", planes, 1, 1, ds)    # same structure/keys as ResNet's bottleneck
+        inpl = planes * 4
+    pre = [inpl]
+    ys = [x]
+    for si, sname in enumerate(("stage2", "stage3", "stage4")):
+        sc = hcfg[sname]
+        cur = sc["channels"]
+        tname = f"{prefix}.transition{si + 1}"
+        xs = []
+        for i in range(len(cur)):                                             # _make_transition_layer :347-381
+            if i < len(pre):
+                if cur[i] != pre[i]:
+                    xs.append(F.relu(batchnorm(P, conv2d(P, ys[i], f"{tname}.{i}.0", cur[i], 3, 1, 1, gain=g), f"{tname}.{i}.1")))
+                else:
+                    xs.append(ys[i])
+            else:
+                t = ys[-1]
+                for j in range(i + 1 - len(pre)):
+                    co = cur[i] if j == i - len(pre) else pre[-1]
+                    t = F.relu(batchnorm(P, conv2d(P, t, f"{tname}.{i}.{j}.0", co, 3, 2, 1, gain=g), f"{tname}.{i}.{j}.1"))
+                xs.append(t)
+        for m in range(sc["modules"]):
+            xs = hr_module(P, xs, f"{prefix}.{sname}.{m}", sc["blocks"], cur)
+        ys, pre = xs, cur
+    return ys
+
+
+def hrnet_seg(P, x, nclass=19, hcfg=None):
+    """HighResolutionNet(SegBaseModel).forward (models/hrnet_seg.py:23-29) + _HRNetHead (:54-63): bilinear
+    (align_corners=False) to the /4 branch, cat, 1x1 conv(+bias)+BN+ReLU, 1x1 conv(+bias), bilinear(False) to the input."""
+    hcfg = hcfg or HRNET_W18_SMALL_V1
+    size = x.shape[2:]
+    ys = hrnet_backbone(P, x, "encoder", hcfg)
+    s0 = ys[0].shape[2:]
+    cat = torch.cat([ys[0]] + [F.interpolate(t, size=s0, mode="bilinear", align_corners=False) for t in ys[1:]], 1)
+    c = cat.shape[1]
+    y = conv2d(P, cat, "hrnet_head.last_layer.0", c, 1, bias=True, gain=math.sqrt(2.0))
+    y = F.relu(batchnorm(P, y, "hrnet_head.last_layer.1"))
+    k = hcfg["final_conv_kernel"]
+    y = conv2d(P, y, "hrnet_head.last_layer.3", nclass, k, 1, 1 if k == 3 else 0, bias=True, gain=4.0)
+    return F.interpolate(y, size=size, mode="bilinear", align_corners=False)
+
 # ----------------------------------------------------------------------------------------
 # heads
 # ----------------------------------------------------------------------------------------
@@ -491,6 +597,8 @@ def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
             danet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
         elif model == "ccnet_resnet101":
             ccnet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
+        elif model == "hrnet_w18_small_v1":
+            hrnet_seg(P, torch.zeros(1, 3, 64, 64), nclass=nclass)
         else:
             deeplabv3plus(P, torch.zeros(1, 3, 33, 33), nclass=nclass, **MODELS[model])
     P.frozen = True
@@ -505,4 +613,6 @@ def forward(model: str, P: Params, x, nclass: int = 19, **kw):
             return outs if kw.get("all") else outs[0]
         if model == "ccnet_resnet101":
             return ccnet(P, x, nclass=nclass)
+        if model == "hrnet_w18_small_v1":
+            return hrnet_seg(P, x, nclass=nclass)
         return deeplabv3plus(P, x, nclass=nclass, **MODELS[model], **kw)

@@ -201,6 +201,37 @@ maxpool3x3s2_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int
 }
 
 // -------------------------------------------------------------------------------------------
+// HRNet fuse: y = act(a + nearest_up(z, 2^k))   (k = 0: plain add).  hrnet.py:178-186,215-232
+// -------------------------------------------------------------------------------------------
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const void* __restrict__ a, const void* __restrict__ z, void* __restrict__ y, int n, int h, int w, int c,
+                    int a_ld, int z_ld, int y_ld, int k, int act) {
+  using H = Half2<kBF16>;
+  const int cvn = c / 8;
+  const int hz = h >> k, wz = w >> k;
+  const long long total = (long long)n * h * w * cvn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    long long r = idx / cvn;
+    const int x = (int)(r % w); r /= w;
+    const int yy = (int)(r % h);
+    const int b = (int)(r / h);
+    const uint4 va = ldg_nc_v4(reinterpret_cast<const char*>(a) + ((((long long)b * h + yy) * w + x) * a_ld + cv * 8) * 2);
+    const uint4 vz = ldg_v4(reinterpret_cast<const char*>(z) + ((((long long)b * hz + (yy >> k)) * wz + (x >> k)) * z_ld + cv * 8) * 2);
+    const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w};
+    uint4 o; uint32_t* po = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = H::unpack(ua[j]), fz = H::unpack(uz[j]);
+      po[j] = H::pack(apply_act(fa.x + fz.x, act), apply_act(fa.y + fz.y, act));
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + ((((long long)b * h + yy) * w + x) * y_ld + cv * 8) * 2) = o;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // bilinear resize (torch upsample_bilinear2d index rules, fp32 math)
 // -------------------------------------------------------------------------------------------
 struct Lerp { int i0, i1; float l0, l1; };
@@ -386,6 +417,20 @@ extern "C" int segb200_maxpool3x3s2(const void* x, void* y, int n, int h, int w,
   else
     maxpool3x3s2_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, n, h, w, c, x_ld, ho, wo, y_ld);
   return check_launch("maxpool3x3s2");
+}
+
+extern "C" int segb200_upsample_add(const void* a, const void* z, void* y, int n, int h, int w, int c, int a_ld, int z_ld,
+                                    int y_ld, int k, int act, int dtype, void* stream) {
+  if (!a || !z || !y) return set_error(-1, "upsample_add: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "upsample_add: bad dtype");
+  if ((c & 7) || (a_ld & 7) || (z_ld & 7) || (y_ld & 7) || k < 0 || k > 8 || (h & ((1 << k) - 1)) || (w & ((1 << k) - 1)))
+    return set_error(-4, "upsample_add: sizes must be multiples of 8 channels and of the 2^k scale");
+  const long long total = (long long)n * h * w * (c / 8);
+  if (dtype == DT_BF16)
+    upsample_add_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(a, z, y, n, h, w, c, a_ld, z_ld, y_ld, k, act);
+  else
+    upsample_add_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(a, z, y, n, h, w, c, a_ld, z_ld, y_ld, k, act);
+  return check_launch("upsample_add");
 }
 
 extern "C" int segb200_bilinear_nhwc(const void* x, void* y, int n, int hi, int wi, int c, int x_ld, int ho, int wo,

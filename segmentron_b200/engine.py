@@ -391,6 +391,122 @@ def build_danet(pl, x_shape, holder, nclass, output_stride, multi_grid, multi_di
     return outs
 
 
+HRNET_W18_SMALL_V1 = dict(                     # configs/cityscapes_hrnet_w18_small_v1.yaml:23-64
+    stage1=dict(block="BOTTLENECK", blocks=[1], channels=[32]),
+    stage2=dict(modules=1, block="BASIC", blocks=[2, 2], channels=[16, 32]),
+    stage3=dict(modules=1, block="BASIC", blocks=[2, 2, 2], channels=[16, 32, 64]),
+    stage4=dict(modules=1, block="BASIC", blocks=[2, 2, 2, 2], channels=[16, 32, 64, 128]),
+    final_conv_kernel=1)
+
+
+def _hr_module(pl, xs, prefix, blocks, channels):
+    """HighResolutionModule.forward (backbones/hrnet.py:215-232).  BasicBlocks are two GEMM convs (residual + ReLU fused);
+    every fuse sum is built incrementally: down paths add the running sum as the residual of their last 3x3/2 GEMM, up paths
+    run the 1x1 GEMM at low resolution and one nearest-up + add (+ final ReLU) kernel."""
+    nb = len(xs)
+    xs = list(xs)
+    for i in range(nb):
+        for b in range(blocks[i]):
+            p = f"{prefix}.branches.{i}.{b}"
+            y = pl.conv_bn_act(xs[i], p, channels[i], 3, pad=1, act="relu", conv="conv1", bn="bn1")
+            xs[i] = pl.conv_bn_act(y, p, channels[i], 3, pad=1, act="relu", conv="conv2", bn="bn2", residual=xs[i])
+    if nb == 1:
+        return xs
+    dtc = ops.dt_code(pl.dtype)
+    outs = []
+    for i in range(nb):
+        n, h, w_, c = xs[i].shape
+        acc = None
+        for j in range(nb):
+            last = j == nb - 1
+            act = "relu" if last else None
+            if j == i:
+                if acc is None:
+                    acc = xs[j]                      # first term (i == 0): nothing to add yet; nb > 1 so it is never last
+                else:
+                    out = pl.new(n, h, w_, c)
+                    pl.call("segb200_upsample_add", ops._ptr(acc), ops._ptr(xs[j]), ops._ptr(out), n, h, w_, c, acc.stride(2),
+                            xs[j].stride(2), out.stride(2), 0, L.ACT[act], dtc)
+                    acc = out
+            elif j > i:
+                z = pl.conv_bn_act(xs[j], f"{prefix}.fuse_layers.{i}.{j}", channels[i], 1, act=None, conv="0", bn="1")
+                out = pl.new(n, h, w_, c)
+                pl.call("segb200_upsample_add", ops._ptr(acc), ops._ptr(z), ops._ptr(out), n, h, w_, c, acc.stride(2), z.stride(2),
+                        out.stride(2), j - i, L.ACT[act], dtc)
+                acc = out
+            else:
+                t = xs[j]
+                for k in range(i - j):
+                    lastk = k == i - j - 1
+                    co = channels[i] if lastk else channels[j]
+                    t = pl.conv_bn_act(t, f"{prefix}.fuse_layers.{i}.{j}.{k}", co, 3, stride=2, pad=1,
+                                       act=(act if lastk else "relu"), conv="0", bn="1", residual=acc if lastk else None)
+                acc = t
+        outs.append(acc)
+    return outs
+
+
+def build_hrnet(pl, x_shape, holder, nclass, hcfg, out_dtype, want_argmax):
+    """HighResolutionNet.forward (backbones/hrnet.py:429-479) + _HRNetHead (models/hrnet_seg.py:54-63) + final bilinear
+    (align_corners=False, hrnet_seg.py:28).  The three head up-samplings write their channel slices of the cat buffer."""
+    n, _, H, W = x_shape
+    p = "encoder"
+    x = pl.stem_s2d(x_shape, holder, p + ".conv1", p + ".bn1", 64, 3, 1, "relu", 1e-5)
+    x = pl.conv_bn_act(x, p, 64, 3, stride=2, pad=1, act="relu", conv="conv2", bn="bn2")
+    planes = hcfg["stage1"]["channels"][0]
+    inpl = 64
+    for b in range(hcfg["stage1"]["blocks"][0]):
+        x = _bottleneck(pl, x, f"{p}.layer1.{b}", planes, 1, 1, inpl != planes * 4, 1e-5)
+        inpl = planes * 4
+    pre, ys = [inpl], [x]
+    for si, sname in enumerate(("stage2", "stage3", "stage4")):
+        sc = hcfg[sname]
+        cur = sc["channels"]
+        tname = f"{p}.transition{si + 1}"
+        xs = []
+        for i in range(len(cur)):
+            if i < len(pre):
+                xs.append(ys[i] if cur[i] == pre[i] else
+                          pl.conv_bn_act(ys[i], f"{tname}.{i}", cur[i], 3, pad=1, act="relu", conv="0", bn="1"))
+            else:
+                t = ys[-1]
+                for j in range(i + 1 - len(pre)):
+                    co = cur[i] if j == i - len(pre) else pre[-1]
+                    t = pl.conv_bn_act(t, f"{tname}.{i}.{j}", co, 3, stride=2, pad=1, act="relu", conv="0", bn="1")
+                xs.append(t)
+        for m in range(sc["modules"]):
+            xs = _hr_module(pl, xs, f"{p}.{sname}.{m}", sc["blocks"], cur)
+        ys, pre = xs, cur
+    _, h0, w0, c0 = ys[0].shape
+    ctot = sum(t.shape[3] for t in ys)
+    cat = pl.new(n, h0, w0, ctot)
+    # branch 0 is copied by a k=0 "add" against itself? no: bilinear to the same size is the identity -> use the resize kernel
+    off = 0
+    for t in ys:
+        c = t.shape[3]
+        pl.call("segb200_bilinear_nhwc", ops._ptr(t), ops._ptr(cat[..., off:off + c]), n, t.shape[1], t.shape[2], c, t.stride(2),
+                h0, w0, cat.stride(2), 0, ops.dt_code(pl.dtype))
+        off += c
+    hp = "hrnet_head.last_layer"
+    # conv(+bias) -> BN -> ReLU : fold the conv bias into the BN shift
+    sc_, sh_ = pl.bn(hp + ".1", 1e-5)
+    sh_ = sh_ + pl.w(hp + ".0.bias").float() * sc_
+    y = pl.new(n, h0, w0, ctot)
+    pl.conv(cat, fold.pack_conv_weight(pl.w(hp + ".0.weight"), pl.dtype), y, cin=ctot, cout=ctot, scale=sc_, shift=sh_.contiguous(),
+            act="relu")
+    k = hcfg["final_conv_kernel"]
+    cop = fold.round_up(nclass, 8)
+    logits = pl.new(n, h0, w0, cop, ld=32)
+    pl.conv(y, fold.pack_conv_weight(pl.w(hp + ".3.weight"), pl.dtype, cop), logits, cin=ctot, cout=cop, kh=k, kw=k,
+            pad_t=1 if k == 3 else 0, pad_l=1 if k == 3 else 0, shift=fold.pad_vec(pl.w(hp + ".3.bias"), cop))
+    o = torch.empty(n, nclass, H, W, dtype=out_dtype, device=pl.device)
+    am = torch.empty(n, H, W, dtype=torch.uint8, device=pl.device) if want_argmax else None
+    pl.call("segb200_bilinear_nchw_out", ops._ptr(logits), ops._ptr(o), ops._ptr(am), n, h0, w0, nclass, logits.stride(2), H, W, 0,
+            ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
+    pl.keep += [o] + ([am] if am is not None else [])
+    return [(o, am)]
+
+
 def build_ccnet(pl, x_shape, holder, nclass, output_stride, recurrence, out_dtype, want_argmax):
     """CCNet.forward + _RCCAModule.forward (models/ccnet.py:27-40, :73-82).  The backbone's last block and convb write
     their channel slices of one 2560-channel buffer (no torch.cat); the recurrent criss-cross attention shares weights."""
@@ -545,3 +661,31 @@ class CCNetB200(DANetB200):
         outs = build_ccnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.recurrence, self.out_dtype,
                            self.want_argmax)
         return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)
+
+
+class HRNetB200(DANetB200):
+    """``engine(x) -> logits`` (``HighResolutionNet.forward(x)[0]``, models/hrnet_seg.py:23-29); default = hrnet_w18_small_v1."""
+
+    def __init__(self, state_dict, nclass=19, hcfg=None, dtype=torch.float16, out_dtype=None, device="cuda", cuda_graph=True,
+                 want_argmax=False):
+        DeepLabV3PlusB200.__init__(self, state_dict, backbone="hrnet", nclass=nclass, dtype=dtype, out_dtype=out_dtype,
+                                   device=device, cuda_graph=cuda_graph, want_argmax=want_argmax)
+        self.hcfg = hcfg or HRNET_W18_SMALL_V1
+
+    def _build(self, shape, in_dtype):
+        holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
+        pl = Plan(self.sd, self.dtype, self.device)
+        outs = build_hrnet(pl, shape, holder, self.cfg["nclass"], self.hcfg, self.out_dtype, self.want_argmax)
+        graph = None
+        if self.cuda_graph:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                pl.run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                pl.run()
+        return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=graph, logits=None)

@@ -45,6 +45,7 @@ SYMBOLS = {
     "segb200_global_avgpool": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),
     "segb200_adaptive_avgpool": (C.c_int, [vp, vp] + [C.c_int] * 8 + [vp]),
     "segb200_maxpool3x3s2": (C.c_int, [vp, vp] + [C.c_int] * 7 + [vp]),
+    "segb200_upsample_add": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_bilinear_nhwc": (C.c_int, [vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_bilinear_nchw_out": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_pam_attention": (C.c_int, [vp] * 9 + [C.c_int] * 9 + [vp]),

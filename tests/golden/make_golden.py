@@ -27,6 +27,7 @@ MODEL_CASES = {
     "dlv3p_resnet101_65x129": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (1, 3, 65, 129), 4),
     "danet_resnet101_64x96": ("danet_resnet101", "cityscapes_danet_resnet.yaml", (1, 3, 64, 96), 5),
     "ccnet_resnet101_65x97": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (1, 3, 65, 97), 6),
+    "hrnet_w18s_128x192": ("hrnet_w18_small_v1", "cityscapes_hrnet_w18_small_v1.yaml", (2, 3, 128, 192), 7),
 }
 
 
