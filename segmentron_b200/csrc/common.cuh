@@ -54,6 +54,11 @@ template <> struct Half2<true> {
     v = __hmax2(v, __float2bfloat162_rn(0.f));
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  static __device__ __forceinline__ uint32_t min2(uint32_t u, float c) {   // packed min(x, c)
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    v = __hmin2(v, __float2bfloat162_rn(c));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
   static __device__ __forceinline__ float to_f(T v) { return __bfloat162float(v); }
   static __device__ __forceinline__ T from_f(float v) { return __float2bfloat16_rn(v); }
 };
@@ -71,6 +76,11 @@ template <> struct Half2<false> {
   static __device__ __forceinline__ uint32_t relu2(uint32_t u) {
     __half2 v = *reinterpret_cast<__half2*>(&u);
     v = __hmax2(v, __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ uint32_t min2(uint32_t u, float c) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    v = __hmin2(v, __float2half2_rn(c));
     return *reinterpret_cast<uint32_t*>(&v);
   }
   static __device__ __forceinline__ float to_f(T v) { return __half2float(v); }

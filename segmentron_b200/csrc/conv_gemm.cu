@@ -31,7 +31,9 @@ constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
 constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
 constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+// kEpiGroups (template parameter): number of 4-warp epilogue groups.  Two groups put two epilogue warps on every SM
+// sub-partition, which hides the TMEM-load / smem latencies of the epilogue: HBM-bound layers (K <= 512) go from 4.2 to
+// 6.1 TB/s; tensor-bound layers lose 2-6 % to the extra warps, so the host picks per launch.
 
 struct Control {
   uint64_t full[kMaxStages];
@@ -79,8 +81,8 @@ struct ConvGemmParams {
 #define TIMED_WAIT(bar, parity, slot) mbar_wait(bar, parity)
 #endif
 
-template <bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kBF16, int kEpiGroups>
+__global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -104,7 +106,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); mbar_init(&ctl->res_full[i], 1);
+        mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128 * kEpiGroups); mbar_init(&ctl->res_full[i], 1);
       }
       fence_mbar_init();
     }
@@ -175,20 +177,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..5 [, 6..9]) ------------------------------
+    // kEpiGroups groups of 4 warps walk the same (tile, 64-column chunk) sequence; with two groups, group g owns the chunks
+    // whose running index is g (mod 2), plus its own staging buffer, residual buffer, named barrier and bulk-store group.
     using H = Half2<kBF16>;
-    const int et = threadIdx.x - 64;                 // 0..127
+    const int grp = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int bar_id = 1 + grp;
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                   // tile row == TMEM lane
     uint8_t* epi = smem + kStageRegion;              // 2 store-staging buffers
     uint8_t* resb = smem + kStageRegion - kResRegion;  // 2 residual buffers (ring is shortened by the host)
     const bool has_res = p.residual != nullptr;
-    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0, my_ctr = 0; int staged_n_tile = -1;
 
-    // residual prefetch cursor (leader only): runs exactly one chunk ahead of the consumer
+    // residual prefetch cursor (group leader only) over the global (tile, chunk) sequence
     int pf_tile = blockIdx.x, pf_ch = 0;
-    auto pf_issue = [&](uint32_t idx) {
-      // issue the TMA load of the residual chunk (pf_tile, pf_ch) into resb[idx & 1], then advance the cursor
+    auto pf_step = [&](bool load, uint32_t bi) {
+      // optionally issue the TMA load of the residual chunk under the cursor into resb[bi], then advance the cursor
       if (pf_tile >= p.total_tiles) return;
       const int n_tile = pf_tile % p.n_tiles;
       int m_tile = pf_tile / p.n_tiles;
@@ -197,11 +203,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int img = m_tile / p.htiles;
       const int n0 = n_tile * p.bn;
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
-      mbar_expect_tx(&ctl->res_full[idx & 1], (uint32_t)kEpiBufBytes);
-      tma_load_4d(&tmR, &ctl->res_full[idx & 1], resb + (idx & 1) * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      if (load) {
+        mbar_expect_tx(&ctl->res_full[bi], (uint32_t)kEpiBufBytes);
+        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      }
       if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += gridDim.x; }
     };
-    if (has_res && et == 0) pf_issue(0);
+    if (has_res && et == 0) {
+      if (kEpiGroups == 1) pf_step(true, 0);
+      else { if (grp == 1) pf_step(false, 0); pf_step(true, (uint32_t)grp); }
+    }
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -213,17 +224,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       const int nchunks = (nvalid + 63) >> 6;
 
-      named_bar_sync(1, 128);                        // previous tile's readers of scale/shift are done
-      for (int i = et; i < p.bn; i += 128) {
-        const int c = n0 + i;
-        ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
-        ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
+#ifndef SEGB200_EXP
+#define SEGB200_EXP 0
+#endif
+      if (n_tile != staged_n_tile) {                   // (re)stage the folded-BN scale/shift when the N tile changes
+        if (kEpiGroups == 1) named_bar_sync(1, 128); else named_bar_sync(3, 256);   // previous readers are done
+        if (grp == 0) {
+          for (int i = et; i < p.bn; i += 128) {
+            const int c = n0 + i;
+            ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
+            ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
+          }
+        }
+        if (kEpiGroups == 2) named_bar_sync(3, 256);   // publish to the other group (one group: the chunk barrier does)
+        staged_n_tile = n_tile;
       }
 
       if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       if (p.out_f32) {
+        if (grp == 0) {
         // fp32 output (attention energies etc.): one 32-column x 128-row unit (128 B rows) per staging buffer / TMA store
         const int nunits = (nvalid + 31) >> 5;
         for (int un = 0; un < nunits; ++un, ++chunk_ctr) {
@@ -251,32 +272,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_store_commit();
           }
         }
+        }
       } else
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
-        uint8_t* buf = epi + (chunk_ctr & 1) * kEpiBufBytes;
-        const uint8_t* rbuf = resb + (chunk_ctr & 1) * kEpiBufBytes;
+        if (kEpiGroups == 2 && (int)(chunk_ctr & 1) != grp) continue;
+        const uint32_t bi = kEpiGroups == 1 ? (my_ctr & 1) : (uint32_t)grp;   // staging / residual buffer of this chunk
+        uint8_t* buf = epi + bi * kEpiBufBytes;
+        const uint8_t* rbuf = resb + bi * kEpiBufBytes;
         if (et == 0) {
-          tma_store_wait_read<1>();                  // the store that last used `buf` has drained it
-          if (has_res) pf_issue(chunk_ctr + 1);      // resb[(ctr+1)&1] was last read before the previous chunk's barrier
+          if (kEpiGroups == 1) {
+            tma_store_wait_read<1>();                // the store that last used `buf` has drained it
+            if (has_res) pf_step(true, (my_ctr + 1) & 1);   // resb[other] was last read before the previous chunk's barrier
+          } else {
+            tma_store_wait_read<0>();
+          }
         }
-        named_bar_sync(1, 128);                      // (also publishes scale/shift on the first chunk)
-        if (has_res) mbar_wait(&ctl->res_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
+        named_bar_sync(bar_id, 128);                 // (one group: also publishes scale/shift on the first chunk)
+        if (has_res) mbar_wait(&ctl->res_full[bi], kEpiGroups == 1 ? ((my_ctr >> 1) & 1) : (my_ctr & 1));
+        ++my_ctr;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col0 = ch * 64 + half * 32;
           uint32_t v[32];
           tmem_ld_32x32(t_acc + (uint32_t)col0, v);
           tmem_ld_wait();
-          uint32_t packed[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {              // 4 groups of 8 channels = one 16 B vector each
             const int chunk16 = (half * 4 + g) ^ (row & 7);   // 128B swizzle: 16 B chunk c lives at c ^ (row & 7)
+            const int cl = col0 + g * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(&ctl->scale[cl]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&ctl->scale[cl + 4]);
+            const float4 h0 = *reinterpret_cast<const float4*>(&ctl->shift[cl]);
+            const float4 h1 = *reinterpret_cast<const float4*>(&ctl->shift[cl + 4]);
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = col0 + g * 8 + j;
-              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), ctl->scale[c], ctl->shift[c]);
-            }
+            f[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, h0.x); f[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, h0.y);
+            f[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, h0.z); f[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, h0.w);
+            f[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, h1.x); f[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1.y);
+            f[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1.z); f[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1.w);
             if (has_res) {
               const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + chunk16 * 16);
               const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -286,22 +318,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 f[2 * j] += t2.x; f[2 * j + 1] += t2.y;
               }
             }
+            // activation on the PACKED 16-bit pairs: round(max(v,0)) == max(round(v),0) and 6.0 is representable
+            uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              packed[g * 4 + j] = H::pack(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
-            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) =
-                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+            for (int j = 0; j < 4; ++j) {
+              pk[j] = H::pack(f[2 * j], f[2 * j + 1]);
+              if (p.act != ACT_NONE) pk[j] = H::relu2(pk[j]);
+              if (p.act == ACT_RELU6) pk[j] = H::min2(pk[j], 6.f);
+            }
+            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (et == 0) {
           tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
           tma_store_commit();
+          if (kEpiGroups == 2 && has_res) { pf_step(false, 0); pf_step(true, (uint32_t)grp); }   // rbuf is free again
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctl->tmem_empty[acc]);             // 128 arrivals release the accumulator stage
+      mbar_arrive(&ctl->tmem_empty[acc]);             // 128 * kEpiGroups arrivals release the accumulator stage
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();
@@ -468,12 +505,19 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   if (grid > p.total_tiles) grid = p.total_tiles;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(conv_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(conv_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
-  if (a->dtype == DT_BF16)
-    conv_gemm_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-  else
-    conv_gemm_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
+  const bool two_groups = ktot <= 512 && !a->y_f32;
+  if (a->dtype == DT_BF16) {
+    if (two_groups) conv_gemm_kernel<true, 2><<<grid, 320, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    else conv_gemm_kernel<true, 1><<<grid, 192, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  } else {
+    if (two_groups) conv_gemm_kernel<false, 2><<<grid, 320, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    else conv_gemm_kernel<false, 1><<<grid, 192, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  }
   return check_launch("conv_gemm");
 }

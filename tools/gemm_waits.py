@@ -37,8 +37,7 @@ def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 5 * 1e3
     cnt.zero_()
-    if HAS_DBG:
-        L.segb200_debug_set_counters(C.c_void_p(cnt.data_ptr()))
+    if HAS_DBG and L.segb200_debug_set_counters(C.c_void_p(cnt.data_ptr())) == 0:
         ops.conv_gemm(x, wt, y, **kw)
         torch.cuda.synchronize()
         L.segb200_debug_set_counters(None)
@@ -56,8 +55,6 @@ def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
 modes = [int(m) for m in sys.argv[1:]] or [0]
 for mode in modes:
     print(f"##### debug mode {mode}")
-    if HAS_DBG:
-        L.segb200_debug_set_mode(mode)
     run("pw 128->128 @8x513x1025", 8, 513, 1025, 128, 128)
     run("pw 728->728 @8x65x129", 8, 65, 129, 728, 728)
     run("pw 1536->2048", 8, 65, 129, 1536, 2048)
@@ -65,5 +62,3 @@ for mode in modes:
         run("pw 64->128 @8x513x1025", 8, 513, 1025, 64, 128)
         run("pw 728->728 +res", 8, 65, 129, 728, 728, res=True)
         run("c3 32->64 @8x513x1025", 8, 513, 1025, 32, 64, k=3, pad=1)
-if HAS_DBG:
-    L.segb200_debug_set_mode(0)
