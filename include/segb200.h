@@ -33,6 +33,12 @@ enum { SEGB200_ACT_NONE = 0, SEGB200_ACT_RELU = 1, SEGB200_ACT_RELU6 = 2 };
 
 int segb200_version(void);
 const char* segb200_last_error(void);
+/* Tuning knobs (process-global, not thread-safe; defaults are the measured best for one stream):
+ *   "gemm_ring_kb"  : shared-memory ring of segb200_conv_gemm in KB (0 = 192 = whole SM).  A smaller ring leaves room for
+ *                     a kernel of another stream to co-reside on the SM (dual-stream half-batch overlap).
+ *   "dw_ring_slots" : cap on the row-ring depth of segb200_dwconv3x3 (0 = 12). */
+int segb200_set_option(const char* name, int value);
+
 /* Diagnostics (only in a library built with -DSEGB200_DBG; otherwise returns -20): point subsequent
  * segb200_conv_gemm launches at 16 device uint64 counters that accumulate, over all CTAs, the clock cycles each role
  * spent waiting: [0] producer: ring slot free, [1] MMA: accumulator free, [2] MMA: operands landed, [3] epilogue:

@@ -21,6 +21,7 @@ int check_launch(const char* what);
 int encode_map(CUtensorMap* m, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int swizzle_bytes, const char* what);
 int num_sms();
+int set_dw_ring_slots(int n);   // tuning knob (dwconv.cu): 0 = default
 
 enum : int { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };

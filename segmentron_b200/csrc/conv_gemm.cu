@@ -55,6 +55,7 @@ struct ConvGemmParams {
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
   int a_stage_bytes, b_stage_bytes;
+  int ring_bytes;       // A/B ring region (its top 32 KB hold the residual tiles when a residual is fused); default 192 KB
   int act;
   int out_f32;          // 1: y is fp32 (32-column TMA store units), no residual
   const float* scale;
@@ -88,7 +89,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  Control* ctl = reinterpret_cast<Control*>(smem + kCtlOffset);
+  Control* ctl = reinterpret_cast<Control*>(smem + p.ring_bytes + 2 * kEpiBufBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
@@ -186,8 +187,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int bar_id = 1 + grp;
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                   // tile row == TMEM lane
-    uint8_t* epi = smem + kStageRegion;              // 2 store-staging buffers
-    uint8_t* resb = smem + kStageRegion - kResRegion;  // 2 residual buffers (ring is shortened by the host)
+    uint8_t* epi = smem + p.ring_bytes;              // 2 store-staging buffers
+    uint8_t* resb = smem + p.ring_bytes - kResRegion;  // 2 residual buffers (ring is shortened by the host)
     const bool has_res = p.residual != nullptr;
     int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0, my_ctr = 0; int staged_n_tile = -1;
 
@@ -365,6 +366,13 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 
 using namespace segb200;
 
+static int g_ring_kb = 0;
+extern "C" int segb200_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
+  if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
+  return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
+}
+
 static unsigned long long* g_dbg_counters = nullptr;
 extern "C" int segb200_debug_set_counters(void* dev_ptr_16_u64) {
 #ifdef SEGB200_DBG
@@ -431,7 +439,15 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
   p.a_stage_bytes = 128 * bk_bytes;
   p.b_stage_bytes = ((p.bn * bk_bytes) + 1023) & ~1023;
-  p.num_stages = (kStageRegion - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
+  // ring size: 192 KB by default (1 CTA / SM owns the whole shared memory); segb200_set_option("gemm_ring_kb", n) shrinks
+  // it so that a memory-/FMA-bound kernel of another stream (the depthwise conv of the other half batch) can co-reside
+  int ring = g_ring_kb > 0 ? g_ring_kb * 1024 : kStageRegion;
+  const int min_ring = (a->residual ? kResRegion : 0) + 2 * (p.a_stage_bytes + p.b_stage_bytes);
+  if (ring < min_ring) ring = min_ring;
+  if (ring > kStageRegion) ring = kStageRegion;
+  ring = (ring + 1023) & ~1023;
+  p.ring_bytes = ring;
+  p.num_stages = (ring - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
   p.out_f32 = a->y_f32 ? 1 : 0;
@@ -510,14 +526,15 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     cudaFuncSetAttribute(conv_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(conv_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
+  const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2304;
   // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
   const bool two_groups = ktot <= 512 && !a->y_f32;
   if (a->dtype == DT_BF16) {
-    if (two_groups) conv_gemm_kernel<true, 2><<<grid, 320, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-    else conv_gemm_kernel<true, 1><<<grid, 192, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    if (two_groups) conv_gemm_kernel<true, 2><<<grid, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    else conv_gemm_kernel<true, 1><<<grid, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
   } else {
-    if (two_groups) conv_gemm_kernel<false, 2><<<grid, 320, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-    else conv_gemm_kernel<false, 1><<<grid, 192, kSmemBytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    if (two_groups) conv_gemm_kernel<false, 2><<<grid, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    else conv_gemm_kernel<false, 1><<<grid, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
   }
   return check_launch("conv_gemm");
 }

@@ -212,6 +212,9 @@ struct DwRingParams {
   int nslots;
 };
 
+static int g_dw_ring_slots = 0;
+int set_dw_ring_slots(int n) { g_dw_ring_slots = n; return 0; }
+
 constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = t >> 3); +1 producer warp = 256 threads
 constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
 
@@ -407,6 +410,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     rp.slot_bytes = rp.twin * 128;
     rp.nslots = 49152 / rp.slot_bytes;
     if (rp.nslots > 12) rp.nslots = 12;
+    if (g_dw_ring_slots > 0 && rp.nslots > g_dw_ring_slots) rp.nslots = g_dw_ring_slots;
     if (rp.nslots < 3) rp.nslots = 3;
     const int smem = rp.nslots * rp.slot_bytes + 2 * rp.nslots * 8;
     CUtensorMap tmX;

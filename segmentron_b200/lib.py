@@ -37,6 +37,7 @@ class DwArgs(C.Structure):
 SYMBOLS = {
     "segb200_version": (C.c_int, []),
     "segb200_last_error": (C.c_char_p, []),
+    "segb200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "segb200_debug_set_counters": (C.c_int, [vp]),
     "segb200_conv_kblock": (C.c_int, [C.c_int]),
     "segb200_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), vp]),
