@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cudnn-ref", action="store_true", help="also time the oracle port on this GPU (cuDNN bf16 eager)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch timing table to this file")
+    ap.add_argument("--no-graph", action="store_true", help="replay the launch list directly instead of one CUDA graph (for profilers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -169,7 +170,7 @@ def main():
     from oracle import segref as R      # parameter generator + cpu_baseline only; never on the timed GPU path
     P = R.build_params(MODEL, 0)
     eng = DeepLabV3PlusB200(P.state_dict(), backbone="xception65", nclass=NCLASS, eps_encoder=1e-3, dtype=torch.bfloat16,
-                            cuda_graph=True, want_argmax=True)
+                            cuda_graph=not args.no_graph, want_argmax=True)
     g = torch.Generator().manual_seed(1024 + rank)
     x_host = torch.randn(bsz, 3, hh, ww, generator=g).pin_memory()
     x_dev = x_host.cuda(non_blocking=True)
@@ -197,6 +198,11 @@ def main():
 
     # ---- kernel-only throughput: input resident in HBM, one CUDA-graph replay per step -------------------
     graph = st["graph"]
+    if graph is None:                                   # --no-graph: same launch list, launched one by one
+        class _Direct:
+            def replay(self_):
+                plan.run()
+        graph = _Direct()
     for _ in range(args.warmup):
         graph.replay()
     sampler = ClockSampler(local) if rank == 0 else None

@@ -29,8 +29,8 @@ constexpr int kStageRegion = 196608;          // bytes for the A/B ring
 constexpr int kEpiBufBytes = 16384;           // 128 rows x 64 ch x 2 B
 constexpr int kCtlOffset = kStageRegion + 2 * kEpiBufBytes;
 constexpr int kResRegion = 2 * kEpiBufBytes;  // residual tiles live at the top of the ring region when used
-constexpr int kSmemBytes = kCtlOffset + 2304;  // 231680 <= 232448
-constexpr int kMaxStages = 8;
+constexpr int kSmemBytes = kCtlOffset + 2432;  // 231680 <= 232448
+constexpr int kMaxStages = 16;
 // kEpiGroups (template parameter): number of 4-warp epilogue groups.  Two groups put two epilogue warps on every SM
 // sub-partition, which hides the TMEM-load / smem latencies of the epilogue: HBM-bound layers (K <= 512) go from 4.2 to
 // 6.1 TB/s; tensor-bound layers lose 2-6 % to the extra warps, so the host picks per launch.
@@ -41,12 +41,13 @@ struct Control {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full[2];
+  uint64_t b_full;      // weights resident in smem (B-stationary mode)
   uint32_t tmem_base;
   uint32_t pad[3];
   float scale[256];
   float shift[256];
 };
-static_assert(sizeof(Control) <= 2304, "control block too large");
+static_assert(sizeof(Control) <= 2432, "control block too large");
 
 struct ConvGemmParams {
   int n_img, ho, wo;
@@ -55,6 +56,7 @@ struct ConvGemmParams {
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
   int a_stage_bytes, b_stage_bytes;
+  int b_resident;       // 1: all K blocks of the (single) N tile stay in smem for the whole kernel; the ring holds A only
   int ring_bytes;       // A/B ring region (its top 32 KB hold the residual tiles when a residual is fused); default 192 KB
   int act;
   int out_f32;          // 1: y is fp32 (32-column TMA store units), no residual
@@ -92,7 +94,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   Control* ctl = reinterpret_cast<Control*>(smem + p.ring_bytes + 2 * kEpiBufBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
   const int num_kb = p.ntaps * p.cblocks;
   const int bk_elems = p.bk_bytes >> 1;
 
@@ -109,6 +111,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int i = 0; i < 2; ++i) {
         mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128 * kEpiGroups); mbar_init(&ctl->res_full[i], 1);
       }
+      mbar_init(&ctl->b_full, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -125,7 +128,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       const CUtensorMap* amaps[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(128 * p.bk_bytes + p.bn * p.bk_bytes);
+      const uint32_t tx = (uint32_t)(128 * p.bk_bytes + (p.b_resident ? 0 : p.bn * p.bk_bytes));
+      if (p.b_resident) {          // weights: loaded once, [num_kb] tiles of {bk, bn} behind the A ring
+        mbar_expect_tx(&ctl->b_full, (uint32_t)(num_kb * p.bn * p.bk_bytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(&tmB, &ctl->b_full, smem + p.num_stages * stage_bytes + kb * p.b_stage_bytes, kb * bk_elems, 0);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int m_tile = tile / p.n_tiles;
@@ -142,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_expect_tx(&ctl->full[stage], tx);
           uint8_t* sa = smem + stage * stage_bytes;
           tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img);
-          tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, kb * bk_elems, n0);
+          if (!p.b_resident) tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, kb * bk_elems, n0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -152,6 +160,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       const int kmma = p.bk_bytes >> 5;          // K=16 elements (32 B) per instruction
+      const uint32_t b_res = smem_u32(smem + p.num_stages * stage_bytes);
+      if (p.b_resident) mbar_wait(&ctl->b_full, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int n0 = n_tile * p.bn;
@@ -166,7 +176,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
-          const uint64_t bdesc = make_kmajor_desc(sa + (uint32_t)p.a_stage_bytes, (uint32_t)p.bk_bytes);
+          const uint64_t bdesc = make_kmajor_desc(p.b_resident ? b_res + (uint32_t)(kb * p.b_stage_bytes) : sa + (uint32_t)p.a_stage_bytes,
+                                                  (uint32_t)p.bk_bytes);
           for (int k = 0; k < kmma; ++k)
             umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           umma_commit(&ctl->empty[stage]);           // frees the smem slot when these MMAs retire
@@ -367,8 +378,10 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 using namespace segb200;
 
 static int g_ring_kb = 0;
+static int g_no_b_resident = 0;
 extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
+  if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -440,14 +453,21 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.a_stage_bytes = 128 * bk_bytes;
   p.b_stage_bytes = ((p.bn * bk_bytes) + 1023) & ~1023;
   // ring size: 192 KB by default (1 CTA / SM owns the whole shared memory); segb200_set_option("gemm_ring_kb", n) shrinks
-  // it so that a memory-/FMA-bound kernel of another stream (the depthwise conv of the other half batch) can co-reside
+  // it so that a memory-/FMA-bound kernel of another stream can co-reside (measured: not worth it)
   int ring = g_ring_kb > 0 ? g_ring_kb * 1024 : kStageRegion;
   const int min_ring = (a->residual ? kResRegion : 0) + 2 * (p.a_stage_bytes + p.b_stage_bytes);
   if (ring < min_ring) ring = min_ring;
   if (ring > kStageRegion) ring = kStageRegion;
   ring = (ring + 1023) & ~1023;
   p.ring_bytes = ring;
-  p.num_stages = (ring - (a->residual ? kResRegion : 0)) / (p.a_stage_bytes + p.b_stage_bytes);
+  // B-stationary: a single N tile whose complete weight matrix is small stays in smem; the ring then streams A only,
+  // halving the TMA instruction count of the small-K-block layers (3x3 on 32 channels, space-to-depth stems)
+  const int nkb = ntaps * cblocks;
+  const long long b_total = (long long)nkb * p.b_stage_bytes;
+  const int avail = ring - (a->residual ? kResRegion : 0);
+  p.b_resident = (p.n_tiles == 1 && b_total <= 72 * 1024 && avail - b_total >= 4 * p.a_stage_bytes && !g_no_b_resident) ? 1 : 0;
+  if (p.b_resident) p.num_stages = (int)((avail - b_total) / p.a_stage_bytes);
+  else p.num_stages = avail / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
   p.out_f32 = a->y_f32 ? 1 : 0;
@@ -526,7 +546,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     cudaFuncSetAttribute(conv_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(conv_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
-  const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2304;
+  const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2432;
   // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
   const bool two_groups = ktot <= 512 && !a->y_f32;
   if (a->dtype == DT_BF16) {

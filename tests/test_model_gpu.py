@@ -97,3 +97,20 @@ def test_engine_vs_oracle_larger(dtype, tol):
     assert torch.equal(y_a, y_b), "graph replay is not deterministic"
     eng2 = _engine(model, P, dtype, cuda_graph=False)
     assert torch.equal(eng2(x.cuda()), y_a), "graph replay differs from direct launch"
+
+
+def test_full_size_batch_invariance_and_determinism():
+    """Size-independent properties at the BASELINE resolution (1025x2049): every image of a batch is computed exactly as
+    it is alone (tiles of the flattened-pixel GEMMs cross image boundaries, the per-element arithmetic must not), replays
+    are bit-reproducible, outputs are finite, and the fused argmax equals torch.argmax of the logits."""
+    model = "deeplabv3plus_xception65"
+    P = R.build_params(model, 11)
+    x = torch.randn(2, 3, 1025, 2049, generator=torch.Generator().manual_seed(12)).cuda()
+    eng = _engine(model, P, torch.bfloat16, cuda_graph=True, want_argmax=True)
+    y2 = eng(x).clone()
+    am2 = eng.argmax(x).clone()
+    assert torch.isfinite(y2.float()).all()
+    assert torch.equal(eng(x), y2)
+    assert torch.equal(am2.long(), y2.float().argmax(1))
+    y1 = eng(x[1:2].contiguous()).clone()
+    assert torch.equal(y1[0], y2[1]), float((y1[0].float() - y2[1].float()).abs().max())
