@@ -21,6 +21,7 @@
 #include "../../include/segb200.h"
 
 #include <mutex>
+#include <stddef.h>
 #include <stdio.h>
 
 namespace segb200 {
@@ -42,12 +43,14 @@ struct Control {
   uint64_t tmem_empty[2];
   uint64_t res_full[2];
   uint64_t b_full;      // weights resident in smem (B-stationary mode)
+  uint64_t pad64;       // keeps scale/shift 16-byte aligned (float4 loads)
   uint32_t tmem_base;
   uint32_t pad[3];
   float scale[256];
   float shift[256];
 };
 static_assert(sizeof(Control) <= 2432, "control block too large");
+static_assert(offsetof(Control, scale) % 16 == 0 && offsetof(Control, shift) % 16 == 0, "scale/shift must be 16 B aligned");
 
 struct ConvGemmParams {
   int n_img, ho, wo;
