@@ -180,6 +180,101 @@ int segb200_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_dtype, int n
  * K-major [C][N] operand of CAM's Gram matrix. */
 int segb200_nhwc_to_cn(const void* x, void* y, int n, int c, int hw, int x_ld, int pitch, int dtype, void* stream);
 
+/* ==========================================================================================
+ * TRAINING PATH: the kernels behind `loss.backward()` of tools/train.py:135-147 for the
+ * conv / BatchNorm / pooling / interpolate / cross-entropy graph of DeepLabv3+.  Activations and activation gradients are
+ * NHWC 16-bit; parameter gradients and BatchNorm statistics are fp32.
+ * ========================================================================================== */
+
+/* Convolution weight gradient on tcgen05 tensor cores:  dw[cout][kh*kw][cin] += sum_pixels dy[p][cout] * x[p + tap][cin]
+ * (fp32, ACCUMULATED with red.global.add -- zero dw first for a plain gradient).  Same geometry arguments as
+ * segb200_conv_gemm (x is the conv INPUT, dy the gradient of its OUTPUT [n][ho][wo][dy_ld]).  Replaces the
+ * cudnnConvolutionBackwardFilter call autograd makes for every nn.Conv2d (groups = 1) of the model.
+ * The [cout][tap][cin] layout is the `channels_last` physical layout of a torch OIHW weight gradient. */
+typedef struct segb200_wgrad_args {
+  const void* x;        /* [n][h][w][x_ld] */
+  const void* dy;       /* [n][ho][wo][dy_ld] */
+  float* dw;            /* [cout][kh*kw][cin] fp32, accumulated */
+  int32_t n, h, w, cin, x_ld;            /* cin, x_ld, dy_ld multiples of 8; cout any >= 1 */
+  int32_t ho, wo, cout, dy_ld;
+  int32_t kh, kw, stride, dilation, pad_t, pad_l;
+  int32_t dtype;        /* SEGB200_BF16 | SEGB200_F16 */
+  int32_t max_ctas;     /* 0 = number of SMs */
+  int32_t splits;       /* pixel splits per (cout tile, cin tile, tap); 0 = automatic (whole waves) */
+} segb200_wgrad_args;
+int segb200_conv_wgrad(const segb200_wgrad_args* a, void* stream);
+int segb200_wgrad_debug_swap(int v);   /* diagnostics only: exchange the LBO/SBO descriptor fields */
+
+/* The data gradient of a conv needs no entry point of its own: it is segb200_conv_gemm on dy with the weights packed
+ * transposed and tap-flipped ([cin][kh*kw reversed][cout_pad]); stride-2 convs go through segb200_stride2_place. */
+
+/* ---- two-level, fixed-order column reductions (bit-reproducible; no float atomics) ----
+ * A reduction over `rows` pixels of `c` channels writes partial[(slab*K + k)*c + ch]; segb200_reduce_slabs() returns the
+ * slab count the kernels will use (size the partial buffer with it). */
+int segb200_reduce_slabs(long long rows, int c, int max_slabs);
+int segb200_reduce_partials(const float* partial, int slabs, int k, int c, float* out, long long stride_k,
+                            long long stride_c, int accumulate, float scale, void* stream);
+
+/* Train-mode BatchNorm2d (F.batch_norm(training=True), modules/batch_norm.py / torch):
+ *   bn_stats    : partial[(slab*2 + {0,1})*c + ch] = per-slab sum / sum of squares of x [rows][x_ld]
+ *   bn_finalize : biased batch variance, mean, invstd; scale = gamma*invstd, shift = beta - mean*scale; running stats
+ *                 updated with `momentum` (running_var with the unbiased variance).  `count` = rows (x world size when
+ *                 the partial sums were all-reduced for SyncBatchNorm, tools/train.py:73-79).
+ *   bn_apply    : z = act(y*scale + shift + residual) * nc_scale[n][c]   (residual: resnet.py:78-79; nc_scale: the
+ *                 Dropout2d channel mask of module.py:60; all three optional) */
+int segb200_bn_stats(const void* x, long long rows, int c, int x_ld, int dtype, float* partial, int max_slabs, void* stream);
+int segb200_bn_finalize(const float* partial, int slabs, int c, double count, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float momentum, float eps, float* mean, float* invstd,
+                        float* scale, float* shift, void* stream);
+int segb200_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, const float* nc_scale,
+                     void* z, long long rows, long long rows_per_img, int c, int y_ld, int res_ld, int z_ld, int act,
+                     int dtype, void* stream);
+/* Backward of the same unit.  g = dz * nc_scale * act'(z);
+ *   bn_bwd_reduce   : per-slab sum(g), sum(g*xhat)         xhat = (y - mean)*invstd
+ *   bn_bwd_finalize : sums[2][c]; dgamma += sum(g*xhat), dbeta += sum(g)
+ *   bn_bwd_apply    : dy = scale*(g - sums[0]/count - xhat*sums[1]/count);  dres (+)= g   (sums == NULL: dy = g*scale) */
+int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                          const float* nc_scale, float* partial, long long rows, long long rows_per_img, int c, int dz_ld,
+                          int z_ld, int y_ld, int act, int dtype, int max_slabs, void* stream);
+int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, float* sums, float* dgamma, float* dbeta, void* stream);
+int segb200_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                         const float* scale, const float* sums, double count, const float* nc_scale, void* dy, void* dres,
+                         int dres_accumulate, long long rows, long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld,
+                         int dy_ld, int dres_ld, int act, int dtype, void* stream);
+
+/* MaxPool2d(3,2,1) backward (first-maximum rule of torch), gather form: dx [n][h][w][dx_ld]. */
+int segb200_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n, int h, int w, int c, int x_ld, int dy_ld,
+                             int dx_ld, int dtype, void* stream);
+/* Backward of segb200_bilinear_nhwc (gather form): dx [n][hi][wi] (+)= gscale * W^T dy [n][ho][wo]; gscale = optional
+ * DEVICE pointer to one float (the 1/valid-pixel-count of the loss). */
+int segb200_bilinear_nhwc_bwd(const void* dy, void* dx, int n, int hi, int wi, int c, int dx_ld, int ho, int wo, int dy_ld,
+                              int align_corners, int accumulate, const float* gscale, int dtype, void* stream);
+/* Fused final up-sampling + nn.CrossEntropyLoss(ignore_index) (models/deeplabv3_plus.py:39 + solver/loss.py:16-46): the
+ * [n][nclass][ho][wo] logits tensor is never materialised.  target: int64 [n][ho][wo].  Writes
+ *   dfull [n][ho][wo][d_ld] = softmax - onehot (0 at ignored pixels), out3 = {mean loss, 1/valid, valid};
+ * partial: workspace of 2*segb200_upsample_ce_blocks() floats. */
+int segb200_upsample_ce_blocks(int n, int ho, int wo);
+int segb200_upsample_ce(const void* logits, const long long* target, void* dfull, float* partial, float* out3, int n,
+                        int hi, int wi, int nclass, int x_ld, int ho, int wo, int d_ld, int align_corners,
+                        int ignore_index, int dtype, void* stream);
+/* Depthwise 3x3 weight gradient (stride 1, padding = dilation): partial[(slab*9 + tap)*c + ch]; finish with
+ * segb200_reduce_partials(k = 9).  The depthwise DATA gradient is segb200_dwconv3x3 with tap-reversed weights. */
+int segb200_dw_wgrad(const void* x, const void* dy, float* partial, int n, int h, int w, int c, int x_ld, int dy_ld,
+                     int dilation, int pre_relu, int dtype, int max_slabs, void* stream);
+/* y[b][p][:] (+)= v[b][:] * scale -- gradient of the global average pool / broadcast of a pooled feature. */
+int segb200_nc_broadcast(const void* v, void* y, int n, long long hw, int c, int v_ld, int y_ld, float scale,
+                         int accumulate, int dtype, void* stream);
+/* Stride-2 data gradients.  t [n][ceil(h/2)][ceil(w/2)], z [n][h][w].  mode 0: z = zero-inserted t (then a stride-1
+ * segb200_conv_gemm with flipped weights is the 3x3/2 data gradient); mode 1: z[2i][2j] += t[i][j] (1x1/2). */
+int segb200_stride2_place(const void* t, void* z, int n, int h, int w, int c, int t_ld, int z_ld, int mode, int dtype,
+                          void* stream);
+/* Weight packing by index table: dst[i] = index[i] >= 0 ? (dst_dtype) src[index[i]] : 0; and its adjoint. */
+int segb200_gather_cast(const float* src, const int* index, void* dst, long long n, int dst_dtype, void* stream);
+int segb200_scatter_add(const float* src, const int* index, float* dst, long long n, void* stream);
+/* torch.optim.SGD(momentum, weight_decay) step on flat fp32 buffers (solver/optimizer.py:50-51). */
+int segb200_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float weight_decay,
+                     float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

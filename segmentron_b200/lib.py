@@ -33,6 +33,18 @@ class DwArgs(C.Structure):
                 ("pre_relu", i32), ("act", i32), ("dtype", i32)]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("x", vp), ("dy", vp), ("dw", vp),
+                ("n", i32), ("h", i32), ("w", i32), ("cin", i32), ("x_ld", i32),
+                ("ho", i32), ("wo", i32), ("cout", i32), ("dy_ld", i32),
+                ("kh", i32), ("kw", i32), ("stride", i32), ("dilation", i32), ("pad_t", i32), ("pad_l", i32),
+                ("dtype", i32), ("max_ctas", i32), ("splits", i32)]
+
+
+ll = C.c_longlong
+ci = C.c_int
+cf = C.c_float
+
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
 SYMBOLS = {
     "segb200_version": (C.c_int, []),
@@ -56,6 +68,27 @@ SYMBOLS = {
     "segb200_nhwc_to_cn": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),
     "segb200_nchw_to_nhwc": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
     "segb200_nhwc_to_nchw": (C.c_int, [vp, C.c_int, vp, C.c_int] + [C.c_int] * 5 + [vp]),
+    # ---- training path ----
+    "segb200_conv_wgrad": (ci, [C.POINTER(WgradArgs), vp]),
+    "segb200_wgrad_debug_swap": (ci, [ci]),
+    "segb200_reduce_slabs": (ci, [ll, ci, ci]),
+    "segb200_reduce_partials": (ci, [vp, ci, ci, ci, vp, ll, ll, ci, cf, vp]),
+    "segb200_bn_stats": (ci, [vp, ll, ci, ci, ci, vp, ci, vp]),
+    "segb200_bn_finalize": (ci, [vp, ci, ci, C.c_double, vp, vp, vp, vp, cf, cf, vp, vp, vp, vp, vp]),
+    "segb200_bn_apply": (ci, [vp, vp, vp, vp, vp, vp, ll, ll, ci, ci, ci, ci, ci, ci, vp]),
+    "segb200_bn_bwd_reduce": (ci, [vp, vp, vp, vp, vp, vp, vp, ll, ll, ci, ci, ci, ci, ci, ci, ci, vp]),
+    "segb200_bn_bwd_finalize": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+    "segb200_bn_bwd_apply": (ci, [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, ci, ll, ll] + [ci] * 8 + [vp]),
+    "segb200_maxpool3x3s2_bwd": (ci, [vp, vp, vp] + [ci] * 8 + [vp]),
+    "segb200_bilinear_nhwc_bwd": (ci, [vp, vp] + [ci] * 10 + [vp, ci, vp]),
+    "segb200_upsample_ce_blocks": (ci, [ci, ci, ci]),
+    "segb200_upsample_ce": (ci, [vp, vp, vp, vp, vp] + [ci] * 11 + [vp]),
+    "segb200_dw_wgrad": (ci, [vp, vp, vp] + [ci] * 10 + [vp]),
+    "segb200_nc_broadcast": (ci, [vp, vp, ci, ll, ci, ci, ci, cf, ci, ci, vp]),
+    "segb200_stride2_place": (ci, [vp, vp] + [ci] * 8 + [vp]),
+    "segb200_gather_cast": (ci, [vp, vp, vp, ll, ci, vp]),
+    "segb200_scatter_add": (ci, [vp, vp, vp, ll, vp]),
+    "segb200_sgd_step": (ci, [vp, vp, vp, ll, cf, cf, cf, cf, vp]),
 }
 
 _lib = None
