@@ -47,6 +47,12 @@ class Params:
         self.g.manual_seed(seed)
         self.device, self.dtype = device, dtype
         self.frozen = tensors is not None
+        # training-mode switches (tools/train.py:133 `self.model.train()`): batch-statistics BatchNorm with running-stat
+        # updates, Dropout2d active.  ``dropout_masks[name]`` = explicit [N,C,1,1] keep-mask already scaled by 1/(1-p)
+        # (so that the engine under test and the oracle can share one mask); absent -> F.dropout2d with the torch RNG.
+        self.training = False
+        self.bn_momentum = 0.1
+        self.dropout_masks: Dict[str, torch.Tensor] = {}
 
     # -- creation helpers (always drawn on CPU in fp32, then moved) ----------------------
     def _new(self, name, make):
@@ -119,7 +125,23 @@ def batchnorm(P: Params, x, name, eps=1e-5):
     m = P.vec(name + ".running_mean", c, "mean")
     v = P.vec(name + ".running_var", c, "var")
     P.count(name + ".num_batches_tracked")
+    if P.training:
+        # F.batch_norm(training=True): biased batch variance for the output, running stats updated in place with
+        # momentum (running_var with the unbiased variance) -- SURVEY.md appendix D, torch semantics
+        if name + ".num_batches_tracked" in P.t:
+            P.t[name + ".num_batches_tracked"] = P.t[name + ".num_batches_tracked"] + 1
+        return F.batch_norm(x, m, v, g, b, True, P.bn_momentum, eps)
     return F.batch_norm(x, m, v, g, b, False, 0.0, eps)
+
+
+def dropout2d(P: Params, x, name, p=0.1):
+    """nn.Dropout2d(p): identity in eval; in training zeroes whole (sample, channel) planes and scales by 1/(1-p)
+    (modules/module.py:60,75)."""
+    if not P.training:
+        return x
+    if name in P.dropout_masks:
+        return x * P.dropout_masks[name].to(device=x.device, dtype=x.dtype)
+    return F.dropout2d(x, p, True)
 
 
 def conv_bn_act(P, x, prefix, cout, k, stride=1, padding=0, dilation=1, groups=1, act="relu",
@@ -427,7 +449,8 @@ def aspp(P, x, prefix="head.aspp", out_ch=256, output_stride=16):
     x2 = separable_conv2d(P, x, prefix + ".aspp2", out_ch, 1, d[1], relu_first=False)
     x3 = separable_conv2d(P, x, prefix + ".aspp3", out_ch, 1, d[2], relu_first=False)
     y = torch.cat((pool, x0, x1, x2, x3), dim=1)
-    return conv_bn_act(P, y, prefix, out_ch, 1)                                       # :72-74
+    y = conv_bn_act(P, y, prefix, out_ch, 1)                                          # :72-74
+    return dropout2d(P, y, prefix + ".dropout", 0.1)                                  # :75 (identity in eval)
 
 
 def deeplab_head(P, c4, c1, nclass, prefix="head", use_aspp=True, use_decoder=True,
@@ -603,6 +626,38 @@ def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
             deeplabv3plus(P, torch.zeros(1, 3, 33, 33), nclass=nclass, **MODELS[model])
     P.frozen = True
     return P
+
+
+def trainable(P: Params):
+    """Names of the tensors an optimizer would see (everything except BatchNorm running statistics and the unused
+    ImageNet classifier)."""
+    return [k for k in P.t if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))
+            and ".fc." not in k]
+
+
+def loss_and_grads(model: str, P: Params, x, target, nclass: int = 19, ignore_index: int = -1, **kw):
+    """One training forward/backward of tools/train.py:135-147 for a DeepLabv3+ model: train-mode forward,
+    nn.CrossEntropyLoss(ignore_index=-1) on the full-resolution logits (solver/loss.py:16-46, aux off), backward.
+    -> (loss, {name: grad}, full-res logits, low-res logits).  P must hold fp32 CPU (or same-device) tensors; BatchNorm
+    running statistics in P are updated in place like the reference's buffers."""
+    assert P.frozen, "build the parameters first"
+    names = trainable(P)
+    leaves = {}
+    for k in names:
+        P.t[k] = P.t[k].detach().clone().requires_grad_(True)
+        leaves[k] = P.t[k]
+    was = P.training
+    P.training = True
+    try:
+        out, low = deeplabv3plus(P, x, nclass=nclass, return_lowres=True, **MODELS[model], **kw)
+        loss = F.cross_entropy(out.float(), target, ignore_index=ignore_index)
+        loss.backward()
+    finally:
+        P.training = was
+    grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    for k in names:
+        P.t[k] = P.t[k].detach()
+    return loss.detach(), grads, out.detach(), low.detach()
 
 
 def forward(model: str, P: Params, x, nclass: int = 19, **kw):

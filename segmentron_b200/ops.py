@@ -25,9 +25,15 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Plan DRY RUN (tests only): lets a launch list be BUILT over CPU tensors so that its host logic (buffer routing,
+# accumulate flags, index tables) can be checked without a GPU.  Nothing can be launched in that mode -- the kernels
+# would fault on host pointers -- and no compute path ever sets it.
+_PLAN_DRY_RUN = False
+
+
 def _nhwc(t, name):
     """-> (n, h, w, c, ld) of an NHWC tensor / channel-slice view; validates the layout."""
-    if not t.is_cuda:
+    if not t.is_cuda and not _PLAN_DRY_RUN:
         raise RuntimeError(f"segb200: {name} must be a CUDA tensor (no CPU implementation)")
     if t.dim() != 4:
         raise RuntimeError(f"segb200: {name} must be [N,H,W,C]")

@@ -1,0 +1,796 @@
+"""Training engine for DeepLabv3+ (ResNet backbones): one iteration of the reference's training loop
+(tools/train.py:135-147 -- forward, CrossEntropy(ignore_index=-1), backward, SGD step; DDP gradient all-reduce) as a
+STATIC launch list over the C-ABI kernels, SURVEY.md 8a rows a15/a16.
+
+Design (B200-first, not an autograd port):
+  * the whole step is planned once per input shape: every buffer (activations, gradients, BatchNorm statistics) is
+    allocated up front, every kernel call is pre-marshalled; a step = replaying ~1.5k launches (optionally one CUDA graph);
+  * parameters live in ONE flat fp32 master buffer (+ flat gradient and momentum buffers); conv weights are stored
+    [Cout][kh*kw][Cin] (the channels_last physical layout of an OIHW tensor) so that the tcgen05 weight-gradient kernel
+    accumulates straight into the gradient buffer, SGD is two launches, and the DDP all-reduce works on contiguous
+    buckets of the same buffer, launched asynchronously while backward is still running;
+  * per step the 16-bit GEMM operands (forward packing and the transposed/tap-flipped data-gradient packing) are
+    regenerated from the masters by one index-table gather;
+  * conv -> raw 16-bit output; BatchNorm batch statistics by a fixed-order two-level reduction; normalise + residual +
+    ReLU (+ Dropout2d mask) in one pass.  Backward per unit: BN/ReLU backward (2 passes), weight gradient on the tensor
+    cores straight from the NHWC activations (MN-major UMMA operands), data gradient = the forward implicit-GEMM kernel
+    with transposed weights, accumulating into the consumer-shared gradient through its residual operand;
+  * torch.cat never exists: branch outputs are channel slices of one buffer, and so are their gradients;
+  * the [N,19,H,W] logits are never materialised: up-sampling + softmax cross-entropy + its gradient are one kernel.
+
+``state_dict`` in / out uses the reference's parameter names (a reference checkpoint trains unchanged).
+There is no CPU or PyTorch fallback: everything below calls the C ABI (lib.py) and raises RuntimeError otherwise.
+"""
+import ctypes as C
+
+import torch
+
+from . import fold, lib as L, ops
+from .ops import _ptr
+
+
+class Step:
+    __slots__ = ("kind", "call", "info")
+
+    def __init__(self, kind, call, info):
+        self.kind, self.call, self.info = kind, call, info
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameters: flat fp32 master / gradient / momentum buffers + packed 16-bit operands
+# ------------------------------------------------------------------------------------------------------------
+def _kind(name, t):
+    if t.dim() == 4:
+        return "dw" if (t.shape[1] == 1 and t.shape[0] > 1 and "depthwise" in name) else "conv"
+    return "vec"
+
+
+class ParamStore:
+    SKIP = ("running_mean", "running_var", "num_batches_tracked")
+
+    def __init__(self, state_dict, device, dtype, stem=None):
+        self.device, self.dtype = device, dtype
+        names = [k for k in state_dict if not k.endswith(self.SKIP) and ".fc." not in k]
+        names.sort(key=lambda k: 0 if k.startswith("encoder.") else 1)       # stable: encoder group first
+        self.meta, off = {}, 0
+        for k in names:
+            t = state_dict[k]
+            self.meta[k] = dict(off=off, shape=tuple(t.shape), kind=_kind(k, t), numel=t.numel())
+            off += fold.round_up(t.numel(), 64)
+            if k.startswith("encoder."):
+                self.n_encoder = off
+        self.total = off
+        self.master = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.mom = torch.zeros(off, dtype=torch.float32, device=device)
+        for k in names:
+            self.view(self.master, k).copy_(self.to_internal(k, state_dict[k].detach().float()))
+        # BatchNorm running statistics (not trained): one flat buffer
+        self.stat_meta, soff = {}, 0
+        for k in state_dict:
+            if k.endswith(("running_mean", "running_var")):
+                self.stat_meta[k] = (soff, state_dict[k].numel())
+                soff += fold.round_up(state_dict[k].numel(), 64)
+        self.stats = torch.zeros(max(soff, 64), dtype=torch.float32, device=device)
+        for k, (o, n) in self.stat_meta.items():
+            self.stats[o:o + n].copy_(state_dict[k].detach().float())
+        self.extra = {k: v for k, v in state_dict.items() if k.endswith("num_batches_tracked") or ".fc." in k}
+        # ---- packed operands: index tables (built on the CPU, int64 -> int32) ----
+        self.stem = stem
+        idx16, idx32, self.pk = [], [], {}
+        n16 = n32 = 0
+        for k in names:
+            m = self.meta[k]
+            if m["kind"] == "conv":
+                co, ci, kh, kw = m["shape"]
+                T = kh * kw
+                base = torch.arange(co * T * ci, dtype=torch.int64).reshape(co, T, ci) + m["off"]
+                if k == stem:
+                    fwd, T2, pad2, scat = _stem_indices(base.reshape(co, kh, kw, ci), pad=(kh - 1) // 2)
+                    self.pk[k] = dict(fwd=(n16, tuple(fwd.shape)), T=T2, pad=pad2, scatter=scat.to(torch.int32).to(device))
+                    idx16.append(fwd.flatten()); n16 += fold.round_up(fwd.numel(), 64)
+                    idx16.append(torch.full((fold.round_up(fwd.numel(), 64) - fwd.numel(),), -1, dtype=torch.int64))
+                    continue
+                cip = fold.round_up(ci, fold.conv_kblock(ci))
+                cop = fold.round_up(co, 8)
+                fwd = torch.full((cop, T, cip), -1, dtype=torch.int64)
+                fwd[:co, :, :ci] = base
+                ci8 = fold.round_up(ci, 8)
+                cok = fold.round_up(cop, fold.conv_kblock(cop))
+                dg = torch.full((ci8, T, cok), -1, dtype=torch.int64)
+                dg[:ci, :, :co] = base.permute(2, 1, 0).flip(1)
+                ent = {}
+                for nm, tab in (("fwd", fwd), ("dgrad", dg)):
+                    ent[nm] = (n16, tuple(tab.shape))
+                    pad = fold.round_up(tab.numel(), 64) - tab.numel()
+                    idx16 += [tab.flatten(), torch.full((pad,), -1, dtype=torch.int64)]
+                    n16 += tab.numel() + pad
+                self.pk[k] = ent
+            elif m["kind"] == "dw":
+                c = m["shape"][0]
+                base = torch.arange(c * 9, dtype=torch.int64).reshape(c, 9) + m["off"]
+                ent = {}
+                for nm, tab in (("fwd", base.t().contiguous()), ("flip", base.flip(1).t().contiguous())):
+                    ent[nm] = (n32, (9, c))
+                    pad = fold.round_up(tab.numel(), 64) - tab.numel()
+                    idx32 += [tab.flatten(), torch.full((pad,), -1, dtype=torch.int64)]
+                    n32 += tab.numel() + pad
+                self.pk[k] = ent
+        assert self.total < 2 ** 31 and n16 < 2 ** 31
+        self.idx16 = torch.cat(idx16).to(torch.int32).to(device) if idx16 else None
+        self.idx32 = torch.cat(idx32).to(torch.int32).to(device) if idx32 else None
+        self.w16 = torch.zeros(max(n16, 64), dtype=dtype, device=device)
+        self.w32 = torch.zeros(max(n32, 64), dtype=torch.float32, device=device)
+
+    # ---- layout ----
+    def to_internal(self, k, t):
+        return t.permute(0, 2, 3, 1).reshape(-1) if self.meta[k]["kind"] == "conv" else t.reshape(-1)
+
+    def from_internal(self, k, flat):
+        m = self.meta[k]
+        if m["kind"] == "conv":
+            co, ci, kh, kw = m["shape"]
+            return flat.reshape(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+        return flat.reshape(m["shape"]).clone()
+
+    def view(self, buf, k):
+        m = self.meta[k]
+        return buf[m["off"]:m["off"] + m["numel"]]
+
+    def packed(self, k, which):
+        off, shape = self.pk[k][which]
+        buf = self.w32 if self.meta[k]["kind"] == "dw" else self.w16
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[off:off + n].view(shape)
+
+    def stat(self, k):
+        o, n = self.stat_meta[k]
+        return self.stats[o:o + n]
+
+    def state_dict(self):
+        out = {k: self.from_internal(k, self.view(self.master, k)) for k in self.meta}
+        out.update({k: self.stat(k).clone() for k in self.stat_meta})
+        out.update(self.extra)
+        return out
+
+    def grads(self):
+        """{reference parameter name: gradient in the reference (OIHW) layout} -- a copy, for inspection / tests."""
+        return {k: self.from_internal(k, self.view(self.grad, k)) for k in self.meta}
+
+
+def _stem_indices(base, pad):
+    """Index form of fold.pack_stem_s2d for a stride-2 kxk stem on Cin<=4 channels.  base: int64 [co][k][k][ci] of master
+    offsets.  -> (forward table [co][T*T][16], T, pad2, scatter table [co][T*T][64] for the s2d-space weight gradient)."""
+    co, k, _, ci = base.shape
+    offs = [ky - pad for ky in range(k)]
+    a = [o // 2 for o in offs]
+    par = [o % 2 for o in offs]
+    a_min, a_max = min(a), max(a)
+    T = a_max - a_min + 1
+    ld = fold.round_up(4 * ci, 16)
+    assert ld == 16
+    fwd = torch.full((co, T, T, ld), -1, dtype=torch.int64)
+    scat = torch.full((co, T, T, 64), -1, dtype=torch.int64)
+    for ky in range(k):
+        for kx in range(k):
+            ch0 = (par[ky] * 2 + par[kx]) * ci
+            fwd[:, a[ky] - a_min, a[kx] - a_min, ch0:ch0 + ci] = base[:, ky, kx, :]
+            scat[:, a[ky] - a_min, a[kx] - a_min, ch0:ch0 + ci] = base[:, ky, kx, :]
+    return fwd.reshape(co, T * T, ld), T, -a_min, scat.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# activations with gradient routing
+# ------------------------------------------------------------------------------------------------------------
+class Act:
+    """An NHWC activation (or a channel slice of one) plus its gradient buffer and the overwrite/accumulate state."""
+
+    def __init__(self, plan, t, parent=None, lo=0, needs_grad=True):
+        self.plan, self.t, self.parent, self.lo = plan, t, parent, lo
+        self.g = None
+        self.written = False
+        self.needs_grad = needs_grad
+
+    def slice(self, lo, hi):
+        assert self.parent is None
+        return Act(self.plan, self.t[..., lo:hi], parent=self, lo=lo)
+
+    def _root_grad(self):
+        r = self.parent or self
+        if r.g is None:
+            n, h, w, c = r.t.shape
+            r.g = self.plan.pool_get(n, h, w, c, r.t.stride(2))
+        return r.g
+
+    def grad(self):
+        """the gradient as a tensor view (must have been written by every consumer before it is read)"""
+        r = self.parent or self
+        if not r.written:
+            raise RuntimeError("segb200 train plan: gradient read before any consumer wrote it")
+        g = self._root_grad()
+        return g[..., self.lo:self.lo + self.t.shape[3]] if self.parent is not None else g
+
+    def take(self):
+        """-> (gradient tensor to write into, accumulate?) and mark it written"""
+        if self.parent is not None:
+            raise RuntimeError("segb200 train plan: writing the gradient of a channel slice is not supported")
+        g = self._root_grad()
+        acc = self.written
+        self.written = True
+        return g, acc
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the plan
+# ------------------------------------------------------------------------------------------------------------
+class TrainPlan:
+    def __init__(self, store, shape, nclass, dtype, device, bn_momentum=0.1, ignore_index=-1):
+        self.S, self.dtype, self.device = store, dtype, device
+        self.lib = L.load()
+        self.dt = ops.dt_code(dtype)
+        self.n, _, self.H, self.W = shape
+        self.nclass, self.ignore_index, self.bn_momentum = nclass, ignore_index, bn_momentum
+        self.fwd, self.bwd, self.tape = [], [], []
+        self.cur = self.fwd
+        self.keep, self.pool, self.pool_bytes, self.act_bytes = [], {}, 0, 0
+        self.x_in = torch.zeros(shape, dtype=torch.float32, device=device)
+        self.target = torch.zeros(self.n, self.H, self.W, dtype=torch.int64, device=device)
+        self.out3 = torch.zeros(3, dtype=torch.float32, device=device)
+        self.masks = {}
+        self.done_at = {}                 # parameter name -> number of backward steps after which its gradient is final
+
+    # ---- memory ----
+    def new(self, n, h, w, c, ld=None):
+        ld = ld or fold.round_up(c, 8)
+        buf = torch.zeros(n, h, w, ld, dtype=self.dtype, device=self.device)
+        self.keep.append(buf)
+        self.act_bytes += buf.numel() * 2
+        return buf[..., :c] if ld != c else buf
+
+    def pool_get(self, n, h, w, c, ld=None):
+        ld = ld or fold.round_up(c, 8)
+        key = (n, h, w, ld)
+        lst = self.pool.setdefault(key, [])
+        if lst:
+            buf = lst.pop()
+        else:
+            buf = torch.zeros(n, h, w, ld, dtype=self.dtype, device=self.device)
+            self.keep.append(buf)
+            self.pool_bytes += buf.numel() * 2
+        return buf[..., :c] if ld != c else buf
+
+    def pool_put(self, t):
+        base = t._base if t._base is not None else t
+        self.pool.setdefault((base.shape[0], base.shape[1], base.shape[2], base.shape[3]), []).append(base)
+
+    def f32(self, *shape):
+        t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    # ---- step recording ----
+    def add(self, kind, fn, args, **info):
+        self.cur.append(Step(kind, (lambda s, fn=fn, args=args, kind=kind: L.check(fn(*args, s), kind)), info))
+
+    def conv(self, x, w, y, *, cin, cout, k=1, stride=1, dilation=1, pad=0, shift=None, residual=None):
+        a = ops.make_conv_args(x, w, y, cin=cin, cout=cout, kh=k, kw=k, stride=stride, dilation=dilation, pad_t=pad,
+                               pad_l=pad, shift=shift, residual=residual)
+        fn = self.lib.segb200_conv_gemm
+        self.cur.append(Step("conv", (lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "conv_gemm")),
+                             dict(x=x, w=w, y=y, cin=cin, cout=cout, k=k, stride=stride, dilation=dilation, pad=pad, shift=shift,
+                                  residual=residual, flops=2.0 * a.n * a.ho * a.wo * cout * cin * k * k)))
+
+    def wgrad(self, x, dy, dw, *, cin, cout, k=1, stride=1, dilation=1, pad=0):
+        a = L.WgradArgs()
+        n, h, w_, _, x_ld = ops._nhwc(x, "x")
+        _, ho, wo, _, dy_ld = ops._nhwc(dy, "dy")
+        a.x, a.dy, a.dw = _ptr(x), _ptr(dy), _ptr(dw)
+        a.n, a.h, a.w, a.cin, a.x_ld = n, h, w_, cin, x_ld
+        a.ho, a.wo, a.cout, a.dy_ld = ho, wo, cout, dy_ld
+        a.kh, a.kw, a.stride, a.dilation, a.pad_t, a.pad_l = k, k, stride, dilation, pad, pad
+        a.dtype, a.max_ctas, a.splits = self.dt, 0, 0
+        fn = self.lib.segb200_conv_wgrad
+        self.cur.append(Step("wgrad", (lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "conv_wgrad")),
+                             dict(x=x, dy=dy, dw=dw, cin=cin, cout=cout, k=k, stride=stride, dilation=dilation, pad=pad,
+                                  flops=2.0 * n * ho * wo * cout * cin * k * k)))
+
+    def dwconv(self, x, w, y, dilation):
+        a = ops.make_dw_args(x, w, y, stride=1, dilation=dilation)
+        fn = self.lib.segb200_dwconv3x3
+        self.cur.append(Step("dw", (lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "dwconv3x3")),
+                             dict(x=x, w=w, y=y, dilation=dilation)))
+
+    @staticmethod
+    def _rows(t):
+        n, h, w, c, ld = ops._nhwc(t, "t")
+        return n * h * w, h * w, c, ld
+
+    # ---- BatchNorm(+residual, act, channel mask) unit: forward steps + backward builder ----
+    def bn_act_fwd(self, y, z, bn, act, eps, residual=None, nc_scale=None):
+        rows, hw, c, y_ld = self._rows(y)
+        S = self.S
+        st = dict(mean=self.f32(c), invstd=self.f32(c), scale=self.f32(c), shift=self.f32(c), sums=self.f32(2, c))
+        slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
+        partial = self.f32(slabs * 2 * c)
+        st.update(slabs=slabs, partial=partial)
+        gamma, beta = S.view(S.master, bn + ".weight"), S.view(S.master, bn + ".bias")
+        rm, rv = S.stat(bn + ".running_mean"), S.stat(bn + ".running_var")
+        self.add("bn_stats", self.lib.segb200_bn_stats, (_ptr(y), rows, c, y_ld, self.dt, _ptr(partial), 0), x=y, partial=partial, c=c)
+        self.add("bn_finalize", self.lib.segb200_bn_finalize,
+                 (_ptr(partial), slabs, c, float(rows), _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
+                  _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"])),
+                 partial=partial, slabs=slabs, c=c, count=float(rows), gamma=gamma, beta=beta, rm=rm, rv=rv,
+                 momentum=self.bn_momentum, eps=eps, st=st)
+        res_ld = self._rows(residual)[3] if residual is not None else 0
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(y), _ptr(st["scale"]), _ptr(st["shift"]), _ptr(residual), _ptr(nc_scale), _ptr(z), rows, hw, c, y_ld, res_ld,
+                  self._rows(z)[3], L.ACT[act], self.dt),
+                 y=y, scale=st["scale"], shift=st["shift"], residual=residual, nc_scale=nc_scale, z=z, act=act)
+        return st
+
+    def bn_act_bwd(self, dz, z, y, st, bn, act, dy, residual=None, nc_scale=None):
+        """emit: BN/act backward -> dy; dgamma/dbeta accumulated; residual.grad (+)= g"""
+        rows, hw, c, dz_ld = self._rows(dz)
+        S = self.S
+        zz = z if act is not None else None
+        z_ld = self._rows(z)[3] if zz is not None else 0
+        y_ld = self._rows(y)[3]
+        self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(nc_scale), _ptr(st["partial"]), rows, hw, c,
+                  dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
+                 dz=dz, z=zz, y=y, st=st, nc_scale=nc_scale, act=act, c=c)
+        dgamma, dbeta = S.view(S.grad, bn + ".weight"), S.view(S.grad, bn + ".bias")
+        self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
+                 (_ptr(st["partial"]), st["slabs"], c, _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)), st=st, c=c, dgamma=dgamma,
+                 dbeta=dbeta)
+        dres, dres_acc, dres_ld = None, False, 0
+        if residual is not None:
+            dres, dres_acc = residual.take()
+            dres_ld = self._rows(dres)[3]
+        self.add("bn_bwd_apply", self.lib.segb200_bn_bwd_apply,
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["sums"]), float(rows),
+                  _ptr(nc_scale), _ptr(dy), _ptr(dres), int(dres_acc), rows, hw, c, dz_ld, z_ld, y_ld, self._rows(dy)[3], dres_ld,
+                  L.ACT[act], self.dt),
+                 dz=dz, z=zz, y=y, st=st, count=float(rows), nc_scale=nc_scale, dy=dy, dres=dres, dres_acc=dres_acc, act=act)
+
+    # ---- conv (+BN +act) unit ----
+    def conv_unit(self, x, wname, bn=None, act=None, *, k=1, stride=1, dilation=1, pad=0, residual=None, out=None, bias=None,
+                  nc_scale=None, eps=1e-5, stem=False):
+        S = self.S
+        n, h, w_, cx = x.t.shape
+        co, ci = S.meta[wname]["shape"][:2]
+        cop = fold.round_up(co, 8)
+        if stem:
+            T, pad2 = S.pk[wname]["T"], S.pk[wname]["pad"]
+            ho, wo = (self.H + 2 * pad - k) // 2 + 1, (self.W + 2 * pad - k) // 2 + 1
+            geo = dict(cin=16, k=T, stride=1, dilation=1, pad=pad2)
+        else:
+            ho = (h + 2 * pad - dilation * (k - 1) - 1) // stride + 1
+            wo = (w_ + 2 * pad - dilation * (k - 1) - 1) // stride + 1
+            assert cx == ci, (wname, cx, ci)
+            geo = dict(cin=ci, k=k, stride=stride, dilation=dilation, pad=pad)
+        wf = S.packed(wname, "fwd")
+        if bn is not None:
+            y = self.new(n, ho, wo, cop)
+            z = out if out is not None else Act(self, self.new(n, ho, wo, cop))
+            self.conv(x.t, wf, y, cout=cop, **geo)
+            st = self.bn_act_fwd(y, z.t, bn, act, eps, residual.t if residual is not None else None, nc_scale)
+        else:
+            assert act is None and residual is None and nc_scale is None
+            z = out if out is not None else Act(self, self.new(n, ho, wo, cop))
+            y, st = z.t, None
+            self.conv(x.t, wf, y, cout=cop, shift=S.view(S.master, bias) if bias else None, **geo)
+
+        def backward():
+            dz = z.grad()
+            if bn is not None:
+                dy = self.pool_get(n, ho, wo, cop)
+                self.bn_act_bwd(dz, z.t, y, st, bn, act, dy, residual, nc_scale)
+                if z.parent is None:
+                    self.pool_put(dz)
+            else:
+                dy = dz
+                if bias:
+                    rows, hw, c, ld = self._rows(dz)
+                    slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
+                    partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
+                    self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
+                             (_ptr(dz), None, _ptr(dz), None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
+                             dz=dz, z=None, y=dz, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
+                    self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, _ptr(sums), None, None),
+                             st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)
+                    gb = S.view(S.grad, bias)
+                    self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(sums), 1, 1, co, _ptr(gb), 0, 1, 1, 1.0),
+                             partial=sums, slabs=1, K=1, c=co, out=gb, sk=0, sc=1, accumulate=1, scale=1.0)
+            # weight gradient
+            if stem:
+                dws = self.f32(co * geo["k"] ** 2 * 64)
+                self.cur.append(Step("zero", (lambda s, t=dws: t.zero_()), dict(t=dws)))
+                self.wgrad(x.t.as_strided((n, x.t.shape[1], x.t.shape[2], 64), x.t.stride()) if x.t.shape[3] != 64 else x.t, dy, dws,
+                           cin=64, cout=co, k=geo["k"], stride=1, dilation=1, pad=geo["pad"])
+                sc = S.pk[wname]["scatter"]
+                self.add("scatter_add", self.lib.segb200_scatter_add, (_ptr(dws), _ptr(sc), _ptr(S.grad), dws.numel()), src=dws, index=sc,
+                         dst=S.grad)
+            else:
+                self.wgrad(x.t, dy, S.view(S.grad, wname), cin=ci, cout=co, **{kk: geo[kk] for kk in ("k", "stride", "dilation", "pad")})
+            # data gradient
+            if x.needs_grad:
+                wd = S.packed(wname, "dgrad")
+                gx, acc = x.take()
+                if stride == 1:
+                    assert 2 * pad == dilation * (k - 1), "data gradient via the forward kernel needs 'same' padding"
+                    self.conv(dy, wd, gx, cin=cop, cout=ci, k=k, dilation=dilation, pad=pad, residual=gx if acc else None)
+                elif k == 1:
+                    t = self.pool_get(n, ho, wo, ci)
+                    self.conv(dy, wd, t, cin=cop, cout=ci)
+                    self.add("stride2_place", self.lib.segb200_stride2_place,
+                             (_ptr(t), _ptr(gx), n, h, w_, ci, self._rows(t)[3], self._rows(gx)[3], 1 if acc else 0, self.dt), t=t, z=gx,
+                             mode=1 if acc else 0)
+                    self.pool_put(t)
+                else:
+                    assert dilation == 1 and 2 * pad == k - 1
+                    zb = self.pool_get(n, h, w_, cop)
+                    self.add("stride2_place", self.lib.segb200_stride2_place,
+                             (_ptr(dy), _ptr(zb), n, h, w_, cop, self._rows(dy)[3], self._rows(zb)[3], 0, self.dt), t=dy, z=zb, mode=0)
+                    self.conv(zb, wd, gx, cin=cop, cout=ci, k=k, dilation=1, pad=pad, residual=gx if acc else None)
+                    self.pool_put(zb)
+            if bn is not None:
+                self.pool_put(dy)
+            elif z.parent is None:
+                self.pool_put(dz)
+            self.mark_done(wname, bias, bn + ".weight" if bn else None, bn + ".bias" if bn else None)
+
+        self.tape.append(backward)
+        return z
+
+    # ---- depthwise 3x3 + BN + act (the first half of SeparableConv2d, relu_first=False: modules/basic.py:52-59) ----
+    def dw_unit(self, x, wname, bn, act, dilation, eps=1e-5):
+        S = self.S
+        n, h, w_, c = x.t.shape
+        y = self.new(n, h, w_, c)
+        z = Act(self, self.new(n, h, w_, c))
+        self.dwconv(x.t, S.packed(wname, "fwd"), y, dilation)
+        st = self.bn_act_fwd(y, z.t, bn, act, eps)
+
+        def backward():
+            dz = z.grad()
+            dy = self.pool_get(n, h, w_, c)
+            self.bn_act_bwd(dz, z.t, y, st, bn, act, dy)
+            self.pool_put(dz)
+            rows = n * h * w_
+            slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
+            partial = self.f32(slabs * 9 * c)
+            self.add("dw_wgrad", self.lib.segb200_dw_wgrad,
+                     (_ptr(x.t), _ptr(dy), _ptr(partial), n, h, w_, c, self._rows(x.t)[3], self._rows(dy)[3], dilation, 0, self.dt, 0),
+                     x=x.t, dy=dy, partial=partial, dilation=dilation, c=c)
+            gw = S.view(S.grad, wname)
+            self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(partial), slabs, 9, c, _ptr(gw), 1, 9, 1, 1.0),
+                     partial=partial, slabs=slabs, K=9, c=c, out=gw, sk=1, sc=9, accumulate=1, scale=1.0)
+            if x.needs_grad:
+                gx, acc = x.take()
+                wfl = S.packed(wname, "flip")
+                if acc:
+                    t = self.pool_get(n, h, w_, c)
+                    self.dwconv(dy, wfl, t, dilation)
+                    rws, hw, cc, ld = self._rows(gx)
+                    self.add("bn_apply", self.lib.segb200_bn_apply,
+                             (_ptr(t), None, None, _ptr(gx), None, _ptr(gx), rws, hw, cc, self._rows(t)[3], ld, ld, 0, self.dt),
+                             y=t, scale=None, shift=None, residual=gx, nc_scale=None, z=gx, act=None)
+                    self.pool_put(t)
+                else:
+                    self.dwconv(dy, wfl, gx, dilation)
+            self.pool_put(dy)
+            self.mark_done(wname, bn + ".weight", bn + ".bias")
+
+        self.tape.append(backward)
+        return z
+
+    def mark_done(self, *names):
+        for k in names:
+            if k:
+                self.done_at[k] = len(self.bwd)
+
+    # ---- glue ops ----
+    def maxpool(self, x):
+        n, h, w_, c = x.t.shape
+        y = Act(self, self.new(n, (h - 1) // 2 + 1, (w_ - 1) // 2 + 1, c))
+        self.add("maxpool", self.lib.segb200_maxpool3x3s2, (_ptr(x.t), _ptr(y.t), n, h, w_, c, x.t.stride(2), y.t.stride(2), self.dt),
+                 x=x.t, y=y.t)
+
+        def backward():
+            dy = y.grad()
+            gx, acc = x.take()
+            assert not acc
+            self.add("maxpool_bwd", self.lib.segb200_maxpool3x3s2_bwd,
+                     (_ptr(x.t), _ptr(dy), _ptr(gx), n, h, w_, c, x.t.stride(2), dy.stride(2), gx.stride(2), self.dt), x=x.t, dy=dy, dx=gx)
+            self.pool_put(dy)
+        self.tape.append(backward)
+        return y
+
+    def bilinear(self, x, out):
+        """F.interpolate(x, out.shape, 'bilinear', align_corners=True) into the channel slice `out` (deeplabv3_plus.py:71)."""
+        n, hi, wi, c = x.t.shape
+        _, ho, wo, _ = out.t.shape
+        self.add("bilinear", self.lib.segb200_bilinear_nhwc,
+                 (_ptr(x.t), _ptr(out.t), n, hi, wi, c, x.t.stride(2), ho, wo, out.t.stride(2), 1, self.dt), x=x.t, y=out.t)
+
+        def backward():
+            dy = out.grad()
+            gx, acc = x.take()
+            self.add("bilinear_bwd", self.lib.segb200_bilinear_nhwc_bwd,
+                     (_ptr(dy), _ptr(gx), n, hi, wi, c, gx.stride(2), ho, wo, dy.stride(2), 1, int(acc), None, self.dt), dy=dy, dx=gx,
+                     accumulate=acc, gscale=None)
+        self.tape.append(backward)
+
+    def image_pool(self, x):
+        """nn.AdaptiveAvgPool2d(1) (module.py:52) -> [n,1,1,c]"""
+        n, h, w_, c = x.t.shape
+        y = Act(self, self.new(n, 1, 1, c))
+        self.add("gap", self.lib.segb200_global_avgpool, (_ptr(x.t), _ptr(y.t), n, h, w_, c, x.t.stride(2), self.dt), x=x.t, y=y.t)
+
+        def backward():
+            dy = y.grad()
+            gx, acc = x.take()
+            self.add("nc_broadcast", self.lib.segb200_nc_broadcast,
+                     (_ptr(dy), _ptr(gx), n, h * w_, c, dy.stride(2), gx.stride(2), 1.0 / (h * w_), int(acc), self.dt), v=dy, y=gx,
+                     scale=1.0 / (h * w_), accumulate=acc)
+        self.tape.append(backward)
+        return y
+
+    def broadcast(self, v, out):
+        """bilinear up-sampling from 1x1 == broadcast (module.py:64) into the channel slice `out`"""
+        n, h, w_, c = out.t.shape
+        self.add("nc_broadcast", self.lib.segb200_nc_broadcast,
+                 (_ptr(v.t), _ptr(out.t), n, h * w_, c, v.t.stride(2), out.t.stride(2), 1.0, 0, self.dt), v=v.t, y=out.t, scale=1.0,
+                 accumulate=False)
+
+        def backward():
+            dy = out.grad()                                        # [n,h,w,c] slice -> sum over pixels
+            mean = self.pool_get(n, 1, 1, c)
+            self.add("gap", self.lib.segb200_global_avgpool, (_ptr(dy), _ptr(mean), n, h, w_, c, dy.stride(2), self.dt), x=dy, y=mean)
+            gv, acc = v.take()
+            assert not acc
+            hwv = self.f32(c).fill_(float(h * w_))
+            self.add("bn_apply", self.lib.segb200_bn_apply,
+                     (_ptr(mean), _ptr(hwv), None, None, None, _ptr(gv), n, 1, c, mean.stride(2), 0, gv.stride(2), 0, self.dt),
+                     y=mean, scale=hwv, shift=None, residual=None, nc_scale=None, z=gv, act=None)
+            self.pool_put(mean)
+        self.tape.append(backward)
+
+    def loss(self, logits):
+        """fused F.interpolate(logits, (H, W), align_corners=True) + CrossEntropyLoss(ignore_index) + its gradient"""
+        n, hi, wi, _ = logits.t.shape
+        c8 = fold.round_up(self.nclass, 8)
+        dfull = self.new(n, self.H, self.W, c8)
+        nb = self.lib.segb200_upsample_ce_blocks(n, self.H, self.W)
+        partial = self.f32(2 * nb)
+        self.add("upsample_ce", self.lib.segb200_upsample_ce,
+                 (_ptr(logits.t), _ptr(self.target), _ptr(dfull), _ptr(partial), _ptr(self.out3), n, hi, wi, self.nclass,
+                  logits.t.stride(2), self.H, self.W, dfull.stride(2), 1, self.ignore_index, self.dt),
+                 logits=logits.t, target=self.target, dfull=dfull, out3=self.out3, nclass=self.nclass, ignore_index=self.ignore_index)
+
+        def backward():
+            gl, acc = logits.take()
+            assert not acc
+            inv = self.out3[1:2]
+            self.add("bilinear_bwd", self.lib.segb200_bilinear_nhwc_bwd,
+                     (_ptr(dfull), _ptr(gl), n, hi, wi, c8, gl.stride(2), self.H, self.W, dfull.stride(2), 1, 0, _ptr(inv), self.dt),
+                     dy=dfull, dx=gl, accumulate=False, gscale=inv)
+        self.tape.append(backward)
+
+    def build_backward(self):
+        self.cur = self.bwd
+        for fn in reversed(self.tape):
+            fn()
+        self.cur = self.fwd
+
+    # ---- execution ----
+    def run(self, steps=None):
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for st in (steps if steps is not None else self.fwd + self.bwd):
+            st.call(s)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# model builders (mirror oracle/segref.py <-> the reference forward graphs)
+# ------------------------------------------------------------------------------------------------------------
+def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, out=None):
+    """BottleneckV1b (backbones/resnet.py:44-81).  The downsample branch is recorded FIRST so that its (possibly strided)
+    data gradient is the last contribution to the block input's gradient."""
+    idn = x
+    if downsample:
+        idn = pl.conv_unit(x, prefix + ".downsample.0.weight", prefix + ".downsample.1", None, k=1, stride=stride)
+    y = pl.conv_unit(x, prefix + ".conv1.weight", prefix + ".bn1", "relu")
+    y = pl.conv_unit(y, prefix + ".conv2.weight", prefix + ".bn2", "relu", k=3, stride=stride, dilation=dilation, pad=dilation)
+    return pl.conv_unit(y, prefix + ".conv3.weight", prefix + ".bn3", "relu", residual=idn, out=out)
+
+
+def _resnet(pl, layers, output_stride):
+    """ResNetV1.forward (backbones/resnet.py:183-199), stride/dilation table :90-100,:149-179."""
+    dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
+    p = "encoder"
+    n, H, W = pl.n, pl.H, pl.W
+    s2d = Act(pl, pl.new(n, (H + 1) // 2, (W + 1) // 2, 16, ld=64), needs_grad=False)
+    pl.cur.append(Step("pack_s2d", (lambda s: ops.pack_s2d(pl.x_in, s2d.t._base if s2d.t._base is not None else s2d.t)),
+                       dict(x=pl.x_in, out=s2d.t)))
+    x = pl.conv_unit(s2d, p + ".conv1.weight", p + ".bn1", "relu", k=7, stride=2, pad=3, stem=True)
+    x = pl.maxpool(x)
+    inpl = [64]
+
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1):
+        ds = stride != 1 or inpl[0] != planes * 4
+        first_d = 1 if dilation in (1, 2) else 2
+        x = _bottleneck(pl, x, f"{p}.{name}.0", planes, stride, first_d, ds)
+        inpl[0] = planes * 4
+        for i in range(1, blocks):
+            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, dilation, False)
+        return x
+
+    c1 = make_layer(x, "layer1", 64, layers[0])
+    c2 = make_layer(c1, "layer2", 128, layers[1], 2)
+    c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1])
+    return c1, c2, c3, c4
+
+
+def _sepconv(pl, x, prefix, dilation, out=None):
+    """SeparableConv2d(relu_first=False) (modules/basic.py:52-59): dw -> BN -> ReLU -> pw -> BN -> ReLU."""
+    b = prefix + ".block"
+    z = pl.dw_unit(x, b + ".depthwise.weight", b + ".bn_depth", "relu", dilation)
+    return pl.conv_unit(z, b + ".pointwise.weight", b + ".bn_point", "relu", out=out)
+
+
+def _aspp(pl, c4, prefix, output_stride):
+    """_ASPP.forward (modules/module.py:62-77) in training mode (Dropout2d active, :75)."""
+    d = {16: (6, 12, 18), 8: (12, 24, 36), 32: (6, 12, 18)}[output_stride]
+    n, h, w_, c = c4.t.shape
+    cat = Act(pl, pl.new(n, h, w_, 1280))
+    pooled = pl.image_pool(c4)
+    pf = pl.conv_unit(pooled, prefix + ".image_pooling.conv.weight", prefix + ".image_pooling.bn", "relu")
+    pl.broadcast(pf, cat.slice(0, 256))
+    pl.conv_unit(c4, prefix + ".aspp0.conv.weight", prefix + ".aspp0.bn", "relu", out=cat.slice(256, 512))
+    for i in range(3):
+        _sepconv(pl, c4, f"{prefix}.aspp{i + 1}", d[i], out=cat.slice(512 + 256 * i, 768 + 256 * i))
+    mask = pl.f32(n, 256).fill_(1.0)
+    pl.masks[prefix + ".dropout"] = mask
+    return pl.conv_unit(cat, prefix + ".conv.weight", prefix + ".bn", "relu", nc_scale=mask)
+
+
+def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16):
+    """DeepLabV3Plus.forward + _DeepLabHead (models/deeplabv3_plus.py:33-75) + the loss of solver/loss.py:16-46 (aux off)."""
+    layers = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}[backbone]
+    c1, _, _, c4 = _resnet(pl, layers, output_stride)
+    x = _aspp(pl, c4, "head.aspp", output_stride)
+    n, h1, w1, _ = c1.t.shape
+    cat = Act(pl, pl.new(n, h1, w1, 304))
+    pl.bilinear(x, cat.slice(0, 256))
+    pl.conv_unit(c1, "head.c1_block.conv.weight", "head.c1_block.bn", "relu", out=cat.slice(256, 304))
+    x = _sepconv(pl, cat, "head.block.0", 1)
+    x = _sepconv(pl, x, "head.block.1", 1)
+    logits = Act(pl, pl.new(n, h1, w1, fold.round_up(pl.nclass, 8), ld=32))
+    pl.conv_unit(x, "head.block.2.weight", bias="head.block.2.bias", out=logits)
+    pl.logits = logits
+    pl.loss(logits)
+    pl.build_backward()
+    return pl
+
+
+class DeepLabV3PlusTrainerB200:
+    """``trainer.step(images_nchw_fp32, targets_int64) -> loss`` : one iteration of tools/train.py:135-147 (forward, criterion,
+    zero_grad, backward, optimizer.step) for DeepLabV3_Plus / ResNet on the CUDA engine.  ``state_dict()`` returns reference-named
+    tensors.  Hyper-parameters default to the reference's (config/settings.py:65-75: momentum 0.9, weight decay 1e-4, decoder
+    LR x10; LR from the YAML, cityscapes_deeplabv3_plus_resnet.yaml:15).  Multi-GPU: construct under an initialised
+    torch.distributed NCCL group; gradients are averaged over ranks by bucketed all-reduces overlapped with backward."""
+
+    def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, dtype=torch.bfloat16, device="cuda",
+                 lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
+                 bucket_mb=25, cuda_graph=False):
+        if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
+            raise RuntimeError("segb200: a CUDA device (sm_100a) is required; there is no CPU fallback")
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.cfg = dict(backbone=backbone, output_stride=output_stride)
+        self.nclass, self.bn_momentum = nclass, bn_momentum
+        self.lr, self.momentum, self.weight_decay, self.decoder_lr_factor = lr, momentum, weight_decay, decoder_lr_factor
+        self.dropout = dropout
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        self.cuda_graph = cuda_graph
+        self.store = ParamStore({k: v.detach() for k, v in state_dict.items()}, self.device, dtype, stem="encoder.conv1.weight")
+        self.plans = {}
+        self.world = 1
+        self.dist = None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.dist, self.world = dist, dist.get_world_size()
+        except Exception:                                            # pragma: no cover
+            self.dist = None
+
+    def plan_for(self, shape):
+        shape = tuple(shape)
+        if shape not in self.plans:
+            pl = TrainPlan(self.store, shape, self.nclass, self.dtype, self.device, self.bn_momentum)
+            build_deeplabv3plus_train(pl, **self.cfg)
+            self.plans[shape] = dict(plan=pl, graph=None, buckets=self._buckets(pl))
+        return self.plans[shape]
+
+    def _buckets(self, pl):
+        """contiguous ranges of the flat gradient, cut where backward has finished everything above an offset"""
+        S = self.store
+        names = sorted(S.meta, key=lambda k: -S.meta[k]["off"])          # from the end of the flat buffer (= start of backward)
+        out, hi, pos, prev = [], S.total, 0, 0
+        for k in names:
+            lo = S.meta[k]["off"]
+            pos = max(pos, pl.done_at.get(k, len(pl.bwd)))
+            if (hi - lo) * 4 >= self.bucket_bytes or lo == 0:
+                pos = max(pos, prev)                                      # launch order must follow the step order
+                out.append((pos, lo, hi))
+                hi, prev, pos = lo, pos, 0
+        return out
+
+    # ---- pieces of a step (public so that tests can check gradients before the update) ----
+    def pack_weights(self):
+        S, lib = self.store, L.load()
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if S.idx16 is not None:
+            L.check(lib.segb200_gather_cast(_ptr(S.master), _ptr(S.idx16), _ptr(S.w16), S.idx16.numel(), ops.dt_code(self.dtype), s),
+                    "gather_cast")
+        if S.idx32 is not None:
+            L.check(lib.segb200_gather_cast(_ptr(S.master), _ptr(S.idx32), _ptr(S.w32), S.idx32.numel(), L.F32, s), "gather_cast")
+
+    def forward_backward(self, x, target, dropout_masks=None):
+        """-> loss (device scalar tensor); gradients (SUMMED over ranks; optimizer_step divides by the world size) are left in
+        ``self.store.grad``."""
+        if not x.is_cuda or not target.is_cuda:
+            raise RuntimeError("segb200: inputs must be CUDA tensors (no CPU implementation)")
+        st = self.plan_for(x.shape)
+        pl = st["plan"]
+        pl.x_in.copy_(x)
+        pl.target.copy_(target)
+        for name, m in pl.masks.items():
+            if dropout_masks is not None and name in dropout_masks:
+                m.copy_(dropout_masks[name].reshape(m.shape))
+            elif self.dropout:
+                m.bernoulli_(0.9).div_(0.9)                  # nn.Dropout2d(0.1): [N,C] keep mask / (1-p)  (module.py:60)
+            else:
+                m.fill_(1.0)
+        self.store.grad.zero_()
+        self.pack_weights()
+        if self.dist is None:
+            pl.run()
+        else:
+            pl.run(pl.fwd)
+            works, pos0 = [], 0
+            for pos, lo, hi in st["buckets"]:
+                pl.run(pl.bwd[pos0:pos])
+                pos0 = pos
+                works.append(self.dist.all_reduce(self.store.grad[lo:hi], async_op=True))
+            pl.run(pl.bwd[pos0:])
+            for w in works:
+                w.wait()
+        return pl.out3[0]
+
+    def optimizer_step(self, lr=None):
+        S, lib = self.store, L.load()
+        lr = self.lr if lr is None else lr
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ne = S.n_encoder
+        gs = 1.0 / self.world
+        L.check(lib.segb200_sgd_step(_ptr(S.master), _ptr(S.grad), _ptr(S.mom), ne, lr, self.momentum, self.weight_decay, gs, s), "sgd")
+        if S.total > ne:
+            L.check(lib.segb200_sgd_step(_ptr(S.master[ne:]), _ptr(S.grad[ne:]), _ptr(S.mom[ne:]), S.total - ne,
+                                         lr * self.decoder_lr_factor, self.momentum, self.weight_decay, gs, s), "sgd")
+
+    def step(self, x, target, lr=None, dropout_masks=None):
+        loss = self.forward_backward(x, target, dropout_masks)
+        self.optimizer_step(lr)
+        return loss
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    def n_launches(self, shape):
+        pl = self.plan_for(shape)["plan"]
+        return len(pl.fwd) + len(pl.bwd) + 5

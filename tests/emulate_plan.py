@@ -1,0 +1,236 @@
+"""TEST INFRASTRUCTURE: a torch/CPU interpreter for the training launch list (segmentron_b200.train.TrainPlan).
+
+The product only ever executes ``Step.call`` (the C-ABI kernel launch).  This interpreter executes ``Step.info`` instead --
+the same buffers, the documented semantics of each kernel (include/segb200.h) restated with torch ops -- so that the HOST
+logic of the plan (buffer routing, overwrite/accumulate decisions, channel-slice gradients, index tables, parameter layout,
+bucket ordering) can be checked against the oracle on a machine without a GPU.  It is never imported by the package.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).float()
+
+
+def _act(v, act):
+    return F.relu(v) if act == "relu" else (F.relu6(v) if act == "relu6" else v)
+
+
+def _conv_core(x_nchw, W, info, ho, wo):
+    k, s, d, p = info["k"], info["stride"], info["dilation"], info["pad"]
+    big = d * (k - 1) + s * max(ho, wo) + 8
+    xp = F.pad(x_nchw, (p, big, p, big))
+    return F.conv2d(xp, W, None, s, 0, d)[:, :, :ho, :wo]
+
+
+def _unpack_w(w, cout, cin, k):
+    return w[:cout, :, :cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2).float()
+
+
+def run_step(st):
+    i, kind = st.info, st.kind
+    if kind == "zero":
+        i["t"].zero_()
+    elif kind == "pack_s2d":
+        x, out = i["x"], i["out"]
+        n, c, h, w = x.shape
+        base = out._base if out._base is not None else out
+        base.zero_()
+        hs, ws = base.shape[1], base.shape[2]
+        xp = F.pad(x, (0, 2 * ws - w, 0, 2 * hs - h))
+        for dy in range(2):
+            for dx in range(2):
+                base[..., (dy * 2 + dx) * c:(dy * 2 + dx + 1) * c] = xp[:, :, dy::2, dx::2].permute(0, 2, 3, 1).to(base.dtype)
+    elif kind == "conv":
+        x, w, y = i["x"], i["w"], i["y"]
+        cin, cout, k = i["cin"], i["cout"], i["k"]
+        xin = x if x.shape[3] == cin else x.as_strided((x.shape[0], x.shape[1], x.shape[2], cin), x.stride())
+        o = _conv_core(_nchw(xin), _unpack_w(w, cout, cin, k), i, y.shape[1], y.shape[2]).permute(0, 2, 3, 1)
+        if i["shift"] is not None:
+            sh = torch.zeros(cout)
+            m = min(cout, i["shift"].numel())
+            sh[:m] = i["shift"][:m]
+            o = o + sh
+        if i["residual"] is not None:
+            o = o + i["residual"][..., :cout].float()
+        y[..., :cout] = o.to(y.dtype)
+    elif kind == "wgrad":
+        x, dy, dw = i["x"], i["dy"], i["dw"]
+        cin, cout, k = i["cin"], i["cout"], i["k"]
+        W0 = torch.zeros(cout, cin, k, k, requires_grad=True)
+        o = _conv_core(_nchw(x[..., :cin]), W0, i, dy.shape[1], dy.shape[2])
+        o.backward(_nchw(dy[..., :cout]))
+        dw.view(cout, k * k, cin).add_(W0.grad.permute(0, 2, 3, 1).reshape(cout, k * k, cin))
+    elif kind == "dw":
+        x, w, y, d = i["x"], i["w"], i["y"], i["dilation"]
+        c = x.shape[3]
+        W = w.t().reshape(c, 1, 3, 3).float()
+        y.copy_(F.conv2d(_nchw(x), W, None, 1, d, d, groups=c).permute(0, 2, 3, 1).to(y.dtype))
+    elif kind == "bn_stats":
+        x, partial, c = i["x"], i["partial"], i["c"]
+        xf = x.float().reshape(-1, c)
+        partial.zero_()
+        partial[:c] = xf.sum(0)
+        partial[c:2 * c] = (xf * xf).sum(0)
+    elif kind == "bn_finalize":
+        c, cnt, st_ = i["c"], i["count"], i["st"]
+        p = i["partial"].view(i["slabs"], 2, c).double().sum(0)
+        m = p[0] / cnt
+        var = (p[1] / cnt - m * m).clamp(min=0)
+        inv = 1.0 / torch.sqrt(var + i["eps"])
+        st_["mean"].copy_(m.float()); st_["invstd"].copy_(inv.float())
+        sc = i["gamma"].double() * inv
+        st_["scale"].copy_(sc.float()); st_["shift"].copy_((i["beta"].double() - m * sc).float())
+        mom = i["momentum"]
+        i["rm"].mul_(1 - mom).add_(mom * m.float())
+        i["rv"].mul_(1 - mom).add_(mom * (var * cnt / (cnt - 1) if cnt > 1 else var).float())
+    elif kind == "bn_apply":
+        y, z = i["y"], i["z"]
+        v = y.float()
+        if i["scale"] is not None:
+            v = v * i["scale"]
+        if i["shift"] is not None:
+            v = v + i["shift"]
+        if i["residual"] is not None:
+            v = v + i["residual"].float()
+        v = _act(v, i["act"])
+        if i["nc_scale"] is not None:
+            v = v * i["nc_scale"][:, None, None, :]
+        z.copy_(v.to(z.dtype))
+    elif kind in ("bn_bwd_reduce", "bn_bwd_apply"):
+        dz, z, y, st_, act = i["dz"], i["z"], i["y"], i["st"], i["act"]
+        g = dz.float()
+        if i["nc_scale"] is not None:
+            g = g * i["nc_scale"][:, None, None, :]
+        if act == "relu":
+            g = g * (z.float() > 0)
+        elif act == "relu6":
+            g = g * ((z.float() > 0) & (z.float() < 6))
+        mean = st_["mean"] if st_.get("mean") is not None else 0.0
+        inv = st_["invstd"] if st_.get("invstd") is not None else 1.0
+        xh = (y.float() - mean) * inv
+        c = g.shape[3]
+        if kind == "bn_bwd_reduce":
+            p = st_["partial"]
+            p.zero_()
+            p[:c] = g.reshape(-1, c).sum(0)
+            p[c:2 * c] = (g * xh).reshape(-1, c).sum(0)
+        else:
+            if i["dres"] is not None:
+                dres = i["dres"]
+                dres.copy_(((dres.float() if i["dres_acc"] else 0) + g).to(dres.dtype))
+            if i["dy"] is not None:
+                s = st_["sums"]
+                o = st_["scale"] * (g - s[0] / i["count"] - xh * s[1] / i["count"])
+                i["dy"].copy_(o.to(i["dy"].dtype))
+    elif kind == "bn_bwd_finalize":
+        st_, c = i["st"], i["c"]
+        p = st_["partial"].view(st_["slabs"], 2, c).double().sum(0)
+        st_["sums"][0] = p[0].float(); st_["sums"][1] = p[1].float()
+        if i["dgamma"] is not None:
+            i["dgamma"].add_(p[1].float())
+        if i["dbeta"] is not None:
+            i["dbeta"].add_(p[0].float())
+    elif kind == "reduce_partials":
+        K, c, slabs = i["K"], i["c"], i["slabs"]
+        tot = i["partial"].double()
+        full = tot[:slabs * K * (tot.numel() // (slabs * K))] if False else None
+        # partial[(slab*K + k)*cc + ch] with cc = the channel count the producer used
+        cc = i["partial"].numel() // (slabs * K)
+        p = i["partial"].view(slabs, K, cc).double().sum(0)[:, :c]
+        out = i["out"]
+        for k in range(K):
+            idx = k * i["sk"] + torch.arange(c) * i["sc"]
+            v = (p[k] * i["scale"]).float()
+            out[idx] = out[idx] + v if i["accumulate"] else v
+    elif kind == "maxpool":
+        i["y"].copy_(F.max_pool2d(_nchw(i["x"]), 3, 2, 1).permute(0, 2, 3, 1).to(i["y"].dtype))
+    elif kind == "maxpool_bwd":
+        xr = _nchw(i["x"]).requires_grad_(True)
+        F.max_pool2d(xr, 3, 2, 1).backward(_nchw(i["dy"]))
+        i["dx"].copy_(xr.grad.permute(0, 2, 3, 1).to(i["dx"].dtype))
+    elif kind == "bilinear":
+        y = i["y"]
+        y.copy_(F.interpolate(_nchw(i["x"]), y.shape[1:3], mode="bilinear", align_corners=True).permute(0, 2, 3, 1).to(y.dtype))
+    elif kind == "bilinear_bwd":
+        dy, dx = i["dy"], i["dx"]
+        xr = torch.zeros(dx.shape[0], dy.shape[3], dx.shape[1], dx.shape[2], requires_grad=True)
+        F.interpolate(xr, dy.shape[1:3], mode="bilinear", align_corners=True).backward(_nchw(dy))
+        g = xr.grad.permute(0, 2, 3, 1) * (float(i["gscale"][0]) if i["gscale"] is not None else 1.0)
+        c = dy.shape[3]
+        dx[..., :c] = ((dx[..., :c].float() if i["accumulate"] else 0) + g).to(dx.dtype)
+    elif kind == "gap":
+        i["y"].copy_(i["x"].float().mean((1, 2), keepdim=True).to(i["y"].dtype))
+    elif kind == "nc_broadcast":
+        y = i["y"]
+        v = i["v"].float() * i["scale"]
+        y.copy_(((y.float() if i["accumulate"] else 0) + v.expand_as(y)).to(y.dtype))
+    elif kind == "stride2_place":
+        t, z = i["t"], i["z"]
+        if i["mode"] == 0:
+            z.zero_()
+            z[:, ::2, ::2, :] = t
+        else:
+            z[:, ::2, ::2, :] = (z[:, ::2, ::2, :].float() + t.float()).to(z.dtype)
+    elif kind == "dw_wgrad":
+        x, dy, c, d = i["x"], i["dy"], i["c"], i["dilation"]
+        W0 = torch.zeros(c, 1, 3, 3, requires_grad=True)
+        F.conv2d(_nchw(x), W0, None, 1, d, d, groups=c).backward(_nchw(dy))
+        p = i["partial"]
+        p.zero_()
+        p[:9 * c] = W0.grad.reshape(c, 9).t().reshape(-1)
+    elif kind == "upsample_ce":
+        lg, tgt, dfull, out3, nc = i["logits"], i["target"], i["dfull"], i["out3"], i["nclass"]
+        up = F.interpolate(_nchw(lg[..., :nc]), tgt.shape[1:3], mode="bilinear", align_corners=True)
+        valid = (tgt != i["ignore_index"]) & (tgt >= 0) & (tgt < nc)
+        lsm = F.log_softmax(up, 1)
+        oh = F.one_hot(tgt.clamp(0, nc - 1), nc).permute(0, 3, 1, 2).float()
+        cnt = float(valid.sum())
+        out3[0] = float(-(lsm * oh).sum(1)[valid].sum() / max(cnt, 1.0))
+        out3[1] = 1.0 / cnt if cnt > 0 else 0.0
+        out3[2] = cnt
+        g = (lsm.exp() - oh) * valid[:, None].float()
+        dfull.zero_()
+        dfull[..., :nc] = g.permute(0, 2, 3, 1).to(dfull.dtype)
+    elif kind == "scatter_add":
+        src, idx, dst = i["src"], i["index"].long(), i["dst"]
+        m = idx >= 0
+        dst.index_add_(0, idx[m], src[m])
+    else:
+        raise NotImplementedError(kind)
+
+
+def gather_cast(src, index, dst):
+    idx = index.long()
+    v = torch.where(idx >= 0, src[idx.clamp(min=0)], torch.zeros(()))
+    dst.copy_(v.to(dst.dtype))
+
+
+def forward_backward(trainer, x, target, dropout_masks=None):
+    """CPU interpretation of DeepLabV3PlusTrainerB200.forward_backward (single rank)."""
+    st = trainer.plan_for(x.shape)
+    pl, S = st["plan"], trainer.store
+    pl.x_in.copy_(x)
+    pl.target.copy_(target)
+    for name, m in pl.masks.items():
+        if dropout_masks is not None and name in dropout_masks:
+            m.copy_(dropout_masks[name].reshape(m.shape))
+        else:
+            m.fill_(1.0)
+    S.grad.zero_()
+    gather_cast(S.master, S.idx16, S.w16)
+    if S.idx32 is not None:
+        gather_cast(S.master, S.idx32, S.w32)
+    for s in pl.fwd + pl.bwd:
+        run_step(s)
+    return pl.out3[0].clone()
+
+
+def sgd(trainer, lr=None):
+    S = trainer.store
+    lr = trainer.lr if lr is None else lr
+    for lo, hi, l in ((0, S.n_encoder, lr), (S.n_encoder, S.total, lr * trainer.decoder_lr_factor)):
+        g = S.grad[lo:hi] / trainer.world + trainer.weight_decay * S.master[lo:hi]
+        S.mom[lo:hi] = trainer.momentum * S.mom[lo:hi] + g
+        S.master[lo:hi] -= l * S.mom[lo:hi]

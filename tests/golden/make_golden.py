@@ -86,6 +86,95 @@ def run_model_case(case):
     print(f"{case}: oracle vs reference max-rel {err:.2e}; saved {tuple(y_ref.shape)}")
 
 
+TRAIN_CASES = {
+    # case: (oracle model name, reference yaml, input shape, seed)
+    "train_dlv3p_resnet101_65x97_b4": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (4, 3, 65, 97), 21),
+}
+
+
+def grad_digest(grads, seed=12345):
+    """Per-parameter (norm, projection on a seeded random direction): 2 numbers per tensor pin a gradient to ~1e-6 without
+    storing 190 MB of them."""
+    import torch
+    out = {}
+    for i, k in enumerate(sorted(grads)):
+        g = grads[k].detach().double().flatten()
+        r = torch.randn(g.numel(), generator=torch.Generator().manual_seed(seed + i), dtype=torch.float64)
+        out[k] = (float(g.norm()), float((g * r).sum()))
+    return out
+
+
+def run_train_case(case):
+    """One training iteration of tools/train.py:135-147 on the REAL reference model (train mode, the reference's own
+    criterion and optimizer) vs the oracle's loss_and_grads: loss, every parameter gradient, BatchNorm running statistics and
+    the parameters after one optimizer.step() must agree."""
+    import numpy as np
+    np.int = int
+    import torch
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    from oracle import segref as R
+    name, yaml_file, shape, seed = TRAIN_CASES[case]
+    from segmentron.config import cfg
+    from segmentron.models.model_zoo import get_segmentation_model
+    cfg.update_from_file(os.path.join(REF, "configs", yaml_file))
+    cfg.PHASE = "test"                                   # only suppresses the pretrained-weights download (App. B9)
+    cfg.check_and_freeze()
+    from segmentron.solver.loss import get_segmentation_loss
+    from segmentron.solver.optimizer import get_optimizer
+    model = get_segmentation_model()
+    P = R.build_params(name, seed)
+    model.load_state_dict(P.state_dict(), strict=True)
+    model.train()
+    n, _, h, w = shape
+    g = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randint(-1, 19, (n, h, w), generator=g)
+    criterion = get_segmentation_loss(cfg.MODEL.MODEL_NAME, use_ohem=cfg.SOLVER.OHEM, aux=cfg.SOLVER.AUX,
+                                      aux_weight=cfg.SOLVER.AUX_WEIGHT, ignore_index=-1)
+    optimizer = get_optimizer(model)
+    # Dropout2d mask: torch draws a [N,C,1,1] Bernoulli(0.9) tensor; re-create it from the same RNG state for the oracle
+    torch.manual_seed(777)
+    mask = torch.empty(n, 256, 1, 1).bernoulli_(0.9) / 0.9
+    torch.manual_seed(777)
+    outputs = model(x)
+    loss = sum(criterion(outputs, target).values())
+    optimizer.zero_grad()
+    loss.backward()
+    ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
+    P.dropout_masks["head.aspp.dropout"] = mask
+    o_loss, o_grads, o_out, o_low = R.loss_and_grads(name, P, x, target)
+    assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(loss)), (float(loss), float(o_loss))
+    worst = 0.0
+    for k, gr in ref_grads.items():
+        e = float((gr - o_grads[k]).norm() / (gr.norm() + 1e-20))
+        worst = max(worst, e)
+        assert e < 2e-4, f"grad mismatch {k}: {e}"
+    assert set(ref_grads) == set(k for k in o_grads if float(o_grads[k].abs().max()) > 0 or k in ref_grads)
+    sd = model.state_dict()
+    for k in sd:
+        if k.endswith(("running_mean", "running_var")):
+            e = float((sd[k] - P.t[k]).abs().max())
+            assert e < 1e-5, f"running stat mismatch {k}: {e}"
+    optimizer.step()
+    lrs = {}
+    for gi, grp in enumerate(optimizer.param_groups):
+        for q in grp["params"]:
+            lrs[id(q)] = (grp["lr"], grp["weight_decay"], grp["momentum"])
+    hyper = {k: lrs[id(v)] for k, v in model.named_parameters() if id(v) in lrs}
+    stepped = {k: v.detach().clone() for k, v in model.named_parameters()}
+    small = ["encoder.conv1.weight", "encoder.bn1.weight", "encoder.bn1.bias", "encoder.layer4.2.bn3.weight",
+             "head.block.2.weight", "head.block.2.bias", "head.aspp.image_pooling.bn.weight", "head.c1_block.bn.bias"]
+    out = dict(case=case, model=name, seed=seed, input_seed=2000 + seed, shape=shape, loss=float(loss), mask=mask,
+               low=outputs[0].detach()[:, :, ::8, ::8].contiguous(), digest=grad_digest(ref_grads),
+               grads_small={k: ref_grads[k] for k in small}, hyper=hyper, stepped_digest=grad_digest(stepped, 999),
+               running={k: sd[k].clone() for k in sd if k.endswith(("running_mean", "running_var")) and
+                        (k.startswith("encoder.bn1") or "image_pooling" in k or "layer4.2.bn3" in k)},
+               oracle_vs_ref_worst_grad_rel=worst)
+    torch.save(out, os.path.join(HERE, case + ".pt"))
+    print(f"{case}: loss {float(loss):.6f}; worst grad rel-L2 oracle vs reference {worst:.2e}; {len(ref_grads)} grads")
+
+
 def run_module_cases():
     """Module-level fixtures: PAM, CAM, PyramidPooling from the reference classes; criss-cross
     attention from a line-by-line python transcription of ca_cuda.cu's index map (the CUDA
@@ -166,8 +255,9 @@ def run_module_cases():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        (run_module_cases() if sys.argv[1] == "modules" else run_model_case(sys.argv[1]))
+        c = sys.argv[1]
+        (run_module_cases() if c == "modules" else run_train_case(c) if c in TRAIN_CASES else run_model_case(c))
     else:
         env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
-        for c in list(MODEL_CASES) + ["modules"]:
+        for c in list(MODEL_CASES) + list(TRAIN_CASES) + ["modules"]:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), c], env=env)

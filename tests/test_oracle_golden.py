@@ -52,3 +52,47 @@ def test_param_names_are_reference_names():
         assert k in P.t, k
     assert tuple(P.t["head.aspp.conv.weight"].shape) == (256, 1280, 1, 1)
     assert tuple(P.t["encoder.block3.conv.weight"].shape) == (728, 256, 1, 1)
+
+
+def _digest(grads, seed=12345):
+    out = {}
+    for i, k in enumerate(sorted(grads)):
+        g = grads[k].detach().double().flatten()
+        r = torch.randn(g.numel(), generator=torch.Generator().manual_seed(seed + i), dtype=torch.float64)
+        out[k] = (float(g.norm()), float((g * r).sum()))
+    return out
+
+
+def test_training_step_matches_reference_fixture():
+    """Oracle train step (train-mode BN, Dropout2d mask, CE(ignore -1), backward, SGD groups) against the real reference's
+    tools/train.py iteration recorded in tests/golden/train_dlv3p_resnet101_65x97_b4.pt: loss, a (norm, random projection)
+    digest of all 356 parameter gradients, selected full gradients, BN running statistics, parameters after optimizer.step()."""
+    fx = torch.load(os.path.join(G, "train_dlv3p_resnet101_65x97_b4.pt"))
+    P = R.build_params(fx["model"], fx["seed"])
+    n, _, h, w = fx["shape"]
+    g = torch.Generator().manual_seed(fx["input_seed"])
+    x = torch.randn(*fx["shape"], generator=g)
+    target = torch.randint(-1, 19, (n, h, w), generator=g)
+    P.dropout_masks["head.aspp.dropout"] = fx["mask"]
+    before = {k: v.clone() for k, v in P.t.items()}
+    loss, grads, out, low = R.loss_and_grads(fx["model"], P, x, target)
+    assert abs(float(loss) - fx["loss"]) < 1e-4 * abs(fx["loss"])
+    assert float((out[:, :, ::8, ::8] - fx["low"]).abs().max() / fx["low"].abs().max()) < 1e-4
+    dg = _digest({k: v for k, v in grads.items() if k in fx["digest"]})
+    assert set(dg) == set(fx["digest"])
+    for k, (nrm, proj) in fx["digest"].items():
+        assert abs(dg[k][0] - nrm) <= 2e-3 * nrm + 1e-9, (k, dg[k], (nrm, proj))
+        assert abs(dg[k][1] - proj) <= 1e-2 * nrm + 1e-9, (k, dg[k], (nrm, proj))     # |<e, r>| ~ |e| for a unit-variance r
+    for k, gr in fx["grads_small"].items():
+        assert float((grads[k] - gr).norm() / gr.norm()) < 2e-3, k
+    for k, v in fx["running"].items():
+        assert torch.allclose(P.t[k], v, atol=1e-4), k
+    # torch.optim.SGD first step with the reference's param groups (solver/optimizer.py:14-34,50-51): p -= lr (g + wd p)
+    stepped = {}
+    for k, (lr, wd, mom) in fx["hyper"].items():
+        # parameters without a gradient (the unused ImageNet fc) are skipped by torch.optim.SGD
+        stepped[k] = before[k] - lr * (grads[k] + wd * before[k]) if k in grads else before[k]
+    sd = _digest(stepped, 999)
+    for k, (nrm, proj) in fx["stepped_digest"].items():
+        assert abs(sd[k][0] - nrm) <= 1e-4 * nrm + 1e-9, k
+    assert fx["hyper"]["head.block.2.weight"][0] == pytest.approx(10 * fx["hyper"]["encoder.conv1.weight"][0])

