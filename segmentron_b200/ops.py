@@ -18,6 +18,8 @@ def dt_code(dtype):
     try:
         return _DT[dtype]
     except KeyError:
+        if _PLAN_DRY_RUN:                 # fp64 buffers of the CPU plan interpreter (tests); never launched
+            return L.F32
         raise RuntimeError(f"segb200: unsupported dtype {dtype}")
 
 

@@ -237,7 +237,7 @@ class TrainPlan:
         self.keep, self.pool, self.pool_bytes, self.act_bytes = [], {}, 0, 0
         self.x_in = torch.zeros(shape, dtype=torch.float32, device=device)
         self.target = torch.zeros(self.n, self.H, self.W, dtype=torch.int64, device=device)
-        self.out3 = torch.zeros(3, dtype=torch.float32, device=device)
+        self.out3 = torch.zeros(3, dtype=self.STAT_DTYPE, device=device)
         self.masks = {}
         self.done_at = {}                 # parameter name -> number of backward steps after which its gradient is final
 
@@ -265,8 +265,10 @@ class TrainPlan:
         base = t._base if t._base is not None else t
         self.pool.setdefault((base.shape[0], base.shape[1], base.shape[2], base.shape[3]), []).append(base)
 
+    STAT_DTYPE = torch.float32            # (the CPU plan interpreter of the tests raises it to fp64 for an exact comparison)
+
     def f32(self, *shape):
-        t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        t = torch.zeros(*shape, dtype=self.STAT_DTYPE, device=self.device)
         self.keep.append(t)
         return t
 
@@ -591,6 +593,18 @@ class TrainPlan:
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for st in (steps if steps is not None else self.fwd + self.bwd):
             st.call(s)
+
+    def run_timed(self):
+        """Replay with a CUDA event pair around every launch (events on the launching stream) -> [(Step, ms)]."""
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        steps = self.fwd + self.bwd
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(steps) + 1)]
+        evs[0].record()
+        for i, st in enumerate(steps):
+            st.call(s)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return [(st, evs[i].elapsed_time(evs[i + 1])) for i, st in enumerate(steps)]
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -8,9 +8,11 @@ bucket ordering) can be checked against the oracle on a machine without a GPU.  
 import torch
 import torch.nn.functional as F
 
+CD = torch.float64          # compute dtype of the interpreter (fp64: no ReLU-mask flips from rounding noise)
+
 
 def _nchw(t):
-    return t.permute(0, 3, 1, 2).float()
+    return t.permute(0, 3, 1, 2).to(CD)
 
 
 def _act(v, act):
@@ -25,7 +27,7 @@ def _conv_core(x_nchw, W, info, ho, wo):
 
 
 def _unpack_w(w, cout, cin, k):
-    return w[:cout, :, :cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2).float()
+    return w[:cout, :, :cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2).to(CD)
 
 
 def run_step(st):
@@ -48,28 +50,28 @@ def run_step(st):
         xin = x if x.shape[3] == cin else x.as_strided((x.shape[0], x.shape[1], x.shape[2], cin), x.stride())
         o = _conv_core(_nchw(xin), _unpack_w(w, cout, cin, k), i, y.shape[1], y.shape[2]).permute(0, 2, 3, 1)
         if i["shift"] is not None:
-            sh = torch.zeros(cout)
+            sh = torch.zeros(cout, dtype=CD, device=x.device)
             m = min(cout, i["shift"].numel())
             sh[:m] = i["shift"][:m]
             o = o + sh
         if i["residual"] is not None:
-            o = o + i["residual"][..., :cout].float()
+            o = o + i["residual"][..., :cout].to(CD)
         y[..., :cout] = o.to(y.dtype)
     elif kind == "wgrad":
         x, dy, dw = i["x"], i["dy"], i["dw"]
         cin, cout, k = i["cin"], i["cout"], i["k"]
-        W0 = torch.zeros(cout, cin, k, k, requires_grad=True)
+        W0 = torch.zeros(cout, cin, k, k, dtype=CD, device=x.device, requires_grad=True)
         o = _conv_core(_nchw(x[..., :cin]), W0, i, dy.shape[1], dy.shape[2])
         o.backward(_nchw(dy[..., :cout]))
-        dw.view(cout, k * k, cin).add_(W0.grad.permute(0, 2, 3, 1).reshape(cout, k * k, cin))
+        dw.view(cout, k * k, cin).add_(W0.grad.permute(0, 2, 3, 1).reshape(cout, k * k, cin).to(dw.dtype))
     elif kind == "dw":
         x, w, y, d = i["x"], i["w"], i["y"], i["dilation"]
         c = x.shape[3]
-        W = w.t().reshape(c, 1, 3, 3).float()
+        W = w.t().reshape(c, 1, 3, 3).to(CD)
         y.copy_(F.conv2d(_nchw(x), W, None, 1, d, d, groups=c).permute(0, 2, 3, 1).to(y.dtype))
     elif kind == "bn_stats":
         x, partial, c = i["x"], i["partial"], i["c"]
-        xf = x.float().reshape(-1, c)
+        xf = x.to(CD).reshape(-1, c)
         partial.zero_()
         partial[:c] = xf.sum(0)
         partial[c:2 * c] = (xf * xf).sum(0)
@@ -79,37 +81,37 @@ def run_step(st):
         m = p[0] / cnt
         var = (p[1] / cnt - m * m).clamp(min=0)
         inv = 1.0 / torch.sqrt(var + i["eps"])
-        st_["mean"].copy_(m.float()); st_["invstd"].copy_(inv.float())
+        st_["mean"].copy_(m.to(CD)); st_["invstd"].copy_(inv.to(CD))
         sc = i["gamma"].double() * inv
-        st_["scale"].copy_(sc.float()); st_["shift"].copy_((i["beta"].double() - m * sc).float())
+        st_["scale"].copy_(sc.to(CD)); st_["shift"].copy_((i["beta"].double() - m * sc).to(CD))
         mom = i["momentum"]
-        i["rm"].mul_(1 - mom).add_(mom * m.float())
-        i["rv"].mul_(1 - mom).add_(mom * (var * cnt / (cnt - 1) if cnt > 1 else var).float())
+        i["rm"].mul_(1 - mom).add_((mom * m).to(i["rm"].dtype))
+        i["rv"].mul_(1 - mom).add_((mom * (var * cnt / (cnt - 1) if cnt > 1 else var)).to(i["rv"].dtype))
     elif kind == "bn_apply":
         y, z = i["y"], i["z"]
-        v = y.float()
+        v = y.to(CD)
         if i["scale"] is not None:
             v = v * i["scale"]
         if i["shift"] is not None:
             v = v + i["shift"]
         if i["residual"] is not None:
-            v = v + i["residual"].float()
+            v = v + i["residual"].to(CD)
         v = _act(v, i["act"])
         if i["nc_scale"] is not None:
             v = v * i["nc_scale"][:, None, None, :]
         z.copy_(v.to(z.dtype))
     elif kind in ("bn_bwd_reduce", "bn_bwd_apply"):
         dz, z, y, st_, act = i["dz"], i["z"], i["y"], i["st"], i["act"]
-        g = dz.float()
+        g = dz.to(CD)
         if i["nc_scale"] is not None:
             g = g * i["nc_scale"][:, None, None, :]
         if act == "relu":
-            g = g * (z.float() > 0)
+            g = g * (z.to(CD) > 0)
         elif act == "relu6":
-            g = g * ((z.float() > 0) & (z.float() < 6))
+            g = g * ((z.to(CD) > 0) & (z.to(CD) < 6))
         mean = st_["mean"] if st_.get("mean") is not None else 0.0
         inv = st_["invstd"] if st_.get("invstd") is not None else 1.0
-        xh = (y.float() - mean) * inv
+        xh = (y.to(CD) - mean) * inv
         c = g.shape[3]
         if kind == "bn_bwd_reduce":
             p = st_["partial"]
@@ -119,7 +121,7 @@ def run_step(st):
         else:
             if i["dres"] is not None:
                 dres = i["dres"]
-                dres.copy_(((dres.float() if i["dres_acc"] else 0) + g).to(dres.dtype))
+                dres.copy_(((dres.to(CD) if i["dres_acc"] else 0) + g).to(dres.dtype))
             if i["dy"] is not None:
                 s = st_["sums"]
                 o = st_["scale"] * (g - s[0] / i["count"] - xh * s[1] / i["count"])
@@ -127,23 +129,21 @@ def run_step(st):
     elif kind == "bn_bwd_finalize":
         st_, c = i["st"], i["c"]
         p = st_["partial"].view(st_["slabs"], 2, c).double().sum(0)
-        st_["sums"][0] = p[0].float(); st_["sums"][1] = p[1].float()
+        st_["sums"][0] = p[0].to(CD); st_["sums"][1] = p[1].to(CD)
         if i["dgamma"] is not None:
-            i["dgamma"].add_(p[1].float())
+            i["dgamma"].add_(p[1].to(i["dgamma"].dtype))
         if i["dbeta"] is not None:
-            i["dbeta"].add_(p[0].float())
+            i["dbeta"].add_(p[0].to(i["dbeta"].dtype))
     elif kind == "reduce_partials":
         K, c, slabs = i["K"], i["c"], i["slabs"]
-        tot = i["partial"].double()
-        full = tot[:slabs * K * (tot.numel() // (slabs * K))] if False else None
         # partial[(slab*K + k)*cc + ch] with cc = the channel count the producer used
         cc = i["partial"].numel() // (slabs * K)
         p = i["partial"].view(slabs, K, cc).double().sum(0)[:, :c]
         out = i["out"]
         for k in range(K):
-            idx = k * i["sk"] + torch.arange(c) * i["sc"]
-            v = (p[k] * i["scale"]).float()
-            out[idx] = out[idx] + v if i["accumulate"] else v
+            idx = k * i["sk"] + torch.arange(c, device=out.device) * i["sc"]
+            v = (p[k] * i["scale"]).to(CD)
+            out[idx] = (out[idx].to(CD) + v if i["accumulate"] else v).to(out.dtype)
     elif kind == "maxpool":
         i["y"].copy_(F.max_pool2d(_nchw(i["x"]), 3, 2, 1).permute(0, 2, 3, 1).to(i["y"].dtype))
     elif kind == "maxpool_bwd":
@@ -155,27 +155,27 @@ def run_step(st):
         y.copy_(F.interpolate(_nchw(i["x"]), y.shape[1:3], mode="bilinear", align_corners=True).permute(0, 2, 3, 1).to(y.dtype))
     elif kind == "bilinear_bwd":
         dy, dx = i["dy"], i["dx"]
-        xr = torch.zeros(dx.shape[0], dy.shape[3], dx.shape[1], dx.shape[2], requires_grad=True)
+        xr = torch.zeros(dx.shape[0], dy.shape[3], dx.shape[1], dx.shape[2], dtype=CD, device=dy.device, requires_grad=True)
         F.interpolate(xr, dy.shape[1:3], mode="bilinear", align_corners=True).backward(_nchw(dy))
         g = xr.grad.permute(0, 2, 3, 1) * (float(i["gscale"][0]) if i["gscale"] is not None else 1.0)
         c = dy.shape[3]
-        dx[..., :c] = ((dx[..., :c].float() if i["accumulate"] else 0) + g).to(dx.dtype)
+        dx[..., :c] = ((dx[..., :c].to(CD) if i["accumulate"] else 0) + g).to(dx.dtype)
     elif kind == "gap":
-        i["y"].copy_(i["x"].float().mean((1, 2), keepdim=True).to(i["y"].dtype))
+        i["y"].copy_(i["x"].to(CD).mean((1, 2), keepdim=True).to(i["y"].dtype))
     elif kind == "nc_broadcast":
         y = i["y"]
-        v = i["v"].float() * i["scale"]
-        y.copy_(((y.float() if i["accumulate"] else 0) + v.expand_as(y)).to(y.dtype))
+        v = i["v"].to(CD) * i["scale"]
+        y.copy_(((y.to(CD) if i["accumulate"] else 0) + v.expand_as(y)).to(y.dtype))
     elif kind == "stride2_place":
         t, z = i["t"], i["z"]
         if i["mode"] == 0:
             z.zero_()
             z[:, ::2, ::2, :] = t
         else:
-            z[:, ::2, ::2, :] = (z[:, ::2, ::2, :].float() + t.float()).to(z.dtype)
+            z[:, ::2, ::2, :] = (z[:, ::2, ::2, :].to(CD) + t.to(CD)).to(z.dtype)
     elif kind == "dw_wgrad":
         x, dy, c, d = i["x"], i["dy"], i["c"], i["dilation"]
-        W0 = torch.zeros(c, 1, 3, 3, requires_grad=True)
+        W0 = torch.zeros(c, 1, 3, 3, dtype=CD, device=x.device, requires_grad=True)
         F.conv2d(_nchw(x), W0, None, 1, d, d, groups=c).backward(_nchw(dy))
         p = i["partial"]
         p.zero_()
@@ -185,25 +185,25 @@ def run_step(st):
         up = F.interpolate(_nchw(lg[..., :nc]), tgt.shape[1:3], mode="bilinear", align_corners=True)
         valid = (tgt != i["ignore_index"]) & (tgt >= 0) & (tgt < nc)
         lsm = F.log_softmax(up, 1)
-        oh = F.one_hot(tgt.clamp(0, nc - 1), nc).permute(0, 3, 1, 2).float()
+        oh = F.one_hot(tgt.clamp(0, nc - 1), nc).permute(0, 3, 1, 2).to(CD)
         cnt = float(valid.sum())
         out3[0] = float(-(lsm * oh).sum(1)[valid].sum() / max(cnt, 1.0))
         out3[1] = 1.0 / cnt if cnt > 0 else 0.0
         out3[2] = cnt
-        g = (lsm.exp() - oh) * valid[:, None].float()
+        g = (lsm.exp() - oh) * valid[:, None].to(CD)
         dfull.zero_()
         dfull[..., :nc] = g.permute(0, 2, 3, 1).to(dfull.dtype)
     elif kind == "scatter_add":
         src, idx, dst = i["src"], i["index"].long(), i["dst"]
         m = idx >= 0
-        dst.index_add_(0, idx[m], src[m])
+        dst.index_add_(0, idx[m], src[m].to(dst.dtype))
     else:
         raise NotImplementedError(kind)
 
 
 def gather_cast(src, index, dst):
     idx = index.long()
-    v = torch.where(idx >= 0, src[idx.clamp(min=0)], torch.zeros(()))
+    v = torch.where(idx >= 0, src[idx.clamp(min=0)], torch.zeros((), dtype=src.dtype, device=src.device))
     dst.copy_(v.to(dst.dtype))
 
 

@@ -15,10 +15,15 @@ from oracle import segref as R  # noqa: E402
 
 @pytest.fixture()
 def dry_run():
+    """plan built over CPU buffers; fp64 activations AND statistics so that rounding noise cannot flip ReLU masks (train-mode
+    BatchNorm through 100 layers amplifies a 1e-7 perturbation ~1e4-fold with these synthetic weights)"""
     from segmentron_b200 import ops
+    from segmentron_b200.train import TrainPlan
     ops._PLAN_DRY_RUN = True
+    TrainPlan.STAT_DTYPE = torch.float64
     yield
     ops._PLAN_DRY_RUN = False
+    TrainPlan.STAT_DTYPE = torch.float32
 
 
 def test_train_plan_matches_oracle_on_cpu(dry_run):
@@ -30,30 +35,32 @@ def test_train_plan_matches_oracle_on_cpu(dry_run):
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
     torch.manual_seed(777)
     mask = torch.empty(shape[0], 256, 1, 1).bernoulli_(0.9) / 0.9
-    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.float32, device="cpu", lr=0.02)
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.float64, device="cpu", lr=0.02)
     loss = E.forward_backward(tr, x, target, {"head.aspp.dropout": mask})
     grads = tr.store.grads()
     sd_mid = tr.state_dict()
     P.dropout_masks["head.aspp.dropout"] = mask
     before = {k: v.clone() for k, v in P.t.items()}
-    o_loss, o_grads, _, _ = R.loss_and_grads(model, P, x, target)
-    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss)), (float(loss), float(o_loss))
+    P64 = P.to(dtype=torch.float64)
+    P64.frozen, P64.dropout_masks = True, P.dropout_masks
+    o_loss, o_grads, _, _ = R.loss_and_grads(model, P64, x.double(), target)
+    assert abs(float(loss) - float(o_loss)) < 1e-6 * abs(float(o_loss)), (float(loss), float(o_loss))
     worst = ("", 0.0)
     for k, gr in o_grads.items():
         e = float((grads[k] - gr).norm() / (gr.norm() + 1e-12))
         if e > worst[1]:
             worst = (k, e)
-    assert worst[1] < 2e-3, worst
+    assert worst[1] < 1e-6, worst                  # fp32 gradient buffers: ~3e-8 observed
     for k in sd_mid:
         if k.endswith(("running_mean", "running_var")):
-            assert torch.allclose(sd_mid[k], P.t[k], atol=1e-4, rtol=1e-4), k
+            assert torch.allclose(sd_mid[k].double(), P64.t[k], atol=1e-6, rtol=1e-6), k
     # SGD: encoder lr, decoder lr x10, weight decay on everything (solver/optimizer.py:14-34,50-51)
     E.sgd(tr)
     sd = tr.state_dict()
     for k in ("encoder.conv1.weight", "encoder.layer3.5.conv2.weight", "head.block.2.weight", "head.aspp.bn.bias"):
         lr = 0.02 * (10.0 if k.startswith("head.") else 1.0)
-        ref = before[k] - lr * (o_grads[k] + 1e-4 * before[k])
-        assert float((sd[k] - ref).norm() / ref.norm()) < 1e-4, k
+        ref = before[k].double() - lr * (o_grads[k] + 1e-4 * before[k].double())
+        assert float((sd[k].double() - ref).norm() / ref.norm()) < 1e-6, k
     # bucket plan: contiguous, covers the whole gradient, launch positions non-decreasing
     bk = tr.plan_for(shape)["buckets"]
     assert bk[0][2] == tr.store.total and bk[-1][1] == 0
@@ -66,15 +73,15 @@ def test_train_plan_matches_oracle_on_cpu(dry_run):
                 if t is not None and t.untyped_storage().data_ptr() == tr.store.grad.untyped_storage().data_ptr():
                     off = t.storage_offset()
                     assert not (lo <= off < hi), (st.kind, off, lo, hi)
-            if st.kind == "scatter_add":
-                assert hi <= 64 * 49 * 3 + 64 or lo == 0 or True
+            if st.kind == "scatter_add":               # the stem's s2d-space gradient is un-packed into encoder.conv1.weight
+                assert not (lo <= tr.store.meta["encoder.conv1.weight"]["off"] < hi), "stem gradient written after its bucket"
 
 
 def test_state_dict_roundtrip(dry_run):
     from segmentron_b200.train import DeepLabV3PlusTrainerB200
     P = R.build_params("deeplabv3plus_resnet101", 3)
     sd0 = P.state_dict()
-    tr = DeepLabV3PlusTrainerB200(sd0, dtype=torch.float32, device="cpu")
+    tr = DeepLabV3PlusTrainerB200(sd0, dtype=torch.float64, device="cpu")
     sd = tr.state_dict()
     assert set(sd) == set(sd0)
     for k in sd0:
