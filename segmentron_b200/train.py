@@ -226,8 +226,12 @@ class Act:
 # the plan
 # ------------------------------------------------------------------------------------------------------------
 class TrainPlan:
-    def __init__(self, store, shape, nclass, dtype, device, bn_momentum=0.1, ignore_index=-1):
+    def __init__(self, store, shape, nclass, dtype, device, bn_momentum=0.1, ignore_index=-1, dist=None, sync_bn=False):
         self.S, self.dtype, self.device = store, dtype, device
+        # SyncBatchNorm (the reference's default for distributed training, tools/train.py:73-79): batch statistics and the two
+        # backward sums are all-reduced over the ranks ([2][C] fp32 per layer, count-weighted == equal per-rank counts here)
+        self.dist = dist if (dist is not None and sync_bn) else None
+        self.world = dist.get_world_size() if self.dist is not None else 1
         self.lib = L.load()
         self.dt = ops.dt_code(dtype)
         self.n, _, self.H, self.W = shape
@@ -276,6 +280,10 @@ class TrainPlan:
     def add(self, kind, fn, args, **info):
         self.cur.append(Step(kind, (lambda s, fn=fn, args=args, kind=kind: L.check(fn(*args, s), kind)), info))
 
+    def allreduce(self, t):
+        d = self.dist
+        self.cur.append(Step("allreduce", (lambda s, t=t, d=d: d.all_reduce(t)), dict(t=t)))
+
     def conv(self, x, w, y, *, cin, cout, k=1, stride=1, dilation=1, pad=0, shift=None, residual=None):
         a = ops.make_conv_args(x, w, y, cin=cin, cout=cout, kh=k, kw=k, stride=stride, dilation=dilation, pad_t=pad,
                                pad_l=pad, shift=shift, residual=residual)
@@ -320,10 +328,18 @@ class TrainPlan:
         gamma, beta = S.view(S.master, bn + ".weight"), S.view(S.master, bn + ".bias")
         rm, rv = S.stat(bn + ".running_mean"), S.stat(bn + ".running_var")
         self.add("bn_stats", self.lib.segb200_bn_stats, (_ptr(y), rows, c, y_ld, self.dt, _ptr(partial), 0), x=y, partial=partial, c=c)
+        fin_partial, fin_slabs, count = partial, slabs, float(rows)
+        if self.dist is not None:
+            gsum = self.f32(2 * c)
+            self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(partial), slabs, 2, c, _ptr(gsum), c, 1, 0, 1.0),
+                     partial=partial, slabs=slabs, K=2, c=c, out=gsum, sk=c, sc=1, accumulate=0, scale=1.0)
+            self.allreduce(gsum)
+            fin_partial, fin_slabs, count = gsum, 1, float(rows * self.world)
+        st["count"] = count
         self.add("bn_finalize", self.lib.segb200_bn_finalize,
-                 (_ptr(partial), slabs, c, float(rows), _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
+                 (_ptr(fin_partial), fin_slabs, c, count, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
                   _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"])),
-                 partial=partial, slabs=slabs, c=c, count=float(rows), gamma=gamma, beta=beta, rm=rm, rv=rv,
+                 partial=fin_partial, slabs=fin_slabs, c=c, count=count, gamma=gamma, beta=beta, rm=rm, rv=rv,
                  momentum=self.bn_momentum, eps=eps, st=st)
         res_ld = self._rows(residual)[3] if residual is not None else 0
         self.add("bn_apply", self.lib.segb200_bn_apply,
@@ -347,15 +363,18 @@ class TrainPlan:
         self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
                  (_ptr(st["partial"]), st["slabs"], c, _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)), st=st, c=c, dgamma=dgamma,
                  dbeta=dbeta)
+        if self.dist is not None:
+            self.allreduce(st["sums"])               # dgamma / dbeta above are the LOCAL sums (DDP averages them with the rest)
+        count = st.get("count", float(rows))
         dres, dres_acc, dres_ld = None, False, 0
         if residual is not None:
             dres, dres_acc = residual.take()
             dres_ld = self._rows(dres)[3]
         self.add("bn_bwd_apply", self.lib.segb200_bn_bwd_apply,
-                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["sums"]), float(rows),
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["sums"]), count,
                   _ptr(nc_scale), _ptr(dy), _ptr(dres), int(dres_acc), rows, hw, c, dz_ld, z_ld, y_ld, self._rows(dy)[3], dres_ld,
                   L.ACT[act], self.dt),
-                 dz=dz, z=zz, y=y, st=st, count=float(rows), nc_scale=nc_scale, dy=dy, dres=dres, dres_acc=dres_acc, act=act)
+                 dz=dz, z=zz, y=y, st=st, count=count, nc_scale=nc_scale, dy=dy, dres=dres, dres_acc=dres_acc, act=act)
 
     # ---- conv (+BN +act) unit ----
     def conv_unit(self, x, wname, bn=None, act=None, *, k=1, stride=1, dilation=1, pad=0, residual=None, out=None, bias=None,
@@ -700,7 +719,7 @@ class DeepLabV3PlusTrainerB200:
 
     def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, dtype=torch.bfloat16, device="cuda",
                  lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
-                 bucket_mb=25, cuda_graph=False):
+                 bucket_mb=25, cuda_graph=False, sync_bn=True):
         if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
             raise RuntimeError("segb200: a CUDA device (sm_100a) is required; there is no CPU fallback")
         self.device = torch.device(device)
@@ -711,6 +730,7 @@ class DeepLabV3PlusTrainerB200:
         self.dropout = dropout
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         self.cuda_graph = cuda_graph
+        self.sync_bn = sync_bn                  # cfg.TRAIN.SYNC_BATCH_NORM (config/settings.py:59): only matters when world > 1
         self.store = ParamStore({k: v.detach() for k, v in state_dict.items()}, self.device, dtype, stem="encoder.conv1.weight")
         self.plans = {}
         self.world = 1
@@ -725,7 +745,8 @@ class DeepLabV3PlusTrainerB200:
     def plan_for(self, shape):
         shape = tuple(shape)
         if shape not in self.plans:
-            pl = TrainPlan(self.store, shape, self.nclass, self.dtype, self.device, self.bn_momentum)
+            pl = TrainPlan(self.store, shape, self.nclass, self.dtype, self.device, self.bn_momentum, dist=self.dist,
+                           sync_bn=self.sync_bn)
             build_deeplabv3plus_train(pl, **self.cfg)
             self.plans[shape] = dict(plan=pl, graph=None, buckets=self._buckets(pl))
         return self.plans[shape]
