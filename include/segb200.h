@@ -229,18 +229,21 @@ int segb200_bn_finalize(const float* partial, int slabs, int c, double count, co
 int segb200_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, const float* nc_scale,
                      void* z, long long rows, long long rows_per_img, int c, int y_ld, int res_ld, int z_ld, int act,
                      int dtype, void* stream);
-/* Backward of the same unit.  g = dz * nc_scale * act'(z);
+/* Backward of the same unit.  g = dz * nc_scale * act'(pre-activation); the activation mask is taken from the stored
+ * output z when z != NULL (required when a residual entered the activation), else recomputed as y*scale + shift
+ * (one activation read less per pass).
  *   bn_bwd_reduce   : per-slab sum(g), sum(g*xhat)         xhat = (y - mean)*invstd
  *   bn_bwd_finalize : sums[2][c]; dgamma += sum(g*xhat), dbeta += sum(g)
  *   bn_bwd_apply    : dy = scale*(g - sums[0]/count - xhat*sums[1]/count);  dres (+)= g   (sums == NULL: dy = g*scale) */
 int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                          const float* nc_scale, float* partial, long long rows, long long rows_per_img, int c, int dz_ld,
-                          int z_ld, int y_ld, int act, int dtype, int max_slabs, void* stream);
+                          const float* scale, const float* shift, const float* nc_scale, float* partial, long long rows,
+                          long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld, int act, int dtype, int max_slabs,
+                          void* stream);
 int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, float* sums, float* dgamma, float* dbeta, void* stream);
 int segb200_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                         const float* scale, const float* sums, double count, const float* nc_scale, void* dy, void* dres,
-                         int dres_accumulate, long long rows, long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld,
-                         int dy_ld, int dres_ld, int act, int dtype, void* stream);
+                         const float* scale, const float* shift, const float* sums, double count, const float* nc_scale,
+                         void* dy, void* dres, int dres_accumulate, long long rows, long long rows_per_img, int c, int dz_ld,
+                         int z_ld, int y_ld, int dy_ld, int dres_ld, int act, int dtype, void* stream);
 
 /* MaxPool2d(3,2,1) backward (first-maximum rule of torch), gather form: dx [n][h][w][dx_ld]. */
 int segb200_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n, int h, int w, int c, int x_ld, int dy_ld,

@@ -18,14 +18,14 @@ namespace segb200 {
 // ---------------------------------------------------------------------------------------------
 struct RedGeom { int cls, gx, slabs; long long rows_per_slab; };
 
-static RedGeom red_geom(long long rows, int c, int max_slabs) {
+static RedGeom red_geom(long long rows, int c, int max_slabs, int blocks_target = 148 * 4) {
   RedGeom g;
   const int cvn = c / 8;
   g.cls = 0;
   while ((1 << g.cls) < cvn && g.cls < 4) ++g.cls;
   const int cl = 1 << g.cls, pl = 256 >> g.cls;
   g.gx = (cvn + cl - 1) / cl;
-  long long want = (148LL * 4 + g.gx - 1) / g.gx;                  // ~4 blocks per SM in total
+  long long want = ((long long)blocks_target + g.gx - 1) / g.gx;  // ~4 (reductions) .. 8 (elementwise) blocks per SM in total
   const long long by_rows = (rows + (long long)pl * 4 - 1) / ((long long)pl * 4);   // at least 4 rows per thread
   if (want > by_rows) want = by_rows;
   if (want > max_slabs) want = max_slabs;
@@ -113,18 +113,28 @@ reduce_partials_kernel(const float* __restrict__ partial, int slabs, int K, int 
   *o = accumulate ? *o + v : v;
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per channel: lanes stride over the slabs (fixed order), shuffle tree => deterministic
 __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const float* __restrict__ partial, int slabs, int c, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                    float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
                    float* __restrict__ scale, float* __restrict__ shift) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (ch >= c) return;
   double s = 0.0, q = 0.0;
-  for (int sl = 0; sl < slabs; ++sl) {
+  for (int sl = lane; sl < slabs; sl += 32) {
     s += (double)partial[((long long)sl * 2) * c + ch];
     q += (double)partial[((long long)sl * 2 + 1) * c + ch];
   }
+  s = warp_sum(s); q = warp_sum(q);
+  if (lane != 0) return;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -148,50 +158,70 @@ bn_finalize_kernel(const float* __restrict__ partial, int slabs, int c, double c
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const void* __restrict__ y, int y_ld, const float* __restrict__ scale, const float* __restrict__ shift,
                 const void* __restrict__ res, int res_ld, const float* __restrict__ nc_scale, long long rows_per_img,
-                void* __restrict__ z, int z_ld, long long rows, int c, int act, int dtype) {
-  const int cvn = c / 8;
-  const long long total = rows * cvn;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cvn);
-    const long long row = idx / cvn;
+                void* __restrict__ z, int z_ld, long long rows, int c, int act, int dtype, int cls, long long rows_per_slab) {
+  const int cl = 1 << cls, pl = 256 >> cls;
+  const int lc = threadIdx.x & (cl - 1), lp = threadIdx.x >> cls;
+  const int cv = blockIdx.x * cl + lc;
+  if (cv >= c / 8) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  long long r1 = r0 + rows_per_slab; if (r1 > rows) r1 = rows;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale != nullptr ? scale[cv * 8 + j] : 1.f; sh[j] = shift != nullptr ? shift[cv * 8 + j] : 0.f; }
+  const char* yb = reinterpret_cast<const char*>(y) + (long long)cv * 16;
+  const char* rb = reinterpret_cast<const char*>(res) + (long long)cv * 16;
+  char* zb = reinterpret_cast<char*>(z) + (long long)cv * 16;
+  auto one = [&](long long p, const uint4& vy, const uint4& vr) {
     float f[8];
-    unpack8(ldg_nc_v4(reinterpret_cast<const char*>(y) + (row * y_ld + cv * 8) * 2), dtype, f);
-    if (scale != nullptr) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
-      f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-    }
-    if (shift != nullptr) {
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
-      f[0] += h0.x; f[1] += h0.y; f[2] += h0.z; f[3] += h0.w; f[4] += h1.x; f[5] += h1.y; f[6] += h1.z; f[7] += h1.w;
-    }
+    unpack8(vy, dtype, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
     if (res != nullptr) {
       float r[8];
-      unpack8(ldg_nc_v4(reinterpret_cast<const char*>(res) + (row * res_ld + cv * 8) * 2), dtype, r);
+      unpack8(vr, dtype, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += r[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], act);
     if (nc_scale != nullptr) {
-      const float* m = nc_scale + (row / rows_per_img) * c + cv * 8;
+      const float* m = nc_scale + (p / rows_per_img) * c + cv * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] *= __ldg(m + j);
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(z) + (row * z_ld + cv * 8) * 2) = pack8(f, dtype);
+    *reinterpret_cast<uint4*>(zb + p * z_ld * 2) = pack8(f, dtype);
+  };
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  long long p = r0 + lp;
+  for (; p + pl < r1; p += 2LL * pl) {                 // two rows in flight per thread
+    const uint4 a0 = ldg_nc_v4(yb + p * y_ld * 2), a1 = ldg_nc_v4(yb + (p + pl) * y_ld * 2);
+    uint4 b0 = zero4, b1 = zero4;
+    if (res != nullptr) { b0 = ldg_nc_v4(rb + p * res_ld * 2); b1 = ldg_nc_v4(rb + (p + pl) * res_ld * 2); }
+    one(p, a0, b0); one(p + pl, a1, b1);
+  }
+  if (p < r1) {
+    const uint4 a0 = ldg_nc_v4(yb + p * y_ld * 2);
+    const uint4 b0 = res != nullptr ? ldg_nc_v4(rb + p * res_ld * 2) : zero4;
+    one(p, a0, b0);
   }
 }
 
-// gradient through (optional channel mask, activation): g = dz * nc_scale * [act'(z)]
-__device__ __forceinline__ void act_grad8(float (&g)[8], const void* z, long long zoff, int act, const float* nc_scale,
-                                          long long nc_off, int dtype) {
+// gradient through (optional channel mask, activation): g = dz * nc_scale * [act'(pre-activation)].
+// The activation mask comes from the stored output z when it is given (needed when a residual entered the activation),
+// else it is recomputed from the raw conv output: pre = y * scale + shift  (saves one activation read per pass).
+__device__ __forceinline__ void act_grad8(float (&g)[8], const uint4& vz, bool have_z, const float (&yy)[8], const float (&sc)[8],
+                                          const float (&sh)[8], int act, const float* nc_scale, long long nc_off, int dtype) {
   if (nc_scale != nullptr) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] *= __ldg(nc_scale + nc_off + j);
   }
   if (act != ACT_NONE) {
     float zz[8];
-    unpack8(ldg_nc_v4(reinterpret_cast<const char*>(z) + zoff), dtype, zz);
+    if (have_z) unpack8(vz, dtype, zz);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zz[j] = fmaf(yy[j], sc[j], sh[j]);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool on = act == ACT_RELU6 ? (zz[j] > 0.f && zz[j] < 6.f) : (zz[j] > 0.f);
@@ -204,9 +234,9 @@ __device__ __forceinline__ void act_grad8(float (&g)[8], const void* z, long lon
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restrict__ z, int z_ld,
                      const void* __restrict__ y, int y_ld, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, const float* __restrict__ nc_scale, long long rows_per_img,
-                     long long rows, int c, int act, int dtype, int cls, long long rows_per_slab,
-                     float* __restrict__ partial) {
+                     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ nc_scale, long long rows_per_img, long long rows, int c, int act, int dtype,
+                     int cls, long long rows_per_slab, float* __restrict__ partial) {
   __shared__ float red[256][8];
   const int cl = 1 << cls, pl = 256 >> cls;
   const int lc = threadIdx.x & (cl - 1), lp = threadIdx.x >> cls;
@@ -214,19 +244,40 @@ bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restr
   const bool valid = cv < c / 8;
   const long long r0 = (long long)blockIdx.y * rows_per_slab;
   long long r1 = r0 + rows_per_slab; if (r1 > rows) r1 = rows;
-  float s1[8], s2[8], mu[8], is[8];
+  float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; }
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; sc[j] = 1.f; sh[j] = 0.f; }
+  const bool have_z = z != nullptr;
   if (valid) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean != nullptr ? mean[cv * 8 + j] : 0.f; is[j] = invstd != nullptr ? invstd[cv * 8 + j] : 1.f; }
-    for (long long p = r0 + lp; p < r1; p += pl) {
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean != nullptr ? mean[cv * 8 + j] : 0.f; is[j] = invstd != nullptr ? invstd[cv * 8 + j] : 1.f;
+      sc[j] = scale != nullptr ? scale[cv * 8 + j] : 1.f; sh[j] = shift != nullptr ? shift[cv * 8 + j] : 0.f;
+    }
+    const char* db = reinterpret_cast<const char*>(dz) + (long long)cv * 16;
+    const char* yb = reinterpret_cast<const char*>(y) + (long long)cv * 16;
+    const char* zb = reinterpret_cast<const char*>(z) + (long long)cv * 16;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    auto one = [&](long long p, const uint4& vd, const uint4& vy, const uint4& vz) {
       float g[8], yy[8];
-      unpack8(ldg_nc_v4(reinterpret_cast<const char*>(dz) + (p * dz_ld + cv * 8) * 2), dtype, g);
-      unpack8(ldg_nc_v4(reinterpret_cast<const char*>(y) + (p * y_ld + cv * 8) * 2), dtype, yy);
-      act_grad8(g, z, (p * z_ld + cv * 8) * 2, act, nc_scale, (p / rows_per_img) * c + cv * 8, dtype);
+      unpack8(vd, dtype, g);
+      unpack8(vy, dtype, yy);
+      act_grad8(g, vz, have_z, yy, sc, sh, act, nc_scale, nc_scale != nullptr ? (p / rows_per_img) * c + cv * 8 : 0, dtype);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], (yy[j] - mu[j]) * is[j], s2[j]); }
+    };
+    long long p = r0 + lp;
+    for (; p + pl < r1; p += 2LL * pl) {
+      const uint4 d0 = ldg_nc_v4(db + p * dz_ld * 2), d1 = ldg_nc_v4(db + (p + pl) * dz_ld * 2);
+      const uint4 y0 = ldg_nc_v4(yb + p * y_ld * 2), y1 = ldg_nc_v4(yb + (p + pl) * y_ld * 2);
+      uint4 z0 = zero4, z1 = zero4;
+      if (have_z && act != ACT_NONE) { z0 = ldg_nc_v4(zb + p * z_ld * 2); z1 = ldg_nc_v4(zb + (p + pl) * z_ld * 2); }
+      one(p, d0, y0, z0); one(p + pl, d1, y1, z1);
+    }
+    if (p < r1) {
+      const uint4 d0 = ldg_nc_v4(db + p * dz_ld * 2), y0 = ldg_nc_v4(yb + p * y_ld * 2);
+      const uint4 z0 = (have_z && act != ACT_NONE) ? ldg_nc_v4(zb + p * z_ld * 2) : zero4;
+      one(p, d0, y0, z0);
     }
   }
   float* dst = partial + ((long long)blockIdx.y * 2) * c + cv * 8;
@@ -234,42 +285,68 @@ bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restr
   block_colsum_store(s2, red, cls, lc, lp, valid, dst + c);
 }
 
-// sums[0][c] = sum g, sums[1][c] = sum g*xhat; dgamma += sums[1], dbeta += sums[0]
+// sums[0][c] = sum g, sums[1][c] = sum g*xhat; dgamma += sums[1], dbeta += sums[0]   (one warp per channel)
 __global__ void __launch_bounds__(128)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int c, float* __restrict__ sums,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (ch >= c) return;
   double a = 0.0, b = 0.0;
-  for (int sl = 0; sl < slabs; ++sl) {
+  for (int sl = lane; sl < slabs; sl += 32) {
     a += (double)partial[((long long)sl * 2) * c + ch];
     b += (double)partial[((long long)sl * 2 + 1) * c + ch];
   }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane != 0) return;
   sums[ch] = (float)a;
   sums[c + ch] = (float)b;
   if (dgamma != nullptr) dgamma[ch] += (float)b;
   if (dbeta != nullptr) dbeta[ch] += (float)a;
 }
 
-// BatchNorm backward, pass 2: dy = scale * (g - sum_g/count - xhat * sum_gx/count); dres (+)= g
+// BatchNorm backward, pass 2: dy = scale * (g - sum_g/count - xhat * sum_gx/count) = A*g + B*y + C per channel; dres (+)= g
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const void* __restrict__ dz, int dz_ld, const void* __restrict__ z, int z_ld,
                     const void* __restrict__ y, int y_ld, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ sums,
-                    float inv_count, const float* __restrict__ nc_scale, long long rows_per_img, void* __restrict__ dy,
-                    int dy_ld, void* __restrict__ dres, int dres_ld, int dres_accumulate, long long rows, int c, int act,
-                    int dtype) {
-  const int cvn = c / 8;
-  const long long total = rows * cvn;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cvn);
-    const long long p = idx / cvn;
-    float g[8];
-    unpack8(ldg_nc_v4(reinterpret_cast<const char*>(dz) + (p * dz_ld + cv * 8) * 2), dtype, g);
-    act_grad8(g, z, (p * z_ld + cv * 8) * 2, act, nc_scale, (p / rows_per_img) * c + cv * 8, dtype);
+                    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ sums, float inv_count, const float* __restrict__ nc_scale,
+                    long long rows_per_img, void* __restrict__ dy, int dy_ld, void* __restrict__ dres, int dres_ld,
+                    int dres_accumulate, long long rows, int c, int act, int dtype, int cls, long long rows_per_slab) {
+  const int cl = 1 << cls, pl = 256 >> cls;
+  const int lc = threadIdx.x & (cl - 1), lp = threadIdx.x >> cls;
+  const int cv = blockIdx.x * cl + lc;
+  if (cv >= c / 8) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  long long r1 = r0 + rows_per_slab; if (r1 > rows) r1 = rows;
+  float A[8], B[8], Cc[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cv * 8 + j;
+    sc[j] = scale != nullptr ? scale[ch] : 1.f;
+    sh[j] = shift != nullptr ? shift[ch] : 0.f;
+    if (sums != nullptr) {
+      const float is = invstd[ch], mu = mean[ch], k2 = sc[j] * sums[c + ch] * inv_count * is;
+      A[j] = sc[j]; B[j] = -k2; Cc[j] = fmaf(k2, mu, -sc[j] * sums[ch] * inv_count);
+    } else {
+      A[j] = sc[j]; B[j] = 0.f; Cc[j] = 0.f;
+    }
+  }
+  const bool have_z = z != nullptr;
+  const bool need_y = sums != nullptr || (!have_z && act != ACT_NONE);
+  const char* db = reinterpret_cast<const char*>(dz) + (long long)cv * 16;
+  const char* yb = reinterpret_cast<const char*>(y) + (long long)cv * 16;
+  const char* zb = reinterpret_cast<const char*>(z) + (long long)cv * 16;
+  char* ob = reinterpret_cast<char*>(dy) + (long long)cv * 16;
+  char* rb = reinterpret_cast<char*>(dres) + (long long)cv * 16;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  auto one = [&](long long p, const uint4& vd, const uint4& vy, const uint4& vz) {
+    float g[8], yy[8];
+    unpack8(vd, dtype, g);
+    unpack8(vy, dtype, yy);
+    act_grad8(g, vz, have_z, yy, sc, sh, act, nc_scale, nc_scale != nullptr ? (p / rows_per_img) * c + cv * 8 : 0, dtype);
     if (dres != nullptr) {
-      char* rp = reinterpret_cast<char*>(dres) + (p * dres_ld + cv * 8) * 2;
+      char* rp = rb + p * dres_ld * 2;
       float o[8];
       if (dres_accumulate) {
         unpack8(*reinterpret_cast<const uint4*>(rp), dtype, o);
@@ -283,21 +360,24 @@ bn_bwd_apply_kernel(const void* __restrict__ dz, int dz_ld, const void* __restri
     }
     if (dy != nullptr) {
       float o[8];
-      if (sums != nullptr) {
-        float yy[8];
-        unpack8(ldg_nc_v4(reinterpret_cast<const char*>(y) + (p * y_ld + cv * 8) * 2), dtype, yy);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = cv * 8 + j;
-          const float xh = (yy[j] - __ldg(mean + ch)) * __ldg(invstd + ch);
-          o[j] = __ldg(scale + ch) * (g[j] - __ldg(sums + ch) * inv_count - xh * __ldg(sums + c + ch) * inv_count);
-        }
-      } else {                                         // no normalisation in the unit (bias-only conv): dy = g * scale
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = scale != nullptr ? g[j] * __ldg(scale + cv * 8 + j) : g[j];
-      }
-      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dy) + (p * dy_ld + cv * 8) * 2) = pack8(o, dtype);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(B[j], yy[j], Cc[j]));
+      *reinterpret_cast<uint4*>(ob + p * dy_ld * 2) = pack8(o, dtype);
     }
+  };
+  long long p = r0 + lp;
+  for (; p + pl < r1; p += 2LL * pl) {
+    const uint4 d0 = ldg_nc_v4(db + p * dz_ld * 2), d1 = ldg_nc_v4(db + (p + pl) * dz_ld * 2);
+    uint4 y0 = zero4, y1 = zero4, z0 = zero4, z1 = zero4;
+    if (need_y) { y0 = ldg_nc_v4(yb + p * y_ld * 2); y1 = ldg_nc_v4(yb + (p + pl) * y_ld * 2); }
+    if (have_z && act != ACT_NONE) { z0 = ldg_nc_v4(zb + p * z_ld * 2); z1 = ldg_nc_v4(zb + (p + pl) * z_ld * 2); }
+    one(p, d0, y0, z0); one(p + pl, d1, y1, z1);
+  }
+  if (p < r1) {
+    const uint4 d0 = ldg_nc_v4(db + p * dz_ld * 2);
+    const uint4 y0 = need_y ? ldg_nc_v4(yb + p * y_ld * 2) : zero4;
+    const uint4 z0 = (have_z && act != ACT_NONE) ? ldg_nc_v4(zb + p * z_ld * 2) : zero4;
+    one(p, d0, y0, z0);
   }
 }
 
@@ -541,13 +621,15 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (valid) {
-    for (long long p = r0 + lp; p < r1; p += pl) {
+    const char* xb = reinterpret_cast<const char*>(x) + (long long)cv * 16;
+    const char* gb = reinterpret_cast<const char*>(dy) + (long long)cv * 16;
+    auto pixel = [&](long long p, const uint4& vg) {
       const int xw = (int)(p % w);
       const long long q = p / w;
       const int yh = (int)(q % h);
       const long long b = q / h;
       float g[8];
-      unpack8(ldg_nc_v4(reinterpret_cast<const char*>(dy) + (p * dy_ld + cv * 8) * 2), dtype, g);
+      unpack8(vg, dtype, g);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = yh + (ky - 1) * dilation;
@@ -557,7 +639,7 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
           const int ix = xw + (kx - 1) * dilation;
           if (ix < 0 || ix >= w) continue;
           float f[8];
-          unpack8(ldg_v4(reinterpret_cast<const char*>(x) + ((((long long)b * h + iy) * w + ix) * x_ld + cv * 8) * 2), dtype, f);
+          unpack8(ldg_v4(xb + (((long long)b * h + iy) * w + ix) * x_ld * 2), dtype, f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float xv = pre_relu ? fmaxf(f[j], 0.f) : f[j];
@@ -565,7 +647,13 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
           }
         }
       }
+    };
+    long long p = r0 + lp;
+    for (; p + pl < r1; p += 2LL * pl) {               // two pixels in flight
+      const uint4 g0 = ldg_nc_v4(gb + p * dy_ld * 2), g1 = ldg_nc_v4(gb + (p + pl) * dy_ld * 2);
+      pixel(p, g0); pixel(p + pl, g1);
     }
+    if (p < r1) pixel(p, ldg_nc_v4(gb + p * dy_ld * 2));
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -719,7 +807,7 @@ extern "C" int segb200_bn_finalize(const float* partial, int slabs, int c, doubl
                                    float* mean, float* invstd, float* scale, float* shift, void* stream) {
   if (!partial || !mean || !invstd || !scale || !shift) return set_error(-1, "bn_finalize: null pointer");
   if (slabs < 1 || c < 1 || count < 1.0) return set_error(-4, "bn_finalize: bad sizes");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, STREAM(stream)>>>(partial, slabs, c, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(c + 3) / 4, 128, 0, STREAM(stream)>>>(partial, slabs, c, count, gamma, beta, running_mean,
                                                                  running_var, momentum, eps, mean, invstd, scale, shift);
   return check_launch("bn_finalize");
 }
@@ -731,21 +819,25 @@ extern "C" int segb200_bn_apply(const void* y, const float* scale, const float* 
   if (!half_dt(dtype)) return set_error(-2, "bn_apply: bad dtype");
   if (!vec_ok(c, y_ld) || !vec_ok(c, z_ld) || (residual && !vec_ok(c, res_ld)) || rows < 1 || rows_per_img < 1)
     return set_error(-4, "bn_apply: c and pitches must be multiples of 8");
-  bn_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM(stream)>>>(y, y_ld, scale, shift, residual, res_ld, nc_scale,
-                                                                            rows_per_img, z, z_ld, rows, c, act, dtype);
+  const RedGeom g = red_geom(rows, c, 1 << 20, 148 * 8);
+  bn_apply_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(y, y_ld, scale, shift, residual, res_ld, nc_scale, rows_per_img,
+                                                                   z, z_ld, rows, c, act, dtype, g.cls, g.rows_per_slab);
   return check_launch("bn_apply");
 }
 
 extern "C" int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                                     const float* nc_scale, float* partial, long long rows, long long rows_per_img, int c,
-                                     int dz_ld, int z_ld, int y_ld, int act, int dtype, int max_slabs, void* stream) {
-  if (!dz || !y || !partial || (act != ACT_NONE && !z)) return set_error(-1, "bn_bwd_reduce: null pointer");
+                                     const float* scale, const float* shift, const float* nc_scale, float* partial,
+                                     long long rows, long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld, int act,
+                                     int dtype, int max_slabs, void* stream) {
+  if (!dz || !y || !partial) return set_error(-1, "bn_bwd_reduce: null pointer");
+  if (act != ACT_NONE && !z && (!scale || !shift))
+    return set_error(-1, "bn_bwd_reduce: the activation mask needs z, or scale and shift to recompute it from y");
   if (!half_dt(dtype)) return set_error(-2, "bn_bwd_reduce: bad dtype");
   if (!vec_ok(c, dz_ld) || !vec_ok(c, y_ld) || (z && !vec_ok(c, z_ld)) || rows < 1 || rows_per_img < 1)
     return set_error(-4, "bn_bwd_reduce: c and pitches must be multiples of 8");
   const RedGeom g = red_geom(rows, c, max_slabs > 0 ? max_slabs : 1 << 20);
-  bn_bwd_reduce_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(dz, dz_ld, z, z_ld, y, y_ld, mean, invstd, nc_scale,
-                                                                        rows_per_img, rows, c, act, dtype, g.cls,
+  bn_bwd_reduce_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(dz, dz_ld, z, z_ld, y, y_ld, mean, invstd, scale, shift,
+                                                                        nc_scale, rows_per_img, rows, c, act, dtype, g.cls,
                                                                         g.rows_per_slab, partial);
   return check_launch("bn_bwd_reduce");
 }
@@ -754,23 +846,27 @@ extern "C" int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, f
                                        void* stream) {
   if (!partial || !sums) return set_error(-1, "bn_bwd_finalize: null pointer");
   if (slabs < 1 || c < 1) return set_error(-4, "bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, STREAM(stream)>>>(partial, slabs, c, sums, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(c + 3) / 4, 128, 0, STREAM(stream)>>>(partial, slabs, c, sums, dgamma, dbeta);
   return check_launch("bn_bwd_finalize");
 }
 
 extern "C" int segb200_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                                    const float* scale, const float* sums, double count, const float* nc_scale, void* dy,
-                                    void* dres, int dres_accumulate, long long rows, long long rows_per_img, int c, int dz_ld,
-                                    int z_ld, int y_ld, int dy_ld, int dres_ld, int act, int dtype, void* stream) {
-  if (!dz || (act != ACT_NONE && !z) || (!dy && !dres)) return set_error(-1, "bn_bwd_apply: null pointer");
+                                    const float* scale, const float* shift, const float* sums, double count,
+                                    const float* nc_scale, void* dy, void* dres, int dres_accumulate, long long rows,
+                                    long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld, int dy_ld, int dres_ld, int act,
+                                    int dtype, void* stream) {
+  if (!dz || (!dy && !dres)) return set_error(-1, "bn_bwd_apply: null pointer");
+  if (act != ACT_NONE && !z && (!y || !scale || !shift))
+    return set_error(-1, "bn_bwd_apply: the activation mask needs z, or y with scale and shift to recompute it");
   if (sums && (!y || !mean || !invstd || !scale)) return set_error(-1, "bn_bwd_apply: normalised unit needs y/mean/invstd/scale");
   if (!half_dt(dtype)) return set_error(-2, "bn_bwd_apply: bad dtype");
   if (!vec_ok(c, dz_ld) || (y && !vec_ok(c, y_ld)) || (z && !vec_ok(c, z_ld)) || (dy && !vec_ok(c, dy_ld)) ||
       (dres && !vec_ok(c, dres_ld)) || rows < 1 || rows_per_img < 1 || count < 1.0)
     return set_error(-4, "bn_bwd_apply: c and pitches must be multiples of 8");
-  bn_bwd_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM(stream)>>>(
-      dz, dz_ld, z, z_ld, y, y_ld, mean, invstd, scale, sums, (float)(1.0 / count), nc_scale, rows_per_img, dy, dy_ld, dres,
-      dres_ld, dres_accumulate, rows, c, act, dtype);
+  const RedGeom g = red_geom(rows, c, 1 << 20, 148 * 8);
+  bn_bwd_apply_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(
+      dz, dz_ld, z, z_ld, y, y_ld, mean, invstd, scale, shift, sums, (float)(1.0 / count), nc_scale, rows_per_img, dy, dy_ld, dres,
+      dres_ld, dres_accumulate, rows, c, act, dtype, g.cls, g.rows_per_slab);
   return check_launch("bn_bwd_apply");
 }
 

@@ -352,12 +352,14 @@ class TrainPlan:
         """emit: BN/act backward -> dy; dgamma/dbeta accumulated; residual.grad (+)= g"""
         rows, hw, c, dz_ld = self._rows(dz)
         S = self.S
-        zz = z if act is not None else None
+        # the ReLU mask needs the stored output only when a residual entered the activation; otherwise both passes recompute
+        # it from y (one activation read less in each)
+        zz = z if (act is not None and residual is not None) else None
         z_ld = self._rows(z)[3] if zz is not None else 0
         y_ld = self._rows(y)[3]
         self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
-                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(nc_scale), _ptr(st["partial"]), rows, hw, c,
-                  dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"]),
+                  _ptr(nc_scale), _ptr(st["partial"]), rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
                  dz=dz, z=zz, y=y, st=st, nc_scale=nc_scale, act=act, c=c)
         dgamma, dbeta = S.view(S.grad, bn + ".weight"), S.view(S.grad, bn + ".bias")
         self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
@@ -371,9 +373,9 @@ class TrainPlan:
             dres, dres_acc = residual.take()
             dres_ld = self._rows(dres)[3]
         self.add("bn_bwd_apply", self.lib.segb200_bn_bwd_apply,
-                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["sums"]), count,
-                  _ptr(nc_scale), _ptr(dy), _ptr(dres), int(dres_acc), rows, hw, c, dz_ld, z_ld, y_ld, self._rows(dy)[3], dres_ld,
-                  L.ACT[act], self.dt),
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"]),
+                  _ptr(st["sums"]), count, _ptr(nc_scale), _ptr(dy), _ptr(dres), int(dres_acc), rows, hw, c, dz_ld, z_ld, y_ld,
+                  self._rows(dy)[3], dres_ld, L.ACT[act], self.dt),
                  dz=dz, z=zz, y=y, st=st, count=count, nc_scale=nc_scale, dy=dy, dres=dres, dres_acc=dres_acc, act=act)
 
     # ---- conv (+BN +act) unit ----
@@ -418,7 +420,7 @@ class TrainPlan:
                     slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
                     partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
                     self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
-                             (_ptr(dz), None, _ptr(dz), None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
+                             (_ptr(dz), None, _ptr(dz), None, None, None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
                              dz=dz, z=None, y=dz, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
                     self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, _ptr(sums), None, None),
                              st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)

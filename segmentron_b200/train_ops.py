@@ -78,7 +78,8 @@ def bn_forward(y, z, gamma, beta, running_mean, running_var, momentum, eps, act=
 
 
 def bn_backward(dz, z, y, st, dy, dgamma, dbeta, act=None, dres=None, dres_accumulate=False, nc_scale=None):
-    """dy = dBN(dz * act'(z)); dgamma/dbeta (fp32) are ACCUMULATED; dres (+)= dz * act'(z)."""
+    """dy = dBN(dz * act'(.)); dgamma/dbeta (fp32) are ACCUMULATED; dres (+)= dz * act'(.).  z=None: the activation mask is
+    recomputed from y (only valid when no residual entered the activation)."""
     rows, hw, c, dz_ld = _rows(dz)
     lib = L.load()
     s = _stream()
@@ -86,11 +87,12 @@ def bn_backward(dz, z, y, st, dy, dgamma, dbeta, act=None, dres=None, dres_accum
     partial = torch.empty(slabs * 2 * c, dtype=torch.float32, device=dz.device)
     z_ld = _rows(z)[3] if z is not None else 0
     y_ld = _rows(y)[3]
-    L.check(lib.segb200_bn_bwd_reduce(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(nc_scale), _ptr(partial),
-                                      rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], dt_code(dz.dtype), 0, s), "bn_bwd_reduce")
+    L.check(lib.segb200_bn_bwd_reduce(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift),
+                                      _ptr(nc_scale), _ptr(partial), rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], dt_code(dz.dtype), 0,
+                                      s), "bn_bwd_reduce")
     L.check(lib.segb200_bn_bwd_finalize(_ptr(partial), slabs, c, _ptr(st.sums), _ptr(dgamma), _ptr(dbeta), s), "bn_bwd_finalize")
-    L.check(lib.segb200_bn_bwd_apply(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.sums),
-                                     float(rows), _ptr(nc_scale), _ptr(dy), _ptr(dres), int(bool(dres_accumulate)), rows, hw, c,
+    L.check(lib.segb200_bn_bwd_apply(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift),
+                                     _ptr(st.sums), float(rows), _ptr(nc_scale), _ptr(dy), _ptr(dres), int(bool(dres_accumulate)), rows, hw, c,
                                      dz_ld, z_ld, y_ld, _rows(dy)[3], _rows(dres)[3] if dres is not None else 0, L.ACT[act],
                                      dt_code(dz.dtype), s), "bn_bwd_apply")
     return dy

@@ -107,10 +107,10 @@ def run_step(st):
         g = dz.to(CD)
         if i["nc_scale"] is not None:
             g = g * i["nc_scale"][:, None, None, :]
-        if act == "relu":
-            g = g * (z.to(CD) > 0)
-        elif act == "relu6":
-            g = g * ((z.to(CD) > 0) & (z.to(CD) < 6))
+        if act is not None:
+            # mask source: the stored output when given, else the pre-activation recomputed from y (kernel contract)
+            pre = z.to(CD) if z is not None else y.to(CD) * st_["scale"] + st_["shift"]
+            g = g * ((pre > 0) if act == "relu" else ((pre > 0) & (pre < 6)))
         mean = st_["mean"] if st_.get("mean") is not None else 0.0
         inv = st_["invstd"] if st_.get("invstd") is not None else 1.0
         xh = (y.to(CD) - mean) * inv

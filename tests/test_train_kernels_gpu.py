@@ -176,7 +176,9 @@ def test_batchnorm_train(case, act):
     dres = _rand(n, h, w, c, dtype=dtype, seed=12) if use_res else None
     dres0 = dres.clone() if use_res else None
     dgamma, dbeta = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
-    T.bn_backward(dz, z if act else None, y, st, dy, dgamma, dbeta, act=act, dres=dres, dres_accumulate=True, nc_scale=nc)
+    # the activation mask comes from z when a residual entered the activation, else it is recomputed from y
+    T.bn_backward(dz, z if (act and use_res) else None, y, st, dy, dgamma, dbeta, act=act, dres=dres, dres_accumulate=True,
+                  nc_scale=nc)
     torch.cuda.synchronize()
     _close(dy, yr.grad.permute(0, 2, 3, 1), f"bn dy {name}", tol=2.0 ** -6, max_bad_frac=1e-4)
     _close(dgamma, gr.grad, f"bn dgamma {name}", tol=2.0 ** -7)
