@@ -36,7 +36,9 @@ const char* segb200_last_error(void);
 /* Tuning knobs (process-global, not thread-safe; defaults are the measured best for one stream):
  *   "gemm_ring_kb"  : shared-memory ring of segb200_conv_gemm in KB (0 = 192 = whole SM).  A smaller ring leaves room for
  *                     a kernel of another stream to co-reside on the SM (dual-stream half-batch overlap).
- *   "dw_ring_slots" : cap on the row-ring depth of segb200_dwconv3x3 (0 = 12). */
+ *   "dw_ring_slots" : cap on the row-ring depth of segb200_dwconv3x3 (0 = 12).
+ *   "gemm_bn128"    : 1 (default) lets segb200_conv_gemm pick 128-wide N tiles when that saves >= 5 % of the persistent
+ *                     grid's rounds (wave quantisation); 0 forces 256-wide tiles. */
 int segb200_set_option(const char* name, int value);
 
 /* Diagnostics (only in a library built with -DSEGB200_DBG; otherwise returns -20): point subsequent
@@ -232,14 +234,14 @@ int segb200_bn_apply(const void* y, const float* scale, const float* shift, cons
 /* Backward of the same unit.  g = dz * nc_scale * act'(pre-activation); the activation mask is taken from the stored
  * output z when z != NULL (required when a residual entered the activation), else recomputed as y*scale + shift
  * (one activation read less per pass).
- *   bn_bwd_reduce   : per-slab sum(g), sum(g*xhat)         xhat = (y - mean)*invstd
- *   bn_bwd_finalize : sums[2][c]; dgamma += sum(g*xhat), dbeta += sum(g)
+ *   bn_bwd_reduce   : per-slab sum(g), sum(g*y)
+ *   bn_bwd_finalize : sums[2][c] = {sum(g), sum(g*xhat) = invstd*(sum(g*y) - mean*sum(g))}; dgamma += sums[1], dbeta += sums[0]
  *   bn_bwd_apply    : dy = scale*(g - sums[0]/count - xhat*sums[1]/count);  dres (+)= g   (sums == NULL: dy = g*scale) */
-int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                          const float* scale, const float* shift, const float* nc_scale, float* partial, long long rows,
-                          long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld, int act, int dtype, int max_slabs,
-                          void* stream);
-int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, float* sums, float* dgamma, float* dbeta, void* stream);
+int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* scale, const float* shift,
+                          const float* nc_scale, float* partial, long long rows, long long rows_per_img, int c, int dz_ld,
+                          int z_ld, int y_ld, int act, int dtype, int max_slabs, void* stream);
+int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, const float* mean, const float* invstd, float* sums,
+                            float* dgamma, float* dbeta, void* stream);
 int segb200_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                          const float* scale, const float* shift, const float* sums, double count, const float* nc_scale,
                          void* dy, void* dres, int dres_accumulate, long long rows, long long rows_per_img, int c, int dz_ld,
@@ -248,6 +250,12 @@ int segb200_bn_bwd_apply(const void* dz, const void* z, const void* y, const flo
 /* MaxPool2d(3,2,1) backward (first-maximum rule of torch), gather form: dx [n][h][w][dx_ld]. */
 int segb200_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int n, int h, int w, int c, int x_ld, int dy_ld,
                              int dx_ld, int dtype, void* stream);
+/* The pair the training plan uses: the forward also records the argmax tap (uint8 [n][ho][wo][c], 0..8, first maximum), the
+ * backward reads 4 x (index + gradient) per input vector instead of re-scanning the windows. */
+int segb200_maxpool3x3s2_idx(const void* x, void* y, uint8_t* idx, int n, int h, int w, int c, int x_ld, int y_ld, int dtype,
+                             void* stream);
+int segb200_maxpool3x3s2_bwd_idx(const uint8_t* idx, const void* dy, void* dx, int n, int h, int w, int c, int dy_ld, int dx_ld,
+                                 int dtype, void* stream);
 /* Backward of segb200_bilinear_nhwc (gather form): dx [n][hi][wi] (+)= gscale * W^T dy [n][ho][wo]; gscale = optional
  * DEVICE pointer to one float (the 1/valid-pixel-count of the loss). */
 int segb200_bilinear_nhwc_bwd(const void* dy, void* dx, int n, int hi, int wi, int c, int dx_ld, int ho, int wo, int dy_ld,

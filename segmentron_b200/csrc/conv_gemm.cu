@@ -382,9 +382,11 @@ using namespace segb200;
 
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
+static int g_no_bn128 = 0;
 extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
   if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
+  if (name && !strcmp(name, "gemm_bn128")) { g_no_bn128 = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -448,6 +450,16 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   // ---- N tiling ----
   p.cout = a->cout;
   p.bn = a->cout >= 256 ? 256 : ((a->cout + 15) & ~15);
+  if (a->cout >= 256 && !g_no_bn128) {
+    // wave quantisation: the persistent grid runs ceil(tiles / SMs) rounds of BN-wide tiles; 128-wide tiles halve the
+    // granularity (e.g. 3x3 256->256 on a 65x129 map: 324 tiles = 3 rounds of 256 vs 5 rounds of 128 = 2.5).  Taken only
+    // for a predicted gain of >= 5 % because narrow tiles re-read the A operand from L2 twice as often.
+    const long long m_tiles = (long long)p.wtiles * p.htiles * p.n_img;
+    const long long sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+    const long long r256 = (m_tiles * ((a->cout + 255) / 256) + sms - 1) / sms * 256;
+    const long long r128 = (m_tiles * ((a->cout + 127) / 128) + sms - 1) / sms * 128;
+    if (r128 * 100 <= r256 * 95) p.bn = 128;
+  }
   p.n_tiles = (a->cout + p.bn - 1) / p.bn;
   const long long total = (long long)p.wtiles * p.htiles * p.n_img * p.n_tiles;
   if (total > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many tiles");

@@ -230,11 +230,11 @@ __device__ __forceinline__ void act_grad8(float (&g)[8], const uint4& vz, bool h
   }
 }
 
-// BatchNorm backward, pass 1: per-slab sum(g) and sum(g * xhat) per channel, xhat = (y - mean) * invstd
-__global__ void __launch_bounds__(256)
+// BatchNorm backward, pass 1: per-slab sum(g) and sum(g * y) per channel (the finalize turns the second into
+// sum(g * xhat) = invstd * (sum(g*y) - mean * sum(g)); keeping mean/invstd out of the loop saves 16 registers)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restrict__ z, int z_ld,
-                     const void* __restrict__ y, int y_ld, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const void* __restrict__ y, int y_ld, const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ nc_scale, long long rows_per_img, long long rows, int c, int act, int dtype,
                      int cls, long long rows_per_slab, float* __restrict__ partial) {
   __shared__ float red[256][8];
@@ -244,16 +244,13 @@ bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restr
   const bool valid = cv < c / 8;
   const long long r0 = (long long)blockIdx.y * rows_per_slab;
   long long r1 = r0 + rows_per_slab; if (r1 > rows) r1 = rows;
-  float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
+  float s1[8], s2[8], sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; sc[j] = 1.f; sh[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; sc[j] = 1.f; sh[j] = 0.f; }
   const bool have_z = z != nullptr;
   if (valid) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mu[j] = mean != nullptr ? mean[cv * 8 + j] : 0.f; is[j] = invstd != nullptr ? invstd[cv * 8 + j] : 1.f;
-      sc[j] = scale != nullptr ? scale[cv * 8 + j] : 1.f; sh[j] = shift != nullptr ? shift[cv * 8 + j] : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) { sc[j] = scale != nullptr ? scale[cv * 8 + j] : 1.f; sh[j] = shift != nullptr ? shift[cv * 8 + j] : 0.f; }
     const char* db = reinterpret_cast<const char*>(dz) + (long long)cv * 16;
     const char* yb = reinterpret_cast<const char*>(y) + (long long)cv * 16;
     const char* zb = reinterpret_cast<const char*>(z) + (long long)cv * 16;
@@ -264,7 +261,7 @@ bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restr
       unpack8(vy, dtype, yy);
       act_grad8(g, vz, have_z, yy, sc, sh, act, nc_scale, nc_scale != nullptr ? (p / rows_per_img) * c + cv * 8 : 0, dtype);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], (yy[j] - mu[j]) * is[j], s2[j]); }
+      for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], yy[j], s2[j]); }
     };
     long long p = r0 + lp;
     for (; p + pl < r1; p += 2LL * pl) {
@@ -285,10 +282,12 @@ bn_bwd_reduce_kernel(const void* __restrict__ dz, int dz_ld, const void* __restr
   block_colsum_store(s2, red, cls, lc, lp, valid, dst + c);
 }
 
-// sums[0][c] = sum g, sums[1][c] = sum g*xhat; dgamma += sums[1], dbeta += sums[0]   (one warp per channel)
+// sums[0][c] = sum g, sums[1][c] = sum g*xhat = invstd * (sum g*y - mean * sum g); dgamma += sums[1], dbeta += sums[0]
+// (one warp per channel)
 __global__ void __launch_bounds__(128)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int c, float* __restrict__ sums,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int c, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ sums, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
   const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (ch >= c) return;
@@ -299,6 +298,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int c, floa
   }
   a = warp_sum(a); b = warp_sum(b);
   if (lane != 0) return;
+  b = (invstd != nullptr ? (double)invstd[ch] : 1.0) * (b - (mean != nullptr ? (double)mean[ch] : 0.0) * a);
   sums[ch] = (float)a;
   sums[c + ch] = (float)b;
   if (dgamma != nullptr) dgamma[ch] += (float)b;
@@ -306,7 +306,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int c, floa
 }
 
 // BatchNorm backward, pass 2: dy = scale * (g - sum_g/count - xhat * sum_gx/count) = A*g + B*y + C per channel; dres (+)= g
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const void* __restrict__ dz, int dz_ld, const void* __restrict__ z, int z_ld,
                     const void* __restrict__ y, int y_ld, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -431,6 +431,82 @@ maxpool3x3s2_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy,
       }
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dx) + ((((long long)b * h + iy) * w + ix) * dx_ld + cv * 8) * 2) = pack8(acc, dtype);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(3, 2, 1) forward that also records the argmax tap (0..8, first maximum in row-major scan order = torch's rule),
+// and the backward that uses it: 4 x (8 B index + 16 B gradient) per input vector instead of re-scanning 4 x 9 inputs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_idx_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ idx, int n, int h, int w, int c,
+                        int x_ld, int ho, int wo, int y_ld, int dtype) {
+  const int cvn = c / 8;
+  const long long total = (long long)n * ho * wo * cvn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int ox = (int)(r % wo); r /= wo;
+    const int oy = (int)(r % ho);
+    const long long b = r / ho;
+    float m[8]; int pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; pos[j] = -1; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        float f[8];
+        unpack8(ldg_v4(reinterpret_cast<const char*>(x) + (((b * h + iy) * w + ix) * x_ld + cv * 8) * 2), dtype, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > m[j] || pos[j] < 0) { m[j] = f[j]; pos[j] = ky * 3 + kx; }
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + (((b * ho + oy) * wo + ox) * y_ld + cv * 8) * 2) = pack8(m, dtype);
+    uint2 pk;
+    pk.x = (uint32_t)pos[0] | ((uint32_t)pos[1] << 8) | ((uint32_t)pos[2] << 16) | ((uint32_t)pos[3] << 24);
+    pk.y = (uint32_t)pos[4] | ((uint32_t)pos[5] << 8) | ((uint32_t)pos[6] << 16) | ((uint32_t)pos[7] << 24);
+    *reinterpret_cast<uint2*>(idx + ((b * ho + oy) * wo + ox) * c + cv * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_idx_kernel(const uint8_t* __restrict__ idx, const void* __restrict__ dy, void* __restrict__ dx, int n, int h,
+                            int w, int c, int ho, int wo, int dy_ld, int dx_ld, int dtype) {
+  const int cvn = c / 8;
+  const long long total = (long long)n * h * w * cvn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvn);
+    long long r = i / cvn;
+    const int ix = (int)(r % w); r /= w;
+    const int iy = (int)(r % h);
+    const long long b = r / h;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oy0 = iy / 2, oy1 = (iy + 1) / 2, ox0 = ix / 2, ox1 = (ix + 1) / 2;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      if (oy >= ho) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        if (ox >= wo) continue;
+        const uint32_t me = (uint32_t)((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));
+        const long long o = (b * ho + oy) * wo + ox;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + o * c + cv * 8));
+        float g[8];
+        unpack8(ldg_v4(reinterpret_cast<const char*>(dy) + (o * dy_ld + cv * 8) * 2), dtype, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j] += ((pk.x >> (8 * j)) & 0xffu) == me ? g[j] : 0.f;
+          acc[4 + j] += ((pk.y >> (8 * j)) & 0xffu) == me ? g[4 + j] : 0.f;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dx) + (((b * h + iy) * w + ix) * dx_ld + cv * 8) * 2) = pack8(acc, dtype);
   }
 }
 
@@ -825,10 +901,9 @@ extern "C" int segb200_bn_apply(const void* y, const float* scale, const float* 
   return check_launch("bn_apply");
 }
 
-extern "C" int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                                     const float* scale, const float* shift, const float* nc_scale, float* partial,
-                                     long long rows, long long rows_per_img, int c, int dz_ld, int z_ld, int y_ld, int act,
-                                     int dtype, int max_slabs, void* stream) {
+extern "C" int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* scale, const float* shift,
+                                     const float* nc_scale, float* partial, long long rows, long long rows_per_img, int c,
+                                     int dz_ld, int z_ld, int y_ld, int act, int dtype, int max_slabs, void* stream) {
   if (!dz || !y || !partial) return set_error(-1, "bn_bwd_reduce: null pointer");
   if (act != ACT_NONE && !z && (!scale || !shift))
     return set_error(-1, "bn_bwd_reduce: the activation mask needs z, or scale and shift to recompute it from y");
@@ -836,17 +911,17 @@ extern "C" int segb200_bn_bwd_reduce(const void* dz, const void* z, const void* 
   if (!vec_ok(c, dz_ld) || !vec_ok(c, y_ld) || (z && !vec_ok(c, z_ld)) || rows < 1 || rows_per_img < 1)
     return set_error(-4, "bn_bwd_reduce: c and pitches must be multiples of 8");
   const RedGeom g = red_geom(rows, c, max_slabs > 0 ? max_slabs : 1 << 20);
-  bn_bwd_reduce_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(dz, dz_ld, z, z_ld, y, y_ld, mean, invstd, scale, shift,
-                                                                        nc_scale, rows_per_img, rows, c, act, dtype, g.cls,
+  bn_bwd_reduce_kernel<<<dim3(g.gx, g.slabs), 256, 0, STREAM(stream)>>>(dz, dz_ld, z, z_ld, y, y_ld, scale, shift, nc_scale,
+                                                                        rows_per_img, rows, c, act, dtype, g.cls,
                                                                         g.rows_per_slab, partial);
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, float* sums, float* dgamma, float* dbeta,
-                                       void* stream) {
+extern "C" int segb200_bn_bwd_finalize(const float* partial, int slabs, int c, const float* mean, const float* invstd,
+                                       float* sums, float* dgamma, float* dbeta, void* stream) {
   if (!partial || !sums) return set_error(-1, "bn_bwd_finalize: null pointer");
   if (slabs < 1 || c < 1) return set_error(-4, "bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<(c + 3) / 4, 128, 0, STREAM(stream)>>>(partial, slabs, c, sums, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(c + 3) / 4, 128, 0, STREAM(stream)>>>(partial, slabs, c, mean, invstd, sums, dgamma, dbeta);
   return check_launch("bn_bwd_finalize");
 }
 
@@ -879,6 +954,28 @@ extern "C" int segb200_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx,
   maxpool3x3s2_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(x, dy, dx, n, h, w, c, x_ld,
                                                                                                   ho, wo, dy_ld, dx_ld, dtype);
   return check_launch("maxpool3x3s2_bwd");
+}
+
+extern "C" int segb200_maxpool3x3s2_idx(const void* x, void* y, uint8_t* idx, int n, int h, int w, int c, int x_ld, int y_ld,
+                                        int dtype, void* stream) {
+  if (!x || !y || !idx) return set_error(-1, "maxpool3x3s2_idx: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "maxpool3x3s2_idx: bad dtype");
+  if (!vec_ok(c, x_ld) || !vec_ok(c, y_ld)) return set_error(-4, "maxpool3x3s2_idx: bad c/pitches");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  maxpool3x3s2_idx_kernel<<<grid_for((long long)n * ho * wo * (c / 8), 256), 256, 0, STREAM(stream)>>>(x, y, idx, n, h, w, c, x_ld, ho,
+                                                                                                    wo, y_ld, dtype);
+  return check_launch("maxpool3x3s2_idx");
+}
+
+extern "C" int segb200_maxpool3x3s2_bwd_idx(const uint8_t* idx, const void* dy, void* dx, int n, int h, int w, int c, int dy_ld,
+                                            int dx_ld, int dtype, void* stream) {
+  if (!idx || !dy || !dx) return set_error(-1, "maxpool3x3s2_bwd_idx: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "maxpool3x3s2_bwd_idx: bad dtype");
+  if (!vec_ok(c, dy_ld) || !vec_ok(c, dx_ld)) return set_error(-4, "maxpool3x3s2_bwd_idx: bad c/pitches");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  maxpool3x3s2_bwd_idx_kernel<<<grid_for((long long)n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(idx, dy, dx, n, h, w, c, ho,
+                                                                                                      wo, dy_ld, dx_ld, dtype);
+  return check_launch("maxpool3x3s2_bwd_idx");
 }
 
 extern "C" int segb200_bilinear_nhwc_bwd(const void* dy, void* dx, int n, int hi, int wi, int c, int dx_ld, int ho, int wo,

@@ -76,10 +76,12 @@ SYMBOLS = {
     "segb200_bn_stats": (ci, [vp, ll, ci, ci, ci, vp, ci, vp]),
     "segb200_bn_finalize": (ci, [vp, ci, ci, C.c_double, vp, vp, vp, vp, cf, cf, vp, vp, vp, vp, vp]),
     "segb200_bn_apply": (ci, [vp, vp, vp, vp, vp, vp, ll, ll, ci, ci, ci, ci, ci, ci, vp]),
-    "segb200_bn_bwd_reduce": (ci, [vp] * 9 + [ll, ll] + [ci] * 7 + [vp]),
-    "segb200_bn_bwd_finalize": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+    "segb200_bn_bwd_reduce": (ci, [vp] * 7 + [ll, ll] + [ci] * 7 + [vp]),
+    "segb200_bn_bwd_finalize": (ci, [vp, ci, ci, vp, vp, vp, vp, vp, vp]),
     "segb200_bn_bwd_apply": (ci, [vp] * 8 + [C.c_double, vp, vp, vp, ci, ll, ll] + [ci] * 8 + [vp]),
     "segb200_maxpool3x3s2_bwd": (ci, [vp, vp, vp] + [ci] * 8 + [vp]),
+    "segb200_maxpool3x3s2_idx": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
+    "segb200_maxpool3x3s2_bwd_idx": (ci, [vp, vp, vp] + [ci] * 7 + [vp]),
     "segb200_bilinear_nhwc_bwd": (ci, [vp, vp] + [ci] * 10 + [vp, ci, vp]),
     "segb200_upsample_ce_blocks": (ci, [ci, ci, ci]),
     "segb200_upsample_ce": (ci, [vp, vp, vp, vp, vp] + [ci] * 11 + [vp]),

@@ -358,13 +358,13 @@ class TrainPlan:
         z_ld = self._rows(z)[3] if zz is not None else 0
         y_ld = self._rows(y)[3]
         self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
-                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"]),
-                  _ptr(nc_scale), _ptr(st["partial"]), rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
+                 (_ptr(dz), _ptr(zz), _ptr(y), _ptr(st["scale"]), _ptr(st["shift"]), _ptr(nc_scale), _ptr(st["partial"]), rows, hw, c,
+                  dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
                  dz=dz, z=zz, y=y, st=st, nc_scale=nc_scale, act=act, c=c)
         dgamma, dbeta = S.view(S.grad, bn + ".weight"), S.view(S.grad, bn + ".bias")
         self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
-                 (_ptr(st["partial"]), st["slabs"], c, _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)), st=st, c=c, dgamma=dgamma,
-                 dbeta=dbeta)
+                 (_ptr(st["partial"]), st["slabs"], c, _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)),
+                 st=st, c=c, dgamma=dgamma, dbeta=dbeta)
         if self.dist is not None:
             self.allreduce(st["sums"])               # dgamma / dbeta above are the LOCAL sums (DDP averages them with the rest)
         count = st.get("count", float(rows))
@@ -420,9 +420,9 @@ class TrainPlan:
                     slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
                     partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
                     self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
-                             (_ptr(dz), None, _ptr(dz), None, None, None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
+                             (_ptr(dz), None, _ptr(dz), None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
                              dz=dz, z=None, y=dz, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
-                    self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, _ptr(sums), None, None),
+                    self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, None, None, _ptr(sums), None, None),
                              st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)
                     gb = S.view(S.grad, bias)
                     self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(sums), 1, 1, co, _ptr(gb), 0, 1, 1, 1.0),
@@ -518,16 +518,19 @@ class TrainPlan:
     # ---- glue ops ----
     def maxpool(self, x):
         n, h, w_, c = x.t.shape
-        y = Act(self, self.new(n, (h - 1) // 2 + 1, (w_ - 1) // 2 + 1, c))
-        self.add("maxpool", self.lib.segb200_maxpool3x3s2, (_ptr(x.t), _ptr(y.t), n, h, w_, c, x.t.stride(2), y.t.stride(2), self.dt),
-                 x=x.t, y=y.t)
+        ho, wo = (h - 1) // 2 + 1, (w_ - 1) // 2 + 1
+        y = Act(self, self.new(n, ho, wo, c))
+        idx = torch.zeros(n, ho, wo, c, dtype=torch.uint8, device=self.device)
+        self.keep.append(idx)
+        self.add("maxpool", self.lib.segb200_maxpool3x3s2_idx, (_ptr(x.t), _ptr(y.t), _ptr(idx), n, h, w_, c, x.t.stride(2),
+                                                                y.t.stride(2), self.dt), x=x.t, y=y.t, idx=idx)
 
         def backward():
             dy = y.grad()
             gx, acc = x.take()
             assert not acc
-            self.add("maxpool_bwd", self.lib.segb200_maxpool3x3s2_bwd,
-                     (_ptr(x.t), _ptr(dy), _ptr(gx), n, h, w_, c, x.t.stride(2), dy.stride(2), gx.stride(2), self.dt), x=x.t, dy=dy, dx=gx)
+            self.add("maxpool_bwd", self.lib.segb200_maxpool3x3s2_bwd_idx,
+                     (_ptr(idx), _ptr(dy), _ptr(gx), n, h, w_, c, dy.stride(2), gx.stride(2), self.dt), x=x.t, dy=dy, dx=gx, idx=idx)
             self.pool_put(dy)
         self.tape.append(backward)
         return y

@@ -87,10 +87,10 @@ def bn_backward(dz, z, y, st, dy, dgamma, dbeta, act=None, dres=None, dres_accum
     partial = torch.empty(slabs * 2 * c, dtype=torch.float32, device=dz.device)
     z_ld = _rows(z)[3] if z is not None else 0
     y_ld = _rows(y)[3]
-    L.check(lib.segb200_bn_bwd_reduce(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift),
-                                      _ptr(nc_scale), _ptr(partial), rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], dt_code(dz.dtype), 0,
-                                      s), "bn_bwd_reduce")
-    L.check(lib.segb200_bn_bwd_finalize(_ptr(partial), slabs, c, _ptr(st.sums), _ptr(dgamma), _ptr(dbeta), s), "bn_bwd_finalize")
+    L.check(lib.segb200_bn_bwd_reduce(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.scale), _ptr(st.shift), _ptr(nc_scale), _ptr(partial),
+                                      rows, hw, c, dz_ld, z_ld, y_ld, L.ACT[act], dt_code(dz.dtype), 0, s), "bn_bwd_reduce")
+    L.check(lib.segb200_bn_bwd_finalize(_ptr(partial), slabs, c, _ptr(st.mean), _ptr(st.invstd), _ptr(st.sums), _ptr(dgamma),
+                                        _ptr(dbeta), s), "bn_bwd_finalize")
     L.check(lib.segb200_bn_bwd_apply(_ptr(dz), _ptr(z), _ptr(y), _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift),
                                      _ptr(st.sums), float(rows), _ptr(nc_scale), _ptr(dy), _ptr(dres), int(bool(dres_accumulate)), rows, hw, c,
                                      dz_ld, z_ld, y_ld, _rows(dy)[3], _rows(dres)[3] if dres is not None else 0, L.ACT[act],
@@ -102,6 +102,21 @@ def maxpool3x3s2_bwd(x, dy, dx):
     n, h, w, c, x_ld = _nhwc(x, "x")
     L.check(L.load().segb200_maxpool3x3s2_bwd(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, x_ld, _nhwc(dy, "dy")[4], _nhwc(dx, "dx")[4],
                                               dt_code(x.dtype), _stream()), "maxpool3x3s2_bwd")
+    return dx
+
+
+def maxpool3x3s2_idx(x, y, idx):
+    n, h, w, c, x_ld = _nhwc(x, "x")
+    assert idx.dtype == torch.uint8 and idx.is_contiguous() and idx.numel() == y.shape[0] * y.shape[1] * y.shape[2] * c
+    L.check(L.load().segb200_maxpool3x3s2_idx(_ptr(x), _ptr(y), _ptr(idx), n, h, w, c, x_ld, _nhwc(y, "y")[4], dt_code(x.dtype),
+                                              _stream()), "maxpool3x3s2_idx")
+    return y
+
+
+def maxpool3x3s2_bwd_idx(idx, dy, dx):
+    n, h, w, c, dx_ld = _nhwc(dx, "dx")
+    L.check(L.load().segb200_maxpool3x3s2_bwd_idx(_ptr(idx), _ptr(dy), _ptr(dx), n, h, w, c, _nhwc(dy, "dy")[4], dx_ld,
+                                                  dt_code(dx.dtype), _stream()), "maxpool3x3s2_bwd_idx")
     return dx
 
 

@@ -119,7 +119,7 @@ def run_step(st):
             p = st_["partial"]
             p.zero_()
             p[:c] = g.reshape(-1, c).sum(0)
-            p[c:2 * c] = (g * xh).reshape(-1, c).sum(0)
+            p[c:2 * c] = (g * y.to(CD)).reshape(-1, c).sum(0)            # sum(g*y); the finalize turns it into sum(g*xhat)
         else:
             if i["dres"] is not None:
                 dres = i["dres"]
@@ -131,6 +131,9 @@ def run_step(st):
     elif kind == "bn_bwd_finalize":
         st_, c = i["st"], i["c"]
         p = st_["partial"].view(st_["slabs"], 2, c).double().sum(0)
+        mean = st_["mean"].double() if st_.get("mean") is not None else 0.0
+        inv = st_["invstd"].double() if st_.get("invstd") is not None else 1.0
+        p = torch.stack([p[0], inv * (p[1] - mean * p[0])])
         st_["sums"][0] = p[0].to(CD); st_["sums"][1] = p[1].to(CD)
         if i["dgamma"] is not None:
             i["dgamma"].add_(p[1].to(i["dgamma"].dtype))

@@ -203,6 +203,29 @@ def test_maxpool_bwd_first_max_rule():
     _close(dx, xr.grad.permute(0, 2, 3, 1), "maxpool bwd")
 
 
+def test_maxpool_index_pair():
+    """forward with argmax taps + index-based backward (the pair the training plan uses) == F.max_pool2d autograd, ties included"""
+    from segmentron_b200 import train_ops as T
+    dtype = torch.bfloat16
+    for (n, h, w, c) in ((2, 33, 47, 64), (1, 34, 66, 64), (1, 5, 7, 8)):
+        x = torch.relu(_rand(n, h, w, c, dtype=dtype, seed=113))
+        x = (x * 4).round() / 4
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        dy = _rand(n, ho, wo, c, dtype=dtype, seed=114)
+        xr = _nchw(x).requires_grad_(True)
+        yr = F.max_pool2d(xr, 3, 2, 1)
+        yr.backward(_nchw(dy))
+        y = torch.empty(n, ho, wo, c, dtype=dtype, device="cuda")
+        idx = torch.empty(n, ho, wo, c, dtype=torch.uint8, device="cuda")
+        T.maxpool3x3s2_idx(x, y, idx)
+        dx = torch.empty_like(x)
+        T.maxpool3x3s2_bwd_idx(idx, dy, dx)
+        torch.cuda.synchronize()
+        assert torch.equal(y.float(), yr.detach().permute(0, 2, 3, 1)), "maxpool forward (idx variant)"
+        assert int(idx.max()) <= 8
+        _close(dx, xr.grad.permute(0, 2, 3, 1), f"maxpool idx bwd {(n, h, w, c)}")
+
+
 BIL_CASES = [("x4_ac", 2, 17, 33, 65, 129, 64, True), ("x4_ac_small", 1, 9, 9, 33, 33, 24, True),
              ("noalign_x2", 2, 16, 24, 32, 48, 32, False), ("bcast", 2, 1, 1, 17, 33, 64, True),
              ("same", 1, 17, 33, 17, 33, 16, True), ("down", 1, 33, 65, 17, 33, 16, True)]

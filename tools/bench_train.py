@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -136,6 +137,15 @@ def main():
         out["ref_by_layout"] = ref
         out["speedup"] = out["segb200_img_s"] / max(nums) if nums else None
         out["ref_what"] = "oracle port (the reference's torch ops) fp32 params + autocast(bf16) + torch SGD, cudnn.benchmark"
+    if args.cpu_baseline and rank == 0:
+        import time
+        Pc = R.build_params(MODEL, 0)
+        xc, tc = x[:1].cpu(), target[:1].cpu()
+        t0 = time.perf_counter()
+        R.loss_and_grads(MODEL, Pc, xc, tc)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"1 training iteration (fwd + CE + bwd, fp32) of the oracle port on 1x3x{args.height}x{args.width}"}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

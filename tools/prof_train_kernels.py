@@ -76,8 +76,8 @@ def bn(n, h, w, c):
     P = ops._ptr
     timed(f"bn_stats c{c} @{n}x{h}x{w}", lambda: L.check(lib.segb200_bn_stats(P(y), rows, c, ld, 0, P(part), 0, s())), 0, e)
     timed(f"bn_apply(+res,relu) c{c}", lambda: L.check(lib.segb200_bn_apply(P(y), P(st.scale), P(st.shift), P(res), None, P(z), rows, h * w, c, ld, ld, ld, 1, 0, s())), 0, 3 * e)
-    timed(f"bn_bwd_reduce c{c}", lambda: L.check(lib.segb200_bn_bwd_reduce(P(dz), P(z), P(y), P(st.mean), P(st.invstd), P(st.scale), P(st.shift), None, P(part), rows, h * w, c, ld, ld, ld, 1, 0, 0, s())), 0, 3 * e)
-    timed(f"bn_bwd_reduce(mask from y) c{c}", lambda: L.check(lib.segb200_bn_bwd_reduce(P(dz), None, P(y), P(st.mean), P(st.invstd), P(st.scale), P(st.shift), None, P(part), rows, h * w, c, ld, 0, ld, 1, 0, 0, s())), 0, 2 * e)
+    timed(f"bn_bwd_reduce c{c}", lambda: L.check(lib.segb200_bn_bwd_reduce(P(dz), P(z), P(y), P(st.scale), P(st.shift), None, P(part), rows, h * w, c, ld, ld, ld, 1, 0, 0, s())), 0, 3 * e)
+    timed(f"bn_bwd_reduce(mask from y) c{c}", lambda: L.check(lib.segb200_bn_bwd_reduce(P(dz), None, P(y), P(st.scale), P(st.shift), None, P(part), rows, h * w, c, ld, 0, ld, 1, 0, 0, s())), 0, 2 * e)
     timed(f"bn_bwd_apply(mask from y) c{c}", lambda: L.check(lib.segb200_bn_bwd_apply(P(dz), None, P(y), P(st.mean), P(st.invstd), P(st.scale), P(st.shift), P(st.sums), float(rows), None, P(dy), None, 0, rows, h * w, c, ld, 0, ld, ld, 0, 1, 0, s())), 0, 3 * e)
     timed(f"bn_bwd_apply(+dres) c{c}", lambda: L.check(lib.segb200_bn_bwd_apply(P(dz), P(z), P(y), P(st.mean), P(st.invstd), P(st.scale), P(st.shift), P(st.sums), float(rows), None, P(dy), P(res), 0, rows, h * w, c, ld, ld, ld, ld, ld, 1, 0, s())), 0, 5 * e)
 
