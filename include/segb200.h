@@ -37,8 +37,8 @@ const char* segb200_last_error(void);
  *   "gemm_ring_kb"  : shared-memory ring of segb200_conv_gemm in KB (0 = 192 = whole SM).  A smaller ring leaves room for
  *                     a kernel of another stream to co-reside on the SM (dual-stream half-batch overlap).
  *   "dw_ring_slots" : cap on the row-ring depth of segb200_dwconv3x3 (0 = 12).
- *   "gemm_bn128"    : 1 (default) lets segb200_conv_gemm pick 128-wide N tiles when that saves >= 5 % of the persistent
- *                     grid's rounds (wave quantisation); 0 forces 256-wide tiles. */
+ *   "gemm_bn128"    : 1 lets segb200_conv_gemm pick 128-wide N tiles when that saves >= 5 % of the persistent grid's rounds
+ *                     (wave quantisation).  Default 0: measured slower (operand traffic per FLOP rises by a third). */
 int segb200_set_option(const char* name, int value);
 
 /* Diagnostics (only in a library built with -DSEGB200_DBG; otherwise returns -20): point subsequent

@@ -382,7 +382,7 @@ using namespace segb200;
 
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
-static int g_no_bn128 = 0;
+static int g_no_bn128 = 1;   // measured: 128-wide tiles lose 45 % on the 3x3 256->256 layers (operand traffic per FLOP up 33 %)
 extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
   if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
@@ -451,9 +451,9 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.cout = a->cout;
   p.bn = a->cout >= 256 ? 256 : ((a->cout + 15) & ~15);
   if (a->cout >= 256 && !g_no_bn128) {
-    // wave quantisation: the persistent grid runs ceil(tiles / SMs) rounds of BN-wide tiles; 128-wide tiles halve the
-    // granularity (e.g. 3x3 256->256 on a 65x129 map: 324 tiles = 3 rounds of 256 vs 5 rounds of 128 = 2.5).  Taken only
-    // for a predicted gain of >= 5 % because narrow tiles re-read the A operand from L2 twice as often.
+    // OPT-IN experiment (segb200_set_option("gemm_bn128", 1)): 128-wide N tiles halve the wave-quantisation granularity of
+    // the persistent grid (3x3 256->256 on a 65x129 map: 324 tiles = 3 rounds of 256 vs 5 rounds of 128 = 2.5), but they
+    // raise the operand bytes per FLOP by 33 % and the kernel is bandwidth-delay bound on its smem ring: measured -45 %.
     const long long m_tiles = (long long)p.wtiles * p.htiles * p.n_img;
     const long long sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
     const long long r256 = (m_tiles * ((a->cout + 255) / 256) + sms - 1) / sms * 256;
