@@ -67,6 +67,8 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
+    ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
+    ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
     import __graft_entry__ as ge
@@ -79,10 +81,10 @@ def main():
     torch.backends.cudnn.benchmark = True
     P = R.build_params(MODEL, 0)
     shape = (args.batch, 3, args.height, args.width)
-    g = torch.Generator().manual_seed(1024 + rank)
+    g = torch.Generator().manual_seed(1024 + (0 if args.same_data else rank))
     x = torch.randn(*shape, generator=g).cuda()
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g).cuda()
-    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.02)
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
     losses = [float(tr.step(x, target)) for _ in range(max(args.warmup, 3))]
     parallel.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -121,7 +123,9 @@ def main():
                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
                "sum_kernel_ms": tot,
                "tensor_core_tflops": {k: v["flops"] / (v["ms"] * 1e-3) / 1e12 for k, v in mm.items()},
-               "activation_GB": pl.act_bytes / 1e9, "grad_pool_GB": pl.pool_bytes / 1e9}
+               "activation_GB": pl.act_bytes / 1e9, "grad_pool_GB": pl.pool_bytes / 1e9,
+               "sync_bn": bool(world > 1), "allreduce_buckets": len(tr.plan_for(shape)["buckets"]) if world > 1 else 0,
+               "param_digest": float(tr.store.master.double().abs().sum())}
     if not args.no_ref and world == 1:
         del tr
         torch.cuda.empty_cache()
