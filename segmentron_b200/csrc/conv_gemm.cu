@@ -367,6 +367,310 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variant: two CTAs of a cluster compute one 256 x BN tile.  Each CTA stages ITS 128 rows of A and
+// ITS half of the BN weight rows, so a stage is 16 KB + 16 KB instead of 16 KB + 32 KB: a third fewer operand bytes per FLOP
+// per SM and 6 ring stages instead of 4.  (The single-CTA kernel is bandwidth-delay bound on its ring: profiles/.)
+//   * both CTAs run the TMA producer; the peer's loads signal the LEADER's `full` barrier (cta_group::2 TMA form);
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256); its commits are multicast to both CTAs' barriers;
+//   * each CTA's epilogue drains its own 128 TMEM lanes; the peer's epilogue threads arrive on the leader's tmem_empty.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all previously issued MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA loads whose completion bytes are credited to the barrier of the pair's leader CTA (bit 24 of the cluster address = rank)
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_m256(bool bf16, uint32_t n) {
+  const uint32_t fmt = bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+template <bool kBF16, int kEpiGroups>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * kEpiGroups, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Control* ctl = reinterpret_cast<Control*>(smem + p.ring_bytes + 2 * kEpiBufBytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;           // b_stage_bytes = this CTA's HALF of the N tile
+  const int num_kb = p.ntaps * p.cblocks;
+  const int bk_elems = p.bk_bytes >> 1;
+  const int half_n = p.bn >> 1;
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int m_tiles = p.wtiles * p.htiles * p.n_img;
+  const int pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("segb200: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA0); prefetch_tmap(&tmB); prefetch_tmap(&tmC); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.num_stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&ctl->tmem_full[i], 1);
+        mbar_init(&ctl->tmem_empty[i], 2 * 128 * kEpiGroups);          // both CTAs' epilogue threads (used on the leader only)
+        mbar_init(&ctl->res_full[i], 1);
+      }
+      mbar_init(&ctl->b_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc2(&ctl->tmem_base, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                                  // barriers of both CTAs exist before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  auto decode = [&](int t, int& n_tile, int& wb, int& hb, int& img) {
+    n_tile = t % p.n_tiles;
+    int m_tile = (t / p.n_tiles) * 2 + (int)rank;                       // a phantom tile (m_tile >= m_tiles) decodes to img >= n_img:
+    wb = m_tile % p.wtiles; m_tile /= p.wtiles;                         // its loads are zero-filled, its stores clipped
+    hb = m_tile % p.htiles;
+    img = m_tile / p.htiles;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      const CUtensorMap* amaps[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_pair = (uint32_t)(2 * (128 * p.bk_bytes + half_n * p.bk_bytes));
+      for (int tile = cluster_id; tile < pair_tiles; tile += n_clusters) {
+        int n_tile, wb, hb, img;
+        decode(tile, n_tile, wb, hb, img);
+        const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = n_tile * p.bn + (int)rank * half_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const uint32_t t = p.taps[tap];
+          const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&ctl->full[stage], tx_pair);
+          const uint32_t lbar = mapa_u32(smem_u32(&ctl->full[stage]), 0);      // the LEADER's barrier (shared::cluster address)
+          uint8_t* sa = smem + stage * stage_bytes;
+          tma2_load_4d(amaps[t & 3], lbar, sa, cb * bk_elems, w0 + ow, h0 + oh, img);
+          tma2_load_2d(&tmB, lbar, sa + p.a_stage_bytes, kb * bk_elems, n0);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && leader) {
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      const int kmma = p.bk_bytes >> 5;
+      for (int tile = cluster_id; tile < pair_tiles; tile += n_clusters) {
+        const int n_tile = tile % p.n_tiles;
+        const int n0 = n_tile * p.bn;
+        int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+        // the instruction's N spans both halves: CTA r supplies columns [r*half_n, r*half_n + N/2); keep the split at half_n
+        const uint32_t idesc = make_idesc_m256(kBF16, (uint32_t)p.bn);
+        (void)nvalid;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
+          const uint64_t bdesc = make_kmajor_desc(sa + (uint32_t)p.a_stage_bytes, (uint32_t)p.bk_bytes);
+          for (int k = 0; k < kmma; ++k)
+            umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma2_commit_both(&ctl->empty[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_both(&ctl->tmem_full[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue (warps 2..5 [, 6..9]) of BOTH CTAs: own 128 rows ------------------------------
+    using H = Half2<kBF16>;
+    const int grp = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;
+    const int bar_id = 1 + grp;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint8_t* epi = smem + p.ring_bytes;
+    uint8_t* resb = smem + p.ring_bytes - kResRegion;
+    const bool has_res = p.residual != nullptr;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0, my_ctr = 0; int staged_n_tile = -1;
+    const uint32_t leader_empty0 = mapa_u32(smem_u32(&ctl->tmem_empty[0]), 0), leader_empty1 = mapa_u32(smem_u32(&ctl->tmem_empty[1]), 0);
+
+    int pf_tile = cluster_id, pf_ch = 0;
+    auto pf_step = [&](bool load, uint32_t bi) {
+      if (pf_tile >= pair_tiles) return;
+      int n_tile, wb, hb, img;
+      decode(pf_tile, n_tile, wb, hb, img);
+      const int n0 = n_tile * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      if (load) {
+        mbar_expect_tx(&ctl->res_full[bi], (uint32_t)kEpiBufBytes);
+        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+      }
+      if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += n_clusters; }
+    };
+    if (has_res && et == 0) {
+      if (kEpiGroups == 1) pf_step(true, 0);
+      else { if (grp == 1) pf_step(false, 0); pf_step(true, (uint32_t)grp); }
+    }
+
+    for (int tile = cluster_id; tile < pair_tiles; tile += n_clusters) {
+      int n_tile, wb, hb, img;
+      decode(tile, n_tile, wb, hb, img);
+      const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = n_tile * p.bn;
+      int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
+      const int nchunks = (nvalid + 63) >> 6;
+
+      if (n_tile != staged_n_tile) {
+        if (kEpiGroups == 1) named_bar_sync(1, 128); else named_bar_sync(3, 256);
+        if (grp == 0) {
+          for (int i = et; i < p.bn; i += 128) {
+            const int c = n0 + i;
+            ctl->scale[i] = (p.scale != nullptr && c < p.cout) ? p.scale[c] : 1.f;
+            ctl->shift[i] = (p.shift != nullptr && c < p.cout) ? p.shift[c] : 0.f;
+          }
+        }
+        if (kEpiGroups == 2) named_bar_sync(3, 256);
+        staged_n_tile = n_tile;
+      }
+
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+      for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
+        if (kEpiGroups == 2 && (int)(chunk_ctr & 1) != grp) continue;
+        const uint32_t bi = kEpiGroups == 1 ? (my_ctr & 1) : (uint32_t)grp;
+        uint8_t* buf = epi + bi * kEpiBufBytes;
+        const uint8_t* rbuf = resb + bi * kEpiBufBytes;
+        if (et == 0) {
+          if (kEpiGroups == 1) {
+            tma_store_wait_read<1>();
+            if (has_res) pf_step(true, (my_ctr + 1) & 1);
+          } else {
+            tma_store_wait_read<0>();
+          }
+        }
+        named_bar_sync(bar_id, 128);
+        if (has_res) mbar_wait(&ctl->res_full[bi], kEpiGroups == 1 ? ((my_ctr >> 1) & 1) : (my_ctr & 1));
+        ++my_ctr;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col0 = ch * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk16 = (half * 4 + g) ^ (row & 7);
+            const int cl = col0 + g * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(&ctl->scale[cl]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&ctl->scale[cl + 4]);
+            const float4 h0v = *reinterpret_cast<const float4*>(&ctl->shift[cl]);
+            const float4 h1v = *reinterpret_cast<const float4*>(&ctl->shift[cl + 4]);
+            float f[8];
+            f[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, h0v.x); f[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, h0v.y);
+            f[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, h0v.z); f[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, h0v.w);
+            f[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, h1v.x); f[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1v.y);
+            f[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1v.z); f[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1v.w);
+            if (has_res) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rbuf + row * 128 + chunk16 * 16);
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t2 = H::unpack(rr[j]);
+                f[2 * j] += t2.x; f[2 * j + 1] += t2.y;
+              }
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pk[j] = H::pack(f[2 * j], f[2 * j + 1]);
+              if (p.act != ACT_NONE) pk[j] = H::relu2(pk[j]);
+              if (p.act == ACT_RELU6) pk[j] = H::min2(pk[j], 6.f);
+            }
+            *reinterpret_cast<uint4*>(buf + row * 128 + chunk16 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+        if (et == 0) {
+          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
+          tma_store_commit();
+          if (kEpiGroups == 2 && has_res) { pf_step(false, 0); pf_step(true, (uint32_t)grp); }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);   // 2 x 128 x groups arrivals release the pair's accumulator
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                                  // neither CTA may exit while the peer still uses its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -382,11 +686,13 @@ using namespace segb200;
 
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
+static int g_2cta = 0;        // opt-in: CTA-pair kernel for the tensor-bound shapes
 static int g_no_bn128 = 1;   // measured: 128-wide tiles lose 45 % on the 3x3 256->256 layers (operand traffic per FLOP up 33 %)
 extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
   if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_bn128")) { g_no_bn128 = value ? 0 : 1; return 0; }
+  if (name && !strcmp(name, "gemm_2cta")) { g_2cta = value; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -466,7 +772,11 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   p.total_tiles = (int)total;
   p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
   p.a_stage_bytes = 128 * bk_bytes;
-  p.b_stage_bytes = ((p.bn * bk_bytes) + 1023) & ~1023;
+  // CTA-pair kernel (opt-in): needs an N tile that splits into two UMMA-legal halves, 16-bit output, at least one full pair
+  const long long m_tiles_all = (long long)p.wtiles * p.htiles * p.n_img;
+  const bool use2 = g_2cta != 0 && !a->y_f32 && (p.bn % 32) == 0 && p.bn >= 64 && m_tiles_all >= 2 &&
+                    (g_2cta == 1 || ktot >= 1024);
+  p.b_stage_bytes = ((((use2 ? p.bn / 2 : p.bn) * bk_bytes) + 1023) & ~1023);
   // ring size: 192 KB by default (1 CTA / SM owns the whole shared memory); segb200_set_option("gemm_ring_kb", n) shrinks
   // it so that a memory-/FMA-bound kernel of another stream can co-reside (measured: not worth it)
   int ring = g_ring_kb > 0 ? g_ring_kb * 1024 : kStageRegion;
@@ -480,7 +790,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   const int nkb = ntaps * cblocks;
   const long long b_total = (long long)nkb * p.b_stage_bytes;
   const int avail = ring - (a->residual ? kResRegion : 0);
-  p.b_resident = (p.n_tiles == 1 && b_total <= 72 * 1024 && avail - b_total >= 4 * p.a_stage_bytes && !g_no_b_resident) ? 1 : 0;
+  p.b_resident = (!use2 && p.n_tiles == 1 && b_total <= 72 * 1024 && avail - b_total >= 4 * p.a_stage_bytes && !g_no_b_resident) ? 1 : 0;
   if (p.b_resident) p.num_stages = (int)((avail - b_total) / p.a_stage_bytes);
   else p.num_stages = avail / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
@@ -531,7 +841,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
     const uint64_t str[1] = {(uint64_t)ktot * 2};
-    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)p.bn};
+    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)(use2 ? p.bn / 2 : p.bn)};
     int rc = encode_map(&tmB, a->dtype, 2, a->wgt, dims, str, box, bk_bytes, "B");
     if (rc) return rc;
   }
@@ -564,6 +874,28 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2432;
   // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
   const bool two_groups = ktot <= 512 && !a->y_f32;
+  if (use2) {
+    static std::once_flag attr2_once;
+    std::call_once(attr2_once, [] {
+      cudaFuncSetAttribute(conv_gemm2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      cudaFuncSetAttribute(conv_gemm2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      cudaFuncSetAttribute(conv_gemm2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      cudaFuncSetAttribute(conv_gemm2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    });
+    const long long pair_tiles = ((m_tiles_all + 1) / 2) * p.n_tiles;
+    long long g2 = (a->max_ctas > 0 ? a->max_ctas : num_sms()) & ~1;
+    if (g2 > 2 * pair_tiles) g2 = 2 * pair_tiles;
+    if (g2 < 2) g2 = 2;
+    const int grid2 = (int)g2;
+    if (a->dtype == DT_BF16) {
+      if (two_groups) conv_gemm2_kernel<true, 2><<<grid2, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+      else conv_gemm2_kernel<true, 1><<<grid2, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    } else {
+      if (two_groups) conv_gemm2_kernel<false, 2><<<grid2, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+      else conv_gemm2_kernel<false, 1><<<grid2, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+    }
+    return check_launch("conv_gemm(2cta)");
+  }
   if (a->dtype == DT_BF16) {
     if (two_groups) conv_gemm_kernel<true, 2><<<grid, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
     else conv_gemm_kernel<true, 1><<<grid, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);

@@ -99,6 +99,19 @@ def test_conv_gemm(case, dtype):
         assert (buf[..., mask.cuda()] == 7.0).all(), f"{name}: wrote outside its channel slice"
 
 
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_cta_pair(case):
+    """the opt-in CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles; segb200_set_option("gemm_2cta", 1)) on every conv case;
+    shapes it does not take (N tile not splittable, single M tile) fall through to the single-CTA kernel"""
+    from segmentron_b200 import lib as L
+    lib = L.load()
+    L.check(lib.segb200_set_option(b"gemm_2cta", 1))
+    try:
+        test_conv_gemm(case, torch.bfloat16)
+    finally:
+        L.check(lib.segb200_set_option(b"gemm_2cta", 0))
+
+
 def test_conv_gemm_fp32_out():
     """fp32 epilogue (attention energies): K = 4096 accumulation, y_f32 store path."""
     from segmentron_b200 import fold, ops
