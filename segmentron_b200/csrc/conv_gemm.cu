@@ -883,7 +883,23 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
       cudaFuncSetAttribute(conv_gemm2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     });
     const long long pair_tiles = ((m_tiles_all + 1) / 2) * p.n_tiles;
-    long long g2 = (a->max_ctas > 0 ? a->max_ctas : num_sms()) & ~1;
+    // SM pairs that can host a 2-CTA cluster at this smem size (odd-sized GPCs leave SMs unpaired): a persistent grid larger
+    // than that would run its surplus clusters as a second wave
+    static int max_pairs[2] = {0, 0};
+    if (max_pairs[two_groups ? 1 : 0] == 0) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(num_sms() & ~1)); cfg.blockDim = dim3(two_groups ? 320 : 192); cfg.dynamicSmemBytes = kSmemBytes;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int nclus = 0;
+      cudaError_t e = two_groups ? cudaOccupancyMaxActiveClusters(&nclus, conv_gemm2_kernel<true, 2>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&nclus, conv_gemm2_kernel<true, 1>, &cfg);
+      if (e != cudaSuccess || nclus < 1) { cudaGetLastError(); nclus = num_sms() / 2; }
+      max_pairs[two_groups ? 1 : 0] = nclus;
+    }
+    long long g2 = a->max_ctas > 0 ? (a->max_ctas & ~1) : 2LL * max_pairs[two_groups ? 1 : 0];
     if (g2 > 2 * pair_tiles) g2 = 2 * pair_tiles;
     if (g2 < 2) g2 = 2;
     const int grid2 = (int)g2;
