@@ -37,6 +37,7 @@ const char* segb200_last_error(void);
  *   "gemm_ring_kb"  : shared-memory ring of segb200_conv_gemm in KB (0 = 192 = whole SM).  A smaller ring leaves room for
  *                     a kernel of another stream to co-reside on the SM (dual-stream half-batch overlap).
  *   "dw_ring_slots" : cap on the row-ring depth of segb200_dwconv3x3 (0 = 12).
+ *   "gemm_epi2_maxk": largest K (taps x padded cin) for which segb200_conv_gemm uses two epilogue warp-groups (default 512).
  *   "gemm_2cta"     : 0 (default) single-CTA tiles; 1 = CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles, each CTA stages
  *                     half of the weight rows) for every eligible shape; 2 = only for K >= 1024.  Experimental.
  *   "gemm_bn128"    : 1 lets segb200_conv_gemm pick 128-wide N tiles when that saves >= 5 % of the persistent grid's rounds

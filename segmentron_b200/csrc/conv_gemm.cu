@@ -686,6 +686,7 @@ using namespace segb200;
 
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
+static int g_epi2_maxk = 512;  // K (taps x padded cin) up to which the two-epilogue-group variant is used
 static int g_2cta = 0;        // opt-in: CTA-pair kernel for the tensor-bound shapes
 static int g_no_bn128 = 1;   // measured: 128-wide tiles lose 45 % on the 3x3 256->256 layers (operand traffic per FLOP up 33 %)
 extern "C" int segb200_set_option(const char* name, int value) {
@@ -693,6 +694,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_bn128")) { g_no_bn128 = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_2cta")) { g_2cta = value; return 0; }
+  if (name && !strcmp(name, "gemm_epi2_maxk")) { g_epi2_maxk = value > 0 ? value : 512; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -873,7 +875,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   });
   const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2432;
   // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
-  const bool two_groups = ktot <= 512 && !a->y_f32;
+  const bool two_groups = ktot <= g_epi2_maxk && !a->y_f32;
   if (use2) {
     static std::once_flag attr2_once;
     std::call_once(attr2_once, [] {
