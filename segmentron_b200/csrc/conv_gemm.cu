@@ -55,6 +55,7 @@ static_assert(offsetof(Control, scale) % 16 == 0 && offsetof(Control, shift) % 1
 struct ConvGemmParams {
   int n_img, ho, wo;
   int bw, bh, wtiles, htiles;
+  int bi;               // images per M tile (the TMA box spans bi images); n_img counts image GROUPS
   int n_tiles, total_tiles;
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
@@ -152,7 +153,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           TIMED_WAIT(&ctl->empty[stage], phase ^ 1, 0);
           mbar_expect_tx(&ctl->full[stage], tx);
           uint8_t* sa = smem + stage * stage_bytes;
-          tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img);
+          tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
           if (!p.b_resident) tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, kb * bk_elems, n0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
@@ -220,7 +221,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       if (load) {
         mbar_expect_tx(&ctl->res_full[bi], (uint32_t)kEpiBufBytes);
-        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img * p.bi);
       }
       if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += gridDim.x; }
     };
@@ -283,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           fence_proxy_async();
           named_bar_sync(1, 128);
           if (et == 0) {
-            tma_store_4d(&tmC, buf, n0 + col0, w0, h0, img);
+            tma_store_4d(&tmC, buf, n0 + col0, w0, h0, img * p.bi);
             tma_store_commit();
           }
         }
@@ -347,7 +348,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         fence_proxy_async();
         named_bar_sync(bar_id, 128);
         if (et == 0) {
-          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
+          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img * p.bi);
           tma_store_commit();
           if (kEpiGroups == 2 && has_res) { pf_step(false, 0); pf_step(true, (uint32_t)grp); }   // rbuf is free again
         }
@@ -501,7 +502,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (leader) mbar_expect_tx(&ctl->full[stage], tx_pair);
           const uint32_t lbar = mapa_u32(smem_u32(&ctl->full[stage]), 0);      // the LEADER's barrier (shared::cluster address)
           uint8_t* sa = smem + stage * stage_bytes;
-          tma2_load_4d(amaps[t & 3], lbar, sa, cb * bk_elems, w0 + ow, h0 + oh, img);
+          tma2_load_4d(amaps[t & 3], lbar, sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
           tma2_load_2d(&tmB, lbar, sa + p.a_stage_bytes, kb * bk_elems, n0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
@@ -561,7 +562,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
       if (load) {
         mbar_expect_tx(&ctl->res_full[bi], (uint32_t)kEpiBufBytes);
-        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img);
+        tma_load_4d(&tmR, &ctl->res_full[bi], resb + bi * kEpiBufBytes, n0 + pf_ch * 64, wb * p.bw, hb * p.bh, img * p.bi);
       }
       if (++pf_ch >= ((nvalid + 63) >> 6)) { pf_ch = 0; pf_tile += n_clusters; }
     };
@@ -650,7 +651,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         fence_proxy_async();
         named_bar_sync(bar_id, 128);
         if (et == 0) {
-          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img);
+          tma_store_4d(&tmC, buf, n0 + ch * 64, w0, h0, img * p.bi);
           tma_store_commit();
           if (kEpiGroups == 2 && has_res) { pf_step(false, 0); pf_step(true, (uint32_t)grp); }
         }
@@ -686,6 +687,7 @@ using namespace segb200;
 
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
+static int g_no_img_tiles = 0;
 static int g_epi2_maxk = 512;  // K (taps x padded cin) up to which the two-epilogue-group variant is used
 static int g_2cta = 0;        // opt-in: CTA-pair kernel for the tensor-bound shapes
 static int g_no_bn128 = 1;   // measured: 128-wide tiles lose 45 % on the 3x3 256->256 layers (operand traffic per FLOP up 33 %)
@@ -694,6 +696,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_b_resident")) { g_no_b_resident = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_bn128")) { g_no_bn128 = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_2cta")) { g_2cta = value; return 0; }
+  if (name && !strcmp(name, "gemm_img_tiles")) { g_no_img_tiles = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_epi2_maxk")) { g_epi2_maxk = value > 0 ? value : 512; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
@@ -744,14 +747,29 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     p.bw = 128; p.bh = 1;
   } else {
     Wv_out = a->wo; Hv_out = a->ho; Nv_out = a->n;
+    // 128 output pixels per tile as a BW x BH patch of BI images (BW*BH*BI = 128): the box may span several images, which
+    // cuts the padding of small maps (65x129, batch 4: 4 x 81 patches of 16x8 = 324 tiles -> 289 tiles of 8x4x4) and with
+    // it the rounds of the persistent grid
     long long best = -1;
-    const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
-    for (int i = 0; i < 5; ++i) {
-      const long long t = (long long)((a->wo + cand[i][0] - 1) / cand[i][0]) * ((a->ho + cand[i][1] - 1) / cand[i][1]);
-      if (best < 0 || t < best) { best = t; p.bw = cand[i][0]; p.bh = cand[i][1]; }
+    p.bi = 1;
+    for (int bi = 1; bi <= 16 && bi <= a->n * 2 - 1; bi *= 2)
+      for (int bw = 128 / bi; bw >= 1; bw /= 2) {
+        const int bh = 128 / bi / bw;
+        if (bw > 256 || bh > 256) continue;
+        const long long t = (long long)((a->wo + bw - 1) / bw) * ((a->ho + bh - 1) / bh) * ((a->n + bi - 1) / bi);
+        if (best < 0 || t < best) { best = t; p.bw = bw; p.bh = bh; p.bi = bi; }
+      }
+    if (g_no_img_tiles && p.bi != 1) {                 // (tuning knob: single-image patches only)
+      best = -1; p.bi = 1;
+      for (int bw = 128; bw >= 1; bw /= 2) {
+        const int bh = 128 / bw;
+        const long long t = (long long)((a->wo + bw - 1) / bw) * ((a->ho + bh - 1) / bh) * a->n;
+        if (best < 0 || t < best) { best = t; p.bw = bw; p.bh = bh; }
+      }
     }
   }
-  p.n_img = (int)Nv_out; p.ho = (int)Hv_out; p.wo = (int)Wv_out;
+  if (flat) p.bi = 1;
+  p.n_img = (int)((Nv_out + p.bi - 1) / p.bi); p.ho = (int)Hv_out; p.wo = (int)Wv_out;
   if (Wv_out > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many pixels");
   p.wtiles = (int)((Wv_out + p.bw - 1) / p.bw);
   p.htiles = (int)((Hv_out + p.bh - 1) / p.bh);
@@ -815,7 +833,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
       p.taps[ky * a->kw + kx] = (uint32_t)mid | ((uint32_t)(aw + 128) << 8) | ((uint32_t)(ah + 128) << 16);
     }
   const char* xb = reinterpret_cast<const char*>(a->x);
-  const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+  const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bi};
   for (int mid = 0; mid < 4; ++mid) {
     if (!used[mid]) continue;
     int rc;
@@ -852,7 +870,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     const uint64_t esz = a->y_f32 ? 4 : 2;
     const uint64_t str[3] = {(uint64_t)a->y_ld * esz, (uint64_t)a->y_ld * esz * (uint64_t)Wv_out,
                              (uint64_t)a->y_ld * esz * (uint64_t)Wv_out * (uint64_t)Hv_out};
-    const uint32_t box[4] = {a->y_f32 ? 32u : 64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+    const uint32_t box[4] = {a->y_f32 ? 32u : 64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bi};
     int rc = encode_map(&tmC, a->y_f32 ? (int)DT_F32 : a->dtype, 4, a->y, dims, str, box, 128, "C");
     if (rc) return rc;
     tmR = tmC;

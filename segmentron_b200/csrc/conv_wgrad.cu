@@ -41,6 +41,7 @@ static_assert(sizeof(WgControl) <= kWgCtl, "control block too large");
 
 struct WgradParams {
   int bw, bh, wtiles, htiles;
+  int bi;                      // images per pixel tile (the TMA box spans bi images)
   long long pix_tiles;
   int cout, cin, ntaps;
   int co_tiles, ci_tiles, bn;
@@ -135,9 +136,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           mbar_expect_tx(&ctl->full[stage], tx);
           uint8_t* sa = smem + stage * p.stage_bytes;
           for (int i = 0; i < it.na; ++i)
-            tma_load_4d(&tmDY, &ctl->full[stage], sa + i * kWgBox, it.co0 + i * 64, w0, h0, img);
+            tma_load_4d(&tmDY, &ctl->full[stage], sa + i * kWgBox, it.co0 + i * 64, w0, h0, img * p.bi);
           for (int j = 0; j < it.nb; ++j)
-            tma_load_4d(xm, &ctl->full[stage], sa + 2 * kWgBox + j * kWgBox, it.ci0 + j * 64, w0 + ow, h0 + oh, img);
+            tma_load_4d(xm, &ctl->full[stage], sa + 2 * kWgBox + j * kWgBox, it.ci0 + j * 64, w0 + ow, h0 + oh, img * p.bi);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -249,20 +250,22 @@ extern "C" int segb200_conv_wgrad(const segb200_wgrad_args* a, void* stream_) {
   long long Wv, Hv, Nv;
   if (flat) {
     Wv = (long long)a->n * a->h * a->w; Hv = 1; Nv = 1;
-    p.bw = 64; p.bh = 1;
+    p.bw = 64; p.bh = 1; p.bi = 1;
   } else {
     Wv = a->wo; Hv = a->ho; Nv = a->n;
+    // 64 pixels per K step as a BW x BH patch of BI images (BW*BH*BI = 64): spanning images cuts the padding of small maps
     long long best = -1;
-    const int cand[4][2] = {{64, 1}, {32, 2}, {16, 4}, {8, 8}};
-    for (int i = 0; i < 4; ++i) {
-      const long long t = (long long)((a->wo + cand[i][0] - 1) / cand[i][0]) * ((a->ho + cand[i][1] - 1) / cand[i][1]);
-      if (best < 0 || t < best) { best = t; p.bw = cand[i][0]; p.bh = cand[i][1]; }
-    }
+    for (int bi = 1; bi <= 8 && bi <= a->n * 2 - 1; bi *= 2)
+      for (int bw = 64 / bi; bw >= 1; bw /= 2) {
+        const int bh = 64 / bi / bw;
+        const long long t = (long long)((a->wo + bw - 1) / bw) * ((a->ho + bh - 1) / bh) * ((a->n + bi - 1) / bi);
+        if (best < 0 || t < best) { best = t; p.bw = bw; p.bh = bh; p.bi = bi; }
+      }
   }
   if (Wv > 0x7fffffffLL) return set_error(-8, "conv_wgrad: too many pixels");
   p.wtiles = (int)((Wv + p.bw - 1) / p.bw);
   p.htiles = (int)((Hv + p.bh - 1) / p.bh);
-  p.pix_tiles = (long long)p.wtiles * p.htiles * Nv;
+  p.pix_tiles = (long long)p.wtiles * p.htiles * ((Nv + p.bi - 1) / p.bi);
   p.cout = a->cout; p.cin = a->cin; p.ntaps = ntaps;
   p.co_tiles = (a->cout + 127) / 128;
   p.bn = a->cin >= 256 ? 256 : ((a->cin + 63) & ~63);
@@ -309,7 +312,7 @@ extern "C" int segb200_conv_wgrad(const segb200_wgrad_args* a, void* stream_) {
       p.taps[ky * a->kw + kx] = (uint32_t)mid | ((uint32_t)(aw + 128) << 8) | ((uint32_t)(ah + 128) << 16);
     }
   const char* xb = reinterpret_cast<const char*>(a->x);
-  const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+  const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bi};
   for (int mid = 0; mid < 4; ++mid) {
     if (!used[mid]) continue;
     int rc;
