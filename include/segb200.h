@@ -289,6 +289,21 @@ int segb200_scatter_add(const float* src, const int* index, float* dst, long lon
 int segb200_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float weight_decay,
                      float grad_scale, void* stream);
 
+/* Criss-cross attention BACKWARD (replaces _C.ca_backward / _C.ca_map_backward, csrc/criss_cross_attention/ca_cuda.cu:38-92,
+ * :122-177, plus the softmax backward and the gamma gradient autograd runs around them, modules/cc_attention.py:62-72).
+ *   cca_weight_bwd : D[p][z] = dy[p].v[key(p,z)] (== ca_map_backward's dw), dE = gamma * A * (D - sum_z A D)  -> de [n][h][w][att_ld];
+ *                    dgamma_partial[block] = per-block sum of A.D (finish with segb200_reduce_partials; segb200_cca_weight_bwd_blocks())
+ *   cca_gather     : out[p] (+)= scale * sum_z a[p][z] src[key(p,z)]        (ca_backward's dt with a = dE, src = k; == ca_map_forward)
+ *   cca_scatter    : out[r] (+)= scale * sum_{(p,z): key(p,z)=r} a[p][z] src[p]   (ca_backward's df with a = dE, src = q;
+ *                    ca_map_backward's dg with a = A, src = dy, scale_dev = gamma); scale_dev: optional DEVICE float multiplied in. */
+int segb200_cca_weight_bwd_blocks(int n, int h, int w);
+int segb200_cca_weight_bwd(const void* dy, const void* v, const float* att, float* de, float* dgamma_partial, const float* gamma,
+                           int n, int h, int w, int c, int dy_ld, int v_ld, int att_ld, int dtype, void* stream);
+int segb200_cca_gather(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
+                       float scale, int accumulate, int dtype, void* stream);
+int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
+                        float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

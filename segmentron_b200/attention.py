@@ -90,3 +90,92 @@ def pam_nhwc(x, wq, bq, wk, bk, wv, bv, gamma, out=None):
                                       ops._ptr(sm), ops._ptr(sl), n, ntok, dv, dq, dq, pitch, x_ld, c, ops.dt_code(dt),
                                       ops._stream()), "pam_attention")
     return y
+
+
+# ------------------------------------------------------------------------------------------------------------
+# criss-cross attention with a backward pass (training): torch.autograd.Function over the C-ABI kernels
+# ------------------------------------------------------------------------------------------------------------
+def _colsum(t):
+    """fp32 per-channel sum of an NHWC 16-bit tensor through the fixed-order reduction kernels (conv bias gradients)."""
+    n, h, w, c, ld = ops._nhwc(t, "t")
+    lib = L.load()
+    rows = n * h * w
+    slabs = lib.segb200_reduce_slabs(rows, c, 0)
+    partial = torch.empty(slabs * 2 * c, dtype=torch.float32, device=t.device)
+    out = torch.zeros(2, c, dtype=torch.float32, device=t.device)
+    s = ops._stream()
+    L.check(lib.segb200_bn_stats(ops._ptr(t), rows, c, ld, ops.dt_code(t.dtype), ops._ptr(partial), 0, s), "bn_stats")
+    L.check(lib.segb200_reduce_partials(ops._ptr(partial), slabs, 2, c, ops._ptr(out), c, 1, 0, 1.0, s), "reduce_partials")
+    return out[0]
+
+
+class CrissCrossFunction(torch.autograd.Function):
+    """y = gamma * CCA(q(x), k(x), v(x)) + x  on an NHWC 16-bit tensor; parameters are the reference module's
+    (query_conv / key_conv / value_conv weight [Co,C,1,1] + bias, gamma [1]; modules/cc_attention.py:52-72).
+    Backward = segb200_cca_weight_bwd / cca_gather / cca_scatter (the _C.ca_backward / ca_map_backward pair, softmax backward
+    and gamma gradient fused) + the tcgen05 weight-/data-gradient kernels of the three 1x1 convs."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, gamma):
+        from . import train_ops as T
+        n, h, w, c, x_ld = ops._nhwc(x, "x")
+        dt = x.dtype
+        lib = L.load()
+        cq = wq.shape[0]
+        pk = [fold.pack_conv_weight(t.detach(), dt) for t in (wq, wk, wv)]
+        q = torch.empty(n, h, w, cq, dtype=dt, device=x.device)
+        k = torch.empty(n, h, w, cq, dtype=dt, device=x.device)
+        v = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+        ops.conv_gemm(x, pk[0], q, cin=c, cout=cq, shift=bq.detach().float().contiguous())
+        ops.conv_gemm(x, pk[1], k, cin=c, cout=cq, shift=bk.detach().float().contiguous())
+        ops.conv_gemm(x, pk[2], v, cin=c, cout=c, shift=bv.detach().float().contiguous())
+        att_ld = fold.round_up(h + w - 1, 4)
+        att = torch.empty(n, h, w, att_ld, dtype=torch.float32, device=x.device)
+        L.check(lib.segb200_cca_weight_softmax(ops._ptr(q), ops._ptr(k), ops._ptr(att), n, h, w, cq, cq, cq, att_ld,
+                                               ops.dt_code(dt), ops._stream()), "cca_weight_softmax")
+        y = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+        g = gamma.detach().float().reshape(1).contiguous()
+        L.check(lib.segb200_cca_map(ops._ptr(att), ops._ptr(v), ops._ptr(x), ops._ptr(y), ops._ptr(g), n, h, w, c, att_ld, c, x_ld,
+                                    c, ops.dt_code(dt), ops._stream()), "cca_map")
+        ctx.save_for_backward(x, q, k, v, att, g, wq, wk, wv)
+        ctx.T = T
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        T = ctx.T
+        x, q, k, v, att, g, wq, wk, wv = ctx.saved_tensors
+        lib = L.load()
+        s = ops._stream()
+        dy = dy.contiguous()
+        n, h, w, c, _ = ops._nhwc(x, "x")
+        cq = q.shape[3]
+        dt = x.dtype
+        dtc = ops.dt_code(dt)
+        att_ld = att.shape[3]
+        de = torch.empty_like(att)
+        nb = lib.segb200_cca_weight_bwd_blocks(n, h, w)
+        part = torch.empty(nb, dtype=torch.float32, device=x.device)
+        L.check(lib.segb200_cca_weight_bwd(ops._ptr(dy), ops._ptr(v), ops._ptr(att), ops._ptr(de), ops._ptr(part), ops._ptr(g), n, h,
+                                           w, c, dy.stride(2), c, att_ld, dtc, s), "cca_weight_bwd")
+        dgamma = torch.zeros(1, dtype=torch.float32, device=x.device)
+        L.check(lib.segb200_reduce_partials(ops._ptr(part), nb, 1, 1, ops._ptr(dgamma), 0, 1, 0, 1.0, s), "reduce_partials")
+        dq = torch.empty_like(q)
+        dk = torch.empty_like(k)
+        dv = torch.empty_like(v)
+        L.check(lib.segb200_cca_gather(ops._ptr(de), ops._ptr(k), ops._ptr(dq), n, h, w, cq, att_ld, cq, cq, 1.0, 0, dtc, s), "cca_gather")
+        L.check(lib.segb200_cca_scatter(ops._ptr(de), ops._ptr(q), ops._ptr(dk), n, h, w, cq, att_ld, cq, cq, 1.0, None, 0, dtc, s),
+                "cca_scatter")
+        L.check(lib.segb200_cca_scatter(ops._ptr(att), ops._ptr(dy), ops._ptr(dv), n, h, w, c, att_ld, dy.stride(2), c, 1.0, ops._ptr(g),
+                                        0, dtc, s), "cca_scatter")
+        grads_w, grads_b = [], []
+        dx = torch.empty(n, h, w, c, dtype=dt, device=x.device)
+        res = dy
+        for wt, d, co in ((wq, dq, cq), (wk, dk, cq), (wv, dv, c)):
+            dw = torch.zeros(co, 1, c, dtype=torch.float32, device=x.device)
+            T.conv_wgrad(x, d, dw, cin=c, cout=co)
+            grads_w.append(dw.view(co, c, 1, 1))
+            grads_b.append(_colsum(d))
+            ops.conv_gemm(d, T.pack_dgrad_weight(wt.detach().to(dt), dt), dx, cin=co, cout=c, residual=res)
+            res = dx
+        return dx, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2], dgamma.to(g.dtype)

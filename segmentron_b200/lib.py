@@ -90,6 +90,10 @@ SYMBOLS = {
     "segb200_stride2_place": (ci, [vp, vp] + [ci] * 8 + [vp]),
     "segb200_gather_cast": (ci, [vp, vp, vp, ll, ci, vp]),
     "segb200_scatter_add": (ci, [vp, vp, vp, ll, vp]),
+    "segb200_cca_weight_bwd_blocks": (ci, [ci, ci, ci]),
+    "segb200_cca_weight_bwd": (ci, [vp] * 6 + [ci] * 8 + [vp]),
+    "segb200_cca_gather": (ci, [vp, vp, vp] + [ci] * 7 + [cf, ci, ci, vp]),
+    "segb200_cca_scatter": (ci, [vp, vp, vp] + [ci] * 7 + [cf, vp, ci, ci, vp]),
     "segb200_sgd_step": (ci, [vp, vp, vp, ll, cf, cf, cf, cf, vp]),
 }
 

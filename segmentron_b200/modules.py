@@ -401,6 +401,17 @@ class CrissCrossAttention(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
         self._cache = _Cache()
 
+    def forward_train(self, x):
+        """training mode: differentiable through the CUDA backward kernels (attention.CrissCrossFunction).  x: logical NCHW."""
+        from .attention import CrissCrossFunction
+        if not x.is_cuda:
+            raise RuntimeError("segb200: CrissCrossAttention is not implemented on the CPU (input must be a CUDA tensor)")
+        dt = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else _COMPUTE_DTYPE
+        xh = x.permute(0, 2, 3, 1).contiguous().to(dt)                     # boundary plumbing (autograd-visible)
+        y = CrissCrossFunction.apply(xh, self.query_conv.weight, self.query_conv.bias, self.key_conv.weight, self.key_conv.bias,
+                                     self.value_conv.weight, self.value_conv.bias, self.gamma)
+        return y.permute(0, 3, 1, 2).to(x.dtype)
+
     def forward_nhwc(self, x):
         from .attention import cca_nhwc
         dt = x.dtype
@@ -414,6 +425,8 @@ class CrissCrossAttention(nn.Module):
         return cca_nhwc(x, wq, bq, wk, bk, wv, bv, self.gamma)
 
     def forward(self, x):
+        if self.training:
+            return self.forward_train(x)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 

@@ -96,6 +96,37 @@ def test_attention_modules(dtype, tol):
             _cmp(_load(M.CrissCrossAttention(c), P, "cca")(x.cuda().to(dtype)), ref, tol)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 2.5e-2)], ids=["f16", "bf16"])
+def test_criss_cross_attention_backward(dtype, tol):
+    """Training-mode CrissCrossAttention drop-in: forward and EVERY gradient (input, q/k/v conv weights and biases, gamma)
+    against autograd through the oracle (ca_weight / ca_map are pinned to a scalar transcription of ca_cuda.cu) -- i.e. the
+    replacement of _C.ca_backward / _C.ca_map_backward (csrc/criss_cross_attention/ca_cuda.cu:38-92,122-177)."""
+    from segmentron_b200 import modules as M
+    for (n, c, h, w) in [(2, 64, 9, 13), (1, 512, 16, 24)]:
+        P = R.Params(23)
+        x = _x(n, c, h, w, seed=24).to(dtype).float()
+        R.criss_cross_attention(P, x, "cca", gamma=0.6)                 # creates the parameters
+        names = [k for k in P.t if k.startswith("cca.")]
+        for k in names:
+            P.t[k] = P.t[k].to(dtype).float().detach().requires_grad_(True)     # 16-bit-representable parameters
+        xr = x.clone().requires_grad_(True)
+        ref = R.criss_cross_attention(P, xr, "cca", gamma=0.6)
+        dy = _x(n, c, h, w, seed=25).to(dtype).float()
+        ref.backward(dy)
+        m = M.CrissCrossAttention(c)
+        m.load_state_dict({k[4:]: v.detach() for k, v in P.t.items() if k.startswith("cca.")}, strict=True)
+        m = m.cuda().train()
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        y = m(xg)
+        _cmp(y.detach(), ref.detach(), tol)
+        y.backward(dy.cuda().to(dtype))
+        _cmp(xg.grad, xr.grad, tol)
+        for k in names:
+            g = dict(m.named_parameters())[k[4:]].grad
+            assert g is not None, k
+            assert float((g.float().cpu().reshape(-1) - P.t[k].grad.reshape(-1)).norm() / (P.t[k].grad.norm() + 1e-12)) < 2 * tol, k
+
+
 def test_dropin_errors_and_cache_invalidation():
     from segmentron_b200 import modules as M
     m = M.SeparableConv2d(64, 64).cuda().eval()
