@@ -306,11 +306,11 @@ class TrainPlan:
                              dict(x=x, dy=dy, dw=dw, cin=cin, cout=cout, k=k, stride=stride, dilation=dilation, pad=pad,
                                   flops=2.0 * n * ho * wo * cout * cin * k * k)))
 
-    def dwconv(self, x, w, y, dilation):
-        a = ops.make_dw_args(x, w, y, stride=1, dilation=dilation)
+    def dwconv(self, x, w, y, dilation, stride=1, pre_relu=False):
+        a = ops.make_dw_args(x, w, y, stride=stride, dilation=dilation, pre_relu=pre_relu)
         fn = self.lib.segb200_dwconv3x3
         self.cur.append(Step("dw", (lambda s, a=a, fn=fn: L.check(fn(C.byref(a), s), "dwconv3x3")),
-                             dict(x=x, w=w, y=y, dilation=dilation)))
+                             dict(x=x, w=w, y=y, dilation=dilation, stride=stride, pre_relu=pre_relu)))
 
     @staticmethod
     def _rows(t):
@@ -469,41 +469,63 @@ class TrainPlan:
         return z
 
     # ---- depthwise 3x3 + BN + act (the first half of SeparableConv2d, relu_first=False: modules/basic.py:52-59) ----
-    def dw_unit(self, x, wname, bn, act, dilation, eps=1e-5):
+    def dw_unit(self, x, wname, bn, act, dilation, eps=1e-5, stride=1, pre_relu=False):
+        """depthwise 3x3 (+ optional leading ReLU, modules/basic.py:45-46) + BatchNorm (+ ReLU): the first half of SeparableConv2d"""
         S = self.S
         n, h, w_, c = x.t.shape
-        y = self.new(n, h, w_, c)
-        z = Act(self, self.new(n, h, w_, c))
-        self.dwconv(x.t, S.packed(wname, "fwd"), y, dilation)
+        ho, wo = (h - 1) // stride + 1, (w_ - 1) // stride + 1
+        y = self.new(n, ho, wo, c)
+        z = Act(self, self.new(n, ho, wo, c))
+        self.dwconv(x.t, S.packed(wname, "fwd"), y, dilation, stride, pre_relu)
         st = self.bn_act_fwd(y, z.t, bn, act, eps)
 
         def backward():
             dz = z.grad()
-            dy = self.pool_get(n, h, w_, c)
+            dy = self.pool_get(n, ho, wo, c)
             self.bn_act_bwd(dz, z.t, y, st, bn, act, dy)
             self.pool_put(dz)
+            g_full = dy
+            if stride == 2:                              # zero insertion turns both stride-2 gradients into stride-1 ones
+                assert dilation == 1
+                g_full = self.pool_get(n, h, w_, c)
+                self.add("stride2_place", self.lib.segb200_stride2_place,
+                         (_ptr(dy), _ptr(g_full), n, h, w_, c, self._rows(dy)[3], self._rows(g_full)[3], 0, self.dt), t=dy, z=g_full, mode=0)
             rows = n * h * w_
             slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
             partial = self.f32(slabs * 9 * c)
             self.add("dw_wgrad", self.lib.segb200_dw_wgrad,
-                     (_ptr(x.t), _ptr(dy), _ptr(partial), n, h, w_, c, self._rows(x.t)[3], self._rows(dy)[3], dilation, 0, self.dt, 0),
-                     x=x.t, dy=dy, partial=partial, dilation=dilation, c=c)
+                     (_ptr(x.t), _ptr(g_full), _ptr(partial), n, h, w_, c, self._rows(x.t)[3], self._rows(g_full)[3], dilation,
+                      int(pre_relu), self.dt, 0),
+                     x=x.t, dy=g_full, partial=partial, dilation=dilation, c=c, pre_relu=pre_relu)
             gw = S.view(S.grad, wname)
             self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(partial), slabs, 9, c, _ptr(gw), 1, 9, 1, 1.0),
                      partial=partial, slabs=slabs, K=9, c=c, out=gw, sk=1, sc=9, accumulate=1, scale=1.0)
             if x.needs_grad:
                 gx, acc = x.take()
                 wfl = S.packed(wname, "flip")
-                if acc:
+                if pre_relu:
+                    # dx (+)= dw_dgrad * [x > 0]: the mask of the leading ReLU, applied by the BN-backward kernel's residual path
                     t = self.pool_get(n, h, w_, c)
-                    self.dwconv(dy, wfl, t, dilation)
+                    self.dwconv(g_full, wfl, t, dilation)
+                    rws, hw, cc, ld = self._rows(gx)
+                    self.add("bn_bwd_apply", self.lib.segb200_bn_bwd_apply,
+                             (_ptr(t), _ptr(x.t), None, None, None, None, None, None, float(rws), None, None, _ptr(gx), int(acc), rws, hw,
+                              cc, self._rows(t)[3], self._rows(x.t)[3], 0, 0, ld, L.ACT["relu"], self.dt),
+                             dz=t, z=x.t, y=None, st=dict(mean=None, invstd=None, scale=None, shift=None, sums=None), count=float(rws),
+                             nc_scale=None, dy=None, dres=gx, dres_acc=acc, act="relu")
+                    self.pool_put(t)
+                elif acc:
+                    t = self.pool_get(n, h, w_, c)
+                    self.dwconv(g_full, wfl, t, dilation)
                     rws, hw, cc, ld = self._rows(gx)
                     self.add("bn_apply", self.lib.segb200_bn_apply,
                              (_ptr(t), None, None, _ptr(gx), None, _ptr(gx), rws, hw, cc, self._rows(t)[3], ld, ld, 0, self.dt),
                              y=t, scale=None, shift=None, residual=gx, nc_scale=None, z=gx, act=None)
                     self.pool_put(t)
                 else:
-                    self.dwconv(dy, wfl, gx, dilation)
+                    self.dwconv(g_full, wfl, gx, dilation)
+            if stride == 2:
+                self.pool_put(g_full)
             self.pool_put(dy)
             self.mark_done(wname, bn + ".weight", bn + ".bias")
 
@@ -673,11 +695,48 @@ def _resnet(pl, layers, output_stride):
     return c1, c2, c3, c4
 
 
-def _sepconv(pl, x, prefix, dilation, out=None):
-    """SeparableConv2d(relu_first=False) (modules/basic.py:52-59): dw -> BN -> ReLU -> pw -> BN -> ReLU."""
+def _sepconv(pl, x, prefix, dilation, out=None, planes=None, stride=1, relu_first=False, eps=1e-5, residual=None):
+    """SeparableConv2d (modules/basic.py:34-62).  relu_first=False: dw -> BN -> ReLU -> pw -> BN -> ReLU;
+    relu_first=True: ReLU -> dw -> BN -> pw -> BN (the leading ReLU is NOT in place: the caller's x stays un-rectified)."""
     b = prefix + ".block"
-    z = pl.dw_unit(x, b + ".depthwise.weight", b + ".bn_depth", "relu", dilation)
-    return pl.conv_unit(z, b + ".pointwise.weight", b + ".bn_point", "relu", out=out)
+    z = pl.dw_unit(x, b + ".depthwise.weight", b + ".bn_depth", None if relu_first else "relu", dilation, eps=eps, stride=stride,
+                   pre_relu=relu_first)
+    return pl.conv_unit(z, b + ".pointwise.weight", b + ".bn_point", None if relu_first else "relu", out=out, eps=eps,
+                        residual=residual)
+
+
+def _xception_block(pl, x, prefix, stride=1, dilation=1, skip="conv", relu_first=True, eps=1e-5):
+    """XceptionBlock.forward (backbones/xception.py:32-51): three separable convs + shortcut (1x1 stride-s conv + BN / identity /
+    none); NO ReLU after the add (:40-42).  The shortcut is recorded first: its gradient is the last to reach the block input."""
+    res = None
+    if skip == "conv":
+        res = pl.conv_unit(x, prefix + ".conv.weight", prefix + ".bn", None, k=1, stride=stride, eps=eps)
+    elif skip == "sum":
+        res = x
+    sc1 = _sepconv(pl, x, prefix + ".sep_conv1", dilation, relu_first=relu_first, eps=eps)
+    sc2 = _sepconv(pl, sc1, prefix + ".sep_conv2", dilation, relu_first=relu_first, eps=eps)
+    out = _sepconv(pl, sc2, prefix + ".sep_conv3", dilation, stride=stride, relu_first=relu_first, eps=eps, residual=res)
+    return out, sc2
+
+
+def _xception65(pl, output_stride, eps):
+    """Xception65.forward (backbones/xception.py:129-165)."""
+    b3s, mid_d, exit_d, exit_s = {32: (2, 1, (1, 1), 2), 16: (2, 1, (1, 2), 1), 8: (1, 2, (2, 4), 1)}[output_stride]
+    p = "encoder"
+    n, H, W = pl.n, pl.H, pl.W
+    s2d = Act(pl, pl.new(n, (H + 1) // 2, (W + 1) // 2, 16, ld=64), needs_grad=False)
+    pl.cur.append(Step("pack_s2d", (lambda s: ops.pack_s2d(pl.x_in, s2d.t._base if s2d.t._base is not None else s2d.t)),
+                       dict(x=pl.x_in, out=s2d.t)))
+    x = pl.conv_unit(s2d, p + ".conv1.weight", p + ".bn1", "relu", k=3, stride=2, pad=1, stem=True, eps=eps)
+    x = pl.conv_unit(x, p + ".conv2.weight", p + ".bn2", "relu", k=3, pad=1, eps=eps)
+    x, _ = _xception_block(pl, x, p + ".block1", 2, eps=eps)
+    x, c1 = _xception_block(pl, x, p + ".block2", 2, eps=eps)
+    x, _ = _xception_block(pl, x, p + ".block3", b3s, eps=eps)
+    for i in range(4, 20):
+        x, _ = _xception_block(pl, x, f"{p}.block{i}", 1, mid_d, "sum", eps=eps)
+    x, _ = _xception_block(pl, x, p + ".block20", exit_s, exit_d[0], eps=eps)
+    c4, _ = _xception_block(pl, x, p + ".block21", 1, exit_d[1], "none", False, eps)
+    return c1, c4
 
 
 def _aspp(pl, c4, prefix, output_stride):
@@ -696,10 +755,13 @@ def _aspp(pl, c4, prefix, output_stride):
     return pl.conv_unit(cat, prefix + ".conv.weight", prefix + ".bn", "relu", nc_scale=mask)
 
 
-def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16):
+def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16, eps_encoder=1e-5):
     """DeepLabV3Plus.forward + _DeepLabHead (models/deeplabv3_plus.py:33-75) + the loss of solver/loss.py:16-46 (aux off)."""
-    layers = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}[backbone]
-    c1, _, _, c4 = _resnet(pl, layers, output_stride)
+    if backbone == "xception65":
+        c1, c4 = _xception65(pl, output_stride, eps_encoder)
+    else:
+        layers = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}[backbone]
+        c1, _, _, c4 = _resnet(pl, layers, output_stride)
     x = _aspp(pl, c4, "head.aspp", output_stride)
     n, h1, w1, _ = c1.t.shape
     cat = Act(pl, pl.new(n, h1, w1, 304))
@@ -722,14 +784,17 @@ class DeepLabV3PlusTrainerB200:
     LR x10; LR from the YAML, cityscapes_deeplabv3_plus_resnet.yaml:15).  Multi-GPU: construct under an initialised
     torch.distributed NCCL group; gradients are averaged over ranks by bucketed all-reduces overlapped with backward."""
 
-    def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, dtype=torch.bfloat16, device="cuda",
+    def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, eps_encoder=None, dtype=torch.bfloat16,
+                 device="cuda",
                  lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
                  bucket_mb=25, cuda_graph=False, sync_bn=True):
         if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
             raise RuntimeError("segb200: a CUDA device (sm_100a) is required; there is no CPU fallback")
         self.device = torch.device(device)
         self.dtype = dtype
-        self.cfg = dict(backbone=backbone, output_stride=output_stride)
+        # cfg.MODEL.BN_EPS_FOR_ENCODER (1e-3 in cityscapes_deeplabv3_plus.yaml:20, applied by solver/optimizer.py:18-20)
+        self.cfg = dict(backbone=backbone, output_stride=output_stride,
+                        eps_encoder=eps_encoder if eps_encoder is not None else (1e-3 if backbone == "xception65" else 1e-5))
         self.nclass, self.bn_momentum = nclass, bn_momentum
         self.lr, self.momentum, self.weight_decay, self.decoder_lr_factor = lr, momentum, weight_decay, decoder_lr_factor
         self.dropout = dropout

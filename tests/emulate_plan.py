@@ -70,7 +70,8 @@ def run_step(st):
         x, w, y, d = i["x"], i["w"], i["y"], i["dilation"]
         c = x.shape[3]
         W = w.t().reshape(c, 1, 3, 3).to(CD)
-        y.copy_(F.conv2d(_nchw(x), W, None, 1, d, d, groups=c).permute(0, 2, 3, 1).to(y.dtype))
+        xin = F.relu(_nchw(x)) if i.get("pre_relu") else _nchw(x)
+        y.copy_(F.conv2d(xin, W, None, i.get("stride", 1), d, d, groups=c).permute(0, 2, 3, 1).to(y.dtype))
     elif kind == "bn_stats":
         x, partial, c = i["x"], i["partial"], i["c"]
         xf = x.to(CD).reshape(-1, c)
@@ -113,7 +114,7 @@ def run_step(st):
             g = g * ((pre > 0) if act == "relu" else ((pre > 0) & (pre < 6)))
         mean = st_["mean"] if st_.get("mean") is not None else 0.0
         inv = st_["invstd"] if st_.get("invstd") is not None else 1.0
-        xh = (y.to(CD) - mean) * inv
+        xh = (y.to(CD) - mean) * inv if y is not None else None
         c = g.shape[3]
         if kind == "bn_bwd_reduce":
             p = st_["partial"]
@@ -125,8 +126,11 @@ def run_step(st):
                 dres = i["dres"]
                 dres.copy_(((dres.to(CD) if i["dres_acc"] else 0) + g).to(dres.dtype))
             if i["dy"] is not None:
-                s = st_["sums"]
-                o = st_["scale"] * (g - s[0] / i["count"] - xh * s[1] / i["count"])
+                s = st_.get("sums")
+                if s is not None:
+                    o = st_["scale"] * (g - s[0] / i["count"] - xh * s[1] / i["count"])
+                else:
+                    o = g * st_["scale"] if st_.get("scale") is not None else g
                 i["dy"].copy_(o.to(i["dy"].dtype))
     elif kind == "bn_bwd_finalize":
         st_, c = i["st"], i["c"]
@@ -181,7 +185,8 @@ def run_step(st):
     elif kind == "dw_wgrad":
         x, dy, c, d = i["x"], i["dy"], i["c"], i["dilation"]
         W0 = torch.zeros(c, 1, 3, 3, dtype=CD, device=x.device, requires_grad=True)
-        F.conv2d(_nchw(x), W0, None, 1, d, d, groups=c).backward(_nchw(dy))
+        xin = F.relu(_nchw(x)) if i.get("pre_relu") else _nchw(x)
+        F.conv2d(xin, W0, None, 1, d, d, groups=c).backward(_nchw(dy))
         p = i["partial"]
         p.zero_()
         p[:9 * c] = W0.grad.reshape(c, 9).t().reshape(-1)

@@ -63,11 +63,12 @@ def _digest(grads, seed=12345):
     return out
 
 
-def test_training_step_matches_reference_fixture():
+@pytest.mark.parametrize("case", ["train_dlv3p_resnet101_65x97_b4", "train_dlv3p_xception65_65x97_b4"])
+def test_training_step_matches_reference_fixture(case):
     """Oracle train step (train-mode BN, Dropout2d mask, CE(ignore -1), backward, SGD groups) against the real reference's
     tools/train.py iteration recorded in tests/golden/train_dlv3p_resnet101_65x97_b4.pt: loss, a (norm, random projection)
     digest of all 356 parameter gradients, selected full gradients, BN running statistics, parameters after optimizer.step()."""
-    fx = torch.load(os.path.join(G, "train_dlv3p_resnet101_65x97_b4.pt"))
+    fx = torch.load(os.path.join(G, case + ".pt"))
     P = R.build_params(fx["model"], fx["seed"])
     n, _, h, w = fx["shape"]
     g = torch.Generator().manual_seed(fx["input_seed"])

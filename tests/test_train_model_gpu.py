@@ -111,8 +111,8 @@ def _stepwise_check(tr, x, target, masks):
     return pl, worst
 
 
-def _case(seed=21, shape=(4, 3, 65, 97)):
-    P = R.build_params(MODEL, seed)
+def _case(seed=21, shape=(4, 3, 65, 97), model=MODEL):
+    P = R.build_params(model, seed)
     g = torch.Generator().manual_seed(2000 + seed)
     x = torch.randn(*shape, generator=g)
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
@@ -121,11 +121,12 @@ def _case(seed=21, shape=(4, 3, 65, 97)):
     return P, x, target, mask
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16], ids=["bf16"])     # fp16 training needs loss scaling: per-kernel tests only
-def test_every_launch_of_a_training_step(dtype):
+@pytest.mark.parametrize("model,backbone", [(MODEL, "resnet101"), ("deeplabv3plus_xception65", "xception65")])
+def test_every_launch_of_a_training_step(model, backbone):
     from segmentron_b200.train import DeepLabV3PlusTrainerB200
-    P, x, target, mask = _case()
-    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=dtype)
+    dtype = torch.bfloat16                                   # fp16 training needs loss scaling: per-kernel tests only
+    P, x, target, mask = _case(model=model)
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=backbone, dtype=dtype)
     pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {"head.aspp.dropout": mask.cuda()})
     print(f"[{dtype}] {len(pl.fwd) + len(pl.bwd)} launches checked; worst max-err/rms per kernel:",
           {k: f"{v:.2e}" for k, v in sorted(worst.items())})
