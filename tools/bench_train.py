@@ -17,7 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-MODEL = "deeplabv3plus_resnet101"
+MODEL = "deeplabv3plus_resnet101"          # --backbone xception65 switches to deeplabv3plus_xception65
 
 
 def ref_train_leg(P, x, target, fmt, iters):
@@ -67,10 +67,13 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
+    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65"])
     ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
+    global MODEL
+    MODEL = "deeplabv3plus_" + args.backbone
     import __graft_entry__ as ge
     ge.build()
     from oracle import segref as R          # parameter generator + the reference leg only
@@ -84,7 +87,7 @@ def main():
     g = torch.Generator().manual_seed(1024 + (0 if args.same_data else rank))
     x = torch.randn(*shape, generator=g).cuda()
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g).cuda()
-    tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=args.backbone, dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
     losses = [float(tr.step(x, target)) for _ in range(max(args.warmup, 3))]
     parallel.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -120,7 +123,8 @@ def main():
                     f.write(f"{'fwd' if i < nf else 'bwd'}\t{st.kind}\t{t:.4f}\t{fl / 1e9:.2f}\t{fl / max(t, 1e-6) / 1e9:.1f}\t{desc}\n")
         tot = sum(a["ms"] for a in agg.values())
         mm = {k: agg[k] for k in ("conv", "wgrad") if k in agg and agg[k]["ms"] > 0}
-        out = {"config": "c3_train", "what": "DeepLabv3+/ResNet101 bf16 training step (fwd + CE loss + bwd + SGD) at "
+        out = {"config": "c3_train" if args.backbone == "resnet101" else "train_" + args.backbone,
+               "what": f"DeepLabv3+/{args.backbone} bf16 training step (fwd + CE loss + bwd + SGD) at "
                f"{args.height}x{args.width}, per-GPU batch {args.batch}", "n_gpus": world, "segb200_img_s": world * args.batch / (ms * 1e-3),
                "segb200_ms_per_step": ms, "launches_per_step": tr.n_launches(shape), "loss_first_steps": losses,
                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
