@@ -41,7 +41,9 @@ class Step:
 # ------------------------------------------------------------------------------------------------------------
 def _kind(name, t):
     if t.dim() == 4:
-        return "dw" if (t.shape[1] == 1 and t.shape[0] > 1 and "depthwise" in name) else "conv"
+        # depthwise 3x3: [C, 1, 3, 3] (SeparableConv2d.depthwise, the groups=C _ConvBNReLU of InvertedResidual); no dense conv of
+        # these models has a single input channel
+        return "dw" if (t.shape[1] == 1 and t.shape[0] > 1 and tuple(t.shape[2:]) == (3, 3)) else "conv"
     return "vec"
 
 
@@ -739,6 +741,47 @@ def _xception65(pl, output_stride, eps):
     return c1, c4
 
 
+def _inverted_residual(pl, x, prefix, cout, stride, expand, dilation, eps):
+    """InvertedResidual (modules/basic.py:139-163): [pw + BN + ReLU6] -> dw(stride, dil) + BN + ReLU6 -> pw + BN (+ x)."""
+    cin = x.t.shape[3]
+    y, i = x, 0
+    if expand != 1:
+        y = pl.conv_unit(y, f"{prefix}.conv.{i}.conv.weight", f"{prefix}.conv.{i}.bn", "relu6", eps=eps)
+        i += 1
+    y = pl.dw_unit(y, f"{prefix}.conv.{i}.conv.weight", f"{prefix}.conv.{i}.bn", "relu6", dilation, eps=eps, stride=stride)
+    i += 1
+    res = x if (stride == 1 and cin == cout) else None
+    return pl.conv_unit(y, f"{prefix}.conv.{i}.weight", f"{prefix}.conv.{i + 1}", None, eps=eps, residual=res)
+
+
+def _mobilenet_v2(pl, output_stride, eps):
+    """MobileNetV2.forward (backbones/mobilenet.py:131-143), incl. the first-block-only dilation quirk (:125 vs :128)."""
+    dil = {32: (1, 1), 16: (1, 2), 8: (2, 4)}[output_stride]
+    setting = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2], [6, 320, 1, 1]]
+    p = "encoder"
+    n, H, W = pl.n, pl.H, pl.W
+    s2d = Act(pl, pl.new(n, (H + 1) // 2, (W + 1) // 2, 16, ld=64), needs_grad=False)
+    pl.cur.append(Step("pack_s2d", (lambda s: ops.pack_s2d(pl.x_in, s2d.t._base if s2d.t._base is not None else s2d.t)),
+                       dict(x=pl.x_in, out=s2d.t)))
+    x = pl.conv_unit(s2d, p + ".conv1.conv.weight", p + ".conv1.bn", "relu6", k=3, stride=2, pad=1, stem=True, eps=eps)
+
+    def layer(x, name, rows, dilation=1):
+        j = 0
+        for t, c, nrep, s in rows:
+            stride = s if dilation == 1 else 1
+            x = _inverted_residual(pl, x, f"{p}.{name}.{j}", c, stride, t, dilation, eps); j += 1
+            for _ in range(nrep - 1):
+                x = _inverted_residual(pl, x, f"{p}.{name}.{j}", c, 1, t, 1, eps); j += 1
+        return x
+
+    x = layer(x, "block1", setting[0:1])
+    c1 = layer(x, "block2", setting[1:2])
+    c2 = layer(c1, "block3", setting[2:3])
+    c3 = layer(c2, "block4", setting[3:5], dil[0])
+    c4 = layer(c3, "block5", setting[5:], dil[1])
+    return c1, c4
+
+
 def _aspp(pl, c4, prefix, output_stride):
     """_ASPP.forward (modules/module.py:62-77) in training mode (Dropout2d active, :75)."""
     d = {16: (6, 12, 18), 8: (12, 24, 36), 32: (6, 12, 18)}[output_stride]
@@ -755,21 +798,29 @@ def _aspp(pl, c4, prefix, output_stride):
     return pl.conv_unit(cat, prefix + ".conv.weight", prefix + ".bn", "relu", nc_scale=mask)
 
 
-def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16, eps_encoder=1e-5):
-    """DeepLabV3Plus.forward + _DeepLabHead (models/deeplabv3_plus.py:33-75) + the loss of solver/loss.py:16-46 (aux off)."""
+def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16, eps_encoder=1e-5, use_aspp=True, use_decoder=True):
+    """DeepLabV3Plus.forward + _DeepLabHead (models/deeplabv3_plus.py:33-75) + the loss of solver/loss.py:16-46 (aux off).
+    use_aspp / use_decoder False = the MobileNetV2 YAML (configs/cityscapes_deeplabv3_plus_mobilenet.yaml:21-23)."""
     if backbone == "xception65":
         c1, c4 = _xception65(pl, output_stride, eps_encoder)
+    elif backbone == "mobilenet_v2":
+        c1, c4 = _mobilenet_v2(pl, output_stride, eps_encoder)
     else:
         layers = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}[backbone]
         c1, _, _, c4 = _resnet(pl, layers, output_stride)
-    x = _aspp(pl, c4, "head.aspp", output_stride)
-    n, h1, w1, _ = c1.t.shape
-    cat = Act(pl, pl.new(n, h1, w1, 304))
-    pl.bilinear(x, cat.slice(0, 256))
-    pl.conv_unit(c1, "head.c1_block.conv.weight", "head.c1_block.bn", "relu", out=cat.slice(256, 304))
-    x = _sepconv(pl, cat, "head.block.0", 1)
+    x = c4
+    if use_aspp:
+        x = _aspp(pl, x, "head.aspp", output_stride)
+    if use_decoder:
+        n, h1, w1, _ = c1.t.shape
+        cat = Act(pl, pl.new(n, h1, w1, 304))
+        pl.bilinear(x, cat.slice(0, 256))
+        pl.conv_unit(c1, "head.c1_block.conv.weight", "head.c1_block.bn", "relu", out=cat.slice(256, 304))
+        x = cat
+    x = _sepconv(pl, x, "head.block.0", 1)
     x = _sepconv(pl, x, "head.block.1", 1)
-    logits = Act(pl, pl.new(n, h1, w1, fold.round_up(pl.nclass, 8), ld=32))
+    n, hl, wl, _ = x.t.shape
+    logits = Act(pl, pl.new(n, hl, wl, fold.round_up(pl.nclass, 8), ld=32))
     pl.conv_unit(x, "head.block.2.weight", bias="head.block.2.bias", out=logits)
     pl.logits = logits
     pl.loss(logits)
@@ -784,8 +835,8 @@ class DeepLabV3PlusTrainerB200:
     LR x10; LR from the YAML, cityscapes_deeplabv3_plus_resnet.yaml:15).  Multi-GPU: construct under an initialised
     torch.distributed NCCL group; gradients are averaged over ranks by bucketed all-reduces overlapped with backward."""
 
-    def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, eps_encoder=None, dtype=torch.bfloat16,
-                 device="cuda",
+    def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, eps_encoder=None, use_aspp=None,
+                 use_decoder=None, dtype=torch.bfloat16, device="cuda",
                  lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
                  bucket_mb=25, cuda_graph=False, sync_bn=True):
         if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
@@ -793,15 +844,19 @@ class DeepLabV3PlusTrainerB200:
         self.device = torch.device(device)
         self.dtype = dtype
         # cfg.MODEL.BN_EPS_FOR_ENCODER (1e-3 in cityscapes_deeplabv3_plus.yaml:20, applied by solver/optimizer.py:18-20)
+        lite = backbone == "mobilenet_v2"         # cfg.MODEL.DEEPLABV3_PLUS.USE_ASPP / ENABLE_DECODER are False in the MobileNet YAML
         self.cfg = dict(backbone=backbone, output_stride=output_stride,
-                        eps_encoder=eps_encoder if eps_encoder is not None else (1e-3 if backbone == "xception65" else 1e-5))
+                        eps_encoder=eps_encoder if eps_encoder is not None else (1e-3 if backbone == "xception65" else 1e-5),
+                        use_aspp=(not lite) if use_aspp is None else use_aspp,
+                        use_decoder=(not lite) if use_decoder is None else use_decoder)
         self.nclass, self.bn_momentum = nclass, bn_momentum
         self.lr, self.momentum, self.weight_decay, self.decoder_lr_factor = lr, momentum, weight_decay, decoder_lr_factor
         self.dropout = dropout
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         self.cuda_graph = cuda_graph
         self.sync_bn = sync_bn                  # cfg.TRAIN.SYNC_BATCH_NORM (config/settings.py:59): only matters when world > 1
-        self.store = ParamStore({k: v.detach() for k, v in state_dict.items()}, self.device, dtype, stem="encoder.conv1.weight")
+        stem = "encoder.conv1.conv.weight" if backbone == "mobilenet_v2" else "encoder.conv1.weight"
+        self.store = ParamStore({k: v.detach() for k, v in state_dict.items()}, self.device, dtype, stem=stem)
         self.plans = {}
         self.world = 1
         self.dist = None

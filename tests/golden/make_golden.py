@@ -90,6 +90,7 @@ TRAIN_CASES = {
     # case: (oracle model name, reference yaml, input shape, seed)
     "train_dlv3p_resnet101_65x97_b4": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (4, 3, 65, 97), 21),
     "train_dlv3p_xception65_65x97_b4": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (4, 3, 65, 97), 22),
+    "train_dlv3p_mobilenetv2_64x96_b4": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (4, 3, 64, 96), 23),
 }
 
 
@@ -136,7 +137,7 @@ def run_train_case(case):
     optimizer = get_optimizer(model)
     # Dropout2d mask: torch draws a [N,C,1,1] Bernoulli(0.9) tensor; re-create it from the same RNG state for the oracle
     torch.manual_seed(777)
-    mask = torch.empty(n, 256, 1, 1).bernoulli_(0.9) / 0.9
+    mask = torch.empty(n, 256, 1, 1).bernoulli_(0.9) / 0.9            # (unused by the ASPP-less MobileNetV2 head)
     torch.manual_seed(777)
     outputs = model(x)
     loss = sum(criterion(outputs, target).values())
@@ -168,11 +169,15 @@ def run_train_case(case):
     small = ["encoder.conv1.weight", "encoder.bn1.weight", "encoder.bn1.bias",
              "encoder.layer4.2.bn3.weight" if "resnet" in name else "encoder.block21.sep_conv3.block.bn_point.weight",
              "head.block.2.weight", "head.block.2.bias", "head.aspp.image_pooling.bn.weight", "head.c1_block.bn.bias"]
+    if "mobilenet" in name:
+        small = ["encoder.conv1.conv.weight", "encoder.conv1.bn.weight", "encoder.block5.3.conv.3.bias", "head.block.2.weight",
+                 "head.block.2.bias", "head.block.0.block.depthwise.weight"]
     out = dict(case=case, model=name, seed=seed, input_seed=2000 + seed, shape=shape, loss=float(loss), mask=mask,
                low=outputs[0].detach()[:, :, ::8, ::8].contiguous(), digest=grad_digest(ref_grads),
                grads_small={k: ref_grads[k] for k in small}, hyper=hyper, stepped_digest=grad_digest(stepped, 999),
                running={k: sd[k].clone() for k in sd if k.endswith(("running_mean", "running_var")) and
-                        (k.startswith("encoder.bn1") or "image_pooling" in k or "layer4.2.bn3" in k or "block21.sep_conv3.block.bn_point" in k)},
+                        (k.startswith("encoder.bn1") or "image_pooling" in k or "layer4.2.bn3" in k or "block21.sep_conv3.block.bn_point" in k
+                         or k.startswith("encoder.conv1.bn") or "block5.3.conv.3" in k)},
                oracle_vs_ref_worst_grad_rel=worst)
     torch.save(out, os.path.join(HERE, case + ".pt"))
     print(f"{case}: loss {float(loss):.6f}; worst grad rel-L2 oracle vs reference {worst:.2e}; {len(ref_grads)} grads")

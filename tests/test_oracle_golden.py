@@ -63,7 +63,8 @@ def _digest(grads, seed=12345):
     return out
 
 
-@pytest.mark.parametrize("case", ["train_dlv3p_resnet101_65x97_b4", "train_dlv3p_xception65_65x97_b4"])
+@pytest.mark.parametrize("case", ["train_dlv3p_resnet101_65x97_b4", "train_dlv3p_xception65_65x97_b4",
+                                  "train_dlv3p_mobilenetv2_64x96_b4"])
 def test_training_step_matches_reference_fixture(case):
     """Oracle train step (train-mode BN, Dropout2d mask, CE(ignore -1), backward, SGD groups) against the real reference's
     tools/train.py iteration recorded in tests/golden/train_dlv3p_resnet101_65x97_b4.pt: loss, a (norm, random projection)
@@ -96,4 +97,5 @@ def test_training_step_matches_reference_fixture(case):
     sd = _digest(stepped, 999)
     for k, (nrm, proj) in fx["stepped_digest"].items():
         assert abs(sd[k][0] - nrm) <= 1e-4 * nrm + 1e-9, k
-    assert fx["hyper"]["head.block.2.weight"][0] == pytest.approx(10 * fx["hyper"]["encoder.conv1.weight"][0])
+    enc0 = "encoder.conv1.weight" if "encoder.conv1.weight" in fx["hyper"] else "encoder.conv1.conv.weight"
+    assert fx["hyper"]["head.block.2.weight"][0] == pytest.approx(10 * fx["hyper"][enc0][0])

@@ -121,13 +121,14 @@ def _case(seed=21, shape=(4, 3, 65, 97), model=MODEL):
     return P, x, target, mask
 
 
-@pytest.mark.parametrize("model,backbone", [(MODEL, "resnet101"), ("deeplabv3plus_xception65", "xception65")])
+@pytest.mark.parametrize("model,backbone", [(MODEL, "resnet101"), ("deeplabv3plus_xception65", "xception65"),
+                                            ("deeplabv3plus_mobilenet_v2", "mobilenet_v2")])
 def test_every_launch_of_a_training_step(model, backbone):
     from segmentron_b200.train import DeepLabV3PlusTrainerB200
     dtype = torch.bfloat16                                   # fp16 training needs loss scaling: per-kernel tests only
     P, x, target, mask = _case(model=model)
     tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=backbone, dtype=dtype)
-    pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {"head.aspp.dropout": mask.cuda()})
+    pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {"head.aspp.dropout": mask.cuda()})      # (MobileNetV2 head: no ASPP, no mask)
     print(f"[{dtype}] {len(pl.fwd) + len(pl.bwd)} launches checked; worst max-err/rms per kernel:",
           {k: f"{v:.2e}" for k, v in sorted(worst.items())})
     assert torch.isfinite(tr.store.grad).all()

@@ -26,7 +26,8 @@ def dry_run():
     TrainPlan.STAT_DTYPE = torch.float32
 
 
-@pytest.mark.parametrize("model,backbone", [("deeplabv3plus_resnet101", "resnet101"), ("deeplabv3plus_xception65", "xception65")])
+@pytest.mark.parametrize("model,backbone", [("deeplabv3plus_resnet101", "resnet101"), ("deeplabv3plus_xception65", "xception65"),
+                                            ("deeplabv3plus_mobilenet_v2", "mobilenet_v2")])
 def test_train_plan_matches_oracle_on_cpu(dry_run, model, backbone):
     from segmentron_b200.train import DeepLabV3PlusTrainerB200
     seed, shape = 21, (4, 3, 65, 97)
@@ -61,8 +62,10 @@ def test_train_plan_matches_oracle_on_cpu(dry_run, model, backbone):
     # SGD: encoder lr, decoder lr x10, weight decay on everything (solver/optimizer.py:14-34,50-51)
     E.sgd(tr)
     sd = tr.state_dict()
-    probe = {"resnet101": "encoder.layer3.5.conv2.weight", "xception65": "encoder.block7.sep_conv2.block.depthwise.weight"}[backbone]
-    for k in ("encoder.conv1.weight", probe, "head.block.2.weight", "head.aspp.bn.bias"):
+    probes = {"resnet101": ("encoder.conv1.weight", "encoder.layer3.5.conv2.weight", "head.aspp.bn.bias"),
+              "xception65": ("encoder.conv1.weight", "encoder.block7.sep_conv2.block.depthwise.weight", "head.aspp.bn.bias"),
+              "mobilenet_v2": ("encoder.conv1.conv.weight", "encoder.block4.2.conv.1.conv.weight", "head.block.1.block.bn_point.bias")}
+    for k in probes[backbone] + ("head.block.2.weight",):
         lr = 0.02 * (10.0 if k.startswith("head.") else 1.0)
         ref = before[k].double() - lr * (o_grads[k] + 1e-4 * before[k].double())
         assert float((sd[k].double() - ref).norm() / ref.norm()) < 1e-6, k
@@ -79,7 +82,7 @@ def test_train_plan_matches_oracle_on_cpu(dry_run, model, backbone):
                     off = t.storage_offset()
                     assert not (lo <= off < hi), (st.kind, off, lo, hi)
             if st.kind == "scatter_add":               # the stem's s2d-space gradient is un-packed into encoder.conv1.weight
-                assert not (lo <= tr.store.meta["encoder.conv1.weight"]["off"] < hi), "stem gradient written after its bucket"
+                assert not (lo <= tr.store.meta[tr.store.stem]["off"] < hi), "stem gradient written after its bucket"
 
 
 def test_state_dict_roundtrip(dry_run):
