@@ -699,13 +699,13 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
   if (valid) {
     const char* xb = reinterpret_cast<const char*>(x) + (long long)cv * 16;
     const char* gb = reinterpret_cast<const char*>(dy) + (long long)cv * 16;
-    auto pixel = [&](long long p, const uint4& vg) {
-      const int xw = (int)(p % w);
-      const long long q = p / w;
-      const int yh = (int)(q % h);
-      const long long b = q / h;
+    // no per-pixel divisions / 64-bit multiplies: the (column, row) of the running pixel is tracked incrementally and every
+    // tap address is the pixel's own address plus a precomputed offset
+    const long long row_off = (long long)dilation * w * x_ld * 2, col_off = (long long)dilation * x_ld * 2;
+    auto pixel = [&](long long p, int xw, int yh, const uint4& vg) {
       float g[8];
       unpack8(vg, dtype, g);
+      const char* xp = xb + p * x_ld * 2;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = yh + (ky - 1) * dilation;
@@ -715,7 +715,7 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
           const int ix = xw + (kx - 1) * dilation;
           if (ix < 0 || ix >= w) continue;
           float f[8];
-          unpack8(ldg_v4(xb + (((long long)b * h + iy) * w + ix) * x_ld * 2), dtype, f);
+          unpack8(ldg_v4(xp + (ky - 1) * row_off + (kx - 1) * col_off), dtype, f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float xv = pre_relu ? fmaxf(f[j], 0.f) : f[j];
@@ -724,12 +724,21 @@ dw_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, int n, 
         }
       }
     };
+    auto advance = [&](int& xw, int& yh, int step) {          // (xw, yh) of pixel p -> of pixel p + step (the image index is not needed)
+      xw += step;
+      while (xw >= w) { xw -= w; if (++yh == h) yh = 0; }
+    };
     long long p = r0 + lp;
+    int xw = (int)(p % w), yh = (int)((p / w) % h);
     for (; p + pl < r1; p += 2LL * pl) {               // two pixels in flight
       const uint4 g0 = ldg_nc_v4(gb + p * dy_ld * 2), g1 = ldg_nc_v4(gb + (p + pl) * dy_ld * 2);
-      pixel(p, g0); pixel(p + pl, g1);
+      int xw1 = xw, yh1 = yh;
+      advance(xw1, yh1, pl);
+      pixel(p, xw, yh, g0); pixel(p + pl, xw1, yh1, g1);
+      xw = xw1; yh = yh1;
+      advance(xw, yh, pl);
     }
-    if (p < r1) pixel(p, ldg_nc_v4(gb + p * dy_ld * 2));
+    if (p < r1) pixel(p, xw, yh, ldg_nc_v4(gb + p * dy_ld * 2));
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t)

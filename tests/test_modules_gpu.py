@@ -121,10 +121,16 @@ def test_criss_cross_attention_backward(dtype, tol):
         _cmp(y.detach(), ref.detach(), tol)
         y.backward(dy.cuda().to(dtype))
         _cmp(xg.grad, xr.grad, tol)
+        # key_conv.bias has an analytically ZERO gradient (a per-query constant added to every energy cancels in the softmax):
+        # errors are measured against |g_ref| + 5 % of the largest parameter-gradient norm
+        floor = 0.05 * max(float(P.t[k].grad.norm()) for k in names)
+        errs = {}
         for k in names:
             g = dict(m.named_parameters())[k[4:]].grad
             assert g is not None, k
-            assert float((g.float().cpu().reshape(-1) - P.t[k].grad.reshape(-1)).norm() / (P.t[k].grad.norm() + 1e-12)) < 2 * tol, k
+            errs[k] = float((g.float().cpu().reshape(-1) - P.t[k].grad.reshape(-1)).norm() / (float(P.t[k].grad.norm()) + floor))
+        print(f"[cca bwd {dtype} {(n, c, h, w)}] " + ", ".join(f"{k[4:]}: {v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) < 2 * tol, errs
 
 
 def test_dropin_errors_and_cache_invalidation():

@@ -67,7 +67,7 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
-    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65"])
+    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2"])
     ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
