@@ -11,8 +11,10 @@ Folded BatchNorm / packed weights are caches keyed on parameter versions and ``e
 lazily at the next forward after any change.
 
 No CPU implementation and no PyTorch fallback: a non-CUDA input raises RuntimeError, like the reference's
-native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training-mode forward
-(batch-statistics BN + backward) is not part of this round and raises as well.
+native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training mode: ``SeparableConv2d``,
+``_ConvBNReLU``, ``_ConvBN`` and ``CrissCrossAttention`` are differentiable (train_modules.py / attention.py: train-mode
+BatchNorm + the backward kernels); the composite classes (InvertedResidual, _ASPP, PyramidPooling, PAM / CAM) raise in
+training mode -- train whole models through ``train.DeepLabV3PlusTrainerB200``.
 """
 from collections import OrderedDict
 
@@ -52,6 +54,36 @@ def _enter(x, module):
         buf.zero_()
     ops.nchw_to_nhwc(x, buf[..., :c])
     return (buf[..., :c] if buf.shape[3] != c else buf), x.dtype
+
+
+def _train_enter(x, module):
+    """training mode: logical NCHW -> NHWC 16-bit through autograd-visible torch ops (boundary plumbing)"""
+    if not x.is_cuda:
+        raise RuntimeError(f"segb200: {type(module).__name__} is not implemented on the CPU (input must be a CUDA tensor)")
+    dt = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else _COMPUTE_DTYPE
+    return x.permute(0, 2, 3, 1).contiguous().to(dt)
+
+
+def _train_conv_bn_act(xh, conv, bn, act, pre_relu=False):
+    """one fused training unit (conv or depthwise 3x3 + train-mode BatchNorm + activation) on an NHWC tensor"""
+    from . import train_modules as TM
+    if conv.bias is not None:
+        raise RuntimeError("segb200: conv bias in front of BatchNorm is not supported in training mode")
+    if conv.weight.dtype != torch.float32 or bn.running_mean.dtype != torch.float32:
+        raise RuntimeError("segb200: training mode expects fp32 parameters / BatchNorm buffers (compute is 16-bit)")
+    g, b, rm, rv, mom, eps = TM._bn_args(bn)
+    k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+    if conv.groups == 1:
+        if pre_relu:
+            raise RuntimeError("segb200: leading ReLU is only fused into the depthwise unit")
+        y = TM.ConvBNActFunction.apply(xh, conv.weight, g, b, rm, rv, mom, eps, s, d, p, act)
+    elif conv.groups == conv.in_channels == conv.out_channels and k == 3 and p == d:
+        y = TM.DwBNActFunction.apply(xh, conv.weight, g, b, rm, rv, mom, eps, s, d, pre_relu, act)
+    else:
+        raise RuntimeError(f"segb200: no training kernel for Conv2d(groups={conv.groups}, k={k})")
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
 
 
 def _leave(y_nhwc, out_dtype):
@@ -180,6 +212,12 @@ class SeparableConv2d(nn.Module):
                                 residual=residual)
 
     def forward(self, x):
+        if self.training:                          # differentiable path: train-mode BatchNorm + backward kernels
+            b = self.block
+            act = None if self.relu_first else "relu"
+            y = _train_conv_bn_act(_train_enter(x, self), b.depthwise, b.bn_depth, act, pre_relu=self.relu_first)
+            y = _train_conv_bn_act(y, b.pointwise, b.bn_point, act)
+            return y.permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 
@@ -200,6 +238,8 @@ class _ConvBNReLU(nn.Module):
         return _run_conv_bn_act(x, self.conv, self.bn, self._act, self._cache, x.dtype, out=out)
 
     def forward(self, x):
+        if self.training:
+            return _train_conv_bn_act(_train_enter(x, self), self.conv, self.bn, self._act).permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 
@@ -218,6 +258,8 @@ class _ConvBN(nn.Module):
         return _run_conv_bn_act(x, self.conv, self.bn, None, self._cache, x.dtype, out=out)
 
     def forward(self, x):
+        if self.training:
+            return _train_conv_bn_act(_train_enter(x, self), self.conv, self.bn, None).permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 

@@ -98,6 +98,16 @@ def bn_backward(dz, z, y, st, dy, dgamma, dbeta, act=None, dres=None, dres_accum
     return dy
 
 
+def relu_mask(g, x, out, accumulate=False):
+    """out (+)= g * [x > 0]  -- the backward of a leading ReLU (SeparableConv2d relu_first, modules/basic.py:45-46), through
+    the residual path of the BatchNorm-backward kernel"""
+    rows, hw, c, g_ld = _rows(g)
+    L.check(L.load().segb200_bn_bwd_apply(_ptr(g), _ptr(x), None, None, None, None, None, None, float(rows), None, None, _ptr(out),
+                                          int(bool(accumulate)), rows, hw, c, g_ld, _rows(x)[3], 0, 0, _rows(out)[3], L.ACT["relu"],
+                                          dt_code(g.dtype), _stream()), "bn_bwd_apply")
+    return out
+
+
 def maxpool3x3s2_bwd(x, dy, dx):
     n, h, w, c, x_ld = _nhwc(x, "x")
     L.check(L.load().segb200_maxpool3x3s2_bwd(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, x_ld, _nhwc(dy, "dy")[4], _nhwc(dx, "dx")[4],

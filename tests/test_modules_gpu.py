@@ -133,6 +133,55 @@ def test_criss_cross_attention_backward(dtype, tol):
         assert max(errs.values()) < 2 * tol, errs
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2.5e-2)], ids=["bf16"])
+def test_dropin_modules_train_backward(dtype, tol):
+    """Training-mode SeparableConv2d / _ConvBNReLU / _ConvBN drop-ins (train-mode BatchNorm + backward kernels behind
+    torch.autograd.Function) against autograd through the oracle's functional restatement in train mode: output, input
+    gradient, every parameter gradient, BatchNorm running statistics."""
+    from segmentron_b200 import modules as M
+
+    def run(make_mod, oracle_fn, prefix, x):
+        P = R.Params(41)
+        with torch.no_grad():
+            oracle_fn(P, x)                                           # creates the parameters
+        names = [k for k in P.t if k.startswith(prefix + ".") and not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+        for k in names:
+            P.t[k] = P.t[k].to(dtype).float().detach().requires_grad_(True)
+        sd0 = {k[len(prefix) + 1:]: v.detach().clone() for k, v in P.state_dict().items() if k.startswith(prefix + ".")}
+        P.training = True
+        xr = x.clone().requires_grad_(True)
+        ref = oracle_fn(P, xr)
+        dy = _x(*ref.shape, seed=43).to(dtype).float()
+        ref.backward(dy)
+        m = make_mod()
+        m.load_state_dict(sd0, strict=True)
+        m = m.cuda().train()
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        y = m(xg)
+        _cmp(y.detach(), ref.detach(), tol)
+        y.backward(dy.cuda().to(dtype))
+        _cmp(xg.grad, xr.grad, tol)
+        floor = 0.05 * max(float(P.t[k].grad.norm()) for k in names)
+        errs = {}
+        for k in names:
+            g = dict(m.named_parameters())[k[len(prefix) + 1:]].grad
+            assert g is not None, k
+            errs[k] = float((g.float().cpu() - P.t[k].grad).norm() / (float(P.t[k].grad.norm()) + floor))
+        assert max(errs.values()) < 2 * tol, errs
+        for k, v in m.state_dict().items():
+            if k.endswith(("running_mean", "running_var")):
+                assert torch.allclose(v.cpu(), P.t[prefix + "." + k], atol=2e-2, rtol=2e-2), k
+
+    x = (_x(2, 64, 33, 41, seed=42)).to(dtype).float()
+    for relu_first, stride, dil in [(True, 1, 1), (True, 2, 1), (False, 1, 2)]:
+        run(lambda: M.SeparableConv2d(64, 128, 3, stride, dil, relu_first),
+            lambda P, t: R.separable_conv2d(P, t, "m", 128, stride, dil, relu_first, 1e-5), "m", x)
+    run(lambda: M._ConvBNReLU(64, 128, 3, 1, 2, 2), lambda P, t: R.conv_bn_act(P, t, "m", 128, 3, 1, 2, 2), "m", x)
+    run(lambda: M._ConvBNReLU(64, 64, 3, 2, 1, 1, relu6=True), lambda P, t: R.conv_bn_act(P, t, "m", 64, 3, 2, 1, 1, act="relu6"), "m", x)
+    run(lambda: M._ConvBN(64, 256, 1, 2), lambda P, t: R.conv_bn_act(P, t, "m", 256, 1, 2, act=None), "m", x)
+    run(lambda: M._ConvBNReLU(64, 64, 3, 1, 1, 1, groups=64), lambda P, t: R.conv_bn_act(P, t, "m", 64, 3, 1, 1, 1, groups=64), "m", x)
+
+
 def test_dropin_errors_and_cache_invalidation():
     from segmentron_b200 import modules as M
     m = M.SeparableConv2d(64, 64).cuda().eval()
@@ -147,6 +196,6 @@ def test_dropin_errors_and_cache_invalidation():
         assert not torch.equal(y1, y2)
     with pytest.raises(RuntimeError):
         m(x.cpu())
-    m.train()
+    a = M._ASPP(64, 64, output_stride=16).cuda().train()          # composite classes have no training-mode kernels: loud error
     with pytest.raises(RuntimeError):
-        m(x)
+        a(x)
