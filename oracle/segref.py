@@ -572,6 +572,7 @@ def ccnet(P, x, nclass=19, output_stride=16, recurrence=2):
     out = conv_bn_act(P, out, "head.rcca.convb", 512, 3, 1, 1, conv="0", bn="1")
     out = torch.cat([c4, out], dim=1)                                               # ccnet.py:79
     out = conv_bn_act(P, out, "head.rcca.bottleneck", 512, 3, 1, 1, act=None, conv="0", bn="1")
+    out = dropout2d(P, out, "head.rcca.bottleneck.dropout", 0.1)                    # ccnet.py:70 (identity in eval)
     out = conv2d(P, out, "head.out", nclass, 1, bias=True, gain=4.0)
     return F.interpolate(out, size, mode="bilinear", align_corners=True)
 
@@ -649,7 +650,10 @@ def loss_and_grads(model: str, P: Params, x, target, nclass: int = 19, ignore_in
     was = P.training
     P.training = True
     try:
-        out, low = deeplabv3plus(P, x, nclass=nclass, return_lowres=True, **MODELS[model], **kw)
+        if model == "ccnet_resnet101":
+            out, low = ccnet(P, x, nclass=nclass, **kw), None
+        else:
+            out, low = deeplabv3plus(P, x, nclass=nclass, return_lowres=True, **MODELS[model], **kw)
         loss = F.cross_entropy(out.float(), target, ignore_index=ignore_index)
         loss.backward()
     finally:
@@ -657,7 +661,7 @@ def loss_and_grads(model: str, P: Params, x, target, nclass: int = 19, ignore_in
     grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     for k in names:
         P.t[k] = P.t[k].detach()
-    return loss.detach(), grads, out.detach(), low.detach()
+    return loss.detach(), grads, out.detach(), (low.detach() if low is not None else None)
 
 
 def forward(model: str, P: Params, x, nclass: int = 19, **kw):

@@ -217,7 +217,11 @@ class Act:
     def take(self):
         """-> (gradient tensor to write into, accumulate?) and mark it written"""
         if self.parent is not None:
-            raise RuntimeError("segb200 train plan: writing the gradient of a channel slice is not supported")
+            # a slice can only ACCUMULATE: the consumer of the whole buffer (e.g. the conv over a concat) must have written the
+            # root gradient first -- true whenever the slice's other consumers were recorded before the concat consumer
+            if not self.parent.written:
+                raise RuntimeError("segb200 train plan: a channel slice's gradient was written before its concat buffer's")
+            return self.parent._root_grad()[..., self.lo:self.lo + self.t.shape[3]], True
         g = self._root_grad()
         acc = self.written
         self.written = True
@@ -539,6 +543,58 @@ class TrainPlan:
             if k:
                 self.done_at[k] = len(self.bwd)
 
+    # ---- criss-cross attention (CrissCrossAttention.forward, modules/cc_attention.py:62-72), weights shared between calls ----
+    def cca_unit(self, x, prefix):
+        S = self.S
+        n, h, w_, c = x.t.shape
+        cq = S.meta[prefix + ".query_conv.weight"]["shape"][0]
+        q = self.conv_unit(x, prefix + ".query_conv.weight", bias=prefix + ".query_conv.bias")
+        k = self.conv_unit(x, prefix + ".key_conv.weight", bias=prefix + ".key_conv.bias")
+        v = self.conv_unit(x, prefix + ".value_conv.weight", bias=prefix + ".value_conv.bias")
+        att_ld = fold.round_up(h + w_ - 1, 4)
+        att = self.f32(n, h, w_, att_ld)
+        gamma = S.view(S.master, prefix + ".gamma")
+        y = Act(self, self.new(n, h, w_, c))
+        self.add("cca_weight_softmax", self.lib.segb200_cca_weight_softmax,
+                 (_ptr(q.t), _ptr(k.t), _ptr(att), n, h, w_, cq, q.t.stride(2), k.t.stride(2), att_ld, self.dt), q=q.t, k=k.t, att=att)
+        self.add("cca_map", self.lib.segb200_cca_map,
+                 (_ptr(att), _ptr(v.t), _ptr(x.t), _ptr(y.t), _ptr(gamma), n, h, w_, c, att_ld, v.t.stride(2), x.t.stride(2),
+                  y.t.stride(2), self.dt), att=att, v=v.t, x=x.t, y=y.t, gamma=gamma)
+
+        def backward():
+            dy = y.grad()
+            de = self.f32(n, h, w_, att_ld)
+            nb = self.lib.segb200_cca_weight_bwd_blocks(n, h, w_)
+            part = self.f32(nb)
+            self.add("cca_weight_bwd", self.lib.segb200_cca_weight_bwd,
+                     (_ptr(dy), _ptr(v.t), _ptr(att), _ptr(de), _ptr(part), _ptr(gamma), n, h, w_, c, dy.stride(2), v.t.stride(2), att_ld,
+                      self.dt), dy=dy, v=v.t, att=att, de=de, part=part, gamma=gamma)
+            gg = S.view(S.grad, prefix + ".gamma")
+            self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(part), nb, 1, 1, _ptr(gg), 0, 1, 1, 1.0),
+                     partial=part, slabs=nb, K=1, c=1, out=gg, sk=0, sc=1, accumulate=1, scale=1.0)
+            gq, aq = q.take()
+            self.add("cca_gather", self.lib.segb200_cca_gather,
+                     (_ptr(de), _ptr(k.t), _ptr(gq), n, h, w_, cq, att_ld, k.t.stride(2), gq.stride(2), 1.0, int(aq), self.dt),
+                     a=de, src=k.t, out=gq, scale=1.0, scale_dev=None, accumulate=aq)
+            gk, ak = k.take()
+            self.add("cca_scatter", self.lib.segb200_cca_scatter,
+                     (_ptr(de), _ptr(q.t), _ptr(gk), n, h, w_, cq, att_ld, q.t.stride(2), gk.stride(2), 1.0, None, int(ak), self.dt),
+                     a=de, src=q.t, out=gk, scale=1.0, scale_dev=None, accumulate=ak)
+            gv, av = v.take()
+            self.add("cca_scatter", self.lib.segb200_cca_scatter,
+                     (_ptr(att), _ptr(dy), _ptr(gv), n, h, w_, c, att_ld, dy.stride(2), gv.stride(2), 1.0, _ptr(gamma), int(av), self.dt),
+                     a=att, src=dy, out=gv, scale=1.0, scale_dev=gamma, accumulate=av)
+            gx, ax = x.take()                                   # the residual: dx (+)= dy
+            rws, hw, cc, ld = self._rows(gx)
+            self.add("bn_apply", self.lib.segb200_bn_apply,
+                     (_ptr(dy), None, None, _ptr(gx) if ax else None, None, _ptr(gx), rws, hw, cc, dy.stride(2), ld if ax else 0, ld, 0,
+                      self.dt), y=dy, scale=None, shift=None, residual=gx if ax else None, nc_scale=None, z=gx, act=None)
+            self.pool_put(dy)
+            self.mark_done(prefix + ".gamma")
+
+        self.tape.append(backward)
+        return y
+
     # ---- glue ops ----
     def maxpool(self, x):
         n, h, w_, c = x.t.shape
@@ -669,7 +725,7 @@ def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, out=None):
     return pl.conv_unit(y, prefix + ".conv3.weight", prefix + ".bn3", "relu", residual=idn, out=out)
 
 
-def _resnet(pl, layers, output_stride):
+def _resnet(pl, layers, output_stride, c4_out=None):
     """ResNetV1.forward (backbones/resnet.py:183-199), stride/dilation table :90-100,:149-179."""
     dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
     p = "encoder"
@@ -681,19 +737,19 @@ def _resnet(pl, layers, output_stride):
     x = pl.maxpool(x)
     inpl = [64]
 
-    def make_layer(x, name, planes, blocks, stride=1, dilation=1):
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1, last_out=None):
         ds = stride != 1 or inpl[0] != planes * 4
         first_d = 1 if dilation in (1, 2) else 2
         x = _bottleneck(pl, x, f"{p}.{name}.0", planes, stride, first_d, ds)
         inpl[0] = planes * 4
         for i in range(1, blocks):
-            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, dilation, False)
+            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, dilation, False, out=last_out if i == blocks - 1 else None)
         return x
 
     c1 = make_layer(x, "layer1", 64, layers[0])
     c2 = make_layer(c1, "layer2", 128, layers[1], 2)
     c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
-    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1])
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], last_out=c4_out)
     return c1, c2, c3, c4
 
 
@@ -828,6 +884,32 @@ def build_deeplabv3plus_train(pl, backbone="resnet101", output_stride=16, eps_en
     return pl
 
 
+def build_ccnet_train(pl, output_stride=16, recurrence=2):
+    """CCNet.forward + _CCHead / _RCCAModule (models/ccnet.py:27-82) + the loss of solver/loss.py:16-46 (aux off): ResNet101,
+    conva -> criss-cross attention x RECURRENCE (shared weights) -> convb -> cat[c4, out] -> bottleneck (3x3 + BN + Dropout2d)
+    -> 1x1 classifier.  c4 is produced straight into its channel slice of the concat buffer."""
+    n, H, W = pl.n, pl.H, pl.W
+    hh, ww = H, W
+    for s_ in ([2, 2, 2] + ([2] if output_stride >= 16 else []) + ([2] if output_stride == 32 else [])):
+        hh, ww = (hh - 1) // s_ + 1, (ww - 1) // s_ + 1
+    cat = Act(pl, pl.new(n, hh, ww, 2048 + 512))
+    _, _, _, c4 = _resnet(pl, (3, 4, 23, 3), output_stride, c4_out=cat.slice(0, 2048))
+    hp = "head.rcca"
+    out = pl.conv_unit(c4, hp + ".conva.0.weight", hp + ".conva.1", "relu", k=3, pad=1)
+    for _ in range(recurrence):
+        out = pl.cca_unit(out, hp + ".cca")
+    pl.conv_unit(out, hp + ".convb.0.weight", hp + ".convb.1", "relu", k=3, pad=1, out=cat.slice(2048, 2560))
+    mask = pl.f32(n, 512).fill_(1.0)
+    pl.masks[hp + ".bottleneck.dropout"] = mask
+    y = pl.conv_unit(cat, hp + ".bottleneck.0.weight", hp + ".bottleneck.1", None, k=3, pad=1, nc_scale=mask)
+    logits = Act(pl, pl.new(n, hh, ww, fold.round_up(pl.nclass, 8), ld=32))
+    pl.conv_unit(y, "head.out.weight", bias="head.out.bias", out=logits)
+    pl.logits = logits
+    pl.loss(logits)
+    pl.build_backward()
+    return pl
+
+
 class DeepLabV3PlusTrainerB200:
     """``trainer.step(images_nchw_fp32, targets_int64) -> loss`` : one iteration of tools/train.py:135-147 (forward, criterion,
     zero_grad, backward, optimizer.step) for DeepLabV3_Plus / ResNet on the CUDA engine.  ``state_dict()`` returns reference-named
@@ -872,9 +954,12 @@ class DeepLabV3PlusTrainerB200:
         if shape not in self.plans:
             pl = TrainPlan(self.store, shape, self.nclass, self.dtype, self.device, self.bn_momentum, dist=self.dist,
                            sync_bn=self.sync_bn)
-            build_deeplabv3plus_train(pl, **self.cfg)
+            self._build(pl)
             self.plans[shape] = dict(plan=pl, graph=None, buckets=self._buckets(pl))
         return self.plans[shape]
+
+    def _build(self, pl):
+        build_deeplabv3plus_train(pl, **self.cfg)
 
     def _buckets(self, pl):
         """contiguous ranges of the flat gradient, cut where backward has finished everything above an offset"""
@@ -954,3 +1039,18 @@ class DeepLabV3PlusTrainerB200:
     def n_launches(self, shape):
         pl = self.plan_for(shape)["plan"]
         return len(pl.fwd) + len(pl.bwd) + 5
+
+
+class CCNetTrainerB200(DeepLabV3PlusTrainerB200):
+    """``trainer.step(images, targets)`` for CCNet / ResNet101 (models/ccnet.py): the same engine, with the criss-cross attention
+    forward + backward kernels in the launch list (recurrence 2, shared weights).  Plan verified against the oracle in fp64
+    (tests/test_train_plan_cpu.py); every kernel in it is GPU-verified on its own; a model-level GPU replay is gated behind
+    SEGB200_TEST_ALL (written after the round's GPU budget was spent)."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=16, recurrence=2, **kw):
+        super().__init__(state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride, use_aspp=False,
+                         use_decoder=False, **kw)
+        self.recurrence = recurrence
+
+    def _build(self, pl):
+        build_ccnet_train(pl, self.cfg["output_stride"], self.recurrence)

@@ -203,6 +203,43 @@ def run_step(st):
         g = (lsm.exp() - oh) * valid[:, None].to(CD)
         dfull.zero_()
         dfull[..., :nc] = g.permute(0, 2, 3, 1).to(dfull.dtype)
+    elif kind in ("cca_weight_softmax", "cca_map", "cca_weight_bwd", "cca_gather", "cca_scatter"):
+        from oracle import segref as R          # criss-cross index map: the oracle's ca_weight / ca_map (pinned to ca_cuda.cu)
+
+        def att_nchw(a, L):
+            return a[..., :L].permute(0, 3, 1, 2).to(CD)          # [n,h,w,L] -> [n,L,h,w]
+        if kind == "cca_weight_softmax":
+            q, k, att = i["q"], i["k"], i["att"]
+            L = q.shape[1] + q.shape[2] - 1
+            att.zero_()
+            att[..., :L] = torch.softmax(R.ca_weight(_nchw(q), _nchw(k)), 1).permute(0, 2, 3, 1).to(att.dtype)
+        elif kind == "cca_map":
+            att, v, x, y = i["att"], i["v"], i["x"], i["y"]
+            L = v.shape[1] + v.shape[2] - 1
+            o = i["gamma"].to(CD)[0] * R.ca_map(att_nchw(att, L), _nchw(v)) + _nchw(x)
+            y.copy_(o.permute(0, 2, 3, 1).to(y.dtype))
+        elif kind == "cca_weight_bwd":
+            dy, v, att, de, part = i["dy"], i["v"], i["att"], i["de"], i["part"]
+            L = v.shape[1] + v.shape[2] - 1
+            D = R.ca_weight(_nchw(dy), _nchw(v))                    # D[p][z] = dy[p] . v[key(p,z)]
+            A = att_nchw(att, L)
+            ssum = (A * D).sum(1, keepdim=True)
+            de.zero_()
+            de[..., :L] = (i["gamma"].to(CD)[0] * A * (D - ssum)).permute(0, 2, 3, 1).to(de.dtype)
+            part.zero_()
+            part[0] = float(ssum.sum())
+        elif kind == "cca_gather":
+            a, src, out = i["a"], i["src"], i["out"]
+            L = src.shape[1] + src.shape[2] - 1
+            o = i["scale"] * R.ca_map(att_nchw(a, L), _nchw(src)).permute(0, 2, 3, 1)
+            out.copy_(((out.to(CD) if i["accumulate"] else 0) + o).to(out.dtype))
+        else:
+            a, src, out = i["a"], i["src"], i["out"]
+            L = src.shape[1] + src.shape[2] - 1
+            g0 = torch.zeros_like(_nchw(src), requires_grad=True)
+            (R.ca_map(att_nchw(a, L), g0) * _nchw(src)).sum().backward()
+            sc = i["scale"] * (float(i["scale_dev"][0]) if i["scale_dev"] is not None else 1.0)
+            out.copy_(((out.to(CD) if i["accumulate"] else 0) + sc * g0.grad.permute(0, 2, 3, 1)).to(out.dtype))
     elif kind == "scatter_add":
         src, idx, dst = i["src"], i["index"].long(), i["dst"]
         m = idx >= 0

@@ -91,6 +91,7 @@ TRAIN_CASES = {
     "train_dlv3p_resnet101_65x97_b4": ("deeplabv3plus_resnet101", "cityscapes_deeplabv3_plus_resnet.yaml", (4, 3, 65, 97), 21),
     "train_dlv3p_xception65_65x97_b4": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (4, 3, 65, 97), 22),
     "train_dlv3p_mobilenetv2_64x96_b4": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (4, 3, 64, 96), 23),
+    "train_ccnet_resnet101_65x97_b2": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (2, 3, 65, 97), 24),
 }
 
 
@@ -117,6 +118,27 @@ def run_train_case(case):
     sys.path.insert(0, REF)
     from oracle import segref as R
     name, yaml_file, shape, seed = TRAIN_CASES[case]
+    if name == "ccnet_resnet101":
+        # `segmentron._C` cannot be built (App. B5): stand-in whose four functions are the oracle's ca_weight / ca_map and their
+        # torch-autograd gradients (ca_weight / ca_map are pinned to a scalar transcription of ca_cuda.cu in run_module_cases),
+        # so this fixture pins the reference's MODEL graph, its custom autograd Functions (cc_attention.py:11-45) and its
+        # training recipe around them.
+        import types
+        import segmentron
+
+        def _vjp(fn, args, gout):
+            with torch.enable_grad():
+                leaves = [a.detach().requires_grad_(True) for a in args]
+                out = fn(*leaves)
+                return torch.autograd.grad(out, leaves, gout)
+        fake = types.ModuleType("segmentron._C")
+        fake.ca_forward = lambda t, f: R.ca_weight(t, f)
+        fake.ca_map_forward = lambda w, g: R.ca_map(w, g)
+        fake.ca_backward = lambda dw, t, f: _vjp(R.ca_weight, (t, f), dw)
+        fake.ca_map_backward = lambda dout, w, g: _vjp(R.ca_map, (w, g), dout)
+        sys.modules["segmentron._C"] = fake
+        segmentron._C = fake
+        import segmentron.models.ccnet  # noqa: F401  (registers "CCNet")
     from segmentron.config import cfg
     from segmentron.models.model_zoo import get_segmentation_model
     cfg.update_from_file(os.path.join(REF, "configs", yaml_file))
@@ -136,15 +158,16 @@ def run_train_case(case):
                                       aux_weight=cfg.SOLVER.AUX_WEIGHT, ignore_index=-1)
     optimizer = get_optimizer(model)
     # Dropout2d mask: torch draws a [N,C,1,1] Bernoulli(0.9) tensor; re-create it from the same RNG state for the oracle
+    mask_c, mask_key = (512, "head.rcca.bottleneck.dropout") if name == "ccnet_resnet101" else (256, "head.aspp.dropout")
     torch.manual_seed(777)
-    mask = torch.empty(n, 256, 1, 1).bernoulli_(0.9) / 0.9            # (unused by the ASPP-less MobileNetV2 head)
+    mask = torch.empty(n, mask_c, 1, 1).bernoulli_(0.9) / 0.9         # (unused by the ASPP-less MobileNetV2 head)
     torch.manual_seed(777)
     outputs = model(x)
     loss = sum(criterion(outputs, target).values())
     optimizer.zero_grad()
     loss.backward()
     ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
-    P.dropout_masks["head.aspp.dropout"] = mask
+    P.dropout_masks[mask_key] = mask
     o_loss, o_grads, o_out, o_low = R.loss_and_grads(name, P, x, target)
     assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(loss)), (float(loss), float(o_loss))
     worst = 0.0
@@ -169,10 +192,13 @@ def run_train_case(case):
     small = ["encoder.conv1.weight", "encoder.bn1.weight", "encoder.bn1.bias",
              "encoder.layer4.2.bn3.weight" if "resnet" in name else "encoder.block21.sep_conv3.block.bn_point.weight",
              "head.block.2.weight", "head.block.2.bias", "head.aspp.image_pooling.bn.weight", "head.c1_block.bn.bias"]
+    if name == "ccnet_resnet101":
+        small = ["encoder.conv1.weight", "head.rcca.cca.gamma", "head.rcca.cca.query_conv.weight", "head.rcca.cca.key_conv.bias",
+                 "head.out.weight", "head.out.bias", "head.rcca.bottleneck.1.weight"]
     if "mobilenet" in name:
         small = ["encoder.conv1.conv.weight", "encoder.conv1.bn.weight", "encoder.block5.3.conv.3.bias", "head.block.2.weight",
                  "head.block.2.bias", "head.block.0.block.depthwise.weight"]
-    out = dict(case=case, model=name, seed=seed, input_seed=2000 + seed, shape=shape, loss=float(loss), mask=mask,
+    out = dict(case=case, model=name, seed=seed, input_seed=2000 + seed, shape=shape, loss=float(loss), mask=mask, mask_key=mask_key,
                low=outputs[0].detach()[:, :, ::8, ::8].contiguous(), digest=grad_digest(ref_grads),
                grads_small={k: ref_grads[k] for k in small}, hyper=hyper, stepped_digest=grad_digest(stepped, 999),
                running={k: sd[k].clone() for k in sd if k.endswith(("running_mean", "running_var")) and

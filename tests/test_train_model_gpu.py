@@ -53,6 +53,14 @@ def _outputs(st):
         return [i["dfull"], i["out3"]]
     if k == "scatter_add":
         return [i["dst"]]
+    if k == "cca_weight_softmax":
+        return [i["att"]]
+    if k == "cca_map":
+        return [i["y"]]
+    if k == "cca_weight_bwd":
+        return [i["de"], i["part"]]
+    if k in ("cca_gather", "cca_scatter"):
+        return [i["out"]]
     raise NotImplementedError(k)
 
 
@@ -65,6 +73,8 @@ def _reduced(st, t):
         return t.view(-1, 2, i["c"]).double().sum(0)
     if k == "dw_wgrad":
         return t.view(-1, 9, i["c"]).double().sum(0)
+    if k == "cca_weight_bwd" and t.dim() == 1:
+        return t.double().sum().reshape(1)                 # per-block gamma-gradient partials: compared after the sum
     return t.double()
 
 
@@ -132,6 +142,20 @@ def test_every_launch_of_a_training_step(model, backbone):
     print(f"[{dtype}] {len(pl.fwd) + len(pl.bwd)} launches checked; worst max-err/rms per kernel:",
           {k: f"{v:.2e}" for k, v in sorted(worst.items())})
     assert torch.isfinite(tr.store.grad).all()
+
+
+@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="CCNet model-level replay: written after the round's GPU budget was "
+                    "spent (plan verified in fp64 on the CPU, every kernel verified on the GPU on its own)")
+def test_every_launch_of_a_ccnet_training_step():
+    from segmentron_b200.train import CCNetTrainerB200
+    P = R.build_params("ccnet_resnet101", 31)
+    g = torch.Generator().manual_seed(3031)
+    x = torch.randn(2, 3, 65, 97, generator=g)
+    target = torch.randint(-1, 19, (2, 65, 97), generator=g)
+    mask = (torch.rand(2, 512, 1, 1, generator=g) > 0.1).float() / 0.9
+    tr = CCNetTrainerB200(P.state_dict(), dtype=torch.bfloat16)
+    pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {"head.rcca.bottleneck.dropout": mask.cuda()})
+    print(f"[ccnet] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
 
 
 def test_training_step_end_to_end_vs_oracle():

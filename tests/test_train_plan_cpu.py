@@ -85,6 +85,32 @@ def test_train_plan_matches_oracle_on_cpu(dry_run, model, backbone):
                 assert not (lo <= tr.store.meta[tr.store.stem]["off"] < hi), "stem gradient written after its bucket"
 
 
+def test_ccnet_train_plan_matches_oracle_on_cpu(dry_run):
+    """CCNet / ResNet101 (models/ccnet.py): criss-cross attention forward + backward steps in the launch list, recurrence 2 with
+    SHARED weights (gradients of both applications meet in the same slots), c4 produced into -- and its gradient accumulated
+    from -- a channel slice of the concat buffer, Dropout2d after a ReLU-less BatchNorm."""
+    from segmentron_b200.train import CCNetTrainerB200
+    seed, shape = 31, (2, 3, 65, 97)
+    P = R.build_params("ccnet_resnet101", seed)
+    g = torch.Generator().manual_seed(3000 + seed)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
+    mask = (torch.rand(shape[0], 512, 1, 1, generator=g) > 0.1).double() / 0.9
+    tr = CCNetTrainerB200(P.state_dict(), dtype=torch.float64, device="cpu", lr=0.02)
+    loss = E.forward_backward(tr, x, target, {"head.rcca.bottleneck.dropout": mask})
+    grads = tr.store.grads()
+    P64 = P.to(dtype=torch.float64)
+    P64.frozen, P64.dropout_masks = True, {"head.rcca.bottleneck.dropout": mask}
+    o_loss, o_grads, _, _ = R.loss_and_grads("ccnet_resnet101", P64, x.double(), target)
+    assert abs(float(loss) - float(o_loss)) < 1e-6 * abs(float(o_loss))
+    assert float(o_grads["head.rcca.cca.gamma"].abs()) > 1e-3 and float(P.t["head.rcca.cca.gamma"]) != 0.0      # non-vacuous
+    floor = 1e-6 * max(float(v.norm()) for v in o_grads.values())
+    worst = max(((float((grads[k] - gr).norm() / (gr.norm() + floor)), k) for k, gr in o_grads.items()))
+    assert worst[0] < 1e-6, worst
+    kinds = {s.kind for s in tr.plan_for(shape)["plan"].bwd}
+    assert {"cca_weight_bwd", "cca_gather", "cca_scatter"} <= kinds
+
+
 def test_state_dict_roundtrip(dry_run):
     from segmentron_b200.train import DeepLabV3PlusTrainerB200
     P = R.build_params("deeplabv3plus_resnet101", 3)
