@@ -98,3 +98,37 @@ def test_stem_space_to_depth_is_exact(k, pad):
     ho, wo = ref.shape[2:]
     full = F.conv2d(F.pad(s2d, (pad2, T, pad2, T)), w2)
     assert torch.allclose(full[:, :, :ho, :wo], ref, atol=1e-5)   # packing goes through fp32
+
+
+def test_param_store_index_tables_match_the_standalone_packers():
+    """ParamStore regenerates every 16-bit GEMM operand from the fp32 masters with ONE index-table gather per step; the tables
+    must reproduce fold.pack_conv_weight (forward), train_ops.pack_dgrad_weight (data gradient: transposed, taps reversed),
+    fold.pack_stem_s2d (space-to-depth stem) and the depthwise [9][C] / flipped layouts that the per-kernel GPU tests use."""
+    import torch
+    from segmentron_b200 import fold, ops, train_ops as T
+    from segmentron_b200.train import ParamStore
+    ops._PLAN_DRY_RUN = True
+    try:
+        g = torch.Generator().manual_seed(0)
+        sd = {"encoder.conv1.weight": torch.randn(64, 3, 7, 7, generator=g),
+              "encoder.a.weight": torch.randn(48, 304, 1, 1, generator=g),
+              "encoder.b.weight": torch.randn(128, 64, 3, 3, generator=g),
+              "head.c.depthwise.weight": torch.randn(72, 1, 3, 3, generator=g),
+              "head.d.weight": torch.randn(19, 256, 1, 1, generator=g), "head.d.bias": torch.randn(19, generator=g)}
+        S = ParamStore(sd, "cpu", torch.float32, stem="encoder.conv1.weight")
+        idx16, idx32 = S.idx16.long(), S.idx32.long()
+        S.w16.copy_(torch.where(idx16 >= 0, S.master[idx16.clamp(min=0)], torch.zeros(())))
+        S.w32.copy_(torch.where(idx32 >= 0, S.master[idx32.clamp(min=0)], torch.zeros(())))
+        for k in ("encoder.a.weight", "encoder.b.weight", "head.d.weight"):
+            assert torch.equal(S.packed(k, "fwd"), fold.pack_conv_weight(sd[k], torch.float32)), k
+            assert torch.equal(S.packed(k, "dgrad"), T.pack_dgrad_weight(sd[k], torch.float32)), k
+        stem, t, pad2, ld = fold.pack_stem_s2d(sd["encoder.conv1.weight"], 3, torch.float32)
+        assert (S.pk["encoder.conv1.weight"]["T"], S.pk["encoder.conv1.weight"]["pad"], ld) == (t, pad2, 16)
+        assert torch.equal(S.packed("encoder.conv1.weight", "fwd"), stem)
+        dw = sd["head.c.depthwise.weight"].reshape(72, 9)
+        assert torch.equal(S.packed("head.c.depthwise.weight", "fwd"), dw.t())
+        assert torch.equal(S.packed("head.c.depthwise.weight", "flip"), dw.flip(1).t())
+        out = S.state_dict()
+        assert all(torch.equal(out[k], sd[k]) for k in sd)
+    finally:
+        ops._PLAN_DRY_RUN = False
