@@ -12,9 +12,9 @@ lazily at the next forward after any change.
 
 No CPU implementation and no PyTorch fallback: a non-CUDA input raises RuntimeError, like the reference's
 native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training mode: ``SeparableConv2d``,
-``_ConvBNReLU``, ``_ConvBN`` and ``CrissCrossAttention`` are differentiable (train_modules.py / attention.py: train-mode
-BatchNorm + the backward kernels); the composite classes (InvertedResidual, _ASPP, PyramidPooling, PAM / CAM) raise in
-training mode -- train whole models through ``train.DeepLabV3PlusTrainerB200``.
+``_ConvBNReLU``, ``_ConvBN``, ``InvertedResidual``, ``_ASPP`` and ``CrissCrossAttention`` are differentiable
+(train_modules.py / attention.py: train-mode BatchNorm + the backward kernels, composed unit by unit); PyramidPooling and
+PAM / CAM raise in training mode -- whole models train fastest through ``train.DeepLabV3PlusTrainerB200``.
 """
 from collections import OrderedDict
 
@@ -73,6 +73,9 @@ def _train_conv_bn_act(xh, conv, bn, act, pre_relu=False):
         raise RuntimeError("segb200: training mode expects fp32 parameters / BatchNorm buffers (compute is 16-bit)")
     g, b, rm, rv, mom, eps = TM._bn_args(bn)
     k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+    ho, wo = _out_hw(xh.shape[1], xh.shape[2], k, s, p, d)
+    if xh.shape[0] * ho * wo < 2:                # torch.nn.functional.batch_norm raises the same way
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {[xh.shape[0], conv.out_channels, ho, wo]}")
     if conv.groups == 1:
         if pre_relu:
             raise RuntimeError("segb200: leading ReLU is only fused into the depthwise unit")
@@ -291,6 +294,16 @@ class InvertedResidual(nn.Module):
                                 residual=x if self.use_res_connect else None)
 
     def forward(self, x):
+        if self.training:                          # unit by unit through the training kernels; the skip is a torch add
+            xh = _train_enter(x, self)
+            mods = list(self.conv)
+            y = xh
+            for m in mods[:-2]:
+                y = _train_conv_bn_act(y, m.conv, m.bn, m._act)
+            y = _train_conv_bn_act(y, mods[-2], mods[-1], None)
+            if self.use_res_connect:
+                y = y + xh
+            return y.permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 
@@ -343,7 +356,27 @@ class _ASPP(nn.Module):
             m.forward_nhwc(x, out=cat[..., (2 + i) * oc:(3 + i) * oc])
         return _run_conv_bn_act(cat, self.conv, self.bn, "relu", self._cproj, dt)     # Dropout2d: identity in eval
 
+    def forward_train(self, x):
+        """training mode (module.py:62-77 with batch statistics): every conv+BN(+ReLU) is one differentiable unit of the training
+        kernels; GAP / broadcast are their own Functions; the concat is a torch.cat of NHWC tensors (boundary plumbing) and
+        Dropout2d is torch's own on the logical-NCHW result, so it draws the same random planes as the reference would."""
+        from . import train_modules as TM
+        xh = _train_enter(x, self)
+        _, h, w, _ = xh.shape
+        ip = self.image_pooling
+        pool = TM.BroadcastFunction.apply(_train_conv_bn_act(TM.GlobalAvgPoolFunction.apply(xh), ip.conv, ip.bn, "relu"), h, w)
+        branches = [pool, _train_conv_bn_act(xh, self.aspp0.conv, self.aspp0.bn, "relu")]
+        for m in (self.aspp1, self.aspp2, self.aspp3):
+            b = m.block
+            act = None if m.relu_first else "relu"
+            y = _train_conv_bn_act(xh, b.depthwise, b.bn_depth, act, pre_relu=m.relu_first)
+            branches.append(_train_conv_bn_act(y, b.pointwise, b.bn_point, act))
+        y = _train_conv_bn_act(torch.cat(branches, dim=3), self.conv, self.bn, "relu")
+        return self.dropout(y.permute(0, 3, 1, 2).to(x.dtype))
+
     def forward(self, x):
+        if self.training:
+            return self.forward_train(x)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 

@@ -7,6 +7,8 @@ One Function = one fused unit of the training plan (``train.py``), in eager form
   backward: BN/activation backward (mask recomputed from y) -> tcgen05 weight gradient -> data gradient on the forward GEMM
   kernel with transposed, tap-reversed weights (zero insertion / strided placement for stride 2).
 The depthwise unit is the first half of SeparableConv2d (optional leading ReLU, modules/basic.py:45-46).
+``GlobalAvgPoolFunction`` / ``BroadcastFunction`` are the two ends of _ASPP's image-pooling branch (module.py:52,64: a
+bilinear up-sampling from 1x1 is a broadcast); each one's backward is the other's forward kernel with a scale.
 
 BatchNorm semantics are torch's (batch statistics, running-stat update with ``momentum``, ``num_batches_tracked``); statistics
 are per process -- for SyncBatchNorm across ranks use the whole-model engine (``train.DeepLabV3PlusTrainerB200``).
@@ -143,3 +145,43 @@ class DwBNActFunction(torch.autograd.Function):
             else:
                 ops.dwconv3x3(g_full, wflip, dx, stride=1, dilation=dilation)
         return dx, dwk.view(c, 1, 3, 3), dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+class GlobalAvgPoolFunction(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(1) on NHWC: [n,h,w,c] -> [n,1,1,c];  backward: dx = dy / (h w) at every pixel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, h, w, c, _ = ops._nhwc(x, "x")
+        y = torch.empty(n, 1, 1, c, dtype=x.dtype, device=x.device)
+        ops.global_avgpool(x, y)
+        ctx.geo = (n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, h, w, c = ctx.geo
+        dx = torch.empty(n, h, w, c, dtype=dy.dtype, device=dy.device)
+        T.nc_broadcast(dy.contiguous(), dx, scale=1.0 / (h * w))
+        return dx
+
+
+class BroadcastFunction(torch.autograd.Function):
+    """F.interpolate(v[n,c,1,1], (h, w), 'bilinear', align_corners=True) == broadcast;  backward: dv = sum over pixels."""
+
+    @staticmethod
+    def forward(ctx, v, h, w):
+        n, _, _, c, _ = ops._nhwc(v, "v")
+        y = torch.empty(n, h, w, c, dtype=v.dtype, device=v.device)
+        T.nc_broadcast(v, y)
+        ctx.geo = (n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, h, w, c = ctx.geo
+        mean = torch.empty(n, 1, 1, c, dtype=dy.dtype, device=dy.device)
+        ops.global_avgpool(dy.contiguous(), mean)
+        dv = torch.empty_like(mean)
+        T.nc_broadcast(mean, dv, scale=float(h * w))
+        return dv, None, None

@@ -132,3 +132,72 @@ def test_param_store_index_tables_match_the_standalone_packers():
         assert all(torch.equal(out[k], sd[k]) for k in sd)
     finally:
         ops._PLAN_DRY_RUN = False
+
+
+def test_composite_dropins_training_wiring(monkeypatch):
+    """InvertedResidual / _ASPP in training mode are compositions of the differentiable units (train_modules.py).  The units
+    themselves are GPU kernels (tested with -m gpu); here they are substituted by their torch definitions so that the WIRING --
+    unit order, activations, leading ReLU, skip, concat order, pooling branch, state_dict names -- is checked against the oracle
+    (basic.py:139-163, module.py:62-77) in fp32 on the CPU: output, input gradient and every parameter gradient."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import segref as R
+    from segmentron_b200 import modules as M, train_modules as TM
+
+    def unit(xh, conv, bn, act, pre_relu=False):
+        t = xh.permute(0, 3, 1, 2)
+        if pre_relu:
+            t = F.relu(t)
+        t = F.conv2d(t, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        t = F.batch_norm(t, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+        t = F.relu(t) if act == "relu" else F.relu6(t) if act == "relu6" else t
+        return t.permute(0, 2, 3, 1)
+
+    class Gap:
+        apply = staticmethod(lambda t: t.mean((1, 2), keepdim=True))
+
+    class Bcast:
+        apply = staticmethod(lambda v, h, w: v.expand(-1, h, w, -1))
+
+    monkeypatch.setattr(M, "_train_conv_bn_act", unit)
+    monkeypatch.setattr(M, "_train_enter", lambda x, m: x.permute(0, 2, 3, 1).contiguous())
+    monkeypatch.setattr(TM, "GlobalAvgPoolFunction", Gap)
+    monkeypatch.setattr(TM, "BroadcastFunction", Bcast)
+
+    def aspp(P, t):
+        P.dropout_masks["m.dropout"] = torch.ones(1)
+        return R.aspp(P, t, "m", 32, 16)
+
+    cases = {
+        "ir_skip": (lambda: M.InvertedResidual(16, 16, 1, 6), lambda P, t: R.inverted_residual(P, t, "m", 16, 1, 6)),
+        "ir_s2": (lambda: M.InvertedResidual(16, 24, 2, 6), lambda P, t: R.inverted_residual(P, t, "m", 24, 2, 6)),
+        "ir_t1_d2": (lambda: M.InvertedResidual(16, 8, 1, 1, dilation=2), lambda P, t: R.inverted_residual(P, t, "m", 8, 1, 1, 2)),
+        "aspp": (lambda: M._ASPP(16, 32, output_stride=16), aspp),
+    }
+    for name, (make, oracle_fn) in cases.items():
+        x = torch.randn(2, 16, 21, 19, generator=torch.Generator().manual_seed(5))
+        P = R.Params(7)
+        with torch.no_grad():
+            oracle_fn(P, x)
+        keys = [k for k in P.t if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+        for k in keys:
+            P.t[k] = P.t[k].detach().requires_grad_(True)
+        sd0 = {k[2:]: v.detach().clone() for k, v in P.state_dict().items()}
+        P.training = True
+        xr = x.clone().requires_grad_(True)
+        ref = oracle_fn(P, xr)
+        dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+        ref.backward(dy)
+        m = make()
+        m.load_state_dict(sd0, strict=True)
+        m.train()
+        if hasattr(m, "dropout"):
+            m.dropout.p = 0.0
+        xg = x.clone().requires_grad_(True)
+        y = m(xg)
+        y.backward(dy)
+        assert torch.allclose(y, ref, atol=1e-5, rtol=1e-5), name
+        assert torch.allclose(xg.grad, xr.grad, atol=1e-5, rtol=1e-4), name
+        for k in keys:
+            g = dict(m.named_parameters())[k[2:]].grad
+            assert g is not None and torch.allclose(g, P.t[k].grad, atol=1e-4, rtol=1e-4), (name, k)

@@ -168,7 +168,22 @@ TRAIN_DROPIN_CASES_MORE = {
     "cbr6_3x3_s2": (lambda M: M._ConvBNReLU(64, 64, 3, 2, 1, 1, relu6=True), lambda P, t: R.conv_bn_act(P, t, "m", 64, 3, 2, 1, 1, act="relu6")),
     "cb_1x1_s2": (lambda M: M._ConvBN(64, 256, 1, 2), lambda P, t: R.conv_bn_act(P, t, "m", 256, 1, 2, act=None)),
     "dw_cbr": (lambda M: M._ConvBNReLU(64, 64, 3, 1, 1, 1, groups=64), lambda P, t: R.conv_bn_act(P, t, "m", 64, 3, 1, 1, 1, groups=64)),
+    # composite classes, unit by unit through the same Functions (wiring checked on the CPU: test_host_cpu.py)
+    "inverted_residual_skip": (lambda M: M.InvertedResidual(64, 64, 1, 6), lambda P, t: R.inverted_residual(P, t, "m", 64, 1, 6)),
+    "inverted_residual_s2": (lambda M: M.InvertedResidual(64, 96, 2, 6), lambda P, t: R.inverted_residual(P, t, "m", 96, 2, 6)),
+    "inverted_residual_t1_d2": (lambda M: M.InvertedResidual(64, 32, 1, 1, dilation=2), lambda P, t: R.inverted_residual(P, t, "m", 32, 1, 1, 2)),
+    "aspp": (lambda M: _no_dropout(M._ASPP(64, 64, output_stride=16)), lambda P, t: _aspp_no_dropout(P, t)),
 }
+
+
+def _no_dropout(m):
+    m.dropout.p = 0.0
+    return m
+
+
+def _aspp_no_dropout(P, t):
+    P.dropout_masks["m.dropout"] = torch.ones(1)
+    return R.aspp(P, t, "m", 64, 16)
 _ALL_TRAIN_CASES = dict(TRAIN_DROPIN_CASES, **(TRAIN_DROPIN_CASES_MORE if os.environ.get("SEGB200_TEST_ALL") else {}))
 
 
@@ -224,6 +239,9 @@ def test_dropin_errors_and_cache_invalidation():
         assert not torch.equal(y1, y2)
     with pytest.raises(RuntimeError):
         m(x.cpu())
-    a = M._ASPP(64, 64, output_stride=16).cuda().train()          # composite classes have no training-mode kernels: loud error
+    a = M.PyramidPooling(64).cuda().train()                       # no training-mode kernels for this class: loud error
     with pytest.raises(RuntimeError):
         a(x)
+    b = M._ASPP(64, 64, output_stride=16).cuda().train()          # batch statistics over ONE value (1x1 image pooling, batch 1):
+    with pytest.raises(ValueError):                                # the same error torch's batch_norm raises
+        b(x)
