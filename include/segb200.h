@@ -304,6 +304,28 @@ int segb200_cca_gather(const float* a, const void* src, void* out, int n, int h,
 int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
                         float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * EVALUATION METRIC -- replaces segmentron/utils/score.py:83-113 (batch_pix_accuracy,
+ * batch_intersection_union: two argmax passes, three host transfers and three torch.histc calls behind a device synchronise,
+ * score.py:49,108-110) and the accumulation of SegmentationMetric.update (score.py:50-55).
+ *   counts: unsigned 64-bit [2 + 3*nclass], ACCUMULATED by seg_metric / seg_metric_lowres:
+ *     [0] correct (label >= 0 and argmax of the logits TRUNCATED to integers == label, score.py:86-90), [1] labeled (label >= 0),
+ *     [2+c] inter[c], [2+nclass+c] pred[c] (argmax of the float logits over labeled pixels), [2+2*nclass+c] lab[c] (label == c);
+ *     argmax ties go to the lowest class (torch.argmax).  target: int64 [n][h][w], negative = ignored.
+ *   seg_metric        : logits = full-resolution NCHW [n][nclass][h][w], dtype SEGB200_BF16 / F16 / F32.
+ *   seg_metric_lowres : logits = the classifier's NHWC 16-bit output [n][hi][wi][x_ld]; the final bilinear up-sampling to (ho, wo)
+ *                       (deeplabv3_plus.py:39) is fused with the arithmetic and out_dtype rounding of segb200_bilinear_nchw_out.
+ *   seg_metric_accumulate : total_pixels[0..1] (int64) += correct, labeled; total_inter[c] (f32) += inter; total_union[c] (f32) +=
+ *                       pred + lab - inter (score.py:112, float32 like the reference's totals); then counts := 0.  No host sync.
+ * 1 <= nclass <= 64. */
+int segb200_seg_metric(const void* logits, int dtype, const long long* target, int n, int nclass, int h, int w,
+                       unsigned long long* counts, void* stream);
+int segb200_seg_metric_lowres(const void* logits_nhwc, int dtype, int x_ld, int hi, int wi, int align_corners, int out_dtype,
+                              const long long* target, int n, int nclass, int ho, int wo, unsigned long long* counts,
+                              void* stream);
+int segb200_seg_metric_accumulate(unsigned long long* counts, int nclass, long long* total_pixels, float* total_inter,
+                                  float* total_union, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

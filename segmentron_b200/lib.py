@@ -95,6 +95,10 @@ SYMBOLS = {
     "segb200_cca_gather": (ci, [vp, vp, vp] + [ci] * 7 + [cf, ci, ci, vp]),
     "segb200_cca_scatter": (ci, [vp, vp, vp] + [ci] * 7 + [cf, vp, ci, ci, vp]),
     "segb200_sgd_step": (ci, [vp, vp, vp, ll, cf, cf, cf, cf, vp]),
+    # ---- evaluation metric ----
+    "segb200_seg_metric": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp]),
+    "segb200_seg_metric_lowres": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp]),
+    "segb200_seg_metric_accumulate": (ci, [vp, ci, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -45,6 +45,24 @@ def install(verbose=False):
     return count
 
 
+def install_metric(verbose=False):
+    """Opt-in: rebind ``SegmentationMetric`` (segmentron/utils/score.py:11) to the device-resident drop-in
+    (``segmentron_b200.metric.SegmentationMetric``: one kernel per update, no host synchronisation before ``get()``) in every
+    loaded ``segmentron.*`` namespace.  Call before ``tools/eval.py`` / ``tools/train.py`` import the name."""
+    from .metric import SegmentationMetric
+    if "segmentron.utils.score" not in sys.modules:
+        import segmentron.utils.score  # noqa: F401
+    orig = sys.modules["segmentron.utils.score"].SegmentationMetric
+    count = 0
+    for modname, mod in list(sys.modules.items()):
+        if mod is not None and modname.startswith("segmentron") and getattr(mod, "SegmentationMetric", None) is orig:
+            mod.SegmentationMetric = SegmentationMetric
+            count += 1
+            if verbose:
+                print(f"[segb200] {modname}.SegmentationMetric -> segmentron_b200.metric.SegmentationMetric")
+    return count
+
+
 def _adopt(cls, ref):
     """Build a drop-in instance that shares ``ref``'s sub-modules, parameters and buffers."""
     new = cls.__new__(cls)

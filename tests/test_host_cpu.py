@@ -201,3 +201,31 @@ def test_composite_dropins_training_wiring(monkeypatch):
         for k in keys:
             g = dict(m.named_parameters())[k[2:]].grad
             assert g is not None and torch.allclose(g, P.t[k].grad, atol=1e-4, rtol=1e-4), (name, k)
+
+
+def test_metric_dropin_api_without_gpu(built):
+    """segmentron_b200.metric.SegmentationMetric mirrors score.py:11-81 (constructor, update / get / reset, attribute names); with
+    no update it returns the reference's (0.0, 0.0); CPU tensors raise (no host implementation in the product); the C entry
+    points reject null pointers and class counts beyond 64 without touching a GPU."""
+    import ctypes as C
+    import torch
+    from segmentron_b200 import lib as L
+    from segmentron_b200.metric import SegmentationMetric
+    m = SegmentationMetric(19, False)
+    assert m.get() == (0.0, 0.0) and (m.total_correct, m.total_label) == (0, 0)
+    assert tuple(m.total_inter.shape) == tuple(m.total_union.shape) == (19,)
+    pix, miou, iou = m.get(return_category_iou=True)
+    assert iou.shape == (19,)
+    with pytest.raises(RuntimeError, match="not implemented on the CPU"):
+        m.update(torch.zeros(1, 19, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        SegmentationMetric(65, False)
+    m.reset()
+    lib = L.load()
+    buf = (C.c_ulonglong * 64)()
+    assert lib.segb200_seg_metric(None, L.F32, None, 1, 19, 4, 4, None, None) < 0
+    assert lib.segb200_seg_metric(buf, L.F32, buf, 1, 65, 4, 4, buf, None) < 0
+    assert b"nclass" in lib.segb200_last_error()
+    assert lib.segb200_seg_metric_lowres(buf, L.F32, 24, 4, 4, 1, L.F32, buf, 1, 19, 8, 8, buf, None) < 0     # 16-bit logits only
+    assert lib.segb200_seg_metric_lowres(buf, L.BF16, 16, 4, 4, 1, L.F32, buf, 1, 19, 8, 8, buf, None) < 0    # x_ld < round_up(19, 8)
+    assert lib.segb200_seg_metric_accumulate(None, 19, None, None, None, None) < 0

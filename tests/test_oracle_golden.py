@@ -100,3 +100,35 @@ def test_training_step_matches_reference_fixture(case):
     enc0 = "encoder.conv1.weight" if "encoder.conv1.weight" in fx["hyper"] else "encoder.conv1.conv.weight"
     head0 = "head.block.2.weight" if "head.block.2.weight" in fx["hyper"] else "head.out.weight"
     assert fx["hyper"][head0][0] == pytest.approx(10 * fx["hyper"][enc0][0])
+
+
+def test_score_oracle_matches_reference_fixture():
+    """oracle/scoreref.py (integer bincount restatement) against the outputs of the reference's own segmentron/utils/score.py
+    (batch_pix_accuracy, batch_intersection_union, SegmentationMetric accumulated over six updates), recorded by
+    tests/golden/make_score_golden.py: every count and the float32 totals are EXACT; pixAcc / mIoU bit-identical."""
+    import importlib.util
+    import numpy as np
+    from oracle import scoreref as S
+    spec = importlib.util.spec_from_file_location("make_score_golden", os.path.join(G, "make_score_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fx = torch.load(os.path.join(G, "score_cases.pt"))
+    assert len(fx["cases"]) == len(gen.CASES)
+    m = S.SegmentationMetric(19)
+    for i, (case, args) in enumerate(zip(fx["cases"], gen.CASES)):
+        assert tuple(case["args"]) == tuple(args)
+        x, t = gen.make_inputs(*args)
+        c = args[2]
+        cnt = S.counts(x.numpy(), t.numpy(), c)
+        assert (int(cnt[0]), int(cnt[1])) == (case["correct"], case["labeled"]), args
+        inter = cnt[2:2 + c].astype(np.float32)
+        union = cnt[2 + c:2 + 2 * c].astype(np.float32) + cnt[2 + 2 * c:].astype(np.float32) - inter
+        assert np.array_equal(inter, case["inter"].numpy()) and np.array_equal(union, case["union"].numpy()), args
+        if i < 6:
+            m.update_counts(cnt)
+    acc = fx["accumulated"]
+    assert (m.total_correct, m.total_label) == (acc["total_correct"], acc["total_label"])
+    assert np.array_equal(m.total_inter, acc["total_inter"].numpy()) and np.array_equal(m.total_union, acc["total_union"].numpy())
+    pix_acc, miou, iou = m.get()
+    assert pix_acc == acc["pixAcc"] and np.array_equal(iou, acc["IoU"].numpy())
+    assert abs(miou - acc["mIoU"]) <= 1e-7
