@@ -326,6 +326,20 @@ int segb200_seg_metric_lowres(const void* logits_nhwc, int dtype, int x_ld, int 
 int segb200_seg_metric_accumulate(unsigned long long* counts, int nclass, long long* total_pixels, float* total_inter,
                                   float* total_union, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * MULTI-SCALE + FLIP EVALUATION -- the data movement of SegBaseModel.evaluate (segmentron/models/segbase.py:44-79).
+ *   eval_prepare    : image fp32 NCHW [b][c][h][w] -> out fp32 [(1+flip) b][c][hp][wp]: images 0..b-1 = F.interpolate(image,
+ *                     (height, width), bilinear, align_corners=True) (:63, _resize_image :82) zero padded at the bottom / right
+ *                     to (hp, wp) (_pad_image :86-107); images b..2b-1 (flip != 0) = the same, horizontally flipped AFTER the
+ *                     padding (_flip_image :114, applied to the padded image :71), so one model call serves both passes.
+ *   eval_accumulate : logits [(1+flip) b][k][hp][wp] (dtype) -> scores [b][k][h][w] (same dtype):
+ *                     outputs = logits[0:b][..., :height, :width] (+ flip(logits[b:2b])[..., :height, :width], rounded to dtype, :69-71);
+ *                     scores (accumulate ? += : =) F.interpolate(outputs, (h, w), bilinear, align_corners=True) (:73-78). */
+int segb200_eval_prepare(const float* image, float* out, int b, int c, int h, int w, int height, int width, int hp, int wp,
+                         int flip, void* stream);
+int segb200_eval_accumulate(const void* logits, void* scores, int dtype, int b, int k, int hp, int wp, int height, int width,
+                            int h, int w, int flip, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

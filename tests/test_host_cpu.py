@@ -229,3 +229,29 @@ def test_metric_dropin_api_without_gpu(built):
     assert lib.segb200_seg_metric_lowres(buf, L.F32, 24, 4, 4, 1, L.F32, buf, 1, 19, 8, 8, buf, None) < 0     # 16-bit logits only
     assert lib.segb200_seg_metric_lowres(buf, L.BF16, 16, 4, 4, 1, L.F32, buf, 1, 19, 8, 8, buf, None) < 0    # x_ld < round_up(19, 8)
     assert lib.segb200_seg_metric_accumulate(None, 19, None, None, None, None) < 0
+
+
+def test_evaluate_driver_size_rules_and_errors(built):
+    """segmentron_b200.evaluate: the host-side size rules equal the oracle's (which is pinned to SegBaseModel.evaluate,
+    segbase.py:53-68,93, by tests/golden/evaluate_cases.pt) over a sweep of shapes / scales / crops; CPU images raise; the C entry
+    points validate their arguments without a GPU."""
+    import ctypes as C
+    import itertools
+    import torch
+    from oracle import evalref as E
+    from segmentron_b200 import evaluate as V, lib as L
+    for (h, w), scale in itertools.product([(1024, 2048), (1025, 2049), (57, 31), (33, 65), (480, 480), (769, 769)],
+                                           [0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0]):
+        assert V.scaled_size(h, w, scale) == E.scaled_size(h, w, scale)
+        hh, ww = V.scaled_size(h, w, scale)
+        for crop in (None, (max(h, w), max(h, w)), (h, w), (h + 7, w + 64)):
+            assert V.padded_size(hh, ww, crop, scale) == E.padded_size(hh, ww, crop, scale)
+    assert V._to_tuple(769) == (769, 769) and V._to_tuple([512, 1024]) == (512, 1024)
+    with pytest.raises(RuntimeError, match="not implemented on the CPU"):
+        V.evaluate(lambda x: x, torch.zeros(1, 3, 8, 8))
+    lib = L.load()
+    buf = (C.c_float * 16)()
+    assert lib.segb200_eval_prepare(None, None, 1, 3, 8, 8, 8, 8, 8, 8, 0, None) < 0
+    assert lib.segb200_eval_prepare(buf, buf, 1, 3, 8, 8, 12, 12, 8, 8, 0, None) < 0          # padded size smaller than the resize
+    assert lib.segb200_eval_accumulate(buf, buf, 7, 1, 3, 8, 8, 8, 8, 8, 8, 0, 0, None) < 0   # bad dtype
+    assert lib.segb200_eval_accumulate(buf, buf, L.F32, 1, 3, 8, 8, 9, 8, 8, 8, 0, 0, None) < 0

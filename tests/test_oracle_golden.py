@@ -132,3 +132,26 @@ def test_score_oracle_matches_reference_fixture():
     pix_acc, miou, iou = m.get()
     assert pix_acc == acc["pixAcc"] and np.array_equal(iou, acc["IoU"].numpy())
     assert abs(miou - acc["mIoU"]) <= 1e-7
+
+
+def test_evaluate_oracle_matches_reference_fixture():
+    """oracle/evalref.py against the scores the reference's own SegBaseModel.evaluate (segbase.py:44-79) produced for six
+    (scales, flip, crop) configurations of a seeded stub model (tests/golden/make_eval_golden.py): same torch ops in the same
+    order, so bit-identical on the machine that wrote the fixture (1e-6 elsewhere: CPU conv kernels differ by ISA)."""
+    import importlib.util
+    from oracle import evalref as E
+    spec = importlib.util.spec_from_file_location("make_eval_golden", os.path.join(G, "make_eval_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fx = torch.load(os.path.join(G, "evaluate_cases.pt"))
+    assert len(fx) == len(gen.CASES)
+    for case, args in zip(fx, gen.CASES):
+        seed, b, h, w, scales, flip, crop = args
+        with torch.no_grad():
+            got = E.evaluate(gen.stub_forward(seed), gen.make_image(seed, b, h, w), scales, flip, crop)
+        ref = case["scores"]
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 1e-6 * float(ref.abs().max()), args
+    assert E.scaled_size(1024, 2048, 0.75) == (768, 1536) and E.scaled_size(57, 31, 1.5) == (86, 47)
+    assert E.padded_size(28, 40, (48, 64), 0.75) == (36, 48)
+    assert E.padded_size(29, 16, (64, 64), 0.5) == (45, 19)            # the reference's swapped F.pad amounts (segbase.py:93)
