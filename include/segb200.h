@@ -304,6 +304,13 @@ int segb200_cca_gather(const float* a, const void* src, void* out, int n, int h,
 int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
                         float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
 
+/* OPT-IN variant of segb200_dw_wgrad (same arguments, same partial[(slab*9 + tap)*c + ch] layout, slab count from
+ * segb200_dw_wgrad_v2_slabs): a thread owns four channels and walks contiguous pixels of an image row with the 3x3 window held in
+ * registers (3 new 8-byte loads per pixel instead of 9 16-byte ones) and packed fma.rn.f32x2.  Not the default until measured. */
+int segb200_dw_wgrad_v2_slabs(long long rows, int c, int max_slabs);
+int segb200_dw_wgrad_v2(const void* x, const void* dy, float* partial, int n, int h, int w, int c, int x_ld, int dy_ld,
+                        int dilation, int pre_relu, int dtype, int max_slabs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * EVALUATION METRIC -- replaces segmentron/utils/score.py:83-113 (batch_pix_accuracy,
  * batch_intersection_union: two argmax passes, three host transfers and three torch.histc calls behind a device synchronise,

@@ -155,15 +155,17 @@ def upsample_ce(logits, target, dfull, nclass, align_corners=True, ignore_index=
     return out3
 
 
-def dw_wgrad(x, dy, dw, dilation=1, pre_relu=False, accumulate=True):
-    """dw: fp32 [c][9] (torch depthwise weight [C,1,3,3] flattened), accumulated."""
+def dw_wgrad(x, dy, dw, dilation=1, pre_relu=False, accumulate=True, variant=1):
+    """dw: fp32 [c][9] (torch depthwise weight [C,1,3,3] flattened), accumulated.  variant=2: the opt-in sliding-window kernel
+    (csrc/dw_wgrad2.cu)."""
     n, h, w, c, x_ld = _nhwc(x, "x")
     lib = L.load()
-    slabs = reduce_slabs(n * h * w, c)
+    fn, slabs = (lib.segb200_dw_wgrad, reduce_slabs(n * h * w, c)) if variant == 1 else \
+        (lib.segb200_dw_wgrad_v2, lib.segb200_dw_wgrad_v2_slabs(n * h * w, c, 0))
     partial = torch.empty(slabs * 9 * c, dtype=torch.float32, device=x.device)
     s = _stream()
-    L.check(lib.segb200_dw_wgrad(_ptr(x), _ptr(dy), _ptr(partial), n, h, w, c, x_ld, _nhwc(dy, "dy")[4], dilation,
-                                 int(bool(pre_relu)), dt_code(x.dtype), 0, s), "dw_wgrad")
+    L.check(fn(_ptr(x), _ptr(dy), _ptr(partial), n, h, w, c, x_ld, _nhwc(dy, "dy")[4], dilation,
+               int(bool(pre_relu)), dt_code(x.dtype), 0, s), "dw_wgrad")
     L.check(lib.segb200_reduce_partials(_ptr(partial), slabs, 9, c, _ptr(dw), 1, 9, int(bool(accumulate)), 1.0, s),
             "reduce_partials")
     return dw

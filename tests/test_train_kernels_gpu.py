@@ -336,3 +336,27 @@ def test_sgd_matches_torch():
         T.sgd_step(mine, g, m, 0.02, 0.9, 1e-4)
     torch.cuda.synchronize()
     assert torch.allclose(mine, p.detach(), rtol=1e-5, atol=1e-6), float((mine - p.detach()).abs().max())
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SEGB200_TEST_ALL"), reason="opt-in kernel, not yet run on a B200; set SEGB200_TEST_ALL=1")
+@pytest.mark.parametrize("geo", [(2, 17, 33, 128, 1, False), (2, 17, 33, 128, 6, False), (1, 65, 129, 728, 1, True), (4, 33, 41, 24, 2, True),
+                                 (1, 5, 3, 8, 1, False)])
+def test_depthwise_wgrad_v2(geo):
+    """csrc/dw_wgrad2.cu (sliding window, four channels per thread, packed FMA) against autograd AND against the default kernel
+    (same inputs: the two differ only in summation order)."""
+    from segmentron_b200 import train_ops as T
+    n, h, w, c, dil, pre_relu = geo
+    dtype = torch.bfloat16
+    x = _rand(n, h, w, c, dtype=dtype, seed=31)
+    dy = _rand(n, h, w, c, dtype=dtype, seed=32)
+    xr = _nchw(x)
+    wr = torch.zeros(c, 1, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(F.relu(xr) if pre_relu else xr, wr, None, 1, dil, dil, groups=c).backward(_nchw(dy))
+    dw1 = torch.zeros(c, 9, device="cuda")
+    dw2 = torch.zeros(c, 9, device="cuda")
+    T.dw_wgrad(x, dy, dw1, dilation=dil, pre_relu=pre_relu)
+    T.dw_wgrad(x, dy, dw2, dilation=dil, pre_relu=pre_relu, variant=2)
+    T.dw_wgrad(x, dy, dw2, dilation=dil, pre_relu=pre_relu, variant=2)          # accumulates
+    torch.cuda.synchronize()
+    _close(dw2 * 0.5, wr.grad.reshape(c, 9), f"dw wgrad v2 {geo}", tol=2.0 ** -9)
+    _close(dw2 * 0.5, dw1, f"dw wgrad v2 vs v1 {geo}", tol=2.0 ** -12)

@@ -89,9 +89,10 @@ def _stepwise_check(tr, x, target, masks):
     w16 = S.w16.clone()
     E.gather_cast(S.master, S.idx16, S.w16)
     assert torch.equal(w16, S.w16), "gather_cast (16-bit operand packing) is not exact"
-    w32 = S.w32.clone()
-    E.gather_cast(S.master, S.idx32, S.w32)
-    assert torch.equal(w32, S.w32), "gather_cast (fp32 depthwise packing) is not exact"
+    if S.idx32 is not None:                                # models without depthwise weights (ResNet + RCCA) have no fp32 table
+        w32 = S.w32.clone()
+        E.gather_cast(S.master, S.idx32, S.w32)
+        assert torch.equal(w32, S.w32), "gather_cast (fp32 depthwise packing) is not exact"
     stream = __import__("ctypes").c_void_p(torch.cuda.current_stream().cuda_stream)
     worst = {}
     for n_, step in enumerate(pl.fwd + pl.bwd):
