@@ -7,7 +7,6 @@ reference's unbound ``SegBaseModel.evaluate`` on a stub object in the build cont
 """
 import math
 
-import torch
 import torch.nn.functional as F
 
 

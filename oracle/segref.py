@@ -23,7 +23,7 @@ Every function cites the reference file:line it follows (paths relative to /root
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F

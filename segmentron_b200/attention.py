@@ -5,8 +5,6 @@ CAM_Module (modules/module.py:142-162):  E = X^T X -> softmax(rowmax - E) -> gam
 CrissCrossAttention (modules/cc_attention.py:62-72): q/k/v 1x1 convs (GEMMs, bias as shift) ->
   cca_weight_softmax (ca_forward + softmax fused) -> cca_map (ca_map_forward + gamma*out + x fused).
 """
-import ctypes as C
-
 import torch
 
 from . import fold, lib as L, ops
