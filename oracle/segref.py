@@ -652,6 +652,8 @@ def loss_and_grads(model: str, P: Params, x, target, nclass: int = 19, ignore_in
     try:
         if model == "ccnet_resnet101":
             out, low = ccnet(P, x, nclass=nclass, **kw), None
+        elif model == "hrnet_w18_small_v1":
+            out, low = hrnet_seg(P, x, nclass=nclass, **kw), None
         else:
             out, low = deeplabv3plus(P, x, nclass=nclass, return_lowres=True, **MODELS[model], **kw)
         loss = F.cross_entropy(out.float(), target, ignore_index=ignore_index)

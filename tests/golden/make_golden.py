@@ -92,6 +92,7 @@ TRAIN_CASES = {
     "train_dlv3p_xception65_65x97_b4": ("deeplabv3plus_xception65", "cityscapes_deeplabv3_plus.yaml", (4, 3, 65, 97), 22),
     "train_dlv3p_mobilenetv2_64x96_b4": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (4, 3, 64, 96), 23),
     "train_ccnet_resnet101_65x97_b2": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (2, 3, 65, 97), 24),
+    "train_hrnet_w18s_64x96_b2": ("hrnet_w18_small_v1", "cityscapes_hrnet_w18_small_v1.yaml", (2, 3, 64, 96), 25),
 }
 
 
@@ -168,6 +169,10 @@ def run_train_case(case):
     loss.backward()
     ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
     P.dropout_masks[mask_key] = mask
+    # MODEL.BN_MOMENTUM (None -> torch's 0.1) is applied to every BatchNorm by get_optimizer (solver/optimizer.py:37-39); the
+    # HRNet YAML sets 0.01
+    bn_momentum = float(cfg.MODEL.BN_MOMENTUM) if cfg.MODEL.BN_MOMENTUM else 0.1
+    P.bn_momentum = bn_momentum
     o_loss, o_grads, o_out, o_low = R.loss_and_grads(name, P, x, target)
     assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(loss)), (float(loss), float(o_loss))
     worst = 0.0
@@ -195,6 +200,12 @@ def run_train_case(case):
     if name == "ccnet_resnet101":
         small = ["encoder.conv1.weight", "head.rcca.cca.gamma", "head.rcca.cca.query_conv.weight", "head.rcca.cca.key_conv.bias",
                  "head.out.weight", "head.out.bias", "head.rcca.bottleneck.1.weight"]
+    if "hrnet" in name:
+        small = ["encoder.conv1.weight", "encoder.bn2.bias", "encoder.layer1.0.conv3.weight", "encoder.transition1.1.0.0.weight",
+                 "encoder.stage2.0.fuse_layers.0.1.0.weight", "encoder.stage4.0.fuse_layers.3.0.1.0.weight",
+                 "encoder.stage4.0.fuse_layers.3.0.1.1.bias", "encoder.stage4.0.branches.3.1.conv2.weight",
+                 "hrnet_head.last_layer.0.weight", "hrnet_head.last_layer.0.bias", "hrnet_head.last_layer.1.weight",
+                 "hrnet_head.last_layer.3.weight", "hrnet_head.last_layer.3.bias"]
     if "mobilenet" in name:
         small = ["encoder.conv1.conv.weight", "encoder.conv1.bn.weight", "encoder.block5.3.conv.3.bias", "head.block.2.weight",
                  "head.block.2.bias", "head.block.0.block.depthwise.weight"]
@@ -203,8 +214,9 @@ def run_train_case(case):
                grads_small={k: ref_grads[k] for k in small}, hyper=hyper, stepped_digest=grad_digest(stepped, 999),
                running={k: sd[k].clone() for k in sd if k.endswith(("running_mean", "running_var")) and
                         (k.startswith("encoder.bn1") or "image_pooling" in k or "layer4.2.bn3" in k or "block21.sep_conv3.block.bn_point" in k
-                         or k.startswith("encoder.conv1.bn") or "block5.3.conv.3" in k)},
-               oracle_vs_ref_worst_grad_rel=worst)
+                         or k.startswith("encoder.conv1.bn") or "block5.3.conv.3" in k or "hrnet_head.last_layer.1" in k
+                         or "stage4.0.fuse_layers.3.0.1.1" in k)},
+               bn_momentum=bn_momentum, oracle_vs_ref_worst_grad_rel=worst)
     torch.save(out, os.path.join(HERE, case + ".pt"))
     print(f"{case}: loss {float(loss):.6f}; worst grad rel-L2 oracle vs reference {worst:.2e}; {len(ref_grads)} grads")
 
