@@ -304,6 +304,12 @@ int segb200_cca_gather(const float* a, const void* src, void* out, int n, int h,
 int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
                         float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
 
+/* Backward of segb200_upsample_add, y = act(a + nearest_up_{2^k}(z)) -- the HRNet fuse sum (backbones/hrnet.py:178-186,215-232):
+ * g = dy * [y > 0] (act = relu, mask from the stored output); da (+)= g; dz (+)= sum of g over each 2^k x 2^k block.  da or dz may
+ * be NULL. */
+int segb200_upsample_add_bwd(const void* dy, const void* y, void* da, void* dz, int n, int h, int w, int c, int dy_ld, int y_ld,
+                             int da_ld, int dz_ld, int k, int act, int accumulate_a, int accumulate_z, int dtype, void* stream);
+
 /* OPT-IN variant of segb200_dw_wgrad (same arguments, same partial[(slab*9 + tap)*c + ch] layout, slab count from
  * segb200_dw_wgrad_v2_slabs): a thread owns four channels and walks contiguous pixels of an image row with the 3x3 window held in
  * registers (3 new 8-byte loads per pixel instead of 9 16-byte ones) and packed fma.rn.f32x2.  Not the default until measured. */

@@ -404,7 +404,8 @@ class TrainPlan:
         if bn is not None:
             y = self.new(n, ho, wo, cop)
             z = out if out is not None else Act(self, self.new(n, ho, wo, cop))
-            self.conv(x.t, wf, y, cout=cop, **geo)
+            # a conv bias in front of BatchNorm (hrnet_seg.py:42-47) is the GEMM's shift; its gradient is the column sum of dy
+            self.conv(x.t, wf, y, cout=cop, shift=S.view(S.master, bias) if bias else None, **geo)
             st = self.bn_act_fwd(y, z.t, bn, act, eps, residual.t if residual is not None else None, nc_scale)
         else:
             assert act is None and residual is None and nc_scale is None
@@ -421,18 +422,18 @@ class TrainPlan:
                     self.pool_put(dz)
             else:
                 dy = dz
-                if bias:
-                    rows, hw, c, ld = self._rows(dz)
-                    slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
-                    partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
-                    self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
-                             (_ptr(dz), None, _ptr(dz), None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
-                             dz=dz, z=None, y=dz, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
-                    self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, None, None, _ptr(sums), None, None),
-                             st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)
-                    gb = S.view(S.grad, bias)
-                    self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(sums), 1, 1, co, _ptr(gb), 0, 1, 1, 1.0),
-                             partial=sums, slabs=1, K=1, c=co, out=gb, sk=0, sc=1, accumulate=1, scale=1.0)
+            if bias:
+                rows, hw, c, ld = self._rows(dy)
+                slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
+                partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
+                self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
+                         (_ptr(dy), None, _ptr(dy), None, None, None, _ptr(partial), rows, hw, c, ld, 0, ld, 0, self.dt, 0),
+                         dz=dy, z=None, y=dy, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
+                self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, None, None, _ptr(sums), None, None),
+                         st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)
+                gb = S.view(S.grad, bias)
+                self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(sums), 1, 1, co, _ptr(gb), 0, 1, 1, 1.0),
+                         partial=sums, slabs=1, K=1, c=co, out=gb, sk=0, sc=1, accumulate=1, scale=1.0)
             # weight gradient
             if stem:
                 dws = self.f32(co * geo["k"] ** 2 * 64)
@@ -615,20 +616,44 @@ class TrainPlan:
         self.tape.append(backward)
         return y
 
-    def bilinear(self, x, out):
-        """F.interpolate(x, out.shape, 'bilinear', align_corners=True) into the channel slice `out` (deeplabv3_plus.py:71)."""
+    def bilinear(self, x, out, align=True):
+        """F.interpolate(x, out.shape, 'bilinear', align_corners=align) into the channel slice `out` (deeplabv3_plus.py:71;
+        align_corners=False in _HRNetHead, hrnet_seg.py:57-59)."""
         n, hi, wi, c = x.t.shape
         _, ho, wo, _ = out.t.shape
         self.add("bilinear", self.lib.segb200_bilinear_nhwc,
-                 (_ptr(x.t), _ptr(out.t), n, hi, wi, c, x.t.stride(2), ho, wo, out.t.stride(2), 1, self.dt), x=x.t, y=out.t)
+                 (_ptr(x.t), _ptr(out.t), n, hi, wi, c, x.t.stride(2), ho, wo, out.t.stride(2), int(align), self.dt), x=x.t, y=out.t,
+                 align=align)
 
         def backward():
             dy = out.grad()
             gx, acc = x.take()
             self.add("bilinear_bwd", self.lib.segb200_bilinear_nhwc_bwd,
-                     (_ptr(dy), _ptr(gx), n, hi, wi, c, gx.stride(2), ho, wo, dy.stride(2), 1, int(acc), None, self.dt), dy=dy, dx=gx,
-                     accumulate=acc, gscale=None)
+                     (_ptr(dy), _ptr(gx), n, hi, wi, c, gx.stride(2), ho, wo, dy.stride(2), int(align), int(acc), None, self.dt), dy=dy,
+                     dx=gx, accumulate=acc, gscale=None, align=align)
         self.tape.append(backward)
+
+    def upsample_add(self, a, t, k, act=None):
+        """y = act(a + nearest_up_{2^k}(t)): one term of the HRNet fuse sum (backbones/hrnet.py:178-186,215-232)"""
+        n, h, w_, c = a.t.shape
+        assert tuple(t.t.shape) == (n, h >> k, w_ >> k, c) and h % (1 << k) == 0 and w_ % (1 << k) == 0, (a.t.shape, t.t.shape, k)
+        y = Act(self, self.new(n, h, w_, c))
+        self.add("upsample_add", self.lib.segb200_upsample_add,
+                 (_ptr(a.t), _ptr(t.t), _ptr(y.t), n, h, w_, c, a.t.stride(2), t.t.stride(2), y.t.stride(2), k, L.ACT[act], self.dt),
+                 a=a.t, z=t.t, y=y.t, k=k, act=act)
+
+        def backward():
+            dy = y.grad()
+            ga, acc_a = a.take()
+            gt, acc_t = t.take()
+            self.add("upsample_add_bwd", self.lib.segb200_upsample_add_bwd,
+                     (_ptr(dy), _ptr(y.t), _ptr(ga), _ptr(gt), n, h, w_, c, dy.stride(2), y.t.stride(2), ga.stride(2), gt.stride(2), k,
+                      L.ACT[act], int(acc_a), int(acc_t), self.dt),
+                     dy=dy, y=y.t, da=ga, dz=gt, k=k, act=act, acc_a=acc_a, acc_z=acc_t)
+            if y.parent is None:
+                self.pool_put(dy)
+        self.tape.append(backward)
+        return y
 
     def image_pool(self, x):
         """nn.AdaptiveAvgPool2d(1) (module.py:52) -> [n,1,1,c]"""
@@ -665,8 +690,8 @@ class TrainPlan:
             self.pool_put(mean)
         self.tape.append(backward)
 
-    def loss(self, logits):
-        """fused F.interpolate(logits, (H, W), align_corners=True) + CrossEntropyLoss(ignore_index) + its gradient"""
+    def loss(self, logits, align=True):
+        """fused F.interpolate(logits, (H, W), align_corners=align) + CrossEntropyLoss(ignore_index) + its gradient"""
         n, hi, wi, _ = logits.t.shape
         c8 = fold.round_up(self.nclass, 8)
         dfull = self.new(n, self.H, self.W, c8)
@@ -674,16 +699,17 @@ class TrainPlan:
         partial = self.f32(2 * nb)
         self.add("upsample_ce", self.lib.segb200_upsample_ce,
                  (_ptr(logits.t), _ptr(self.target), _ptr(dfull), _ptr(partial), _ptr(self.out3), n, hi, wi, self.nclass,
-                  logits.t.stride(2), self.H, self.W, dfull.stride(2), 1, self.ignore_index, self.dt),
-                 logits=logits.t, target=self.target, dfull=dfull, out3=self.out3, nclass=self.nclass, ignore_index=self.ignore_index)
+                  logits.t.stride(2), self.H, self.W, dfull.stride(2), int(align), self.ignore_index, self.dt),
+                 logits=logits.t, target=self.target, dfull=dfull, out3=self.out3, nclass=self.nclass, ignore_index=self.ignore_index,
+                 align=align)
 
         def backward():
             gl, acc = logits.take()
             assert not acc
             inv = self.out3[1:2]
             self.add("bilinear_bwd", self.lib.segb200_bilinear_nhwc_bwd,
-                     (_ptr(dfull), _ptr(gl), n, hi, wi, c8, gl.stride(2), self.H, self.W, dfull.stride(2), 1, 0, _ptr(inv), self.dt),
-                     dy=dfull, dx=gl, accumulate=False, gscale=inv)
+                     (_ptr(dfull), _ptr(gl), n, hi, wi, c8, gl.stride(2), self.H, self.W, dfull.stride(2), int(align), 0, _ptr(inv),
+                      self.dt), dy=dfull, dx=gl, accumulate=False, gscale=inv, align=align)
         self.tape.append(backward)
 
     def build_backward(self):
@@ -910,6 +936,98 @@ def build_ccnet_train(pl, output_stride=16, recurrence=2):
     return pl
 
 
+def _hr_basic_block(pl, x, prefix):
+    """BasicBlock (backbones/hrnet.py:25-55): conv3x3-BN-ReLU, conv3x3-BN, + x, ReLU"""
+    y = pl.conv_unit(x, prefix + ".conv1.weight", prefix + ".bn1", "relu", k=3, pad=1)
+    return pl.conv_unit(y, prefix + ".conv2.weight", prefix + ".bn2", "relu", k=3, pad=1, residual=x)
+
+
+def _hr_module(pl, xs, prefix, blocks):
+    """HighResolutionModule.forward (backbones/hrnet.py:215-232) with the fuse layers of _make_fuse_layers (:165-209).  The sum of
+    output i starts from the identity term x_i, the stride-2 chains (j < i) are added through their last BatchNorm's residual
+    operand, the 1x1 + BN + nearest-up terms (j > i) through upsample_add; the last term carries the ReLU."""
+    nb = len(xs)
+    xs = list(xs)
+    for i in range(nb):
+        for b in range(blocks[i]):
+            xs[i] = _hr_basic_block(pl, xs[i], f"{prefix}.branches.{i}.{b}")
+    if nb == 1:
+        return xs
+    outs = []
+    for i in range(nb):
+        terms = [j for j in range(nb) if j != i]
+        cur = xs[i]
+        for q, j in enumerate(terms):
+            act = "relu" if q == len(terms) - 1 else None
+            f = f"{prefix}.fuse_layers.{i}.{j}"
+            if j > i:
+                t = pl.conv_unit(xs[j], f + ".0.weight", f + ".1", None)
+                cur = pl.upsample_add(cur, t, j - i, act)
+            else:
+                t = xs[j]
+                for k in range(i - j):
+                    if k == i - j - 1:
+                        cur = pl.conv_unit(t, f"{f}.{k}.0.weight", f"{f}.{k}.1", act, k=3, stride=2, pad=1, residual=cur)
+                    else:
+                        t = pl.conv_unit(t, f"{f}.{k}.0.weight", f"{f}.{k}.1", "relu", k=3, stride=2, pad=1)
+        outs.append(cur)
+    return outs
+
+
+def build_hrnet_train(pl, hcfg):
+    """HighResolutionNet.forward (backbones/hrnet.py:429-479) + _HRNetHead (models/hrnet_seg.py:32-63) + the final bilinear
+    (align_corners=False, hrnet_seg.py:28) fused into the loss."""
+    p = "encoder"
+    n, H, W = pl.n, pl.H, pl.W
+    if H % 32 or W % 32:
+        raise RuntimeError("segb200: the HRNet training plan needs input sizes that are multiples of 32 (the reference's nearest "
+                           "up-sampling + add has the same requirement, backbones/hrnet.py:178-186)")
+    s2d = Act(pl, pl.new(n, H // 2, W // 2, 16, ld=64), needs_grad=False)
+    pl.cur.append(Step("pack_s2d", (lambda s: ops.pack_s2d(pl.x_in, s2d.t._base if s2d.t._base is not None else s2d.t)),
+                       dict(x=pl.x_in, out=s2d.t)))
+    x = pl.conv_unit(s2d, p + ".conv1.weight", p + ".bn1", "relu", k=3, stride=2, pad=1, stem=True)
+    x = pl.conv_unit(x, p + ".conv2.weight", p + ".bn2", "relu", k=3, stride=2, pad=1)
+    planes, inpl = hcfg["stage1"]["channels"][0], 64
+    for b in range(hcfg["stage1"]["blocks"][0]):
+        x = _bottleneck(pl, x, f"{p}.layer1.{b}", planes, 1, 1, inpl != planes * 4)
+        inpl = planes * 4
+    pre, ys = [inpl], [x]
+    for si, sname in enumerate(("stage2", "stage3", "stage4")):
+        sc = hcfg[sname]
+        cur = sc["channels"]
+        tname = f"{p}.transition{si + 1}"
+        xs = []
+        for i in range(len(cur)):                                            # _make_transition_layer, hrnet.py:347-381
+            if i < len(pre):
+                xs.append(ys[i] if cur[i] == pre[i] else
+                          pl.conv_unit(ys[i], f"{tname}.{i}.0.weight", f"{tname}.{i}.1", "relu", k=3, pad=1))
+            else:
+                t = ys[-1]
+                for j in range(i + 1 - len(pre)):
+                    t = pl.conv_unit(t, f"{tname}.{i}.{j}.0.weight", f"{tname}.{i}.{j}.1", "relu", k=3, stride=2, pad=1)
+                xs.append(t)
+        for m in range(sc["modules"]):
+            xs = _hr_module(pl, xs, f"{p}.{sname}.{m}", sc["blocks"])
+        ys, pre = xs, cur
+    _, h0, w0, _ = ys[0].t.shape
+    ctot = sum(t.t.shape[3] for t in ys)
+    cat = Act(pl, pl.new(n, h0, w0, ctot))
+    off = 0
+    for t in ys:                                                             # hrnet_seg.py:55-61 (same-size resize == identity)
+        c = t.t.shape[3]
+        pl.bilinear(t, cat.slice(off, off + c), align=False)
+        off += c
+    hp = "hrnet_head.last_layer"
+    y = pl.conv_unit(cat, hp + ".0.weight", hp + ".1", "relu", bias=hp + ".0.bias")
+    k = hcfg["final_conv_kernel"]
+    logits = Act(pl, pl.new(n, h0, w0, fold.round_up(pl.nclass, 8), ld=32))
+    pl.conv_unit(y, hp + ".3.weight", bias=hp + ".3.bias", k=k, pad=1 if k == 3 else 0, out=logits)
+    pl.logits = logits
+    pl.loss(logits, align=False)
+    pl.build_backward()
+    return pl
+
+
 class DeepLabV3PlusTrainerB200:
     """``trainer.step(images_nchw_fp32, targets_int64) -> loss`` : one iteration of tools/train.py:135-147 (forward, criterion,
     zero_grad, backward, optimizer.step) for DeepLabV3_Plus / ResNet on the CUDA engine.  ``state_dict()`` returns reference-named
@@ -1054,3 +1172,19 @@ class CCNetTrainerB200(DeepLabV3PlusTrainerB200):
 
     def _build(self, pl):
         build_ccnet_train(pl, self.cfg["output_stride"], self.recurrence)
+
+
+class HRNetTrainerB200(DeepLabV3PlusTrainerB200):
+    """``trainer.step(images, targets)`` for HRNet (models/hrnet_seg.py + backbones/hrnet.py; default: hrnet_w18_small_v1).
+    Defaults follow configs/cityscapes_hrnet_w18_small_v1.yaml: BatchNorm momentum 0.01 (MODEL.BN_MOMENTUM, applied by
+    solver/optimizer.py:37-39) and no decoder LR factor.  Plan verified against the oracle in fp64 on the CPU
+    (tests/test_train_plan_cpu.py); GPU replay: tests/test_train_model_gpu.py (SEGB200_TEST_ALL until it has run once)."""
+
+    def __init__(self, state_dict, nclass=19, hcfg=None, bn_momentum=0.01, decoder_lr_factor=1.0, lr=0.01, **kw):
+        from .engine import HRNET_W18_SMALL_V1
+        self.hcfg = hcfg or HRNET_W18_SMALL_V1
+        super().__init__(state_dict, backbone="hrnet", nclass=nclass, use_aspp=False, use_decoder=False, bn_momentum=bn_momentum,
+                         decoder_lr_factor=decoder_lr_factor, lr=lr, dropout=False, **kw)
+
+    def _build(self, pl):
+        build_hrnet_train(pl, self.hcfg)

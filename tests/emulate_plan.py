@@ -161,14 +161,30 @@ def run_step(st):
         i["dx"].copy_(xr.grad.permute(0, 2, 3, 1).to(i["dx"].dtype))
     elif kind == "bilinear":
         y = i["y"]
-        y.copy_(F.interpolate(_nchw(i["x"]), y.shape[1:3], mode="bilinear", align_corners=True).permute(0, 2, 3, 1).to(y.dtype))
+        y.copy_(F.interpolate(_nchw(i["x"]), y.shape[1:3], mode="bilinear", align_corners=i.get("align", True)).permute(0, 2, 3, 1).to(y.dtype))
     elif kind == "bilinear_bwd":
         dy, dx = i["dy"], i["dx"]
         xr = torch.zeros(dx.shape[0], dy.shape[3], dx.shape[1], dx.shape[2], dtype=CD, device=dy.device, requires_grad=True)
-        F.interpolate(xr, dy.shape[1:3], mode="bilinear", align_corners=True).backward(_nchw(dy))
+        F.interpolate(xr, dy.shape[1:3], mode="bilinear", align_corners=i.get("align", True)).backward(_nchw(dy))
         g = xr.grad.permute(0, 2, 3, 1) * (float(i["gscale"][0]) if i["gscale"] is not None else 1.0)
         c = dy.shape[3]
         dx[..., :c] = ((dx[..., :c].to(CD) if i["accumulate"] else 0) + g).to(dx.dtype)
+    elif kind == "upsample_add":                # y = act(a + nearest_up_{2^k}(z))   (segb200_upsample_add)
+        a, z, y, k = i["a"], i["z"], i["y"], i["k"]
+        up = z.to(CD).repeat_interleave(1 << k, dim=1).repeat_interleave(1 << k, dim=2)
+        y.copy_(_act(a.to(CD) + up, i["act"]).to(y.dtype))
+    elif kind == "upsample_add_bwd":            # g = dy * act'(y); da (+)= g; dz (+)= block sums of g
+        dy, y, da, dz, k = i["dy"], i["y"], i["da"], i["dz"], i["k"]
+        g = dy.to(CD)
+        if i["act"] == "relu":
+            g = g * (y.to(CD) > 0)
+        elif i["act"] == "relu6":
+            g = g * ((y.to(CD) > 0) & (y.to(CD) < 6))
+        n, h, w, c = g.shape
+        s_ = 1 << k
+        gz = g.reshape(n, h // s_, s_, w // s_, s_, c).sum((2, 4))
+        da.copy_(((da.to(CD) if i["acc_a"] else 0) + g).to(da.dtype))
+        dz.copy_(((dz.to(CD) if i["acc_z"] else 0) + gz).to(dz.dtype))
     elif kind == "gap":
         i["y"].copy_(i["x"].to(CD).mean((1, 2), keepdim=True).to(i["y"].dtype))
     elif kind == "nc_broadcast":
@@ -192,7 +208,7 @@ def run_step(st):
         p[:9 * c] = W0.grad.reshape(c, 9).t().reshape(-1)
     elif kind == "upsample_ce":
         lg, tgt, dfull, out3, nc = i["logits"], i["target"], i["dfull"], i["out3"], i["nclass"]
-        up = F.interpolate(_nchw(lg[..., :nc]), tgt.shape[1:3], mode="bilinear", align_corners=True)
+        up = F.interpolate(_nchw(lg[..., :nc]), tgt.shape[1:3], mode="bilinear", align_corners=i.get("align", True))
         valid = (tgt != i["ignore_index"]) & (tgt >= 0) & (tgt < nc)
         lsm = F.log_softmax(up, 1)
         oh = F.one_hot(tgt.clamp(0, nc - 1), nc).permute(0, 3, 1, 2).to(CD)

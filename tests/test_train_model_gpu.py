@@ -61,6 +61,10 @@ def _outputs(st):
         return [i["de"], i["part"]]
     if k in ("cca_gather", "cca_scatter"):
         return [i["out"]]
+    if k == "upsample_add":
+        return [i["y"]]
+    if k == "upsample_add_bwd":
+        return [i["da"], i["dz"]]
     raise NotImplementedError(k)
 
 
@@ -157,6 +161,21 @@ def test_every_launch_of_a_ccnet_training_step():
     tr = CCNetTrainerB200(P.state_dict(), dtype=torch.bfloat16)
     pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {"head.rcca.bottleneck.dropout": mask.cuda()})
     print(f"[ccnet] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
+
+
+@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="HRNet model-level replay: written after the round's GPU budget was "
+                    "spent (plan verified in fp64 on the CPU); includes the new upsample_add_bwd kernel")
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_every_launch_of_an_hrnet_training_step(dtype):
+    from segmentron_b200.train import HRNetTrainerB200
+    P = R.build_params("hrnet_w18_small_v1", 41)
+    g = torch.Generator().manual_seed(4041)
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    target = torch.randint(-1, 19, (2, 64, 96), generator=g)
+    tr = HRNetTrainerB200(P.state_dict(), dtype=dtype)
+    pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {})
+    print(f"[hrnet {dtype}] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
+    assert {"upsample_add", "upsample_add_bwd"} <= set(worst)
 
 
 def test_training_step_end_to_end_vs_oracle():

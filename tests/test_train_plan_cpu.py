@@ -121,3 +121,40 @@ def test_state_dict_roundtrip(dry_run):
     for k in sd0:
         assert tuple(sd[k].shape) == tuple(sd0[k].shape), k
         assert torch.equal(sd[k].float(), sd0[k].float()), k
+
+
+def test_hrnet_train_plan_matches_oracle_on_cpu(dry_run):
+    """HRNet-w18-small-v1 (backbones/hrnet.py + models/hrnet_seg.py): stride-4 stem of two 3x3/2 convs, Bottleneck + BasicBlock
+    branches, transition layers, the fuse sums (identity + stride-2 conv chains through the BatchNorm residual operand + 1x1 /
+    BatchNorm / nearest-up terms through upsample_add, one ReLU at the end), the head's align_corners=False resizes into concat
+    slices, a conv bias in front of BatchNorm, BatchNorm momentum 0.01, no decoder LR factor (the YAML's recipe)."""
+    from segmentron_b200.train import HRNetTrainerB200
+    seed, shape = 41, (2, 3, 64, 96)
+    P = R.build_params("hrnet_w18_small_v1", seed)
+    g = torch.Generator().manual_seed(4000 + seed)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
+    tr = HRNetTrainerB200(P.state_dict(), dtype=torch.float64, device="cpu", lr=0.01)
+    loss = E.forward_backward(tr, x, target, {})
+    grads = tr.store.grads()
+    sd_mid = tr.state_dict()
+    before = {k: v.clone() for k, v in P.t.items()}
+    P64 = P.to(dtype=torch.float64)
+    P64.frozen, P64.bn_momentum = True, 0.01
+    o_loss, o_grads, _, _ = R.loss_and_grads("hrnet_w18_small_v1", P64, x.double(), target)
+    assert abs(float(loss) - float(o_loss)) < 1e-6 * abs(float(o_loss)), (float(loss), float(o_loss))
+    floor = 1e-6 * max(float(v.norm()) for v in o_grads.values())
+    assert set(grads) == set(o_grads)
+    worst = max(((float((grads[k] - gr).norm() / (gr.norm() + floor)), k) for k, gr in o_grads.items()))
+    assert worst[0] < 1e-6, worst
+    for k in sd_mid:
+        if k.endswith(("running_mean", "running_var")):
+            assert torch.allclose(sd_mid[k].double(), P64.t[k], atol=1e-6, rtol=1e-6), k
+    E.sgd(tr)
+    sd = tr.state_dict()
+    for k in ("encoder.conv1.weight", "encoder.stage3.0.fuse_layers.2.0.1.0.weight", "hrnet_head.last_layer.0.bias",
+              "hrnet_head.last_layer.3.weight"):
+        ref = before[k].double() - 0.01 * (o_grads[k] + 1e-4 * before[k].double())          # one LR for encoder and head
+        assert float((sd[k].double() - ref).norm() / (ref.norm() + 1e-12)) < 1e-6, k
+    kinds = {s.kind for s in tr.plan_for(shape)["plan"].fwd + tr.plan_for(shape)["plan"].bwd}
+    assert {"upsample_add", "upsample_add_bwd"} <= kinds
