@@ -34,12 +34,15 @@ def ref_train_leg(P, x, target, fmt, iters):
         Pg.t[k] = v.detach().clone().requires_grad_(True)
     enc = [Pg.t[k] for k in names if k.startswith("encoder.")]
     head = [Pg.t[k] for k in names if not k.startswith("encoder.")]
-    opt = torch.optim.SGD([{"params": enc, "lr": 0.02}, {"params": head, "lr": 0.2}], lr=0.02, momentum=0.9, weight_decay=1e-4)
+    hr = MODEL.startswith("hrnet")             # the HRNet YAML: lr 0.01, no decoder factor, BatchNorm momentum 0.01
+    Pg.bn_momentum = 0.01 if hr else 0.1
+    opt = torch.optim.SGD([{"params": enc, "lr": 0.01 if hr else 0.02}, {"params": head, "lr": 0.01 if hr else 0.2}], lr=0.02,
+                          momentum=0.9, weight_decay=1e-4)
     xb = x.contiguous(memory_format=torch.channels_last) if fmt == "channels_last" else x
 
     def step():
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = R.deeplabv3plus(Pg, xb, nclass=19, **R.MODELS[MODEL])
+            out = R.hrnet_seg(Pg, xb, nclass=19) if hr else R.deeplabv3plus(Pg, xb, nclass=19, **R.MODELS[MODEL])
             loss = F.cross_entropy(out.float(), target, ignore_index=-1)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -67,18 +70,20 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
-    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2"])
+    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2", "hrnet"])
     ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
     global MODEL
-    MODEL = "deeplabv3plus_" + args.backbone
+    MODEL = "hrnet_w18_small_v1" if args.backbone == "hrnet" else "deeplabv3plus_" + args.backbone
+    if args.backbone == "hrnet" and (args.height, args.width) == (1025, 2049):
+        args.height, args.width = 1024, 2048         # HRNet needs multiples of 32 (nearest up-sampling + add in the fuse layers)
     import __graft_entry__ as ge
     ge.build()
     from oracle import segref as R          # parameter generator + the reference leg only
     from segmentron_b200 import parallel
-    from segmentron_b200.train import DeepLabV3PlusTrainerB200
+    from segmentron_b200.train import DeepLabV3PlusTrainerB200, HRNetTrainerB200
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     rank, world, local = parallel.init_from_env("nccl")
     torch.backends.cudnn.benchmark = True
@@ -87,7 +92,10 @@ def main():
     g = torch.Generator().manual_seed(1024 + (0 if args.same_data else rank))
     x = torch.randn(*shape, generator=g).cuda()
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g).cuda()
-    tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=args.backbone, dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
+    if args.backbone == "hrnet":
+        tr = HRNetTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.01)
+    else:
+        tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=args.backbone, dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
     losses = [float(tr.step(x, target)) for _ in range(max(args.warmup, 3))]
     parallel.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -124,7 +132,7 @@ def main():
         tot = sum(a["ms"] for a in agg.values())
         mm = {k: agg[k] for k in ("conv", "wgrad") if k in agg and agg[k]["ms"] > 0}
         out = {"config": "c3_train" if args.backbone == "resnet101" else "train_" + args.backbone,
-               "what": f"DeepLabv3+/{args.backbone} bf16 training step (fwd + CE loss + bwd + SGD) at "
+               "what": f"{'HRNet-w18-small-v1' if args.backbone == 'hrnet' else 'DeepLabv3+/' + args.backbone} bf16 training step (fwd + CE loss + bwd + SGD) at "
                f"{args.height}x{args.width}, per-GPU batch {args.batch}", "n_gpus": world, "segb200_img_s": world * args.batch / (ms * 1e-3),
                "segb200_ms_per_step": ms, "launches_per_step": tr.n_launches(shape), "loss_first_steps": losses,
                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
