@@ -310,6 +310,24 @@ int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h
 int segb200_upsample_add_bwd(const void* dy, const void* y, void* da, void* dz, int n, int h, int w, int c, int dy_ld, int y_ld,
                              int da_ld, int dz_ld, int k, int act, int accumulate_a, int accumulate_z, int dtype, void* stream);
 
+/* CAM_Module backward glue (modules/module.py:134-162; autograd through bmm / softmax / bmm in the reference).  With
+ * G[c1][c2] = sum_p dy[p,c1] x[p,c2] (a segb200_conv_gemm with fp32 output):
+ *   cam_softmax_bwd : r[c1] = sum_c2 A G -> dgamma_partial[c1];  dE = -(*gamma) * A * (G - r)         (fp32 [c][de_ld])
+ *   cam_bwd_pack    : w1[c2][c1] = (*gamma) A[c1][c2],  w2 = dE + dE^T   as 16-bit GEMM weights [c][w_ld] (zero K padding), so that
+ *                     dx = dy + conv_gemm(dy, w1) + conv_gemm(x, w2). */
+int segb200_cam_softmax_bwd(const void* att, const float* g, const float* gamma, float* de, float* dgamma_partial, int c, int att_ld,
+                            int g_ld, int de_ld, int dtype, void* stream);
+int segb200_cam_bwd_pack(const void* att, const float* de, const float* gamma, void* w1, void* w2, int c, int att_ld, int de_ld,
+                         int w_ld, int dtype, void* stream);
+
+/* TRAINING-mode PAM_Module (modules/module.py:100-131) on a materialised attention matrix, like the reference's bmm / softmax / bmm:
+ *   row_softmax     : P[r][j] = softmax_j(S[r][j]) for j < n (16-bit), columns n .. p_ld-1 = 0   (S: fp32 GEMM output Q K^T)
+ *   row_softmax_bwd : r = sum_j P D -> partial[r] (the gamma-gradient term);  dS = (*gamma) * P * (D - r), zero padded
+ *                     (D = dy V^T, fp32 GEMM output).  dV, dQ, dK then are tcgen05 GEMMs over P^T, dS, dS^T (segb200_nhwc_to_cn). */
+int segb200_row_softmax(const float* s, void* p, int rows, int n, int s_ld, int p_ld, int dtype, void* stream);
+int segb200_row_softmax_bwd(const void* p, const float* d, const float* gamma, void* ds, float* partial, int rows, int n, int p_ld,
+                            int d_ld, int ds_ld, int dtype, void* stream);
+
 /* OPT-IN variant of segb200_dw_wgrad (same arguments, same partial[(slab*9 + tap)*c + ch] layout, slab count from
  * segb200_dw_wgrad_v2_slabs): a thread owns four channels and walks contiguous pixels of an image row with the 3x3 window held in
  * registers (3 new 8-byte loads per pixel instead of 9 16-byte ones) and packed fma.rn.f32x2.  Not the default until measured. */

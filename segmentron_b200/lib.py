@@ -95,6 +95,10 @@ SYMBOLS = {
     "segb200_cca_gather": (ci, [vp, vp, vp] + [ci] * 7 + [cf, ci, ci, vp]),
     "segb200_cca_scatter": (ci, [vp, vp, vp] + [ci] * 7 + [cf, vp, ci, ci, vp]),
     "segb200_sgd_step": (ci, [vp, vp, vp, ll, cf, cf, cf, cf, vp]),
+    "segb200_row_softmax": (ci, [vp, vp] + [ci] * 5 + [vp]),
+    "segb200_row_softmax_bwd": (ci, [vp, vp, vp, vp, vp] + [ci] * 6 + [vp]),
+    "segb200_cam_softmax_bwd": (ci, [vp, vp, vp, vp, vp] + [ci] * 5 + [vp]),
+    "segb200_cam_bwd_pack": (ci, [vp, vp, vp, vp, vp] + [ci] * 5 + [vp]),
     "segb200_upsample_add_bwd": (ci, [vp, vp, vp, vp] + [ci] * 13 + [vp]),
     "segb200_dw_wgrad_v2_slabs": (ci, [ll, ci, ci]),
     "segb200_dw_wgrad_v2": (ci, [vp, vp, vp] + [ci] * 10 + [vp]),

@@ -12,9 +12,9 @@ lazily at the next forward after any change.
 
 No CPU implementation and no PyTorch fallback: a non-CUDA input raises RuntimeError, like the reference's
 native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training mode: ``SeparableConv2d``,
-``_ConvBNReLU``, ``_ConvBN``, ``InvertedResidual``, ``_ASPP`` and ``CrissCrossAttention`` are differentiable
+``_ConvBNReLU``, ``_ConvBN``, ``InvertedResidual``, ``_ASPP``, ``CrissCrossAttention`` and ``CAM_Module`` are differentiable
 (train_modules.py / attention.py: train-mode BatchNorm + the backward kernels, composed unit by unit); PyramidPooling and
-PAM / CAM raise in training mode -- whole models train fastest through ``train.DeepLabV3PlusTrainerB200``.
+PAM_Module raise in training mode -- whole models train fastest through ``train.DeepLabV3PlusTrainerB200``.
 """
 from collections import OrderedDict
 
@@ -441,6 +441,11 @@ class PAM_Module(nn.Module):
         return pam_nhwc(x, wq, bq, wk, bk, wv, bv, self.gamma)
 
     def forward(self, x):
+        if self.training:                          # differentiable path (attention.PamFunction: materialised attention, like the reference)
+            from .attention import PamFunction
+            y = PamFunction.apply(_train_enter(x, self), self.query_conv.weight, self.query_conv.bias, self.key_conv.weight,
+                                  self.key_conv.bias, self.value_conv.weight, self.value_conv.bias, self.gamma)
+            return y.permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 
@@ -460,6 +465,10 @@ class CAM_Module(nn.Module):
         return cam_nhwc(x, self.gamma)
 
     def forward(self, x):
+        if self.training:                          # differentiable path (attention.CamFunction / csrc/cam_bwd.cu)
+            from .attention import CamFunction
+            y = CamFunction.apply(_train_enter(x, self), self.gamma)
+            return y.permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 

@@ -187,6 +187,72 @@ def _aspp_no_dropout(P, t):
 _ALL_TRAIN_CASES = TRAIN_DROPIN_CASES
 
 
+@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="PAM backward: written after round 1's GPU budget was spent (math and "
+                    "plumbing verified on the CPU against the oracle through the C-ABI emulation, tests/test_cam_train_cpu.py)")
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 2.5e-2)], ids=["f16", "bf16"])
+def test_pam_module_backward(dtype, tol):
+    """Training-mode PAM_Module drop-in (attention.PamFunction, csrc/softmax_rows.cu): output and EVERY gradient (input, q/k/v conv
+    weights and biases, gamma) against autograd through the oracle's pam() (modules/module.py:112-131)."""
+    from segmentron_b200 import modules as M
+    for (n, c, h, w) in [(2, 512, 12, 20), (1, 512, 16, 24), (2, 64, 8, 12)]:
+        P = R.Params(25)
+        x = (_x(n, c, h, w, seed=26) * 0.5).to(dtype).float()
+        with torch.no_grad():
+            R.pam(P, x, "pam", gamma=0.8)
+        names = [k for k in P.t if k.startswith("pam.")]
+        for k in names:
+            P.t[k] = P.t[k].to(dtype).float().detach().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        ref = R.pam(P, xr, "pam", gamma=0.8)
+        dy = _x(n, c, h, w, seed=27).to(dtype).float()
+        ref.backward(dy)
+        m = M.PAM_Module(c)
+        m.load_state_dict({k[4:]: v.detach() for k, v in P.t.items() if k.startswith("pam.")}, strict=True)
+        m = m.cuda().train()
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        y = m(xg)
+        _cmp(y.detach(), ref.detach(), tol)
+        y.backward(dy.cuda().to(dtype))
+        _cmp(xg.grad, xr.grad, tol)
+        floor = 0.05 * max(float(P.t[k].grad.norm()) for k in names)       # key_conv.bias: analytically zero gradient
+        errs = {}
+        for k in names:
+            g = dict(m.named_parameters())[k[4:]].grad
+            assert g is not None, k
+            errs[k] = float((g.float().cpu().reshape(-1) - P.t[k].grad.reshape(-1)).norm() / (float(P.t[k].grad.norm()) + floor))
+        print(f"[pam bwd {dtype} {(n, c, h, w)}] " + ", ".join(f"{k[4:]}: {v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) < 2 * tol, errs
+
+
+@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="CAM backward: written after round 1's GPU budget was spent (math and "
+                    "plumbing verified on the CPU against the oracle through the C-ABI emulation, tests/test_cam_train_cpu.py)")
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 2.5e-2)], ids=["f16", "bf16"])
+def test_cam_module_backward(dtype, tol):
+    """Training-mode CAM_Module drop-in (attention.CamFunction, csrc/cam_bwd.cu): output, input gradient and gamma gradient against
+    autograd through the oracle's cam() (modules/module.py:142-162)."""
+    from segmentron_b200 import modules as M
+    for (n, c, h, w, s) in [(2, 64, 12, 20, 0.2), (1, 512, 16, 24, 0.05)]:       # scales as in test_attention_modules (soft attention)
+        P = R.Params(27)
+        x = (_x(n, c, h, w, seed=28) * s).to(dtype).float()
+        with torch.no_grad():
+            R.cam(P, x, "cam", gamma=0.8)
+        P.t["cam.gamma"] = P.t["cam.gamma"].to(dtype).float().detach().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        ref = R.cam(P, xr, "cam", gamma=0.8)
+        dy = _x(n, c, h, w, seed=29).to(dtype).float()
+        ref.backward(dy)
+        m = M.CAM_Module(c)
+        m.load_state_dict({"gamma": P.t["cam.gamma"].detach()}, strict=True)
+        m = m.cuda().train()
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        y = m(xg)
+        _cmp(y.detach(), ref.detach(), tol)
+        y.backward(dy.cuda().to(dtype))
+        _cmp(xg.grad, xr.grad, tol)
+        g_ref = float(P.t["cam.gamma"].grad)
+        assert abs(float(m.gamma.grad) - g_ref) <= 2 * tol * abs(g_ref) + 1e-3, (float(m.gamma.grad), g_ref)
+
+
 @pytest.mark.parametrize("case", list(_ALL_TRAIN_CASES))
 def test_dropin_modules_train_backward(case):
     """Training-mode drop-ins (train-mode BatchNorm + backward kernels behind torch.autograd.Function) against autograd through

@@ -9,6 +9,7 @@ run() { echo "=== $*"; timeout 300 "$@" 2>&1 | tail -25; echo "=== exit ${PIPEST
 run python -m pytest tests/test_modules_gpu.py -q -k "errors_and_cache"                      # gated part: _ASPP batch-1 ValueError
 run python -m pytest tests/test_train_model_gpu.py -q -s -k "ccnet"                         # CCNet training plan, every launch
 run python -m pytest tests/test_train_model_gpu.py -q -s -k "hrnet"                         # HRNet training plan, every launch (+ upsample_add_bwd)
+run python -m pytest tests/test_modules_gpu.py -q -k "cam_module_backward or pam_module_backward"   # CAM / PAM training drop-ins
 run python -m pytest tests/test_metric_gpu.py -q                                            # device-resident pixAcc / mIoU counts
 run python -m pytest tests/test_evaluate_gpu.py -q                                          # multi-scale + flip driver
 run python -m pytest tests/test_train_kernels_gpu.py -q -k "wgrad_v2 or upsample_add"                     # opt-in sliding-window depthwise weight gradient
