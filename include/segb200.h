@@ -320,6 +320,11 @@ int segb200_cam_softmax_bwd(const void* att, const float* g, const float* gamma,
 int segb200_cam_bwd_pack(const void* att, const float* de, const float* gamma, void* w1, void* w2, int c, int att_ld, int de_ld,
                          int w_ld, int dtype, void* stream);
 
+/* Backward of segb200_adaptive_avgpool (nn.AdaptiveAvgPool2d(s) of PyramidPooling, modules/module.py:82-97): dx[p] (+)= sum over the
+ * (possibly overlapping) bins containing p of dy[bin] / area(bin). */
+int segb200_adaptive_avgpool_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dy_ld, int dx_ld, int s, int accumulate,
+                                 int dtype, void* stream);
+
 /* TRAINING-mode PAM_Module (modules/module.py:100-131) on a materialised attention matrix, like the reference's bmm / softmax / bmm:
  *   row_softmax     : P[r][j] = softmax_j(S[r][j]) for j < n (16-bit), columns n .. p_ld-1 = 0   (S: fp32 GEMM output Q K^T)
  *   row_softmax_bwd : r = sum_j P D -> partial[r] (the gamma-gradient term);  dS = (*gamma) * P * (D - r), zero padded

@@ -83,3 +83,61 @@ extern "C" int segb200_upsample_add_bwd(const void* dy, const void* y, void* da,
                                                                             accumulate_a ? 1 : 0, accumulate_z ? 1 : 0, dtype);
   return check_launch("upsample_add_bwd");
 }
+
+// -------------------------------------------------------------------------------------------
+// backward of nn.AdaptiveAvgPool2d(s) (PyramidPooling, modules/module.py:82-97; forward: adaptive_pool_kernel, misc.cu):
+// bin (bi, bj) covers rows [floor(bi h / s), ceil((bi+1) h / s)) x the same rule in w (bins overlap when s does not divide the size);
+// dx[p] (+)= sum over the bins that contain p of dy[bin] / area(bin).  One thread per input pixel and 8-channel vector (gather).
+// -------------------------------------------------------------------------------------------
+namespace segb200 {
+
+__global__ void __launch_bounds__(256)
+adaptive_pool_bwd_kernel(const void* __restrict__ dy, void* __restrict__ dx, int n, int h, int w, int c, int dy_ld, int dx_ld, int s,
+                         int accumulate, int dtype) {
+  const int cvn = c / 8;
+  const long long total = (long long)n * h * w * cvn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    long long r = idx / cvn;
+    const int x = (int)(r % w); r /= w;
+    const int y = (int)(r % h);
+    const long long b = r / h;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int bi = 0; bi < s; ++bi) {
+      const int h0 = (bi * h) / s, h1 = ((bi + 1) * h + s - 1) / s;
+      if (y < h0 || y >= h1) continue;
+      for (int bj = 0; bj < s; ++bj) {
+        const int w0 = (bj * w) / s, w1 = ((bj + 1) * w + s - 1) / s;
+        if (x < w0 || x >= w1) continue;
+        float g[8];
+        unpack8(ldg_v4(reinterpret_cast<const char*>(dy) + (((b * s + bi) * s + bj) * dy_ld + cv * 8) * 2), dtype, g);
+        const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], inv, acc[j]);
+      }
+    }
+    char* op = reinterpret_cast<char*>(dx) + (((b * h + y) * w + x) * dx_ld + cv * 8) * 2;
+    if (accumulate) {
+      float o[8];
+      unpack8(*reinterpret_cast<const uint4*>(op), dtype, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += o[j];
+    }
+    *reinterpret_cast<uint4*>(op) = pack8(acc, dtype);
+  }
+}
+
+}  // namespace segb200
+
+extern "C" int segb200_adaptive_avgpool_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dy_ld, int dx_ld, int s,
+                                            int accumulate, int dtype, void* stream) {
+  if (!dy || !dx) return set_error(-1, "adaptive_avgpool_bwd: null pointer");
+  if (!half_dt(dtype)) return set_error(-2, "adaptive_avgpool_bwd: bad dtype");
+  if (c < 8 || (c & 7) || (dy_ld & 7) || (dx_ld & 7) || dy_ld < c || dx_ld < c || s < 1 || n < 1 || h < 1 || w < 1)
+    return set_error(-4, "adaptive_avgpool_bwd: bad sizes");
+  adaptive_pool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(dy, dx, n, h, w, c, dy_ld, dx_ld, s,
+                                                                                                  accumulate ? 1 : 0, dtype);
+  return check_launch("adaptive_avgpool_bwd");
+}

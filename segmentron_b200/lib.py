@@ -95,6 +95,7 @@ SYMBOLS = {
     "segb200_cca_gather": (ci, [vp, vp, vp] + [ci] * 7 + [cf, ci, ci, vp]),
     "segb200_cca_scatter": (ci, [vp, vp, vp] + [ci] * 7 + [cf, vp, ci, ci, vp]),
     "segb200_sgd_step": (ci, [vp, vp, vp, ll, cf, cf, cf, cf, vp]),
+    "segb200_adaptive_avgpool_bwd": (ci, [vp, vp] + [ci] * 9 + [vp]),
     "segb200_row_softmax": (ci, [vp, vp] + [ci] * 5 + [vp]),
     "segb200_row_softmax_bwd": (ci, [vp, vp, vp, vp, vp] + [ci] * 6 + [vp]),
     "segb200_cam_softmax_bwd": (ci, [vp, vp, vp, vp, vp] + [ci] * 5 + [vp]),

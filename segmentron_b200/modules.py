@@ -12,9 +12,9 @@ lazily at the next forward after any change.
 
 No CPU implementation and no PyTorch fallback: a non-CUDA input raises RuntimeError, like the reference's
 native op does (csrc/criss_cross_attention/ca.h:34 "Not implemented on the CPU").  Training mode: ``SeparableConv2d``,
-``_ConvBNReLU``, ``_ConvBN``, ``InvertedResidual``, ``_ASPP``, ``CrissCrossAttention`` and ``CAM_Module`` are differentiable
-(train_modules.py / attention.py: train-mode BatchNorm + the backward kernels, composed unit by unit); PyramidPooling and
-PAM_Module raise in training mode -- whole models train fastest through ``train.DeepLabV3PlusTrainerB200``.
+``_ConvBNReLU``, ``_ConvBN``, ``InvertedResidual``, ``_ASPP``, ``PyramidPooling``, ``PAM_Module``, ``CAM_Module`` and
+``CrissCrossAttention`` -- every class -- are differentiable (train_modules.py / attention.py: train-mode BatchNorm + the backward
+kernels, composed unit by unit) -- whole models train fastest through ``train.DeepLabV3PlusTrainerB200``.
 """
 from collections import OrderedDict
 
@@ -408,6 +408,15 @@ class PyramidPooling(nn.Module):
         return out
 
     def forward(self, x):
+        if self.training:                          # unit by unit: adaptive pool / conv+BN+ReLU / bilinear Functions, torch.cat of NHWC tensors
+            from . import train_modules as TM
+            xh = _train_enter(x, self)
+            _, h, w, _ = xh.shape
+            feats = [xh]
+            for s, conv in zip(self.sizes, self.convs):
+                f = _train_conv_bn_act(TM.AdaptiveAvgPoolFunction.apply(xh, s), conv.conv, conv.bn, conv._act)
+                feats.append(TM.BilinearFunction.apply(f, h, w, True))
+            return torch.cat(feats, dim=3).permute(0, 3, 1, 2).to(x.dtype)
         xh, odt = _enter(x, self)
         return _leave(self.forward_nhwc(xh), odt)
 

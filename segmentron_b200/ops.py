@@ -40,7 +40,8 @@ def _nhwc(t, name):
     if t.dim() != 4:
         raise RuntimeError(f"segb200: {name} must be [N,H,W,C]")
     n, h, w, c = t.shape
-    ld = t.stride(2)
+    # the pixel pitch; a size-1 dimension carries an arbitrary stride (torch keeps whatever a permute left there)
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else max(c, t.stride(2))))
     if t.stride(3) != 1 or ld < c or (h > 1 and t.stride(1) != w * ld) or (n > 1 and t.stride(0) != h * w * ld):
         raise RuntimeError(f"segb200: {name} is not an NHWC tensor / channel slice (shape {tuple(t.shape)}, "
                            f"strides {t.stride()})")

@@ -185,3 +185,44 @@ class BroadcastFunction(torch.autograd.Function):
         dv = torch.empty_like(mean)
         T.nc_broadcast(mean, dv, scale=float(h * w))
         return dv, None, None
+
+
+class AdaptiveAvgPoolFunction(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(s) on NHWC: [n,h,w,c] -> [n,s,s,c]  (PyramidPooling, modules/module.py:82-97)"""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        n, h, w, c, _ = ops._nhwc(x, "x")
+        y = torch.empty(n, s, s, c, dtype=x.dtype, device=x.device)
+        ops.adaptive_avgpool(x, y, s)
+        ctx.geo = (n, h, w, c, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import lib as L
+        n, h, w, c, s = ctx.geo
+        dy = dy.contiguous()
+        dx = torch.empty(n, h, w, c, dtype=dy.dtype, device=dy.device)
+        L.check(L.load().segb200_adaptive_avgpool_bwd(ops._ptr(dy), ops._ptr(dx), n, h, w, c, c, c, s, 0, ops.dt_code(dy.dtype),
+                                                      ops._stream()), "adaptive_avgpool_bwd")
+        return dx, None
+
+
+class BilinearFunction(torch.autograd.Function):
+    """F.interpolate(x, (ho, wo), mode='bilinear', align_corners=align) on NHWC; backward = the gather kernel of the training plan"""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo, align):
+        n, hi, wi, c, _ = ops._nhwc(x, "x")
+        y = torch.empty(n, ho, wo, c, dtype=x.dtype, device=x.device)
+        ops.bilinear_nhwc(x, y, align_corners=align)
+        ctx.geo = (n, hi, wi, c, align)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, hi, wi, c, align = ctx.geo
+        dx = torch.empty(n, hi, wi, c, dtype=dy.dtype, device=dy.device)
+        T.bilinear_nhwc_bwd(dy.contiguous(), dx, align_corners=align)
+        return dx, None, None, None

@@ -144,3 +144,57 @@ def _more(cls):
 
 
 _more(FakeLib)
+
+
+def _pooling(cls):
+    import torch
+    import torch.nn.functional as F
+
+    def segb200_adaptive_avgpool(self, x, out, n, h, w, c, x_ld, s, out_ld, dtype, stream):
+        xs = view(x, (n, h, w, x_ld))[..., :c]
+        o = view(out, (n, s, s, out_ld))
+        for bi in range(s):
+            h0, h1 = (bi * h) // s, ((bi + 1) * h + s - 1) // s
+            for bj in range(s):
+                w0, w1 = (bj * w) // s, ((bj + 1) * w + s - 1) // s
+                o[:, bi, bj, :c] = xs[:, h0:h1, w0:w1].mean((1, 2), dtype=np.float64)
+        return 0
+
+    def segb200_adaptive_avgpool_bwd(self, dy, dx, n, h, w, c, dy_ld, dx_ld, s, accumulate, dtype, stream):
+        """transcription of adaptive_pool_bwd_kernel: per input pixel, gather over the bins that contain it"""
+        g = view(dy, (n, s, s, dy_ld))[..., :c]
+        o = view(dx, (n, h, w, dx_ld))
+        for y in range(h):
+            for x in range(w):
+                acc = np.zeros((n, c), dtype=np.float32)
+                for bi in range(s):
+                    h0, h1 = (bi * h) // s, ((bi + 1) * h + s - 1) // s
+                    if y < h0 or y >= h1:
+                        continue
+                    for bj in range(s):
+                        w0, w1 = (bj * w) // s, ((bj + 1) * w + s - 1) // s
+                        if x < w0 or x >= w1:
+                            continue
+                        acc += g[:, bi, bj] * np.float32(1.0 / ((h1 - h0) * (w1 - w0)))
+                o[:, y, x, :c] = acc + (o[:, y, x, :c] if accumulate else 0)
+        return 0
+
+    def segb200_bilinear_nhwc(self, x, y, n, hi, wi, c, x_ld, ho, wo, y_ld, align, dtype, stream):
+        xs = torch.from_numpy(view(x, (n, hi, wi, x_ld))[..., :c].copy()).permute(0, 3, 1, 2)
+        view(y, (n, ho, wo, y_ld))[..., :c] = F.interpolate(xs, (ho, wo), mode="bilinear", align_corners=bool(align)).permute(0, 2, 3, 1).numpy()
+        return 0
+
+    def segb200_bilinear_nhwc_bwd(self, dy, dx, n, hi, wi, c, dx_ld, ho, wo, dy_ld, align, accumulate, gscale, dtype, stream):
+        g = torch.from_numpy(view(dy, (n, ho, wo, dy_ld))[..., :c].copy()).permute(0, 3, 1, 2)
+        with torch.enable_grad():                                  # called from inside an autograd backward
+            xr = torch.zeros(n, c, hi, wi, requires_grad=True)
+            F.interpolate(xr, (ho, wo), mode="bilinear", align_corners=bool(align)).backward(g)
+        o = view(dx, (n, hi, wi, dx_ld))
+        sc = float(view(gscale, (1,))[0]) if (gscale is not None and getattr(gscale, "value", gscale)) else 1.0
+        o[..., :c] = xr.grad.permute(0, 2, 3, 1).numpy() * sc + (o[..., :c] if accumulate else 0)
+        return 0
+    for f in (segb200_adaptive_avgpool, segb200_adaptive_avgpool_bwd, segb200_bilinear_nhwc, segb200_bilinear_nhwc_bwd):
+        setattr(cls, f.__name__, f)
+
+
+_pooling(FakeLib)

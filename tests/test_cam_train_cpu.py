@@ -77,3 +77,49 @@ def test_pam_function_matches_oracle_autograd(shape, monkeypatch):
         gr, go = P.t[k].grad, prm[k].grad
         assert go is not None, k
         assert float((go.reshape(-1) - gr.reshape(-1)).abs().max()) <= 5e-5 * float(gr.abs().max()) + 1e-2 * floor, k
+
+
+@pytest.mark.parametrize("hw", [(12, 18), (7, 11)])
+def test_pyramid_pooling_training_matches_oracle_autograd(hw, monkeypatch):
+    """Training-mode PyramidPooling (modules/module.py:82-97): adaptive pool (forward kernel by its semantics, the new backward
+    kernel by transcription -- overlapping bins when the size is not a multiple of s), 1x1 conv + BN + ReLU units (substituted
+    by their torch definition here; they are GPU kernels tested with -m gpu), bilinear up-sampling and its gather backward, concat
+    order [x, 1, 2, 3, 6] -- against autograd through the oracle."""
+    import torch.nn.functional as F
+    from segmentron_b200 import lib as L, modules as M, ops
+
+    def unit(xh, conv, bn, act, pre_relu=False):
+        t = F.conv2d(xh.permute(0, 3, 1, 2), conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        t = F.batch_norm(t, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+        return (F.relu(t) if act == "relu" else t).permute(0, 2, 3, 1).contiguous()
+    monkeypatch.setattr(ops, "_PLAN_DRY_RUN", True)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(L, "load", lambda: FakeLib())
+    monkeypatch.setattr(M, "_train_conv_bn_act", unit)
+    monkeypatch.setattr(M, "_train_enter", lambda x, m: x.permute(0, 2, 3, 1).contiguous())
+    h, w = hw
+    g = torch.Generator().manual_seed(h)
+    x = torch.randn(2, 32, h, w, generator=g)
+    P = R.Params(9)
+    with torch.no_grad():
+        R.pyramid_pooling(P, x, "m")
+    keys = [k for k in P.t if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    for k in keys:
+        P.t[k] = P.t[k].detach().requires_grad_(True)
+    sd0 = {k[2:]: v.detach().clone() for k, v in P.state_dict().items()}
+    P.training = True
+    xr = x.clone().requires_grad_(True)
+    ref = R.pyramid_pooling(P, xr, "m")
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    m = M.PyramidPooling(32)
+    m.load_state_dict(sd0, strict=True)
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    y = m(xg)
+    y.backward(dy)
+    assert torch.allclose(y, ref, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(xg.grad, xr.grad, atol=1e-5, rtol=1e-4)
+    for k in keys:
+        gm = dict(m.named_parameters())[k[2:]].grad
+        assert gm is not None and torch.allclose(gm, P.t[k].grad, atol=1e-4, rtol=1e-4), k
