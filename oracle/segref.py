@@ -578,16 +578,17 @@ def ccnet(P, x, nclass=19, output_stride=16, recurrence=2):
 
 
 def danet_head(P, x, nclass, prefix="head"):
-    """DANetHead.forward (models/danet.py:70-88).  Dropout2d is identity in eval."""
+    """DANetHead.forward (models/danet.py:70-88).  Each classifier is nn.Sequential(Dropout2d(0.1), Conv2d) (:64-68): the three
+    dropouts are identity in eval and, in training, draw their masks in the order conv6, conv7, conv8."""
     def cbr(x, name):                                  # nn.Sequential(conv3x3(pad 1, no bias), BN, ReLU)  danet.py:48-61
         return conv_bn_act(P, x, f"{prefix}.{name}", 512, 3, 1, 1, conv="0", bn="1")
     feat1 = cbr(x, "conv5a")
     sa_conv = cbr(pam(P, feat1, prefix + ".sa"), "conv51")
-    sa_output = conv2d(P, sa_conv, prefix + ".conv6.1", nclass, 1, bias=True, gain=4.0)
+    sa_output = conv2d(P, dropout2d(P, sa_conv, prefix + ".conv6.0"), prefix + ".conv6.1", nclass, 1, bias=True, gain=4.0)
     feat2 = cbr(x, "conv5c")
     sc_conv = cbr(cam(P, feat2, prefix + ".sc"), "conv52")
-    sc_output = conv2d(P, sc_conv, prefix + ".conv7.1", nclass, 1, bias=True, gain=4.0)
-    sasc_output = conv2d(P, sa_conv + sc_conv, prefix + ".conv8.1", nclass, 1, bias=True, gain=4.0)
+    sc_output = conv2d(P, dropout2d(P, sc_conv, prefix + ".conv7.0"), prefix + ".conv7.1", nclass, 1, bias=True, gain=4.0)
+    sasc_output = conv2d(P, dropout2d(P, sa_conv + sc_conv, prefix + ".conv8.0"), prefix + ".conv8.1", nclass, 1, bias=True, gain=4.0)
     return sasc_output, sa_output, sc_output
 
 
@@ -654,9 +655,15 @@ def loss_and_grads(model: str, P: Params, x, target, nclass: int = 19, ignore_in
             out, low = ccnet(P, x, nclass=nclass, **kw), None
         elif model == "hrnet_w18_small_v1":
             out, low = hrnet_seg(P, x, nclass=nclass, **kw), None
+        elif model == "danet_resnet101":
+            outs = danet(P, x, nclass=nclass, **kw)
+            out, low = outs[0], None
         else:
             out, low = deeplabv3plus(P, x, nclass=nclass, return_lowres=True, **MODELS[model], **kw)
-        loss = F.cross_entropy(out.float(), target, ignore_index=ignore_index)
+        if model == "danet_resnet101":                 # MixSoftmaxCrossEntropyLoss._multiple_forward (solver/loss.py:31-36)
+            loss = sum(F.cross_entropy(o.float(), target, ignore_index=ignore_index) for o in outs)
+        else:
+            loss = F.cross_entropy(out.float(), target, ignore_index=ignore_index)
         loss.backward()
     finally:
         P.training = was

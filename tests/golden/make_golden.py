@@ -93,6 +93,7 @@ TRAIN_CASES = {
     "train_dlv3p_mobilenetv2_64x96_b4": ("deeplabv3plus_mobilenet_v2", "cityscapes_deeplabv3_plus_mobilenet.yaml", (4, 3, 64, 96), 23),
     "train_ccnet_resnet101_65x97_b2": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (2, 3, 65, 97), 24),
     "train_hrnet_w18s_64x96_b2": ("hrnet_w18_small_v1", "cityscapes_hrnet_w18_small_v1.yaml", (2, 3, 64, 96), 25),
+    "train_danet_resnet101_64x96_b2": ("danet_resnet101", "cityscapes_danet_resnet.yaml", (2, 3, 64, 96), 26),
 }
 
 
@@ -162,6 +163,12 @@ def run_train_case(case):
     mask_c, mask_key = (512, "head.rcca.bottleneck.dropout") if name == "ccnet_resnet101" else (256, "head.aspp.dropout")
     torch.manual_seed(777)
     mask = torch.empty(n, mask_c, 1, 1).bernoulli_(0.9) / 0.9         # (unused by the ASPP-less MobileNetV2 head)
+    more_masks = {}
+    if name == "danet_resnet101":                                    # three Dropout2d(0.1): conv6, conv7, conv8 in call order
+        torch.manual_seed(777)
+        for key in ("head.conv6.0", "head.conv7.0", "head.conv8.0"):
+            more_masks[key] = torch.empty(n, 512, 1, 1).bernoulli_(0.9) / 0.9
+        mask, mask_key = more_masks["head.conv6.0"], "head.conv6.0"
     torch.manual_seed(777)
     outputs = model(x)
     loss = sum(criterion(outputs, target).values())
@@ -169,6 +176,7 @@ def run_train_case(case):
     loss.backward()
     ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
     P.dropout_masks[mask_key] = mask
+    P.dropout_masks.update(more_masks)
     # MODEL.BN_MOMENTUM (None -> torch's 0.1) is applied to every BatchNorm by get_optimizer (solver/optimizer.py:37-39); the
     # HRNet YAML sets 0.01
     bn_momentum = float(cfg.MODEL.BN_MOMENTUM) if cfg.MODEL.BN_MOMENTUM else 0.1
@@ -200,6 +208,10 @@ def run_train_case(case):
     if name == "ccnet_resnet101":
         small = ["encoder.conv1.weight", "head.rcca.cca.gamma", "head.rcca.cca.query_conv.weight", "head.rcca.cca.key_conv.bias",
                  "head.out.weight", "head.out.bias", "head.rcca.bottleneck.1.weight"]
+    if "danet" in name:
+        small = ["encoder.conv1.weight", "encoder.layer4.2.bn2.weight", "head.conv5a.1.weight", "head.sa.gamma", "head.sa.query_conv.weight",
+                 "head.sa.key_conv.bias", "head.sa.value_conv.bias", "head.sc.gamma", "head.conv52.1.weight", "head.conv6.1.weight",
+                 "head.conv7.1.bias", "head.conv8.1.weight"]
     if "hrnet" in name:
         small = ["encoder.conv1.weight", "encoder.bn2.bias", "encoder.layer1.0.conv3.weight", "encoder.transition1.1.0.0.weight",
                  "encoder.stage2.0.fuse_layers.0.1.0.weight", "encoder.stage4.0.fuse_layers.3.0.1.0.weight",
@@ -216,7 +228,7 @@ def run_train_case(case):
                         (k.startswith("encoder.bn1") or "image_pooling" in k or "layer4.2.bn3" in k or "block21.sep_conv3.block.bn_point" in k
                          or k.startswith("encoder.conv1.bn") or "block5.3.conv.3" in k or "hrnet_head.last_layer.1" in k
                          or "stage4.0.fuse_layers.3.0.1.1" in k)},
-               bn_momentum=bn_momentum, oracle_vs_ref_worst_grad_rel=worst)
+               bn_momentum=bn_momentum, more_masks=more_masks, oracle_vs_ref_worst_grad_rel=worst)
     torch.save(out, os.path.join(HERE, case + ".pt"))
     print(f"{case}: loss {float(loss):.6f}; worst grad rel-L2 oracle vs reference {worst:.2e}; {len(ref_grads)} grads")
 

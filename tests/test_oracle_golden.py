@@ -65,7 +65,7 @@ def _digest(grads, seed=12345):
 
 @pytest.mark.parametrize("case", ["train_dlv3p_resnet101_65x97_b4", "train_dlv3p_xception65_65x97_b4",
                                   "train_dlv3p_mobilenetv2_64x96_b4", "train_ccnet_resnet101_65x97_b2",
-                                  "train_hrnet_w18s_64x96_b2"])
+                                  "train_hrnet_w18s_64x96_b2", "train_danet_resnet101_64x96_b2"])
 def test_training_step_matches_reference_fixture(case):
     """Oracle train step (train-mode BN, Dropout2d mask, CE(ignore -1), backward, SGD groups) against the real reference's
     tools/train.py iteration recorded in tests/golden/train_dlv3p_resnet101_65x97_b4.pt: loss, a (norm, random projection)
@@ -77,6 +77,7 @@ def test_training_step_matches_reference_fixture(case):
     x = torch.randn(*fx["shape"], generator=g)
     target = torch.randint(-1, 19, (n, h, w), generator=g)
     P.dropout_masks[fx.get("mask_key", "head.aspp.dropout")] = fx["mask"]
+    P.dropout_masks.update(fx.get("more_masks", {}))      # DANet: three Dropout2d layers
     P.bn_momentum = fx.get("bn_momentum", 0.1)          # MODEL.BN_MOMENTUM of the YAML (HRNet: 0.01), solver/optimizer.py:37-39
     before = {k: v.clone() for k, v in P.t.items()}
     loss, grads, out, low = R.loss_and_grads(fx["model"], P, x, target)
@@ -100,7 +101,7 @@ def test_training_step_matches_reference_fixture(case):
     for k, (nrm, proj) in fx["stepped_digest"].items():
         assert abs(sd[k][0] - nrm) <= 1e-4 * nrm + 1e-9, k
     enc0 = "encoder.conv1.weight" if "encoder.conv1.weight" in fx["hyper"] else "encoder.conv1.conv.weight"
-    head0 = next(k for k in ("head.block.2.weight", "head.out.weight", "hrnet_head.last_layer.3.weight") if k in fx["hyper"])
+    head0 = next(k for k in ("head.block.2.weight", "head.out.weight", "hrnet_head.last_layer.3.weight", "head.conv8.1.weight") if k in fx["hyper"])
     factor = 1.0 if "hrnet" in case else 10.0            # SOLVER.DECODER_LR_FACTOR: 10 in the DeepLab / CCNet YAMLs, default 1
     assert fx["hyper"][head0][0] == pytest.approx(factor * fx["hyper"][enc0][0])
 
