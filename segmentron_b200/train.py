@@ -655,6 +655,201 @@ class TrainPlan:
         self.tape.append(backward)
         return y
 
+    def sum_losses(self, triples):
+        """out3 = sum of the per-output (loss, 1/valid, valid) triples (MixSoftmaxCrossEntropyLoss._multiple_forward,
+        solver/loss.py:31-36); `triples` is one contiguous [k][3] buffer."""
+        k = triples.numel() // 3
+        self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(triples), k, 1, 3, _ptr(self.out3), 0, 1, 0, 1.0),
+                 partial=triples, slabs=k, K=1, c=3, out=self.out3, sk=0, sc=1, accumulate=0, scale=1.0)
+
+    def dropout(self, x, name):
+        """nn.Dropout2d on an activation that is not followed by BatchNorm (DANetHead.conv6/7/8, models/danet.py:64-68): the
+        [n][c] mask (already scaled by 1/(1-p)) is an input of the plan, refreshed per step by the trainer."""
+        n, h, w_, c = x.t.shape
+        mask = self.f32(n, c)
+        mask.fill_(1.0)
+        self.masks[name] = mask
+        z = Act(self, self.new(n, h, w_, c))
+        rows, hw = n * h * w_, h * w_
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(x.t), None, None, None, _ptr(mask), _ptr(z.t), rows, hw, c, x.t.stride(2), 0, z.t.stride(2), 0, self.dt),
+                 y=x.t, scale=None, shift=None, residual=None, nc_scale=mask, z=z.t, act=None)
+
+        def backward():
+            dz = z.grad()
+            gx, acc = x.take()
+            self.add("bn_bwd_apply", self.lib.segb200_bn_bwd_apply,
+                     (_ptr(dz), None, None, None, None, None, None, None, float(rows), _ptr(mask), None, _ptr(gx), int(acc), rows, hw, c,
+                      dz.stride(2), 0, 0, 0, gx.stride(2), 0, self.dt),
+                     dz=dz, z=None, y=None, st={}, count=float(rows), nc_scale=mask, dy=None, dres=gx, dres_acc=acc, act=None)
+            if z.parent is None:
+                self.pool_put(dz)
+        self.tape.append(backward)
+        return z
+
+    def _gamma_vec(self, gname, c):
+        """[c] fp32 copies of a scalar parameter (gather_cast with a constant index table): refreshed inside the step because the
+        optimizer moves gamma"""
+        S = self.S
+        idx = torch.full((c,), S.meta[gname]["off"], dtype=torch.int32, device=self.device)
+        vec = self.f32(c)
+        self.keep.append(idx)
+        self.add("gather_cast", self.lib.segb200_gather_cast, (_ptr(S.master), _ptr(idx), _ptr(vec), c, L.F32), src=S.master, index=idx,
+                 dst=vec)
+        return vec
+
+    def _transpose(self, x2d, rows, cols, x_ld, out, pitch):
+        """out[cols][pitch] (16-bit) <- x2d[rows][x_ld] transposed (segb200_nhwc_to_cn; columns rows..pitch-1 of `out` stay zero)"""
+        self.add("transpose", self.lib.segb200_nhwc_to_cn, (_ptr(x2d), _ptr(out), 1, cols, rows, x_ld, pitch, self.dt), x=x2d, y=out,
+                 rows=rows, cols=cols, x_ld=x_ld, pitch=pitch)
+
+    def _gamma_residual_bwd(self, y, o, x, gname, gvec, c):
+        """shared tail of the two attention units, y = gamma * o + x:  dx (+)= dy;  dgamma += sum(dy * o);  -> do = gamma * dy"""
+        S = self.S
+        dy = y.grad()
+        n, h, w_, _ = dy.shape
+        rows, hw = n * h * w_, h * w_
+        gx, acc = x.take()
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(dy), None, None, _ptr(gx) if acc else None, None, _ptr(gx), rows, hw, c, dy.stride(2), gx.stride(2) if acc else 0,
+                  gx.stride(2), 0, self.dt), y=dy, scale=None, shift=None, residual=gx if acc else None, nc_scale=None, z=gx, act=None)
+        slabs = self.lib.segb200_reduce_slabs(rows, c, 0)
+        partial, sums = self.f32(slabs * 2 * c), self.f32(2, c)
+        self.add("bn_bwd_reduce", self.lib.segb200_bn_bwd_reduce,
+                 (_ptr(dy), None, _ptr(o), None, None, None, _ptr(partial), rows, hw, c, dy.stride(2), 0, o.stride(2), 0, self.dt, 0),
+                 dz=dy, z=None, y=o, st=dict(mean=None, invstd=None, partial=partial), nc_scale=None, act=None, c=c)
+        self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize, (_ptr(partial), slabs, c, None, None, _ptr(sums), None, None),
+                 st=dict(partial=partial, slabs=slabs, sums=sums), c=c, dgamma=None, dbeta=None)
+        gg = S.view(S.grad, gname)
+        self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(sums[1]), c, 1, 1, _ptr(gg), 0, 1, 1, 1.0),
+                 partial=sums[1], slabs=c, K=1, c=1, out=gg, sk=0, sc=1, accumulate=1, scale=1.0)
+        do = self.pool_get(n, h, w_, c)
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(dy), _ptr(gvec), None, None, None, _ptr(do), rows, hw, c, dy.stride(2), 0, do.stride(2), 0, self.dt),
+                 y=dy, scale=gvec, shift=None, residual=None, nc_scale=None, z=do, act=None)
+        if y.parent is None:
+            self.pool_put(dy)
+        return do, gx
+
+    def pam_unit(self, x, prefix):
+        """PAM_Module in training (modules/module.py:100-131), attention materialised per image like the reference's
+        bmm / softmax / bmm: S = Q K^T -> row_softmax -> P (kept, 16-bit) -> o = P V; y = gamma o + x.  Backward: D = do V^T ->
+        row_softmax_bwd -> dV = P^T do, dQ = dS K, dK = dS^T Q (GEMMs over transposed copies); the three 1x1 convs are conv_units."""
+        S = self.S
+        n, h, w_, c = x.t.shape
+        ntok = h * w_
+        if ntok % 8 or c % 64:
+            raise RuntimeError("segb200: the PAM training unit needs h*w % 8 == 0 and channels % 64 == 0")
+        q = self.conv_unit(x, prefix + ".query_conv.weight", bias=prefix + ".query_conv.bias")
+        k = self.conv_unit(x, prefix + ".key_conv.weight", bias=prefix + ".key_conv.bias")
+        v = self.conv_unit(x, prefix + ".value_conv.weight", bias=prefix + ".value_conv.bias")
+        cq = q.t.shape[3]
+        if cq % fold.conv_kblock(cq):
+            raise RuntimeError("segb200: the PAM training unit needs a query depth that is a multiple of the GEMM K block")
+        pitch = fold.round_up(ntok, 64)
+        gname = prefix + ".gamma"
+        gvec = self._gamma_vec(gname, c)
+        one = self.f32(1)
+        one.fill_(1.0)
+        probs = [self.new(1, 1, ntok, pitch) for _ in range(n)]
+        energy = self.f32(1, 1, ntok, ntok)
+        vt = self.new(1, 1, c, pitch)[0, 0]
+        o = self.new(n, h, w_, c)
+        y = Act(self, self.new(n, h, w_, c))
+        for b in range(n):
+            self.conv(q.t[b].view(1, 1, ntok, cq), k.t[b].view(ntok, 1, cq), energy, cin=cq, cout=ntok)
+            self.add("row_softmax", self.lib.segb200_row_softmax, (_ptr(energy), _ptr(probs[b]), ntok, ntok, ntok, pitch, self.dt),
+                     s=energy, p=probs[b], n=ntok)
+            self._transpose(v.t[b], ntok, c, c, vt, pitch)
+            self.conv(probs[b], vt.view(c, 1, pitch), o[b].view(1, 1, ntok, c), cin=pitch, cout=c)
+        rows, hw = n * ntok, ntok
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(o), _ptr(gvec), None, _ptr(x.t), None, _ptr(y.t), rows, hw, c, o.stride(2), x.t.stride(2), y.t.stride(2), 0, self.dt),
+                 y=o, scale=gvec, shift=None, residual=x.t, nc_scale=None, z=y.t, act=None)
+
+        def backward():
+            do, _ = self._gamma_residual_bwd(y, o, x, gname, gvec, c)
+            gq, aq = q.take()
+            gk, ak = k.take()
+            gv, av = v.take()
+            assert not (aq or ak or av)
+            dmat = self.f32(1, 1, ntok, ntok)
+            ds = self.pool_get(1, 1, ntok, pitch)
+            tr = self.pool_get(1, 1, ntok, pitch)
+            dot = self.pool_get(1, 1, c, pitch)
+            kt = self.pool_get(1, 1, cq, pitch)
+            part = self.f32(ntok)
+            for t in (tr, dot, kt):                           # K tails of the transposed operands must be zero
+                self.cur.append(Step("zero", (lambda s_, t=t: t.zero_()), dict(t=t)))
+            for b in range(n):
+                self.conv(do[b].view(1, 1, ntok, c), v.t[b].view(ntok, 1, c), dmat, cin=c, cout=ntok)
+                self.add("row_softmax_bwd", self.lib.segb200_row_softmax_bwd,
+                         (_ptr(probs[b]), _ptr(dmat), _ptr(one), _ptr(ds), _ptr(part), ntok, ntok, pitch, ntok, pitch, self.dt),
+                         p=probs[b], d=dmat, gamma=one, ds=ds, part=part, n=ntok)
+                self._transpose(probs[b][0, 0], ntok, ntok, pitch, tr[0, 0], pitch)
+                self._transpose(do[b], ntok, c, do.stride(2), dot[0, 0], pitch)
+                self.conv(tr, dot[0, 0].view(c, 1, pitch), gv[b].view(1, 1, ntok, c), cin=pitch, cout=c)
+                self._transpose(k.t[b], ntok, cq, cq, kt[0, 0], pitch)
+                self.conv(ds, kt[0, 0].view(cq, 1, pitch), gq[b].view(1, 1, ntok, cq), cin=pitch, cout=cq)
+                self._transpose(ds[0, 0], ntok, ntok, pitch, tr[0, 0], pitch)
+                self._transpose(q.t[b], ntok, cq, cq, kt[0, 0], pitch)
+                self.conv(tr, kt[0, 0].view(cq, 1, pitch), gk[b].view(1, 1, ntok, cq), cin=pitch, cout=cq)
+            for t in (ds, tr, dot, kt, do):
+                self.pool_put(t)
+            self.mark_done(gname)
+        self.tape.append(backward)
+        return y
+
+    def cam_unit(self, x, prefix):
+        """CAM_Module in training (modules/module.py:134-162): E = X^T X -> cam_softmax -> A (kept); o = A X; y = gamma o + x.
+        Backward (csrc/cam_bwd.cu): G = do^T x -> dE = -A (G - sum A G) -> dx += do A + x (dE + dE^T)."""
+        n, h, w_, c = x.t.shape
+        ntok = h * w_
+        pitch = fold.round_up(ntok, 64)
+        cpad = fold.round_up(c, fold.conv_kblock(c))
+        gname = prefix + ".gamma"
+        gvec = self._gamma_vec(gname, c)
+        one = self.f32(1)
+        one.fill_(1.0)
+        xts = [self.new(1, 1, c, pitch) for _ in range(n)]
+        atts = [self.new(1, 1, c, cpad) for _ in range(n)]
+        energy = self.f32(1, 1, c, c)
+        o = self.new(n, h, w_, c)
+        y = Act(self, self.new(n, h, w_, c))
+        for b in range(n):
+            self._transpose(x.t[b], ntok, c, x.t.stride(2), xts[b][0, 0], pitch)
+            self.conv(xts[b], xts[b][0, 0].view(c, 1, pitch), energy, cin=pitch, cout=c)
+            self.add("cam_softmax", self.lib.segb200_cam_softmax, (_ptr(energy), _ptr(atts[b]), c, c, c, cpad, self.dt), e=energy,
+                     att=atts[b], c=c)
+            self.conv(x.t[b:b + 1], atts[b][0, 0].view(c, 1, cpad), o[b:b + 1], cin=c, cout=c)
+        rows, hw = n * ntok, ntok
+        self.add("bn_apply", self.lib.segb200_bn_apply,
+                 (_ptr(o), _ptr(gvec), None, _ptr(x.t), None, _ptr(y.t), rows, hw, c, o.stride(2), x.t.stride(2), y.t.stride(2), 0, self.dt),
+                 y=o, scale=gvec, shift=None, residual=x.t, nc_scale=None, z=y.t, act=None)
+
+        def backward():
+            do, gx = self._gamma_residual_bwd(y, o, x, gname, gvec, c)
+            dot = self.pool_get(1, 1, c, pitch)
+            self.cur.append(Step("zero", (lambda s_, t=dot: t.zero_()), dict(t=dot)))
+            gmat, de, part = self.f32(1, 1, c, c), self.f32(c, c), self.f32(c)
+            w1, w2 = self.pool_get(1, 1, c, cpad), self.pool_get(1, 1, c, cpad)
+            for b in range(n):
+                self._transpose(do[b], ntok, c, do.stride(2), dot[0, 0], pitch)
+                self.conv(dot, xts[b][0, 0].view(c, 1, pitch), gmat, cin=pitch, cout=c)
+                self.add("cam_softmax_bwd", self.lib.segb200_cam_softmax_bwd,
+                         (_ptr(atts[b]), _ptr(gmat), _ptr(one), _ptr(de), _ptr(part), c, cpad, c, c, self.dt),
+                         att=atts[b], g=gmat, gamma=one, de=de, part=part, c=c)
+                self.add("cam_bwd_pack", self.lib.segb200_cam_bwd_pack,
+                         (_ptr(atts[b]), _ptr(de), _ptr(one), _ptr(w1), _ptr(w2), c, cpad, c, cpad, self.dt),
+                         att=atts[b], de=de, gamma=one, w1=w1, w2=w2, c=c)
+                self.conv(do[b:b + 1], w1[0, 0].view(c, 1, cpad), gx[b:b + 1], cin=c, cout=c, residual=gx[b:b + 1])
+                self.conv(x.t[b:b + 1], w2[0, 0].view(c, 1, cpad), gx[b:b + 1], cin=c, cout=c, residual=gx[b:b + 1])
+            for t in (dot, w1, w2, do):
+                self.pool_put(t)
+            self.mark_done(gname)
+        self.tape.append(backward)
+        return y
+
     def image_pool(self, x):
         """nn.AdaptiveAvgPool2d(1) (module.py:52) -> [n,1,1,c]"""
         n, h, w_, c = x.t.shape
@@ -690,23 +885,26 @@ class TrainPlan:
             self.pool_put(mean)
         self.tape.append(backward)
 
-    def loss(self, logits, align=True):
-        """fused F.interpolate(logits, (H, W), align_corners=align) + CrossEntropyLoss(ignore_index) + its gradient"""
+    def loss(self, logits, align=True, out3=None):
+        """fused F.interpolate(logits, (H, W), align_corners=align) + CrossEntropyLoss(ignore_index) + its gradient.  out3: where
+        (mean loss, 1/valid, valid) go -- the plan's own triple by default; models with several outputs pass one triple per output
+        and sum them with sum_losses()."""
+        out3 = self.out3 if out3 is None else out3
         n, hi, wi, _ = logits.t.shape
         c8 = fold.round_up(self.nclass, 8)
         dfull = self.new(n, self.H, self.W, c8)
         nb = self.lib.segb200_upsample_ce_blocks(n, self.H, self.W)
         partial = self.f32(2 * nb)
         self.add("upsample_ce", self.lib.segb200_upsample_ce,
-                 (_ptr(logits.t), _ptr(self.target), _ptr(dfull), _ptr(partial), _ptr(self.out3), n, hi, wi, self.nclass,
+                 (_ptr(logits.t), _ptr(self.target), _ptr(dfull), _ptr(partial), _ptr(out3), n, hi, wi, self.nclass,
                   logits.t.stride(2), self.H, self.W, dfull.stride(2), int(align), self.ignore_index, self.dt),
-                 logits=logits.t, target=self.target, dfull=dfull, out3=self.out3, nclass=self.nclass, ignore_index=self.ignore_index,
+                 logits=logits.t, target=self.target, dfull=dfull, out3=out3, nclass=self.nclass, ignore_index=self.ignore_index,
                  align=align)
 
         def backward():
             gl, acc = logits.take()
             assert not acc
-            inv = self.out3[1:2]
+            inv = out3[1:2]
             self.add("bilinear_bwd", self.lib.segb200_bilinear_nhwc_bwd,
                      (_ptr(dfull), _ptr(gl), n, hi, wi, c8, gl.stride(2), self.H, self.W, dfull.stride(2), int(align), 0, _ptr(inv),
                       self.dt), dy=dfull, dx=gl, accumulate=False, gscale=inv, align=align)
@@ -751,7 +949,7 @@ def _bottleneck(pl, x, prefix, planes, stride, dilation, downsample, out=None):
     return pl.conv_unit(y, prefix + ".conv3.weight", prefix + ".bn3", "relu", residual=idn, out=out)
 
 
-def _resnet(pl, layers, output_stride, c4_out=None):
+def _resnet(pl, layers, output_stride, c4_out=None, multi_dilation=None):
     """ResNetV1.forward (backbones/resnet.py:183-199), stride/dilation table :90-100,:149-179."""
     dil, strides = {32: ((1, 1), (2, 2)), 16: ((1, 2), (2, 1)), 8: ((2, 4), (1, 1))}[output_stride]
     p = "encoder"
@@ -763,19 +961,20 @@ def _resnet(pl, layers, output_stride, c4_out=None):
     x = pl.maxpool(x)
     inpl = [64]
 
-    def make_layer(x, name, planes, blocks, stride=1, dilation=1, last_out=None):
+    def make_layer(x, name, planes, blocks, stride=1, dilation=1, last_out=None, mg=None):
         ds = stride != 1 or inpl[0] != planes * 4
-        first_d = 1 if dilation in (1, 2) else 2
+        first_d = mg[0] if mg else (1 if dilation in (1, 2) else 2)            # resnet.py:151-161 (multi-grid: DANet)
         x = _bottleneck(pl, x, f"{p}.{name}.0", planes, stride, first_d, ds)
         inpl[0] = planes * 4
         for i in range(1, blocks):
-            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, dilation, False, out=last_out if i == blocks - 1 else None)
+            d = mg[i % len(mg)] if mg else dilation                              # resnet.py:166-175
+            x = _bottleneck(pl, x, f"{p}.{name}.{i}", planes, 1, d, False, out=last_out if i == blocks - 1 else None)
         return x
 
     c1 = make_layer(x, "layer1", 64, layers[0])
     c2 = make_layer(c1, "layer2", 128, layers[1], 2)
     c3 = make_layer(c2, "layer3", 256, layers[2], strides[0], dil[0])
-    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], last_out=c4_out)
+    c4 = make_layer(c3, "layer4", 512, layers[3], strides[1], dil[1], last_out=c4_out, mg=multi_dilation)
     return c1, c2, c3, c4
 
 
@@ -1028,6 +1227,32 @@ def build_hrnet_train(pl, hcfg):
     return pl
 
 
+def build_danet_train(pl, output_stride=8, multi_dilation=(4, 8, 16)):
+    """DANet.forward (models/danet.py:26-41) + DANetHead (:44-88): ResNet101 (OS8, multi-grid) -> conv5a -> PAM -> conv51 and
+    conv5c -> CAM -> conv52; three classifiers, each behind its own Dropout2d, on sa_conv, sc_conv and their sum; the loss is
+    the sum of the three cross-entropies (solver/loss.py:31-36)."""
+    _, _, _, c4 = _resnet(pl, (3, 4, 23, 3), output_stride, multi_dilation=list(multi_dilation) if multi_dilation else None)
+    n, hh, ww, _ = c4.t.shape
+    hd = "head"
+    feat1 = pl.conv_unit(c4, hd + ".conv5a.0.weight", hd + ".conv5a.1", "relu", k=3, pad=1)
+    sa_conv = pl.conv_unit(pl.pam_unit(feat1, hd + ".sa"), hd + ".conv51.0.weight", hd + ".conv51.1", "relu", k=3, pad=1)
+    feat2 = pl.conv_unit(c4, hd + ".conv5c.0.weight", hd + ".conv5c.1", "relu", k=3, pad=1)
+    sc_conv = pl.conv_unit(pl.cam_unit(feat2, hd + ".sc"), hd + ".conv52.0.weight", hd + ".conv52.1", "relu", k=3, pad=1)
+    feat_sum = pl.upsample_add(sa_conv, sc_conv, 0)
+    triples = pl.f32(3, 3)
+    c8 = fold.round_up(pl.nclass, 8)
+    # output order of DANetHead.forward: (sasc, sa, sc); the dropout masks are drawn in the order conv6, conv7, conv8
+    for i, (src, name) in enumerate(((feat_sum, "conv8"), (sa_conv, "conv6"), (sc_conv, "conv7"))):
+        logits = Act(pl, pl.new(n, hh, ww, c8, ld=32))
+        pl.conv_unit(pl.dropout(src, f"{hd}.{name}.0"), f"{hd}.{name}.1.weight", bias=f"{hd}.{name}.1.bias", out=logits)
+        if i == 0:
+            pl.logits = logits
+        pl.loss(logits, out3=triples[i])
+    pl.sum_losses(triples)
+    pl.build_backward()
+    return pl
+
+
 class DeepLabV3PlusTrainerB200:
     """``trainer.step(images_nchw_fp32, targets_int64) -> loss`` : one iteration of tools/train.py:135-147 (forward, criterion,
     zero_grad, backward, optimizer.step) for DeepLabV3_Plus / ResNet on the CUDA engine.  ``state_dict()`` returns reference-named
@@ -1188,3 +1413,19 @@ class HRNetTrainerB200(DeepLabV3PlusTrainerB200):
 
     def _build(self, pl):
         build_hrnet_train(pl, self.hcfg)
+
+
+
+class DANetTrainerB200(DeepLabV3PlusTrainerB200):
+    """``trainer.step(images, targets)`` for DANet / ResNet101 (models/danet.py; OS8, multi-grid 4/8/16): position and channel
+    attention run with the attention matrices materialised per image (as the reference does), three classifiers behind three
+    Dropout2d layers, loss = sum of the three cross-entropies.  Plan verified against the oracle in fp64 on the CPU
+    (tests/test_train_plan_cpu.py); GPU replay: SEGB200_TEST_ALL until it has run once.  Needs (H/8)*(W/8) % 8 == 0."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=8, multi_dilation=(4, 8, 16), **kw):
+        super().__init__(state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride, use_aspp=False,
+                         use_decoder=False, **kw)
+        self.multi_dilation = multi_dilation
+
+    def _build(self, pl):
+        build_danet_train(pl, self.cfg["output_stride"], self.multi_dilation)

@@ -185,6 +185,49 @@ def run_step(st):
         gz = g.reshape(n, h // s_, s_, w // s_, s_, c).sum((2, 4))
         da.copy_(((da.to(CD) if i["acc_a"] else 0) + g).to(da.dtype))
         dz.copy_(((dz.to(CD) if i["acc_z"] else 0) + gz).to(dz.dtype))
+    elif kind == "gather_cast":
+        gather_cast(i["src"], i["index"], i["dst"])
+    elif kind == "transpose":                   # segb200_nhwc_to_cn: y[col][row] = x[row][col]; y's columns >= rows are left alone
+        x, y, rows, cols = i["x"], i["y"], i["rows"], i["cols"]
+        x2 = x.reshape(-1, x.shape[-1]) if x.dim() > 2 else x
+        src = torch.as_strided(x2, (rows, cols), (i["x_ld"], 1), x2.storage_offset())
+        y2 = y.reshape(-1, y.shape[-1])
+        y2[:cols, :rows] = src.t().to(y.dtype)
+    elif kind == "row_softmax":
+        n = i["n"]
+        s2, p2 = i["s"].reshape(-1, i["s"].shape[-1]), i["p"].reshape(-1, i["p"].shape[-1])
+        p2.zero_()
+        p2[:n, :n] = torch.softmax(s2[:n, :n].to(CD), 1).to(p2.dtype)
+    elif kind == "row_softmax_bwd":             # r = sum_j P D; dS = gamma P (D - r)
+        n = i["n"]
+        p2 = i["p"].reshape(-1, i["p"].shape[-1])[:n, :n].to(CD)
+        d2 = i["d"].reshape(-1, i["d"].shape[-1])[:n, :n].to(CD)
+        r = (p2 * d2).sum(1, keepdim=True)
+        ds2 = i["ds"].reshape(-1, i["ds"].shape[-1])
+        ds2.zero_()
+        ds2[:n, :n] = (float(i["gamma"][0]) * p2 * (d2 - r)).to(ds2.dtype)
+        i["part"][:n] = r[:, 0].to(i["part"].dtype)
+    elif kind == "cam_softmax":                 # A = softmax(rowmax(E) - E)
+        c = i["c"]
+        e = i["e"].reshape(-1, i["e"].shape[-1])[:c, :c].to(CD)
+        a2 = i["att"].reshape(-1, i["att"].shape[-1])
+        a2.zero_()
+        a2[:c, :c] = torch.softmax(e.max(1, keepdim=True)[0] - e, 1).to(a2.dtype)
+    elif kind == "cam_softmax_bwd":             # r = sum A G; dE = -gamma A (G - r)
+        c = i["c"]
+        a2 = i["att"].reshape(-1, i["att"].shape[-1])[:c, :c].to(CD)
+        g2 = i["g"].reshape(-1, i["g"].shape[-1])[:c, :c].to(CD)
+        r = (a2 * g2).sum(1, keepdim=True)
+        i["de"][:c, :c] = (-float(i["gamma"][0]) * a2 * (g2 - r)).to(i["de"].dtype)
+        i["part"][:c] = r[:, 0].to(i["part"].dtype)
+    elif kind == "cam_bwd_pack":                # w1 = gamma A^T, w2 = dE + dE^T (zero K padding)
+        c = i["c"]
+        a2 = i["att"].reshape(-1, i["att"].shape[-1])[:c, :c].to(CD)
+        de = i["de"][:c, :c].to(CD)
+        w1, w2 = i["w1"].reshape(-1, i["w1"].shape[-1]), i["w2"].reshape(-1, i["w2"].shape[-1])
+        w1.zero_(); w2.zero_()
+        w1[:c, :c] = (float(i["gamma"][0]) * a2.t()).to(w1.dtype)
+        w2[:c, :c] = (de + de.t()).to(w2.dtype)
     elif kind == "gap":
         i["y"].copy_(i["x"].to(CD).mean((1, 2), keepdim=True).to(i["y"].dtype))
     elif kind == "nc_broadcast":

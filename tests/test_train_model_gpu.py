@@ -61,8 +61,20 @@ def _outputs(st):
         return [i["de"], i["part"]]
     if k in ("cca_gather", "cca_scatter"):
         return [i["out"]]
-    if k == "upsample_add":
+    if k in ("upsample_add", "transpose"):
         return [i["y"]]
+    if k == "gather_cast":
+        return [i["dst"]]
+    if k == "row_softmax":
+        return [i["p"]]
+    if k == "row_softmax_bwd":
+        return [i["ds"], i["part"]]
+    if k == "cam_softmax":
+        return [i["att"]]
+    if k == "cam_softmax_bwd":
+        return [i["de"], i["part"]]
+    if k == "cam_bwd_pack":
+        return [i["w1"], i["w2"]]
     if k == "upsample_add_bwd":
         return [i["da"], i["dz"]]
     raise NotImplementedError(k)
@@ -176,6 +188,21 @@ def test_every_launch_of_an_hrnet_training_step(dtype):
     pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), {})
     print(f"[hrnet {dtype}] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
     assert {"upsample_add", "upsample_add_bwd"} <= set(worst)
+
+
+@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="DANet model-level replay: written after the round's GPU budget was "
+                    "spent (plan verified in fp64 on the CPU); includes the PAM / CAM training kernels")
+def test_every_launch_of_a_danet_training_step():
+    from segmentron_b200.train import DANetTrainerB200
+    P = R.build_params("danet_resnet101", 51)
+    g = torch.Generator().manual_seed(5051)
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    target = torch.randint(-1, 19, (2, 64, 96), generator=g)
+    masks = {f"head.conv{j}.0": ((torch.rand(2, 512, 1, 1, generator=g) > 0.1).float() / 0.9).cuda() for j in (6, 7, 8)}
+    tr = DANetTrainerB200(P.state_dict(), dtype=torch.bfloat16)
+    pl, worst = _stepwise_check(tr, x.cuda(), target.cuda(), masks)
+    print(f"[danet] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
+    assert {"row_softmax", "row_softmax_bwd", "cam_softmax_bwd", "cam_bwd_pack"} <= set(worst)
 
 
 def test_training_step_end_to_end_vs_oracle():

@@ -158,3 +158,35 @@ def test_hrnet_train_plan_matches_oracle_on_cpu(dry_run):
         assert float((sd[k].double() - ref).norm() / (ref.norm() + 1e-12)) < 1e-6, k
     kinds = {s.kind for s in tr.plan_for(shape)["plan"].fwd + tr.plan_for(shape)["plan"].bwd}
     assert {"upsample_add", "upsample_add_bwd"} <= kinds
+
+
+def test_danet_train_plan_matches_oracle_on_cpu(dry_run):
+    """DANet / ResNet101 (models/danet.py; OS8 with the multi-grid dilations 4/8/16 in layer4): position attention with the
+    attention matrix materialised per image (Q K^T, row softmax, P V and the four backward GEMMs over transposed copies), channel
+    attention (Gram matrix, softmax(rowmax - E), its backward through dE + dE^T), the gamma residuals and their gradients, three
+    Dropout2d + classifier heads on sa, sc and sa + sc, and the summed cross-entropy of the three outputs."""
+    from segmentron_b200.train import DANetTrainerB200
+    seed, shape = 51, (2, 3, 64, 96)                         # 8 x 12 = 96 positions per image
+    P = R.build_params("danet_resnet101", seed)
+    g = torch.Generator().manual_seed(5000 + seed)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g)
+    masks = {f"head.conv{j}.0": (torch.rand(shape[0], 512, 1, 1, generator=g) > 0.1).double() / 0.9 for j in (6, 7, 8)}
+    tr = DANetTrainerB200(P.state_dict(), dtype=torch.float64, device="cpu", lr=0.02)
+    loss = E.forward_backward(tr, x, target, masks)
+    grads = tr.store.grads()
+    sd_mid = tr.state_dict()
+    P64 = P.to(dtype=torch.float64)
+    P64.frozen, P64.dropout_masks = True, dict(masks)
+    o_loss, o_grads, _, _ = R.loss_and_grads("danet_resnet101", P64, x.double(), target)
+    assert abs(float(loss) - float(o_loss)) < 1e-6 * abs(float(o_loss)), (float(loss), float(o_loss))
+    assert float(P.t["head.sa.gamma"]) != 0.0 and float(P.t["head.sc.gamma"]) != 0.0                  # non-vacuous attention
+    floor = 1e-6 * max(float(v.norm()) for v in o_grads.values())
+    assert set(grads) == set(o_grads)
+    worst = max(((float((grads[k] - gr).norm() / (gr.norm() + floor)), k) for k, gr in o_grads.items()))
+    assert worst[0] < 1e-6, worst
+    for k in sd_mid:
+        if k.endswith(("running_mean", "running_var")):
+            assert torch.allclose(sd_mid[k].double(), P64.t[k], atol=1e-6, rtol=1e-6), k
+    kinds = {s.kind for s in tr.plan_for(shape)["plan"].fwd + tr.plan_for(shape)["plan"].bwd}
+    assert {"row_softmax", "row_softmax_bwd", "cam_softmax", "cam_softmax_bwd", "cam_bwd_pack", "transpose", "upsample_add_bwd"} <= kinds

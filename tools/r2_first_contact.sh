@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 run() { echo "=== $*"; timeout 300 "$@" 2>&1 | tail -25; echo "=== exit ${PIPESTATUS[0]}"; }
 run python -m pytest tests/test_modules_gpu.py -q -k "errors_and_cache"                      # gated part: _ASPP batch-1 ValueError
 run python -m pytest tests/test_train_model_gpu.py -q -s -k "ccnet"                         # CCNet training plan, every launch
+run python -m pytest tests/test_train_model_gpu.py -q -s -k "danet"                         # DANet training plan, every launch (PAM / CAM training kernels)
 run python -m pytest tests/test_train_model_gpu.py -q -s -k "hrnet"                         # HRNet training plan, every launch (+ upsample_add_bwd)
 run python -m pytest tests/test_modules_gpu.py -q -k "cam_module_backward or pam_module_backward"   # CAM / PAM training drop-ins
 run python -m pytest tests/test_metric_gpu.py -q                                            # device-resident pixAcc / mIoU counts
