@@ -42,8 +42,12 @@ def ref_train_leg(P, x, target, fmt, iters):
 
     def step():
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = R.hrnet_seg(Pg, xb, nclass=19) if hr else R.deeplabv3plus(Pg, xb, nclass=19, **R.MODELS[MODEL])
-            loss = F.cross_entropy(out.float(), target, ignore_index=-1)
+            if MODEL == "danet_resnet101":            # three outputs, summed cross-entropy (solver/loss.py:31-36)
+                loss = sum(F.cross_entropy(o.float(), target, ignore_index=-1) for o in R.danet(Pg, xb, nclass=19))
+            else:
+                out = R.hrnet_seg(Pg, xb, nclass=19) if hr else (R.ccnet(Pg, xb, nclass=19) if MODEL == "ccnet_resnet101" else
+                                                                R.deeplabv3plus(Pg, xb, nclass=19, **R.MODELS[MODEL]))
+                loss = F.cross_entropy(out.float(), target, ignore_index=-1)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -70,20 +74,22 @@ def main():
     ap.add_argument("--width", type=int, default=2049)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--kernels", default=None)
-    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2", "hrnet"])
+    ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2", "hrnet", "danet", "ccnet"])
     ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
     global MODEL
-    MODEL = "hrnet_w18_small_v1" if args.backbone == "hrnet" else "deeplabv3plus_" + args.backbone
+    MODEL = {"hrnet": "hrnet_w18_small_v1", "danet": "danet_resnet101", "ccnet": "ccnet_resnet101"}.get(args.backbone, "deeplabv3plus_" + args.backbone)
     if args.backbone == "hrnet" and (args.height, args.width) == (1025, 2049):
         args.height, args.width = 1024, 2048         # HRNet needs multiples of 32 (nearest up-sampling + add in the fuse layers)
+    if args.backbone == "danet" and (args.height, args.width) == (1025, 2049):
+        args.height, args.width, args.batch = 768, 768, min(args.batch, 2)   # the DANet YAML's training crop; attention is O(N^2)
     import __graft_entry__ as ge
     ge.build()
     from oracle import segref as R          # parameter generator + the reference leg only
     from segmentron_b200 import parallel
-    from segmentron_b200.train import DeepLabV3PlusTrainerB200, HRNetTrainerB200
+    from segmentron_b200.train import CCNetTrainerB200, DANetTrainerB200, DeepLabV3PlusTrainerB200, HRNetTrainerB200
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     rank, world, local = parallel.init_from_env("nccl")
     torch.backends.cudnn.benchmark = True
@@ -94,6 +100,9 @@ def main():
     target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g).cuda()
     if args.backbone == "hrnet":
         tr = HRNetTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.01)
+    elif args.backbone in ("danet", "ccnet"):
+        tr = (DANetTrainerB200 if args.backbone == "danet" else CCNetTrainerB200)(P.state_dict(), dtype=torch.bfloat16, lr=0.02,
+                                                                                 dropout=not args.no_dropout)
     else:
         tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=args.backbone, dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout)
     losses = [float(tr.step(x, target)) for _ in range(max(args.warmup, 3))]
@@ -132,7 +141,7 @@ def main():
         tot = sum(a["ms"] for a in agg.values())
         mm = {k: agg[k] for k in ("conv", "wgrad") if k in agg and agg[k]["ms"] > 0}
         out = {"config": "c3_train" if args.backbone == "resnet101" else "train_" + args.backbone,
-               "what": f"{'HRNet-w18-small-v1' if args.backbone == 'hrnet' else 'DeepLabv3+/' + args.backbone} bf16 training step (fwd + CE loss + bwd + SGD) at "
+               "what": f"{MODEL} bf16 training step (fwd + CE loss + bwd + SGD) at "
                f"{args.height}x{args.width}, per-GPU batch {args.batch}", "n_gpus": world, "segb200_img_s": world * args.batch / (ms * 1e-3),
                "segb200_ms_per_step": ms, "launches_per_step": tr.n_launches(shape), "loss_first_steps": losses,
                "per_kind_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
