@@ -8,6 +8,7 @@
 //                                                                        W2 = dE + dE^T are packed here)
 // Both kernels work on C x C matrices (C = 512 in DANet): latency-bound, one warp per row.
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

@@ -10,6 +10,7 @@
 // Out-of-image taps are ZERO window entries, so the inner loop has no branches.  Bound: FP32 issue, then L2 (each x element is
 // read 3 times from L1/L2, once from HBM).
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

@@ -11,6 +11,7 @@
 // lerp_coord), the arithmetic order of upsample_bilinear2d; every place where the reference materialises a tensor in the model
 // dtype (outputs +=, the resized score, scores +=) rounds to that dtype here too.
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

@@ -6,6 +6,7 @@
 //   dz (+)= sum of g over each 2^k x 2^k block (fp32, fixed order)
 // One thread per low-resolution pixel and 8-channel vector.  Bound: HBM (reads dy and y once, writes da once).
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

@@ -21,6 +21,7 @@
 #include <climits>
 
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

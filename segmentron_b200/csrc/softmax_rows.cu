@@ -6,6 +6,7 @@
 //   row_softmax_bwd : r = sum_j P D (-> partial[r], the gamma gradient term);  dS = (*gamma) * P * (D - r), zero padding as above
 // One warp per row; S / D are fp32 GEMM outputs.  Bound: HBM (N^2 elements read once, written once).
 #include "vec.cuh"
+#include "../../include/segb200.h"
 
 namespace segb200 {
 

@@ -255,3 +255,40 @@ def test_evaluate_driver_size_rules_and_errors(built):
     assert lib.segb200_eval_prepare(buf, buf, 1, 3, 8, 8, 12, 12, 8, 8, 0, None) < 0          # padded size smaller than the resize
     assert lib.segb200_eval_accumulate(buf, buf, 7, 1, 3, 8, 8, 8, 8, 8, 8, 0, 0, None) < 0   # bad dtype
     assert lib.segb200_eval_accumulate(buf, buf, L.F32, 1, 3, 8, 8, 9, 8, 8, 8, 0, 0, None) < 0
+
+
+def test_ctypes_signatures_match_the_header():
+    """lib.SYMBOLS (the ctypes argtypes) against the prototypes of include/segb200.h, parameter by parameter: pointer / int /
+    long long / float / double classes must agree (every .cu includes the header, so the compiler already checks the definitions
+    against it; this closes the loop on the Python side)."""
+    import ctypes as C
+    import re
+    from segmentron_b200 import lib as L
+    src = open(os.path.join(ROOT, "include", "segb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|const char\s*\*)\s+(segb200_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(protos) == set(L.SYMBOLS), set(protos) ^ set(L.SYMBOLS)
+
+    def cls_of_c(param):
+        p = " ".join(param.split())
+        if p in ("void", ""):
+            return None
+        if "*" in p:
+            return "ptr"
+        if "long long" in p:
+            return "ll"
+        if "double" in p:
+            return "f64"
+        if "float" in p:
+            return "f32"
+        assert "int" in p, p
+        return "int"
+
+    def cls_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "int", C.c_int32: "int", C.c_longlong: "ll", C.c_float: "f32", C.c_double: "f64"}[t]
+    for name, params in protos.items():
+        want = [c for c in (cls_of_c(p) for p in params.split(",")) if c is not None]
+        got = [cls_of_ctypes(t) for t in L.SYMBOLS[name][1]]
+        assert want == got, (name, want, got)

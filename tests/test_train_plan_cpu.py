@@ -190,3 +190,37 @@ def test_danet_train_plan_matches_oracle_on_cpu(dry_run):
             assert torch.allclose(sd_mid[k].double(), P64.t[k], atol=1e-6, rtol=1e-6), k
     kinds = {s.kind for s in tr.plan_for(shape)["plan"].fwd + tr.plan_for(shape)["plan"].bwd}
     assert {"row_softmax", "row_softmax_bwd", "cam_softmax", "cam_softmax_bwd", "cam_bwd_pack", "transpose", "upsample_add_bwd"} <= kinds
+
+
+def test_every_plan_step_matches_its_c_signature(dry_run, monkeypatch):
+    """Arity / type-position check of EVERY kernel call the plans record (all six model families): the argument tuple handed to
+    TrainPlan.add must line up with the ctypes signature declared from include/segb200.h (pointers where pointers go, ints where
+    ints go, floats where floats go) -- a mistake here would otherwise only surface as a TypeError or a wild pointer on the GPU."""
+    import ctypes as C
+    from segmentron_b200 import train as T
+    seen = {}
+    orig_add = T.TrainPlan.add
+
+    def checked_add(self, kind, fn, args, **info):
+        sig = fn.argtypes
+        assert sig is not None and len(args) + 1 == len(sig), (kind, fn.__name__, len(args), len(sig) if sig else None)
+        for pos, (a, t) in enumerate(zip(args, sig)):
+            if t is C.c_void_p:
+                assert a is None or isinstance(a, C.c_void_p), (kind, fn.__name__, pos, type(a))
+            elif t in (C.c_int, C.c_longlong):
+                assert isinstance(a, int) and not isinstance(a, bool), (kind, fn.__name__, pos, a)
+            elif t in (C.c_float, C.c_double):
+                assert isinstance(a, (int, float)) and not isinstance(a, bool), (kind, fn.__name__, pos, a)
+        seen[fn.__name__] = seen.get(fn.__name__, 0) + 1
+        return orig_add(self, kind, fn, args, **info)
+    monkeypatch.setattr(T.TrainPlan, "add", checked_add)
+    cases = [(T.DeepLabV3PlusTrainerB200, "deeplabv3plus_resnet101", dict(backbone="resnet101"), (2, 3, 65, 97)),
+             (T.DeepLabV3PlusTrainerB200, "deeplabv3plus_xception65", dict(backbone="xception65"), (2, 3, 65, 97)),
+             (T.DeepLabV3PlusTrainerB200, "deeplabv3plus_mobilenet_v2", dict(backbone="mobilenet_v2"), (2, 3, 64, 96)),
+             (T.CCNetTrainerB200, "ccnet_resnet101", {}, (2, 3, 65, 97)), (T.HRNetTrainerB200, "hrnet_w18_small_v1", {}, (2, 3, 64, 96)),
+             (T.DANetTrainerB200, "danet_resnet101", {}, (2, 3, 64, 96))]
+    for cls, model, kw, shape in cases:
+        tr = cls(R.build_params(model, 1).state_dict(), dtype=torch.float64, device="cpu", **kw)
+        tr.plan_for(shape)
+    assert {"segb200_upsample_add_bwd", "segb200_row_softmax_bwd", "segb200_cam_bwd_pack", "segb200_cca_weight_bwd",
+            "segb200_upsample_ce", "segb200_dw_wgrad"} <= set(seen), sorted(seen)
