@@ -292,3 +292,40 @@ def test_ctypes_signatures_match_the_header():
         want = [c for c in (cls_of_c(p) for p in params.split(",")) if c is not None]
         got = [cls_of_ctypes(t) for t in L.SYMBOLS[name][1]]
         assert want == got, (name, want, got)
+
+
+def test_metric_wrapper_call_sites_match_the_signatures(monkeypatch):
+    """segmentron_b200.metric's three C calls (update, update_lowres, accumulate): argument tuples checked against lib.SYMBOLS by a
+    recording stand-in library (the wrappers themselves need CUDA tensors, so the device check is bypassed for this test only)."""
+    import ctypes as C
+    import torch
+    from segmentron_b200 import lib as L, metric as MM, ops
+    calls = []
+
+    class Rec:
+        def __getattr__(self, name):
+            sig = L.SYMBOLS[name][1]
+
+            def fn(*args):
+                assert len(args) == len(sig), (name, len(args), len(sig))
+                for pos, (a, t) in enumerate(zip(args, sig)):
+                    if t is C.c_void_p:
+                        assert a is None or isinstance(a, C.c_void_p), (name, pos, type(a))
+                    else:
+                        assert isinstance(a, (int, float)) and not isinstance(a, bool), (name, pos, a)
+                calls.append(name)
+                return 0
+            return fn
+    monkeypatch.setattr(L, "load", lambda: Rec())
+    monkeypatch.setattr(ops, "_PLAN_DRY_RUN", True)
+    monkeypatch.setattr(MM, "_stream", lambda: None)
+
+    def check(self, t, labels, what):
+        if self._counts is None:
+            self._alloc(t.device)
+        return labels.long().contiguous()
+    monkeypatch.setattr(MM.SegmentationMetric, "_check", check)
+    m = MM.SegmentationMetric(19, False)
+    m.update(torch.zeros(2, 19, 8, 8), torch.zeros(2, 8, 8, dtype=torch.long))
+    m.update_lowres(torch.zeros(2, 4, 4, 24)[..., :19], torch.zeros(2, 16, 16, dtype=torch.long), out_dtype=torch.float32)
+    assert calls == ["segb200_seg_metric", "segb200_seg_metric_accumulate", "segb200_seg_metric_lowres", "segb200_seg_metric_accumulate"]
