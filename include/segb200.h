@@ -376,6 +376,12 @@ int segb200_eval_prepare(const float* image, float* out, int b, int c, int h, in
 int segb200_eval_accumulate(const void* logits, void* scores, int dtype, int b, int k, int hp, int wp, int height, int width,
                             int h, int w, int flip, int accumulate, void* stream);
 
+/* GPU-side input transform: transforms.ToTensor() + transforms.Normalize(mean, std) (tools/train.py:36-39) on a
+ * batch of decoded uint8 HWC images on the device: out[n][c][y][x] = (img[n][y][x][c] / 255 - mean[c]) / std[c], fp32, bit-identical
+ * to torchvision.  mean / stdv: device pointers to c floats; c <= 4. */
+int segb200_image_normalize(const unsigned char* img, float* out, int n, int h, int w, int c, const float* mean, const float* stdv,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

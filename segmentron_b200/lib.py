@@ -107,6 +107,7 @@ SYMBOLS = {
     "segb200_seg_metric": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp]),
     "segb200_seg_metric_lowres": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp]),
     "segb200_seg_metric_accumulate": (ci, [vp, ci, vp, vp, vp, vp]),
+    "segb200_image_normalize": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp]),
     # ---- multi-scale + flip evaluation ----
     "segb200_eval_prepare": (ci, [vp, vp] + [ci] * 9 + [vp]),
     "segb200_eval_accumulate": (ci, [vp, vp] + [ci] * 11 + [vp]),

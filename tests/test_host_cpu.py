@@ -329,3 +329,25 @@ def test_metric_wrapper_call_sites_match_the_signatures(monkeypatch):
     m.update(torch.zeros(2, 19, 8, 8), torch.zeros(2, 8, 8, dtype=torch.long))
     m.update_lowres(torch.zeros(2, 4, 4, 24)[..., :19], torch.zeros(2, 16, 16, dtype=torch.long), out_dtype=torch.float32)
     assert calls == ["segb200_seg_metric", "segb200_seg_metric_accumulate", "segb200_seg_metric_lowres", "segb200_seg_metric_accumulate"]
+
+
+def test_input_normalize_is_torchvision_bit_for_bit(built):
+    """segmentron_b200.data.normalize == transforms.ToTensor() + transforms.Normalize (the reference's input transform,
+    tools/train.py:36-39): the kernel's formula, transcribed with numpy float32 IEEE operations in the kernel's order, equals
+    torchvision on random uint8 images EXACTLY (all 256 byte values x the Cityscapes mean/std); CPU tensors raise."""
+    import numpy as np
+    import torch
+    from torchvision import transforms
+    from segmentron_b200 import data as D
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (37, 53, 3), generator=g, dtype=torch.uint8)
+    img[0, :, 0] = torch.arange(53) % 256
+    img[1:6, :51, 1] = torch.arange(255).reshape(5, 51).to(torch.uint8)
+    for mean, std in (([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]), ([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])):
+        from PIL import Image
+        ref = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean, std)])(Image.fromarray(img.numpy()))
+        u = img.numpy().astype(np.float32)
+        got = ((u / np.float32(255.0)) - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)      # kernel order, fp32 IEEE
+        assert got.dtype == np.float32 and np.array_equal(got.transpose(2, 0, 1), ref.numpy())
+    with pytest.raises(RuntimeError, match="not implemented on the CPU"):
+        D.normalize(img[None], [0.5] * 3, [0.5] * 3)

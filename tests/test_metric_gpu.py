@@ -115,3 +115,17 @@ def test_full_size_properties():
     assert np.array_equal(inter, torch.bincount(pred[valid & (pred == t)], minlength=c).cpu().numpy())
     assert parea.sum() == cnt[1] == larea.sum() and (inter <= np.minimum(parea, larea)).all()
     assert m.total_label == int(cnt[1])
+
+
+def test_input_normalize_kernel_is_torchvision_bit_for_bit():
+    """segb200_image_normalize against transforms.ToTensor() + transforms.Normalize on the same uint8 images: exact."""
+    from PIL import Image
+    from torchvision import transforms
+    from segmentron_b200 import data as D
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.randint(0, 256, (3, 65, 129, 3), generator=g, dtype=torch.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean, std)])
+    ref = torch.stack([tf(Image.fromarray(im.numpy())) for im in imgs])
+    got = D.normalize(imgs.cuda(), mean, std)
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), ref)
