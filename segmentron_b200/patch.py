@@ -63,6 +63,20 @@ def install_metric(verbose=False):
     return count
 
 
+def install_evaluate():
+    """Opt-in: route ``SegBaseModel.evaluate`` (segmentron/models/segbase.py:44-79, called by tools/eval.py for every batch) through
+    ``segmentron_b200.evaluate.evaluate`` -- same scales / flip / crop rules read from the reference's cfg.TEST, one model call per
+    scale on the stacked [image; mirrored image] batch, two kernels instead of nine torch ops per scale."""
+    from segmentron.config import cfg
+    from segmentron.models.segbase import SegBaseModel
+    from .evaluate import evaluate
+
+    def _evaluate(self, image):
+        return evaluate(self.forward, image, cfg.TEST.SCALES, cfg.TEST.FLIP, cfg.TEST.CROP_SIZE)
+    SegBaseModel.evaluate = _evaluate
+    return SegBaseModel
+
+
 def _adopt(cls, ref):
     """Build a drop-in instance that shares ``ref``'s sub-modules, parameters and buffers."""
     new = cls.__new__(cls)

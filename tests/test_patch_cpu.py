@@ -53,3 +53,34 @@ def test_install_and_convert(yaml_file, oracle, nsep):
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_install_metric_and_evaluate_rebind_the_reference_names():
+    """patch.install_metric / install_evaluate against the real reference tree: the names tools/eval.py uses resolve to the drop-ins
+    (constructor signature of score.py:14 accepted; SegBaseModel.evaluate reads cfg.TEST and refuses CPU images loudly)."""
+    script = r"""
+import sys, numpy as np
+np.int = int
+sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(ref)s")
+import torch
+import segmentron.utils.score as score
+from segmentron.models.segbase import SegBaseModel
+from segmentron_b200 import patch, metric
+assert patch.install_metric() >= 1
+from segmentron.utils.score import SegmentationMetric
+assert SegmentationMetric is metric.SegmentationMetric
+m = SegmentationMetric(19, False)
+assert m.get() == (0.0, 0.0)
+cls = patch.install_evaluate()
+assert cls is SegBaseModel and SegBaseModel.evaluate.__name__ == "_evaluate"
+class Stub:
+    forward = staticmethod(lambda x: (x,))
+try:
+    SegBaseModel.evaluate(Stub(), torch.zeros(1, 3, 8, 8))
+    raise SystemExit("CPU evaluate did not raise")
+except RuntimeError as e:
+    assert "CPU" in str(e), e
+print("OK")
+""" % dict(root=ROOT, ref=REF)
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
