@@ -304,6 +304,23 @@ int segb200_cca_gather(const float* a, const void* src, void* out, int n, int h,
 int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h, int w, int c, int a_ld, int src_ld, int out_ld,
                         float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The reference's only native module, `segmentron._C` (segmentron/modules/csrc/vision.cpp:6-11), function by function, on the
+ * reference's OWN layout: contiguous NCHW tensors of element type `dtype` (SEGB200_F32 / F16 / BF16), fp32 accumulation,
+ * outputs fully written (no zero-initialisation needed), no atomics.  Signatures follow csrc/criss_cross_attention/ca.h:25-72:
+ *   ca_forward(t, f) -> weight            t, f [n][c][h][w];  weight [n][h+w-1][h][w]           (ca_cuda.cu:8-36, :188-212)
+ *   ca_backward(dw, t, f) -> dt, df       dw like weight;  dt, df like t                          (ca_cuda.cu:38-92, :214-248)
+ *   ca_map_forward(weight, g) -> out      g, out [n][c][h][w]                                     (ca_cuda.cu:94-120, :250-276)
+ *   ca_map_backward(dout, weight, g) -> dw, dg                                                   (ca_cuda.cu:122-177, :278-312)
+ * segmentron_b200/c_shim.py wraps them as a module object with exactly the reference's four Python-visible functions so that
+ * segmentron/modules/cc_attention.py:11-45 (_CAWeight / _CAMap) runs unchanged. */
+int segb200_ca_forward(const void* t, const void* f, void* weight, int n, int c, int h, int w, int dtype, void* stream);
+int segb200_ca_backward(const void* dw, const void* t, const void* f, void* dt, void* df, int n, int c, int h, int w, int dtype,
+                        void* stream);
+int segb200_ca_map_forward(const void* weight, const void* g, void* out, int n, int c, int h, int w, int dtype, void* stream);
+int segb200_ca_map_backward(const void* dout, const void* weight, const void* g, void* dw, void* dg, int n, int c, int h, int w,
+                            int dtype, void* stream);
+
 /* Backward of segb200_upsample_add, y = act(a + nearest_up_{2^k}(z)) -- the HRNet fuse sum (backbones/hrnet.py:178-186,215-232):
  * g = dy * [y > 0] (act = relu, mask from the stored output); da (+)= g; dz (+)= sum of g over each 2^k x 2^k block.  da or dz may
  * be NULL. */

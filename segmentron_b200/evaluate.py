@@ -76,7 +76,9 @@ def evaluate(forward, image, scales=(1.0,), flip=False, crop_size=None):
         if not flip and (height, width, hp, wp) == (h, w, h, w):
             logits = _logits(forward(image))                       # both resizes are identities at this scale
             if len(scales) == 1:
-                return logits
+                # a fresh tensor like every other path of this function: an engine forward hands out its static (CUDA-graph)
+                # output buffer, which the next call overwrites
+                return logits.clone()
         else:
             batch = torch.empty((2 if flip else 1) * b, c, hp, wp, dtype=torch.float32, device=image.device)
             L.check(lib.segb200_eval_prepare(_ptr(image), _ptr(batch), b, c, h, w, height, width, hp, wp, int(flip), _stream(image)),

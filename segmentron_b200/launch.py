@@ -4,7 +4,8 @@
         --config-file configs/cityscapes_deeplabv3_plus.yaml
 
 Installs, outside the reference tree, the compatibility shims the reference needs on a current stack
-(``np.int``, a stub ``thop``, ``--local-rank`` -> ``--local_rank``), imports ``segmentron``, rebinds the
+(``np.int``, a stub ``thop``, ``--local-rank`` -> ``--local_rank``), imports ``segmentron``, installs the
+``segmentron._C`` shim (``c_shim``: the four criss-cross functions of vision.cpp:6-11 over the C ABI, which re-enables CCNet), rebinds the
 L1 classes (``patch.install``) and, with ``--accelerate``, wraps ``get_segmentation_model`` so DeepLabV3+ models run the
 fused whole-model plan; then executes the script as ``__main__``.
 """
@@ -27,7 +28,9 @@ def _shims():
         sys.modules["thop"] = thop
     sys.argv = [a.replace("--local-rank", "--local_rank") if a.startswith("--local-rank") else a for a in sys.argv]
     if "LOCAL_RANK" in os.environ and not any(a.startswith("--local_rank") for a in sys.argv[1:]):
-        sys.argv.insert(2, f"--local_rank={os.environ['LOCAL_RANK']}")
+        # index 1 = directly after the script name: anywhere later could split an option from its value, and anything after the
+        # first positional lands in the reference's `opts` REMAINDER (utils/options.py:25-26)
+        sys.argv.insert(1, f"--local_rank={os.environ['LOCAL_RANK']}")
 
 
 def main():
@@ -42,7 +45,10 @@ def main():
     sys.argv = [script] + argv[1:]
     _shims()
     import segmentron  # noqa: F401
-    from . import patch
+    from . import c_shim, patch
+    # the reference's only native module: `segmentron._C` cannot be built on a current torch; install the
+    # C-ABI shim BEFORE anything imports segmentron.modules.cc_attention, and let CCNet register itself (models/__init__.py:11)
+    c_shim.install(register_ccnet=True)
     n = patch.install()
     print(f"[segb200] rebound {n} class references in segmentron.* namespaces", file=sys.stderr)
     if accel:

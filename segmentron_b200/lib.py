@@ -103,6 +103,11 @@ SYMBOLS = {
     "segb200_upsample_add_bwd": (ci, [vp, vp, vp, vp] + [ci] * 13 + [vp]),
     "segb200_dw_wgrad_v2_slabs": (ci, [ll, ci, ci]),
     "segb200_dw_wgrad_v2": (ci, [vp, vp, vp] + [ci] * 10 + [vp]),
+    # ---- segmentron._C (NCHW, the reference's own layout) ----
+    "segb200_ca_forward": (ci, [vp, vp, vp] + [ci] * 5 + [vp]),
+    "segb200_ca_backward": (ci, [vp] * 5 + [ci] * 5 + [vp]),
+    "segb200_ca_map_forward": (ci, [vp, vp, vp] + [ci] * 5 + [vp]),
+    "segb200_ca_map_backward": (ci, [vp] * 5 + [ci] * 5 + [vp]),
     # ---- evaluation metric ----
     "segb200_seg_metric": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp]),
     "segb200_seg_metric_lowres": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp]),

@@ -41,8 +41,8 @@ def _enter(x, module):
     if not x.is_cuda:
         raise RuntimeError(f"segb200: {type(module).__name__} is not implemented on the CPU (input must be a CUDA tensor)")
     if module.training:
-        raise RuntimeError(f"segb200: training-mode forward of {type(module).__name__} is not implemented in this "
-                           "round (inference engine); call .eval()")
+        raise RuntimeError(f"segb200: {type(module).__name__}.forward_nhwc is the inference path (folded BatchNorm); in training "
+                           "mode call the module itself (forward), which runs the differentiable train-mode kernels")
     if x.dim() != 4:
         raise RuntimeError("segb200: expected a 4-D NCHW tensor")
     dt = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else _COMPUTE_DTYPE
@@ -79,7 +79,14 @@ def _train_conv_bn_act(xh, conv, bn, act, pre_relu=False):
     if conv.groups == 1:
         if pre_relu:
             raise RuntimeError("segb200: leading ReLU is only fused into the depthwise unit")
-        y = TM.ConvBNActFunction.apply(xh, conv.weight, g, b, rm, rv, mom, eps, s, d, p, act)
+        weight = conv.weight
+        cpad = (-xh.shape[3]) % 8
+        if cpad:
+            # small-Cin stems (RGB: MobileNetV2 backbones/mobilenet.py:80, FastSCNN, ICNet): zero channels on both operands, like
+            # the inference path does; autograd slices the padding off the weight gradient again
+            xh = torch.nn.functional.pad(xh, (0, cpad))
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
+        y = TM.ConvBNActFunction.apply(xh, weight, g, b, rm, rv, mom, eps, s, d, p, act)
     elif conv.groups == conv.in_channels == conv.out_channels and k == 3 and p == d:
         y = TM.DwBNActFunction.apply(xh, conv.weight, g, b, rm, rv, mom, eps, s, d, pre_relu, act)
     else:

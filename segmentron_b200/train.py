@@ -77,6 +77,7 @@ class ParamStore:
         for k, (o, n) in self.stat_meta.items():
             self.stats[o:o + n].copy_(state_dict[k].detach().float())
         self.extra = {k: v for k, v in state_dict.items() if k.endswith("num_batches_tracked") or ".fc." in k}
+        self.steps = 0                                 # training-mode forwards since construction (-> num_batches_tracked)
         # ---- packed operands: index tables (built on the CPU, int64 -> int32) ----
         self.stem = stem
         idx16, idx32, self.pk = [], [], {}
@@ -155,6 +156,9 @@ class ParamStore:
         out = {k: self.from_internal(k, self.view(self.master, k)) for k in self.meta}
         out.update({k: self.stat(k).clone() for k in self.stat_meta})
         out.update(self.extra)
+        for k, v in self.extra.items():               # nn.BatchNorm2d counts its training-mode forwards (batch_norm.py:126)
+            if k.endswith("num_batches_tracked"):
+                out[k] = v.detach().clone() + self.steps
         return out
 
     def grads(self):
@@ -1345,6 +1349,7 @@ class DeepLabV3PlusTrainerB200:
             else:
                 m.fill_(1.0)
         self.store.grad.zero_()
+        self.store.steps += 1
         self.pack_weights()
         if self.dist is None:
             pl.run()
@@ -1387,10 +1392,10 @@ class DeepLabV3PlusTrainerB200:
 class CCNetTrainerB200(DeepLabV3PlusTrainerB200):
     """``trainer.step(images, targets)`` for CCNet / ResNet101 (models/ccnet.py): the same engine, with the criss-cross attention
     forward + backward kernels in the launch list (recurrence 2, shared weights).  Plan verified against the oracle in fp64
-    (tests/test_train_plan_cpu.py); every kernel in it is GPU-verified on its own; a model-level GPU replay is gated behind
-    SEGB200_TEST_ALL (written after the round's GPU budget was spent)."""
+    (tests/test_train_plan_cpu.py); every launch of a real bf16 step replayed on the B200 (tests/test_train_model_gpu.py)."""
 
-    def __init__(self, state_dict, nclass=19, output_stride=16, recurrence=2, **kw):
+    def __init__(self, state_dict, nclass=19, output_stride=16, recurrence=2, lr=0.003, **kw):
+        kw["lr"] = lr                                  # configs/cityscapes_ccnet_resnet.yaml: SOLVER.LR 0.003
         super().__init__(state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride, use_aspp=False,
                          use_decoder=False, **kw)
         self.recurrence = recurrence
@@ -1403,7 +1408,7 @@ class HRNetTrainerB200(DeepLabV3PlusTrainerB200):
     """``trainer.step(images, targets)`` for HRNet (models/hrnet_seg.py + backbones/hrnet.py; default: hrnet_w18_small_v1).
     Defaults follow configs/cityscapes_hrnet_w18_small_v1.yaml: BatchNorm momentum 0.01 (MODEL.BN_MOMENTUM, applied by
     solver/optimizer.py:37-39) and no decoder LR factor.  Plan verified against the oracle in fp64 on the CPU
-    (tests/test_train_plan_cpu.py); GPU replay: tests/test_train_model_gpu.py (SEGB200_TEST_ALL until it has run once)."""
+    (tests/test_train_plan_cpu.py); every launch of a real step replayed on the B200: tests/test_train_model_gpu.py."""
 
     def __init__(self, state_dict, nclass=19, hcfg=None, bn_momentum=0.01, decoder_lr_factor=1.0, lr=0.01, **kw):
         from .engine import HRNET_W18_SMALL_V1
@@ -1420,9 +1425,10 @@ class DANetTrainerB200(DeepLabV3PlusTrainerB200):
     """``trainer.step(images, targets)`` for DANet / ResNet101 (models/danet.py; OS8, multi-grid 4/8/16): position and channel
     attention run with the attention matrices materialised per image (as the reference does), three classifiers behind three
     Dropout2d layers, loss = sum of the three cross-entropies.  Plan verified against the oracle in fp64 on the CPU
-    (tests/test_train_plan_cpu.py); GPU replay: SEGB200_TEST_ALL until it has run once.  Needs (H/8)*(W/8) % 8 == 0."""
+    (tests/test_train_plan_cpu.py); every launch of a real step replayed on the B200 (tests/test_train_model_gpu.py).  Needs (H/8)*(W/8) % 8 == 0."""
 
-    def __init__(self, state_dict, nclass=19, output_stride=8, multi_dilation=(4, 8, 16), **kw):
+    def __init__(self, state_dict, nclass=19, output_stride=8, multi_dilation=(4, 8, 16), lr=0.003, **kw):
+        kw["lr"] = lr                                  # configs/cityscapes_danet_resnet.yaml: SOLVER.LR 0.003
         super().__init__(state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride, use_aspp=False,
                          use_decoder=False, **kw)
         self.multi_dilation = multi_dilation

@@ -161,8 +161,6 @@ def test_every_launch_of_a_training_step(model, backbone):
     assert torch.isfinite(tr.store.grad).all()
 
 
-@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="CCNet model-level replay: written after the round's GPU budget was "
-                    "spent (plan verified in fp64 on the CPU, every kernel verified on the GPU on its own)")
 def test_every_launch_of_a_ccnet_training_step():
     from segmentron_b200.train import CCNetTrainerB200
     P = R.build_params("ccnet_resnet101", 31)
@@ -175,8 +173,6 @@ def test_every_launch_of_a_ccnet_training_step():
     print(f"[ccnet] {len(pl.fwd) + len(pl.bwd)} launches checked:", {k: f"{v:.2e}" for k, v in sorted(worst.items())})
 
 
-@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="HRNet model-level replay: written after the round's GPU budget was "
-                    "spent (plan verified in fp64 on the CPU); includes the new upsample_add_bwd kernel")
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
 def test_every_launch_of_an_hrnet_training_step(dtype):
     from segmentron_b200.train import HRNetTrainerB200
@@ -190,8 +186,6 @@ def test_every_launch_of_an_hrnet_training_step(dtype):
     assert {"upsample_add", "upsample_add_bwd"} <= set(worst)
 
 
-@pytest.mark.skipif(not os.environ.get("SEGB200_TEST_ALL"), reason="DANet model-level replay: written after the round's GPU budget was "
-                    "spent (plan verified in fp64 on the CPU); includes the PAM / CAM training kernels")
 def test_every_launch_of_a_danet_training_step():
     from segmentron_b200.train import DANetTrainerB200
     P = R.build_params("danet_resnet101", 51)
