@@ -132,6 +132,117 @@ def run_reference(args):
     }), flush=True)
 
 
+def _time_forward(fn, iters=5, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cudnn_reference(P, x_dev, eng, bsz):
+    """The north-star denominator, measured in the same process on the same GPU: the reference's OWN model
+    (`get_segmentation_model()` from the unmodified copy under baseline/_ref, segmentron/models/model_zoo.py:17-24) with the same
+    weights, `.to(bf16)`, eval, cudnn.benchmark on (utils/default_setup.py:18), NCHW and channels_last -- the faster layout counts.
+    Falls back to the oracle port (the same torch ops) only when baseline/_ref is absent.  Also reports the parity the north-star
+    states: this engine's bf16 logits vs the reference's own cuDNN bf16 logits, both against the reference's fp32 forward."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_harness as H
+    torch.backends.cudnn.benchmark = True
+    res, kind, parity = {}, "port", None
+    with torch.no_grad():
+        if H.available():
+            kind = "reference"
+            model = H.build_model("cityscapes_deeplabv3_plus.yaml")
+            model.load_state_dict(P.state_dict(), strict=True)
+            m32 = model.cuda()
+            x1 = x_dev[:1]
+            tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            y32 = m32(x1)[0].float()                                      # the reference's fp32 forward of image 0 (TF32 off)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+            mb = m32.to(torch.bfloat16)
+            xb = x_dev.to(torch.bfloat16)
+            yb = mb(xb[:1])[0].float()
+            yo = eng(x1).float()                                          # this engine, bf16, same image (batch-invariant)
+
+            def rel(a, b):
+                return float((a - b).norm() / b.norm())
+            am32 = y32.argmax(1)
+            parity = {"image": "image 0 of the bench batch, 1x3x%dx%d" % tuple(x1.shape[2:]),
+                      "ours_bf16_vs_ref_fp32_rel_l2": rel(yo, y32), "ref_cudnn_bf16_vs_ref_fp32_rel_l2": rel(yb, y32),
+                      "ours_bf16_vs_ref_cudnn_bf16_rel_l2": rel(yo, yb),
+                      "argmax_mismatch_ours_vs_ref_fp32": int((yo.argmax(1) != am32).sum()),
+                      "argmax_mismatch_refbf16_vs_ref_fp32": int((yb.argmax(1) != am32).sum()),
+                      "argmax_mismatch_ours_vs_refbf16": int((yo.argmax(1) != yb.argmax(1)).sum()), "pixels": int(am32.numel())}
+            del y32, yb, yo
+            res["nchw"] = bsz / (_time_forward(lambda: mb(xb)) * 1e-3)
+            mcl = mb.to(memory_format=torch.channels_last)
+            xcl = xb.contiguous(memory_format=torch.channels_last)
+            res["channels_last"] = bsz / (_time_forward(lambda: mcl(xcl)) * 1e-3)
+            del model, m32, mb, mcl, xb, xcl
+        else:
+            from oracle import segref as R
+            for fmt in ("nchw", "channels_last"):
+                Pg = P.to("cuda", torch.bfloat16)
+                xb = x_dev.to(torch.bfloat16)
+                if fmt == "channels_last":
+                    xb = xb.contiguous(memory_format=torch.channels_last)
+                    for k, v in Pg.t.items():
+                        if v.dim() == 4:
+                            Pg.t[k] = v.contiguous(memory_format=torch.channels_last)
+                res[fmt] = bsz / (_time_forward(lambda: R.forward(MODEL, Pg, xb)) * 1e-3)
+                del Pg, xb
+    torch.cuda.empty_cache()
+    return {"value": max(res.values()), "unit": "images/s", "by_layout": res, "kind": kind, "parity": parity,
+            "what": ("the reference's own model (baseline/_ref, get_segmentation_model) " if kind == "reference" else
+                     "oracle port (same torch ops as the reference) ") + "on this GPU, bf16 eager, cudnn.benchmark on; faster layout"}
+
+
+def train_subrecord(args, rank, world, parallel):
+    """BASELINE.json configs[2], the one path with a data-path collective: DeepLabv3+/ResNet101 bf16 training at 1025x2049,
+    per-GPU batch 4 (weak scaling), SyncBatchNorm + bucketed NCCL gradient all-reduce overlapped with backward.  A step =
+    trainer.step(images, targets) = forward + CrossEntropy(ignore -1) + backward + SGD; CUDA events, barrier on both sides, max over
+    ranks.  Every rank must call this."""
+    import torch
+    from oracle import segref as R
+    from segmentron_b200.train import DeepLabV3PlusTrainerB200
+    model = "deeplabv3plus_resnet101"
+    P = R.build_params(model, 0)
+    shape = (4, 3, H, W)
+    g = torch.Generator().manual_seed(2048 + rank)
+    x = torch.randn(*shape, generator=g).cuda()
+    target = torch.randint(-1, 19, (shape[0], shape[2], shape[3]), generator=g).cuda()
+    tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone="resnet101", dtype=torch.bfloat16, lr=0.02, sync_bn=True)
+    losses = [float(tr.step(x, target)) for _ in range(3)]
+    parallel.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        tr.step(x, target)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1)) / args.train_steps
+    parallel.barrier()
+    st = tr.plan_for(shape)
+    rec = {"workload": "deeplabv3plus_resnet101_bf16_train_1025x2049_b4_per_gpu", "metric": "images/sec", "n_gpus": world,
+           "value": world * shape[0] / (ms * 1e-3), "ms_per_step": ms, "steps": args.train_steps, "scaling": "weak",
+           "sync_bn": world > 1, "allreduce_buckets": len(st["buckets"]) if world > 1 else 0,
+           "collectives_per_step": tr.collectives_per_step(shape) if hasattr(tr, "collectives_per_step") else None,
+           "launches_per_step": tr.n_launches(shape), "loss_first_steps": [round(v, 4) for v in losses],
+           "grad_dtype": str(getattr(tr, "grad_comm_dtype", torch.float32)).replace("torch.", "")}
+    del tr, x, target
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -142,7 +253,10 @@ def main():
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cudnn-ref", action="store_true", help="also time the oracle port on this GPU (cuDNN bf16 eager)")
+    ap.add_argument("--cudnn-ref", action="store_true", help="(default on; kept for compatibility)")
+    ap.add_argument("--no-cudnn-ref", action="store_true", help="skip timing the reference's own cuDNN bf16 forward on this GPU")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-3 training sub-record (the path with a collective)")
+    ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch timing table to this file")
     ap.add_argument("--no-graph", action="store_true", help="replay the launch list directly instead of one CUDA graph (for profilers)")
     args = ap.parse_args()
@@ -263,6 +377,41 @@ def main():
     ms_e2e = timed(e2e_step, args.steps, e2e_finish)
     e2e_val = world * bsz * args.steps / (ms_e2e * 1e-3)
 
+    # ---- the same pipeline returning what forward()[0] returns: the bf16 logits [B,19,H,W] (0.64 GB per step over PCIe) ----
+    logits_host = torch.empty(st["out"].shape, dtype=st["out"].dtype).pin_memory()
+    logits_dev = torch.empty_like(st["out"])
+
+    def e2e_logits_step(i):
+        if i == 0:
+            h2d(0)
+        if i + 1 < e2e_total["k"]:
+            h2d(i + 1)
+        cur.wait_event(ev_in[i & 1])
+        st["holder"]["x"].copy_(stage[i & 1], non_blocking=True)
+        ev_free[i & 1].record(cur)
+        cur.wait_event(ev_read)
+        graph.replay()
+        logits_dev.copy_(st["out"], non_blocking=True)
+        ev_done.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done)
+            logits_host.copy_(logits_dev, non_blocking=True)
+            ev_read.record(s_out)
+
+    k_log = max(3, args.steps // 2)
+    e2e_total["k"] = k_log
+    for i in range(2):
+        ev_free[i].record(cur)
+    ev_read.record(cur)
+    ms_e2e_logits = timed(e2e_logits_step, k_log, e2e_finish)
+    e2e_logits_val = world * bsz * k_log / (ms_e2e_logits * 1e-3)
+    d2h_logits = logits_host.numel() * logits_host.element_size()
+    del logits_host, logits_dev
+
+    train = None
+    if not args.no_train and (bsz, hh, ww) == (B, H, W):
+        train = train_subrecord(args, rank, world, parallel)
+
     out = None
     if rank == 0:
         pk = peaks()
@@ -321,32 +470,8 @@ def main():
             cpu = {"value": 1.0 / t, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": f"1 image 1x3x{hh}x{ww} fp32, 1 forward of the oracle port, {torch.get_num_threads()} threads"}
         cudnn = None
-        if args.cudnn_ref:
-            # the north-star denominator: the same torch ops the reference runs (oracle port), bf16 eager on this GPU,
-            # cudnn.benchmark on (utils/default_setup.py:18), NCHW and channels_last -- the faster one counts
-            torch.backends.cudnn.benchmark = True
-            res = {}
-            for fmt in ("nchw", "channels_last"):
-                Pg = P.to("cuda", torch.bfloat16)
-                xb = x_dev.to(torch.bfloat16)
-                if fmt == "channels_last":
-                    xb = xb.contiguous(memory_format=torch.channels_last)
-                    for k, v in Pg.t.items():
-                        if v.dim() == 4:
-                            Pg.t[k] = v.contiguous(memory_format=torch.channels_last)
-                for _ in range(3):
-                    R.forward(MODEL, Pg, xb)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    R.forward(MODEL, Pg, xb)
-                e1.record(); torch.cuda.synchronize()
-                res[fmt] = bsz * 5 / (e0.elapsed_time(e1) * 1e-3)
-                del Pg, xb
-                torch.cuda.empty_cache()
-            cudnn = {"value": max(res.values()), "unit": "images/s", "by_layout": res,
-                     "what": "oracle port (same torch ops as the reference) on this GPU, bf16 eager, cudnn.benchmark on; faster layout"}
+        if not args.no_cudnn_ref:
+            cudnn = cudnn_reference(P, x_dev, eng, bsz)
         h2d = x_host.numel() * x_host.element_size()
         d2h = amax_host.numel()
         out = {
@@ -360,12 +485,19 @@ def main():
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "input": "pinned fp32 NCHW batch, H2D of step i+1 overlapped with step i",
                     "result": "uint8 argmax class maps"},
+            "e2e_logits": {"value": e2e_logits_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_logits,
+                           "ms_per_step": ms_e2e_logits / k_log, "steps": k_log,
+                           "result": "bf16 logits [B,19,H,W], what forward()[0] returns (PCIe-bound: 0.64 GB per step)"},
             "gpu_launches": plan.n_launch * args.steps, "launches_per_step": plan.n_launch,
             "roofline": roofline, "roofline_all_gemm": roofline_all, "roofline_dw": roofline_dw, "cpu_baseline": cpu, "clocks": clocks,
             "per_kind_ms": {k: round(v["ms"], 3) for k, v in agg.items()},
         }
         if cudnn:
             out["cudnn_ref"] = cudnn
+            out["vs_cudnn_ref"] = {"device_resident": value / world / cudnn["value"], "e2e": e2e_val / world / cudnn["value"],
+                                   "note": "per-GPU images/s of this engine / the reference's cuDNN bf16 forward on the same GPU"}
+        if train:
+            out["train"] = train
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

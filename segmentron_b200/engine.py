@@ -30,6 +30,7 @@ class Plan:
         self.keep = []             # keep packed weights / buffers alive
         self.lib = L.load()
         self.n_launch = 0
+        self._host = {}
 
     # ---- buffers -----------------------------------------------------------------------
     def new(self, n, h, w, c, ld=None):
@@ -39,7 +40,19 @@ class Plan:
         return buf[..., :c] if ld != c else buf
 
     def w(self, name):
-        return self.P[name].to(self.device)
+        """parameter on the HOST: BatchNorm folding and weight packing run on the CPU at plan-build time (a few hundred tiny
+        elementwise ops per model; on the device they would be ~1000 torch launches in front of the first engine kernel), only the
+        folded / packed results are uploaded (``dev``)"""
+        t = self._host.get(name)
+        if t is None:
+            t = self._host[name] = self.P[name].detach().to("cpu")
+        return t
+
+    def dev(self, t):
+        """upload a host-side derived tensor (no-op for device tensors / None)"""
+        if t is None or t.device.type != "cpu":
+            return t
+        return t.contiguous().to(self.device)
 
     def bn(self, prefix, eps):
         return fold.bn_fold(self.w(prefix + ".weight"), self.w(prefix + ".bias"), self.w(prefix + ".running_mean"),
@@ -47,8 +60,10 @@ class Plan:
 
     # ---- op recorders ------------------------------------------------------------------
     def conv(self, x, wpk, y, **kw):
+        wpk = self.dev(wpk)
         for k in ("scale", "shift"):
             if kw.get(k) is not None:
+                kw[k] = self.dev(kw[k])
                 self.keep.append(kw[k])
         self.keep.append(wpk)
         a = ops.make_conv_args(x, wpk, y, **kw)
@@ -64,8 +79,10 @@ class Plan:
         return y
 
     def dw(self, x, wdw, y, **kw):
+        wdw = self.dev(wdw)
         self.keep.append(wdw)
         if kw.get("shift") is not None:
+            kw["shift"] = self.dev(kw["shift"])
             self.keep.append(kw["shift"])
         a = ops.make_dw_args(x, wdw, y, **kw)
         fn = self.lib.segb200_dwconv3x3
@@ -346,13 +363,13 @@ def build_danet(pl, x_shape, holder, nclass, output_stride, multi_grid, multi_di
     def qkv(prefix):
         ws = []
         for nm in ("query_conv", "key_conv", "value_conv"):
-            ws += [fold.pack_conv_weight(pl.w(f"{prefix}.{nm}.weight"), pl.dtype), pl.w(f"{prefix}.{nm}.bias").float().contiguous()]
+            ws += [pl.dev(fold.pack_conv_weight(pl.w(f"{prefix}.{nm}.weight"), pl.dtype)), pl.dev(pl.w(f"{prefix}.{nm}.bias").float())]
         return ws
 
     feat1 = cbr(c4, "conv5a")
     sa_feat = pl.new(*feat1.shape)
     wq, bq, wk, bk, wv, bv = qkv(hp + ".sa")
-    g_sa = pl.w(hp + ".sa.gamma").float()
+    g_sa = pl.dev(pl.w(hp + ".sa.gamma").float())
     pl.keep += [wq, bq, wk, bk, wv, bv, g_sa]
     ntok = feat1.shape[1] * feat1.shape[2]
     pl.steps.append((lambda s: A.pam_nhwc(feat1, wq, bq, wk, bk, wv, bv, g_sa, out=sa_feat),
@@ -362,7 +379,7 @@ def build_danet(pl, x_shape, holder, nclass, output_stride, multi_grid, multi_di
     sa_conv = cbr(sa_feat, "conv51")
     feat2 = cbr(c4, "conv5c")
     sc_feat = pl.new(*feat2.shape)
-    g_sc = pl.w(hp + ".sc.gamma").float()
+    g_sc = pl.dev(pl.w(hp + ".sc.gamma").float())
     pl.keep.append(g_sc)
     pl.steps.append((lambda s: A.cam_nhwc(feat2, g_sc, out=sc_feat),
                      dict(kind="cam", flops=2.0 * 2 * n * ntok * 512 * 512, bytes=2.0 * n * ntok * 512 * 3, desc=f"CAM C=512 N={ntok} b={n}")))
@@ -524,8 +541,8 @@ def build_ccnet(pl, x_shape, holder, nclass, output_stride, recurrence, out_dtyp
     out = pl.conv_bn_act(c4, hp + ".conva", 512, 3, pad=1, act="relu", conv="0", bn="1")
     ws = []
     for nm in ("query_conv", "key_conv", "value_conv"):
-        ws += [fold.pack_conv_weight(pl.w(f"{hp}.cca.{nm}.weight"), pl.dtype), pl.w(f"{hp}.cca.{nm}.bias").float().contiguous()]
-    g = pl.w(hp + ".cca.gamma").float()
+        ws += [pl.dev(fold.pack_conv_weight(pl.w(f"{hp}.cca.{nm}.weight"), pl.dtype)), pl.dev(pl.w(f"{hp}.cca.{nm}.bias").float())]
+    g = pl.dev(pl.w(hp + ".cca.gamma").float())
     pl.keep += ws + [g]
     bufs = [pl.new(*out.shape) for _ in range(recurrence)]
     cur = out
