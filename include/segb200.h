@@ -305,6 +305,30 @@ int segb200_cca_scatter(const float* a, const void* src, void* out, int n, int h
                         float scale, const float* scale_dev, int accumulate, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SyncBatchNorm statistics exchange fused into the finalize kernels, over NVLink peer memory (csrc/syncbn.cu).
+ * Replaces the two per-layer collectives of `nn.SyncBatchNorm` (tools/train.py:73-79; NaiveSyncBatchNorm's all_reduce,
+ * modules/batch_norm.py:161-183): the finalize kernel of every rank stores its [2][c] partial sums into every peer's symmetric
+ * buffer (P2P stores), releases a per-(slot, source rank, CTA) epoch flag, waits for all peers' flags and sums the contributions
+ * in rank order (bit-identical on all ranks).  `peers_dev` = device array [world] of the ranks' buffer base pointers as mapped in
+ * THIS process (torch.distributed._symmetric_memory rendezvous); slot s of a buffer holds data at float offset `data_off` =
+ * s * segb200_syncbn_slot_floats(world, cmax) and flags at u32 offset `flag_off` (host-assigned, identical on all ranks);
+ * `epoch_dev` = device u32 bumped once per training step (segb200_counter_add) before the step's first exchange; flags must be
+ * zero-initialised and epochs start at 1.  world == 1 degenerates to the plain finalize.
+ *   bn_finalize_sync     : partial [slabs][2][c] (local) -> exchange -> mean / invstd / scale / shift (+ running stats), count_total
+ *                          = rows of ALL ranks
+ *   bn_bwd_finalize_sync : partial (local sum g, sum g*y) -> dgamma / dbeta (+)= local sums -> exchange -> sums [2][c] over all ranks */
+int segb200_syncbn_slot_floats(int world, int cmax);
+int segb200_syncbn_slot_flags(int world);
+int segb200_counter_add(void* counter_u32, int value, void* stream);
+int segb200_bn_finalize_sync(const float* partial, int slabs, int c, double count_total, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, float momentum, float eps, float* mean, float* invstd,
+                             float* scale, float* shift, const void* peers_dev, int world, int rank, int cmax, long long data_off,
+                             long long flag_off, const void* epoch_dev, void* stream);
+int segb200_bn_bwd_finalize_sync(const float* partial, int slabs, int c, const float* mean, const float* invstd, float* sums,
+                                 float* dgamma, float* dbeta, const void* peers_dev, int world, int rank, int cmax,
+                                 long long data_off, long long flag_off, const void* epoch_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The reference's only native module, `segmentron._C` (segmentron/modules/csrc/vision.cpp:6-11), function by function, on the
  * reference's OWN layout: contiguous NCHW tensors of element type `dtype` (SEGB200_F32 / F16 / BF16), fp32 accumulation,
  * outputs fully written (no zero-initialisation needed), no atomics.  Signatures follow csrc/criss_cross_attention/ca.h:25-72:

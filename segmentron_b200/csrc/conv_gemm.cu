@@ -59,6 +59,7 @@ struct ConvGemmParams {
   int n_tiles, total_tiles;
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
+  int kmma_tail;        // K=16 MMA steps of the LAST channel block of a tap (the zero-filled K tail beyond it is skipped)
   int a_stage_bytes, b_stage_bytes;
   int b_resident;       // 1: all K blocks of the (single) N tile stay in smem for the whole kernel; the ring holds A only
   int ring_bytes;       // A/B ring region (its top 32 KB hold the residual tiles when a residual is fused); default 192 KB
@@ -69,6 +70,7 @@ struct ConvGemmParams {
   const void* residual;
   long long res_ld;
   unsigned long long* dbg;   // only used when compiled with -DSEGB200_DBG
+  int dbg_mode;              // DBG build only: 1 = skip the MMAs, 2 = skip the TMA loads, 3 = skip the epilogue work (resource decomposition)
   uint32_t taps[64];   // map id (bits 0..1) | (off_w + 128) << 8 | (off_h + 128) << 16
 };
 
@@ -84,8 +86,14 @@ struct ConvGemmParams {
       mbar_wait(bar, parity);                                                     \
     }                                                                             \
   } while (0)
+#define DBG_T0() const long long dbg_t0_ = (p.dbg != nullptr) ? clock64() : 0
+#define DBG_ADD(slot) do { if (p.dbg != nullptr) atomicAdd(p.dbg + (slot), (unsigned long long)(clock64() - dbg_t0_)); } while (0)
+#define DBG_COUNT(slot, v) do { if (p.dbg != nullptr) atomicAdd(p.dbg + (slot), (unsigned long long)(v)); } while (0)
 #else
 #define TIMED_WAIT(bar, parity, slot) mbar_wait(bar, parity)
+#define DBG_T0() do {} while (0)
+#define DBG_ADD(slot) do {} while (0)
+#define DBG_COUNT(slot, v) do {} while (0)
 #endif
 
 template <bool kBF16, int kEpiGroups>
@@ -126,6 +134,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+#ifdef SEGB200_DBG
+  const long long dbg_kernel_t0 = clock64();
+#endif
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -151,6 +162,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t t = p.taps[tap];
           const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
           TIMED_WAIT(&ctl->empty[stage], phase ^ 1, 0);
+#ifdef SEGB200_DBG
+          if (p.dbg_mode == 2) { mbar_arrive(&ctl->full[stage]); if (++stage == p.num_stages) { stage = 0; phase ^= 1; } continue; }
+#endif
           mbar_expect_tx(&ctl->full[stage], tx);
           uint8_t* sa = smem + stage * stage_bytes;
           tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
@@ -182,7 +196,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
           const uint64_t bdesc = make_kmajor_desc(p.b_resident ? b_res + (uint32_t)(kb * p.b_stage_bytes) : sa + (uint32_t)p.a_stage_bytes,
                                                   (uint32_t)p.bk_bytes);
-          for (int k = 0; k < kmma; ++k)
+          const int kcnt = (kb % p.cblocks == p.cblocks - 1) ? p.kmma_tail : kmma;
+#ifdef SEGB200_DBG
+          if (p.dbg_mode != 1)
+#endif
+          for (int k = 0; k < kcnt; ++k)
             umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           umma_commit(&ctl->empty[stage]);           // frees the smem slot when these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -258,6 +276,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       if (et == 0) { TIMED_WAIT(&ctl->tmem_full[acc], acc_phase, 3); } else { mbar_wait(&ctl->tmem_full[acc], acc_phase); }
       tc_fence_after();
+#ifdef SEGB200_DBG
+      const long long dbg_epi_t0 = clock64();
+      if (p.dbg_mode == 3) {
+        chunk_ctr += (uint32_t)nchunks;
+        tc_fence_before();
+        mbar_arrive(&ctl->tmem_empty[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+#endif
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       if (p.out_f32) {
         if (grp == 0) {
@@ -355,6 +383,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);             // 128 * kEpiGroups arrivals release the accumulator stage
+#ifdef SEGB200_DBG
+      if (p.dbg != nullptr && et == 0 && grp == 0) { atomicAdd(p.dbg + 4, (unsigned long long)(clock64() - dbg_epi_t0)); atomicAdd(p.dbg + 6, 1ull); }
+#endif
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();
@@ -362,6 +393,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+#ifdef SEGB200_DBG
+  if (p.dbg != nullptr && threadIdx.x == 0) atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - dbg_kernel_t0));
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -529,7 +563,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
           const uint64_t bdesc = make_kmajor_desc(sa + (uint32_t)p.a_stage_bytes, (uint32_t)p.bk_bytes);
-          for (int k = 0; k < kmma; ++k)
+          const int kcnt = (kb % p.cblocks == p.cblocks - 1) ? p.kmma_tail : kmma;
+          for (int k = 0; k < kcnt; ++k)
             umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           umma2_commit_both(&ctl->empty[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -685,6 +720,7 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 
 using namespace segb200;
 
+static int g_dbg_mode = 0;
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
 static int g_no_img_tiles = 0;
@@ -699,6 +735,8 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_img_tiles")) { g_no_img_tiles = value ? 0 : 1; return 0; }
   if (name && !strcmp(name, "gemm_epi2_maxk")) { g_epi2_maxk = value > 0 ? value : 512; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
+  if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
+  if (name && !strcmp(name, "gemm_dbg_mode")) { g_dbg_mode = value; return 0; }     // effective in -DSEGB200_DBG builds only
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
@@ -791,6 +829,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   if (total > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many tiles");
   p.total_tiles = (int)total;
   p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
+  p.kmma_tail = (a->cin - (cblocks - 1) * bk + 15) / 16;
   p.a_stage_bytes = 128 * bk_bytes;
   // CTA-pair kernel (opt-in): needs an N tile that splits into two UMMA-legal halves, 16-bit output, at least one full pair
   const long long m_tiles_all = (long long)p.wtiles * p.htiles * p.n_img;
@@ -815,6 +854,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   else p.num_stages = avail / (p.a_stage_bytes + p.b_stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
+  p.dbg_mode = g_dbg_mode;
   p.out_f32 = a->y_f32 ? 1 : 0;
   p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
 

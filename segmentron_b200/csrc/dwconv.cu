@@ -210,10 +210,13 @@ struct DwRingParams {
   int twin;          // input columns per ring slot
   int slot_bytes;    // twin * 128
   int nslots;
+  int wblocks, segs; // persistent (4-channel) kernel: column blocks and row segments per image
 };
 
 static int g_dw_ring_slots = 0;
+static int g_dw_v8 = 0;           // 1: the round-1 8-channel ring kernel (A/B knob "dw_v8")
 int set_dw_ring_slots(int n) { g_dw_ring_slots = n; return 0; }
+int set_dw_v8(int v) { g_dw_v8 = v ? 1 : 0; return 0; }
 
 constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = t >> 3); +1 producer warp = 256 threads
 constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
@@ -369,6 +372,194 @@ dwconv3x3_ring_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParam
 }
 
 #undef DW_ROW
+
+// ---------------------------------------------------------------------------------------------
+// Lean ring variant (round 2; default for C >= 64): FOUR channels per thread (16 lanes cover the 128-byte channel block of a
+// column, a warp two adjacent columns), 14 output columns per CTA.  Against the 8-channel kernel above:
+//   * 36 weight registers instead of 72 -> <= 80 registers -> 3 CTAs (21 consumer warps) per SM instead of 2 (14): the 8-channel
+//     kernel sat at 54-57 % issue-slot use with 21 % occupancy -- latency-bound (profiles/r1_ncu_full_summary.md);
+//   * the per-row instruction stream is cut to the arithmetic: activation and leading ReLU are template parameters, the output
+//     pointer and the ring addresses advance incrementally (the 8-channel loop spent ~60 of its ~190 instructions per row on 64-bit
+//     address arithmetic and run-time activation dispatch, cuobjdump).
+// Same producer protocol, same rolling partial-sum recurrence, bit-identical results (same fp32 operation order per channel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kDw4Cols = kDwConsumers / 16;   // 14 output columns per CTA
+
+template <bool kBF16, bool kPreRelu>
+__device__ __forceinline__ void ring_row_sums4(uint32_t row_addr, uint32_t tap_step, const float2 (&wt)[9][2], float2 (&s)[3][2],
+                                               uint32_t empty_bar) {
+  using H = Half2<kBF16>;
+  uint2 v[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[kx].x), "=r"(v[kx].y) : "r"(row_addr + kx * tap_step));
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive_addr(empty_bar);
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    uint32_t u[2] = {v[kx].x, v[kx].y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (kPreRelu) u[j] = H::relu2(u[j]);
+      const float2 f = H::unpack(u[j]);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) s[ky][j] = ffma2(f, wt[ky * 3 + kx][j], s[ky][j]);
+    }
+  }
+}
+
+template <bool kBF16, int kAct>
+__device__ __forceinline__ void store_out4(void* dst, const float2 (&o)[2]) {
+  using H = Half2<kBF16>;
+  uint2 r;
+  r.x = H::pack(o[0].x, o[0].y);
+  r.y = H::pack(o[1].x, o[1].y);
+  if (kAct != ACT_NONE) { r.x = H::relu2(r.x); r.y = H::relu2(r.y); }      // round(max(v,0)) == max(round(v),0)
+  if (kAct == ACT_RELU6) { r.x = H::min2(r.x, 6.f); r.y = H::min2(r.y, 6.f); }
+  *reinterpret_cast<uint2*>(dst) = r;
+}
+
+template <bool kBF16, int kStride, bool kPreRelu, int kAct, bool kD1>
+__global__ void __launch_bounds__(kDwConsumers + 32, 3)
+dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
+  // PERSISTENT: the grid is (at most) 3 CTAs per SM; a CTA walks work items  item = blockIdx.x + k * gridDim.x  with
+  //   item -> (channel block | image | row segment | column block)   (column block fastest: concurrently running CTAs share halos in L2)
+  // and streams their input rows through ONE continuous ring: the producer runs ahead across item boundaries, so the pipeline
+  // fills once per CTA instead of once per (tiny) tile -- at 65x129 a 14-column x 22-row tile is ~3 us of work against ~1.5 us of fill.
+  using H = Half2<kBF16>;
+  using T = typename H::T;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const DwParams& p = rp.b;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + rp.nslots * rp.slot_bytes);
+  uint64_t* empty = full + rp.nslots;
+  const int warp = threadIdx.x >> 5;
+  const int d = kD1 ? 1 : p.dil;                        // kD1: dilation 1 is a compile-time constant (tap offsets become immediates)
+  const int wblocks = rp.wblocks, segs = rp.segs;
+  const int per_cblk = wblocks * segs * p.n;
+  const int total = per_cblk * p.cblocks;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kDwConsumers / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto decode = [&](int item, int& cblk, int& n, int& h_begin, int& h_end, int& w0) {
+    cblk = item / per_cblk;
+    int r = item - cblk * per_cblk;
+    n = r / (wblocks * segs); r -= n * (wblocks * segs);
+    const int seg = r / wblocks;
+    w0 = (r - seg * wblocks) * kDw4Cols;
+    h_begin = seg * p.rows_per_block;
+    h_end = h_begin + p.rows_per_block; if (h_end > p.ho) h_end = p.ho;
+  };
+
+  if (warp == kDwConsumers / 32) {                     // ---- producer warp: identical item / row sequence to the consumers ----
+    if ((threadIdx.x & 31) == 0) {
+      int slot = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int cblk, n, h_begin, h_end, w0;
+        decode(item, cblk, n, h_begin, h_end, w0);
+        auto issue = [&](int r) {
+          mbar_wait(&empty[slot], phase ^ 1);
+          mbar_expect_tx(&full[slot], (uint32_t)rp.slot_bytes);
+          tma_load_4d(&tmX, &full[slot], dsm + slot * rp.slot_bytes, cblk * 64, w0 * kStride - d, r, n);
+          if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+        };
+        if (kStride == 1) {
+          const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
+          for (int ch = 0; ch < nchains; ++ch) {
+            const int h0 = h_begin + ch;
+            const int n_out = (h_end - h0 + d - 1) / d;
+            for (int k = 0; k < n_out + 2; ++k) issue(h0 + (k - 1) * d);
+          }
+        } else {
+          for (int r = 2 * h_begin - 1; r <= 2 * (h_end - 1) + 1; ++r) issue(r);
+        }
+      }
+    }
+    return;
+  }
+
+  const int c4 = threadIdx.x & 15, wl = threadIdx.x >> 4;
+  const long long yrow_bytes = (long long)p.wo * p.y_ld * (long long)sizeof(T);
+  const uint32_t ring0 = smem_u32(dsm) + (uint32_t)(wl * kStride * 128 + c4 * 8);
+  const uint32_t tap_step = (uint32_t)(d * 128);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  const uint32_t slot_bytes = (uint32_t)rp.slot_bytes;
+  const uint32_t bar_end = full0 + (uint32_t)rp.nslots * 8;
+  uint32_t ring = ring0, fbar = full0, ebar = empty0, phase = 0;
+#define DW4_ROW(S) do { \
+    mbar_wait_lean(fbar, phase); \
+    ring_row_sums4<kBF16, kPreRelu>(ring, tap_step, wt, S, ebar); \
+    ring += slot_bytes; fbar += 8; ebar += 8; \
+    if (fbar == bar_end) { ring = ring0; fbar = full0; ebar = empty0; phase ^= 1; } } while (0)
+
+  float2 wt[9][2];
+  float2 sh[2];
+  int cur_cblk = -1;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    int cblk, n, h_begin, h_end, w0;
+    decode(item, cblk, n, h_begin, h_end, w0);
+    const int cq = cblk * 16 + c4;                     // channel quad
+    const int wo = w0 + wl;
+    const bool active = cq * 4 < p.c && wo < p.wo;
+    const int c0 = (cq * 4 < p.c ? cq : 0) * 4;
+    if (cblk != cur_cblk) {                            // (items are channel-block major: this happens once or twice per CTA)
+      cur_cblk = cblk;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0));
+        wt[t][0] = make_float2(a.x, a.y); wt[t][1] = make_float2(a.z, a.w);
+      }
+      if (p.shift != nullptr) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+        sh[0] = make_float2(a.x, a.y); sh[1] = make_float2(a.z, a.w);
+      } else {
+        sh[0] = sh[1] = make_float2(0.f, 0.f);
+      }
+    }
+    uint8_t* ybase = reinterpret_cast<uint8_t*>(reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0);
+
+    if (kStride == 1) {
+      const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
+      const long long ystep = yrow_bytes * d;
+      for (int ch = 0; ch < nchains; ++ch) {
+        const int h0 = h_begin + ch;
+        const int n_out = (h_end - h0 + d - 1) / d;
+        uint8_t* yp = ybase + (long long)h0 * yrow_bytes;
+        float2 acc0[2] = {sh[0], sh[1]}, acc1[2] = {sh[0], sh[1]};
+        // rows k = 0, 1 only feed the accumulators; rows k >= 2 also complete output row h0 + (k-2)*d
+        for (int k = 0; k < n_out + 2; ++k) {
+          float2 s[3][2] = {{sh[0], sh[1]}, {acc0[0], acc0[1]}, {acc1[0], acc1[1]}};      // chain seeds
+          DW4_ROW(s);
+          if (k >= 2) {
+            if (active) store_out4<kBF16, kAct>(yp, s[2]);
+            yp += ystep;
+          }
+          acc1[0] = s[1][0]; acc1[1] = s[1][1]; acc0[0] = s[0][0]; acc0[1] = s[0][1];
+        }
+      }
+    } else {
+      float2 acc0[2];
+      {
+        float2 s[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}};
+        DW4_ROW(s);
+        acc0[0] = s[0][0]; acc0[1] = s[0][1];
+      }
+      uint8_t* yp = ybase + (long long)h_begin * yrow_bytes;
+      for (int ho = h_begin; ho < h_end; ++ho) {
+        float2 sa[3][2] = {{sh[0], sh[1]}, {acc0[0], acc0[1]}, {sh[0], sh[1]}};          // only sa[1] is used
+        DW4_ROW(sa);
+        float2 sb[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sa[1][0], sa[1][1]}};        // sb[2] = out, sb[0] = next acc0
+        DW4_ROW(sb);
+        acc0[0] = sb[0][0]; acc0[1] = sb[0][1];
+        if (active) store_out4<kBF16, kAct>(yp, sb[2]);
+        yp += yrow_bytes;
+      }
+    }
+  }
+#undef DW4_ROW
+}
+
 }  // namespace segb200
 
 using namespace segb200;
@@ -391,7 +582,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   p.cv = a->c / 8;
   const bool ring = a->c >= 64 && (a->stride == 1 || a->dilation == 1) && a->dilation <= 64;
   int lw;
-  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = kDwTW; }
+  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : kDw4Cols; }
   else { p.lc = p.cv <= 8 ? 8 : 16; p.cblocks = (p.cv + p.lc - 1) / p.lc; lw = 128 / p.lc; }
   const int wblocks = (a->wo + lw - 1) / lw;
   // rows per block: long enough to amortise the 2-row halo of each chain, short enough to fill the GPU
@@ -399,6 +590,14 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   if (rows > a->ho) rows = a->ho;
   long long blocks_xy = (long long)p.cblocks * wblocks * a->n;
   while (rows > 4 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 8) rows = (rows + 1) / 2;
+  if (ring && !g_dw_v8) {
+    // persistent kernel: no need to over-decompose for occupancy; balanced segments (65 rows -> 3 x 22, not 32 + 32 + 1)
+    rows = a->stride == 1 ? 32 * a->dilation : 32;
+    if (rows > a->ho) rows = a->ho;
+    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 3 * 2) rows = (rows + 1) / 2;
+    const int nseg = (a->ho + rows - 1) / rows;
+    rows = (a->ho + nseg - 1) / nseg;
+  }
   if (a->stride == 1 && rows < a->ho) rows = ((rows + a->dilation - 1) / a->dilation) * a->dilation;   // whole chains
   p.rows_per_block = rows;
   dim3 grid((unsigned)(p.cblocks * wblocks), (unsigned)((a->ho + rows - 1) / rows), (unsigned)a->n);
@@ -406,10 +605,11 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   if (ring) {
     DwRingParams rp;
     rp.b = p;
-    rp.twin = (kDwTW - 1) * a->stride + 2 * a->dilation + 1;
+    const int tw = g_dw_v8 ? kDwTW : kDw4Cols;
+    rp.twin = (tw - 1) * a->stride + 2 * a->dilation + 1;
     rp.slot_bytes = rp.twin * 128;
     rp.nslots = 49152 / rp.slot_bytes;
-    if (rp.nslots > 12) rp.nslots = 12;
+    if (rp.nslots > (g_dw_v8 ? 12 : 24)) rp.nslots = g_dw_v8 ? 12 : 24;
     if (g_dw_ring_slots > 0 && rp.nslots > g_dw_ring_slots) rp.nslots = g_dw_ring_slots;
     if (rp.nslots < 3) rp.nslots = 3;
     const int smem = rp.nslots * rp.slot_bytes + 2 * rp.nslots * 8;
@@ -420,6 +620,30 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     int rc = encode_map(&tmX, a->dtype, 4, a->x, dims, str, box, 0, "dw/X");
     if (rc) return rc;
     typedef void (*RingFn)(const CUtensorMap, const DwRingParams);
+    const int threads = kDwConsumers + 32;
+    if (!g_dw_v8) {
+      // [dtype][stride-1][pre_relu][act]
+      // [dilation == 1][dtype][stride-1][pre_relu][act]
+#define DW4_ROWS(BF, S, D1) {{dwconv3x3_ring4_kernel<BF, S, false, 0, D1>, dwconv3x3_ring4_kernel<BF, S, false, 1, D1>, dwconv3x3_ring4_kernel<BF, S, false, 2, D1>}, \
+                             {dwconv3x3_ring4_kernel<BF, S, true, 0, D1>, dwconv3x3_ring4_kernel<BF, S, true, 1, D1>, dwconv3x3_ring4_kernel<BF, S, true, 2, D1>}}
+      static const RingFn fns4x[2][2][2][2][3] = {{{DW4_ROWS(false, 1, false), DW4_ROWS(false, 2, false)}, {DW4_ROWS(true, 1, false), DW4_ROWS(true, 2, false)}},
+                                                  {{DW4_ROWS(false, 1, true), DW4_ROWS(false, 2, true)}, {DW4_ROWS(true, 1, true), DW4_ROWS(true, 2, true)}}};
+#undef DW4_ROWS
+      const auto& fns4 = fns4x[a->dilation == 1 ? 1 : 0];
+      static std::once_flag once4;
+      std::call_once(once4, [] {
+        for (int i = 0; i < 48; ++i)
+          cudaFuncSetAttribute(fns4x[i / 24][(i / 12) & 1][(i / 6) & 1][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      });
+      if (a->act < 0 || a->act > 2) return set_error(-3, "dwconv3x3: bad activation code");
+      rp.wblocks = wblocks; rp.segs = (int)grid.y;
+      const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
+      if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
+      long long pgrid = (long long)num_sms() * 3;
+      if (pgrid > total) pgrid = total;
+      fns4[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)pgrid, threads, smem, stream>>>(tmX, rp);
+      return check_launch("dwconv3x3(ring4)");
+    }
     static const RingFn fns[2][2][2] = {
         {{dwconv3x3_ring_kernel<false, 1, false>, dwconv3x3_ring_kernel<false, 1, true>},
          {dwconv3x3_ring_kernel<false, 2, false>, dwconv3x3_ring_kernel<false, 2, true>}},
@@ -430,7 +654,6 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
       for (int i = 0; i < 8; ++i)
         cudaFuncSetAttribute(fns[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     });
-    const int threads = kDwConsumers + 32;
     fns[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0]<<<grid, threads, smem, stream>>>(tmX, rp);
     return check_launch("dwconv3x3(ring)");
   }

@@ -1,0 +1,106 @@
+// segb200 -- tensor-core rate micro-benchmark (diagnostics only; linked into libsegb200_dbg.so, never into the product library).
+//
+// One CTA (or CTA pair) per SM issues `iters` x 4 back-to-back tcgen05.mma (K = 16 each, operands resident in shared memory, no TMA,
+// no epilogue) and reports SM cycles per MMA.  Answers "what does the tensor pipe sustain for THIS tile shape", which bounds the
+// main loop of conv_gemm independently of L2 / TMA / epilogue effects (profiles/r2_gemm_decomposition.md):
+//   variant 0: cta_group::1, M = 128, N = n      (A 4 KB + B n*32 B read from smem per MMA)
+//   variant 1: cta_group::2, M = 256, N = n      (per SM: A 4 KB + B/2)
+#include "common.cuh"
+
+namespace segb200 {
+
+__device__ __forceinline__ uint32_t probe_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int kPair>
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? probe_ctarank() : 0;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // finite values
+  if (threadIdx.x == 0) { mbar_init(&done, 1); fence_mbar_init(); }
+  if (warp == 1) {
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(&tmem_base_s, 512);
+      tmem_relinquish();
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (kPair) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  long long cycles = 0;
+  if (warp == 0 && lane == 0 && rank == 0) {
+    const uint64_t adesc = make_kmajor_desc(smem_u32(smem), 128);
+    const uint64_t bdesc = make_kmajor_desc(smem_u32(smem + 16384), 128);
+    const uint32_t fmt = 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)n >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (kPair)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tmem + (uint32_t)((it & 1) * 256)), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(1u) : "memory");
+        else
+          umma_f16(tmem + (uint32_t)((it & 1) * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+      }
+    }
+    if (kPair)
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                   ::"r"(smem_u32(&done)), "h"((uint16_t)3) : "memory");
+    else
+      umma_commit(&done);
+    mbar_wait(&done, 0);
+    cycles = clock64() - t0;
+    atomicAdd(out, (unsigned long long)cycles);
+    atomicAdd(out + 1, 1ull);
+  } else if (kPair && warp == 0 && lane == 0) {
+    mbar_wait(&done, 0);          // the peer may not exit (its smem / TMEM are in use) before the pair's MMAs retire
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kPair) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    tc_fence_after();
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    else tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace segb200
+
+using namespace segb200;
+
+// out: 2 device u64 {sum of cycles over the issuing CTAs, number of issuing CTAs}.  Returns 0 / cudaError.
+extern "C" int segb200_debug_mma_probe(int variant, int n, int iters, void* out2_u64, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!out2_u64 || n < 16 || n > 256 || (n & 15) || iters < 1) return set_error(-4, "mma_probe: bad arguments");
+  const int smem = 200 * 1024;          // whole-SM shared memory: exactly one CTA per SM (each allocates all 512 TMEM columns)
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(out2_u64);
+  if (variant == 0) {
+    cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    mma_probe_kernel<0><<<num_sms(), 128, smem, stream>>>(n, iters, out);
+  } else {
+    cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_probe_kernel<1>, n, iters, out);
+    if (e != cudaSuccess) return set_error((int)e, "mma_probe: %s", cudaGetErrorString(e));
+  }
+  return check_launch("mma_probe");
+}

@@ -21,6 +21,9 @@ import torch
 from . import fold, lib as L, ops
 
 
+_DEVICE_FOLD = bool(__import__("os").environ.get("SEGB200_DEVICE_FOLD"))     # A/B switch: fold / pack on the device (round-1 behaviour)
+
+
 class Plan:
     def __init__(self, params, dtype, device):
         self.P = params            # name -> tensor (reference state_dict keys)
@@ -45,7 +48,7 @@ class Plan:
         folded / packed results are uploaded (``dev``)"""
         t = self._host.get(name)
         if t is None:
-            t = self._host[name] = self.P[name].detach().to("cpu")
+            t = self._host[name] = self.P[name].detach().to(self.device if _DEVICE_FOLD else "cpu")
         return t
 
     def dev(self, t):
@@ -138,21 +141,25 @@ class Plan:
         return self.conv(x, wpk, out, cin=cin, cout=cop, kh=k, kw=k, stride=stride, dilation=dilation, pad_t=pad,
                          pad_l=pad, scale=scale, shift=shift, act=act, residual=residual)
 
-    def sepconv(self, x, prefix, planes, stride=1, dilation=1, relu_first=True, eps=1e-5, out=None, residual=None):
-        """SeparableConv2d (modules/basic.py:34-62) = dw kernel + GEMM."""
+    def sepconv(self, x, prefix, planes, stride=1, dilation=1, relu_first=True, eps=1e-5, out=None, residual=None,
+                x_is_relu=False, out_relu=False):
+        """SeparableConv2d (modules/basic.py:34-62) = dw kernel + GEMM.  ``x_is_relu``: the producer already applied the leading ReLU
+        of a relu_first block (its only consumer is this block: xception.py:37-42), so the depthwise kernel skips it; ``out_relu``:
+        apply the NEXT block's leading ReLU in this GEMM's epilogue (free there; round(max(v,0)) == max(round(v),0), bit-identical)."""
         n, h, w_, c = x.shape
         p = prefix + ".block"
         s1, t1 = self.bn(p + ".bn_depth", eps)
         wdw = fold.pack_dw_weight(self.w(p + ".depthwise.weight"), s1)
         ho, wo = (h - 1) // stride + 1, (w_ - 1) // stride + 1
         tmp = self.new(n, ho, wo, c)
-        self.dw(x, wdw, tmp, stride=stride, dilation=dilation, shift=t1, pre_relu=relu_first,
+        self.dw(x, wdw, tmp, stride=stride, dilation=dilation, shift=t1, pre_relu=relu_first and not x_is_relu,
                 act=None if relu_first else "relu")
         s2, t2 = self.bn(p + ".bn_point", eps)
         wpk = fold.pack_conv_weight(self.w(p + ".pointwise.weight"), self.dtype)
         if out is None:
             out = self.new(n, ho, wo, planes)
-        return self.conv(tmp, wpk, out, cin=c, cout=planes, scale=s2, shift=t2, act=None if relu_first else "relu",
+        assert not (out_relu and (residual is not None or not relu_first))
+        return self.conv(tmp, wpk, out, cin=c, cout=planes, scale=s2, shift=t2, act="relu" if (out_relu or not relu_first) else None,
                          residual=residual)
 
     def stem_s2d(self, x_nchw_shape, x_holder, prefix_conv, prefix_bn, cout, k, pad, act, eps):
@@ -175,19 +182,23 @@ class Plan:
 # ----------------------------------------------------------------------------------------------
 # model builders (mirror the reference forward graphs; see oracle/segref.py for the line citations)
 # ----------------------------------------------------------------------------------------------
-def _xception_block(pl, x, prefix, chans, stride=1, dilation=1, skip="conv", relu_first=True, eps=1e-5):
-    """XceptionBlock.forward (backbones/xception.py:32-51)."""
+def _xception_block(pl, x, prefix, chans, stride=1, dilation=1, skip="conv", relu_first=True, eps=1e-5, sc2_used=True):
+    """XceptionBlock.forward (backbones/xception.py:32-51).  In a relu_first block sep_conv1's output feeds only sep_conv2's leading
+    ReLU, and sep_conv2's only sep_conv3's unless the caller also takes it (``sc2_used``: the decoder's low-level feature): those
+    ReLUs move into the producing GEMM's epilogue."""
     n, h, w_, cin = x.shape
-    sc1 = pl.sepconv(x, prefix + ".sep_conv1", chans[1], 1, dilation, relu_first, eps)
-    sc2 = pl.sepconv(sc1, prefix + ".sep_conv2", chans[2], 1, dilation, relu_first, eps)
+    f1 = relu_first
+    f2 = relu_first and not sc2_used
+    sc1 = pl.sepconv(x, prefix + ".sep_conv1", chans[1], 1, dilation, relu_first, eps, out_relu=f1)
+    sc2 = pl.sepconv(sc1, prefix + ".sep_conv2", chans[2], 1, dilation, relu_first, eps, x_is_relu=f1, out_relu=f2)
     if skip == "conv":
         res = pl.conv_bn_act(x, prefix, chans[3], 1, stride=stride, act=None, eps=eps, conv="conv", bn="bn")
     elif skip == "sum":
         res = x
     else:
         res = None
-    out = pl.sepconv(sc2, prefix + ".sep_conv3", chans[3], stride, dilation, relu_first, eps, residual=res)
-    return out, sc2
+    out = pl.sepconv(sc2, prefix + ".sep_conv3", chans[3], stride, dilation, relu_first, eps, residual=res, x_is_relu=f2)
+    return out, (sc2 if sc2_used else None)
 
 
 def _xception65(pl, x_shape, holder, output_stride, eps):
@@ -196,13 +207,13 @@ def _xception65(pl, x_shape, holder, output_stride, eps):
     p = "encoder"
     x = pl.stem_s2d(x_shape, holder, p + ".conv1", p + ".bn1", 32, 3, 1, "relu", eps)
     x = pl.conv_bn_act(x, p, 64, 3, pad=1, act="relu", eps=eps, conv="conv2", bn="bn2")
-    x, _ = _xception_block(pl, x, p + ".block1", [64, 128, 128, 128], 2, eps=eps)
+    x, _ = _xception_block(pl, x, p + ".block1", [64, 128, 128, 128], 2, eps=eps, sc2_used=False)
     x, c1 = _xception_block(pl, x, p + ".block2", [128, 256, 256, 256], 2, eps=eps)
     x, c2 = _xception_block(pl, x, p + ".block3", [256, 728, 728, 728], b3s, eps=eps)
     for i in range(4, 20):
-        x, _ = _xception_block(pl, x, f"{p}.block{i}", [728] * 4, 1, mid_d, "sum", eps=eps)
+        x, _ = _xception_block(pl, x, f"{p}.block{i}", [728] * 4, 1, mid_d, "sum", eps=eps, sc2_used=False)
     c3 = x
-    x, _ = _xception_block(pl, c3, p + ".block20", [728, 728, 1024, 1024], exit_s, exit_d[0], eps=eps)
+    x, _ = _xception_block(pl, c3, p + ".block20", [728, 728, 1024, 1024], exit_s, exit_d[0], eps=eps, sc2_used=False)
     c4, _ = _xception_block(pl, x, p + ".block21", [1024, 1536, 1536, 2048], 1, exit_d[1], "none", False, eps)
     return c1, c2, c3, c4
 

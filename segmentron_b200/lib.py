@@ -103,6 +103,12 @@ SYMBOLS = {
     "segb200_upsample_add_bwd": (ci, [vp, vp, vp, vp] + [ci] * 13 + [vp]),
     "segb200_dw_wgrad_v2_slabs": (ci, [ll, ci, ci]),
     "segb200_dw_wgrad_v2": (ci, [vp, vp, vp] + [ci] * 10 + [vp]),
+    # ---- SyncBatchNorm exchange over peer memory ----
+    "segb200_syncbn_slot_floats": (ci, [ci, ci]),
+    "segb200_syncbn_slot_flags": (ci, [ci]),
+    "segb200_counter_add": (ci, [vp, ci, vp]),
+    "segb200_bn_finalize_sync": (ci, [vp, ci, ci, C.c_double, vp, vp, vp, vp, cf, cf, vp, vp, vp, vp, vp, ci, ci, ci, ll, ll, vp, vp]),
+    "segb200_bn_bwd_finalize_sync": (ci, [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, ci, ll, ll, vp, vp]),
     # ---- segmentron._C (NCHW, the reference's own layout) ----
     "segb200_ca_forward": (ci, [vp, vp, vp] + [ci] * 5 + [vp]),
     "segb200_ca_backward": (ci, [vp] * 5 + [ci] * 5 + [vp]),

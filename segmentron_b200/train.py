@@ -236,12 +236,15 @@ class Act:
 # the plan
 # ------------------------------------------------------------------------------------------------------------
 class TrainPlan:
-    def __init__(self, store, shape, nclass, dtype, device, bn_momentum=0.1, ignore_index=-1, dist=None, sync_bn=False):
+    def __init__(self, store, shape, nclass, dtype, device, bn_momentum=0.1, ignore_index=-1, dist=None, sync_bn=False, xchg=None):
         self.S, self.dtype, self.device = store, dtype, device
         # SyncBatchNorm (the reference's default for distributed training, tools/train.py:73-79): batch statistics and the two
         # backward sums are all-reduced over the ranks ([2][C] fp32 per layer, count-weighted == equal per-rank counts here)
         self.dist = dist if (dist is not None and sync_bn) else None
         self.world = dist.get_world_size() if self.dist is not None else 1
+        # xchg (parallel.SyncExchange): the two exchanges become part of the finalize kernels (P2P stores over NVLink, csrc/syncbn.cu)
+        # instead of reduce_partials + NCCL all_reduce + finalize; None -> the all_reduce form (gloo CPU tests, no symmetric memory)
+        self.xchg = xchg if self.dist is not None else None
         self.lib = L.load()
         self.dt = ops.dt_code(dtype)
         self.n, _, self.H, self.W = shape
@@ -339,18 +342,30 @@ class TrainPlan:
         rm, rv = S.stat(bn + ".running_mean"), S.stat(bn + ".running_var")
         self.add("bn_stats", self.lib.segb200_bn_stats, (_ptr(y), rows, c, y_ld, self.dt, _ptr(partial), 0), x=y, partial=partial, c=c)
         fin_partial, fin_slabs, count = partial, slabs, float(rows)
-        if self.dist is not None:
+        if self.xchg is not None:
+            X = self.xchg
+            data_off, flag_off = X.new_slot()
+            count = float(rows * self.world)
+            st["count"] = count
+            self.add("bn_finalize_sync", self.lib.segb200_bn_finalize_sync,
+                     (_ptr(partial), slabs, c, count, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
+                      _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"]), C.c_void_p(X.peers_dev), X.world, X.rank,
+                      X.cmax, data_off, flag_off, _ptr(X.epoch)),
+                     partial=partial, slabs=slabs, c=c, count=count, gamma=gamma, beta=beta, rm=rm, rv=rv, momentum=self.bn_momentum,
+                     eps=eps, st=st, dist=self.dist)
+        elif self.dist is not None:
             gsum = self.f32(2 * c)
             self.add("reduce_partials", self.lib.segb200_reduce_partials, (_ptr(partial), slabs, 2, c, _ptr(gsum), c, 1, 0, 1.0),
                      partial=partial, slabs=slabs, K=2, c=c, out=gsum, sk=c, sc=1, accumulate=0, scale=1.0)
             self.allreduce(gsum)
             fin_partial, fin_slabs, count = gsum, 1, float(rows * self.world)
         st["count"] = count
-        self.add("bn_finalize", self.lib.segb200_bn_finalize,
-                 (_ptr(fin_partial), fin_slabs, c, count, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
-                  _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"])),
-                 partial=fin_partial, slabs=fin_slabs, c=c, count=count, gamma=gamma, beta=beta, rm=rm, rv=rv,
-                 momentum=self.bn_momentum, eps=eps, st=st)
+        if self.xchg is None:
+            self.add("bn_finalize", self.lib.segb200_bn_finalize,
+                     (_ptr(fin_partial), fin_slabs, c, count, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), self.bn_momentum, eps,
+                      _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["scale"]), _ptr(st["shift"])),
+                     partial=fin_partial, slabs=fin_slabs, c=c, count=count, gamma=gamma, beta=beta, rm=rm, rv=rv,
+                     momentum=self.bn_momentum, eps=eps, st=st)
         res_ld = self._rows(residual)[3] if residual is not None else 0
         self.add("bn_apply", self.lib.segb200_bn_apply,
                  (_ptr(y), _ptr(st["scale"]), _ptr(st["shift"]), _ptr(residual), _ptr(nc_scale), _ptr(z), rows, hw, c, y_ld, res_ld,
@@ -372,11 +387,19 @@ class TrainPlan:
                   dz_ld, z_ld, y_ld, L.ACT[act], self.dt, 0),
                  dz=dz, z=zz, y=y, st=st, nc_scale=nc_scale, act=act, c=c)
         dgamma, dbeta = S.view(S.grad, bn + ".weight"), S.view(S.grad, bn + ".bias")
-        self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
-                 (_ptr(st["partial"]), st["slabs"], c, _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)),
-                 st=st, c=c, dgamma=dgamma, dbeta=dbeta)
-        if self.dist is not None:
-            self.allreduce(st["sums"])               # dgamma / dbeta above are the LOCAL sums (DDP averages them with the rest)
+        if self.xchg is not None:
+            X = self.xchg
+            data_off, flag_off = X.new_slot()
+            self.add("bn_bwd_finalize_sync", self.lib.segb200_bn_bwd_finalize_sync,
+                     (_ptr(st["partial"]), st["slabs"], c, _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta),
+                      C.c_void_p(X.peers_dev), X.world, X.rank, X.cmax, data_off, flag_off, _ptr(X.epoch)),
+                     st=st, c=c, dgamma=dgamma, dbeta=dbeta, dist=self.dist)
+        else:
+            self.add("bn_bwd_finalize", self.lib.segb200_bn_bwd_finalize,
+                     (_ptr(st["partial"]), st["slabs"], c, _ptr(st["mean"]), _ptr(st["invstd"]), _ptr(st["sums"]), _ptr(dgamma), _ptr(dbeta)),
+                     st=st, c=c, dgamma=dgamma, dbeta=dbeta)
+            if self.dist is not None:
+                self.allreduce(st["sums"])           # dgamma / dbeta above are the LOCAL sums (DDP averages them with the rest)
         count = st.get("count", float(rows))
         dres, dres_acc, dres_ld = None, False, 0
         if residual is not None:
@@ -1267,7 +1290,7 @@ class DeepLabV3PlusTrainerB200:
     def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, eps_encoder=None, use_aspp=None,
                  use_decoder=None, dtype=torch.bfloat16, device="cuda",
                  lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
-                 bucket_mb=25, cuda_graph=False, sync_bn=True):
+                 bucket_mb=25, cuda_graph=False, sync_bn=True, fused_sync_bn=True):
         if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
             raise RuntimeError("segb200: a CUDA device (sm_100a) is required; there is no CPU fallback")
         self.device = torch.device(device)
@@ -1295,12 +1318,25 @@ class DeepLabV3PlusTrainerB200:
                 self.dist, self.world = dist, dist.get_world_size()
         except Exception:                                            # pragma: no cover
             self.dist = None
+        # SyncBatchNorm exchange over NVLink peer memory (csrc/syncbn.cu); falls back -- loudly -- to per-layer NCCL all-reduces when
+        # symmetric memory cannot be set up (and always under gloo: the CPU tests interpret the all_reduce form)
+        self.xchg = None
+        if self.dist is not None and sync_bn and fused_sync_bn and self.device.type == "cuda" and self.dist.get_backend() == "nccl":
+            try:
+                from .parallel import SyncExchange
+                cmax = max([v.numel() for k, v in state_dict.items() if k.endswith("running_mean")] + [64])
+                self.xchg = SyncExchange(self.dist, self.device, fold.round_up(cmax, 128))
+            except Exception as e:                                   # noqa: BLE001
+                import sys
+                print(f"[segb200] fused SyncBatchNorm exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduces",
+                      file=sys.stderr)
+                self.xchg = None
 
     def plan_for(self, shape):
         shape = tuple(shape)
         if shape not in self.plans:
             pl = TrainPlan(self.store, shape, self.nclass, self.dtype, self.device, self.bn_momentum, dist=self.dist,
-                           sync_bn=self.sync_bn)
+                           sync_bn=self.sync_bn, xchg=self.xchg)
             self._build(pl)
             self.plans[shape] = dict(plan=pl, graph=None, buckets=self._buckets(pl))
         return self.plans[shape]
@@ -1350,6 +1386,9 @@ class DeepLabV3PlusTrainerB200:
                 m.fill_(1.0)
         self.store.grad.zero_()
         self.store.steps += 1
+        if self.xchg is not None:                        # new epoch for this step's SyncBatchNorm exchanges
+            L.check(L.load().segb200_counter_add(_ptr(self.xchg.epoch), 1, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "counter_add")
         self.pack_weights()
         if self.dist is None:
             pl.run()
@@ -1383,6 +1422,12 @@ class DeepLabV3PlusTrainerB200:
 
     def state_dict(self):
         return self.store.state_dict()
+
+    def collectives_per_step(self, shape):
+        """NCCL collectives issued per step: gradient buckets + (only without the fused exchange) 2 per BatchNorm layer"""
+        st = self.plan_for(shape)
+        pl = st["plan"]
+        return (len(st["buckets"]) if self.dist is not None else 0) + sum(1 for s in pl.fwd + pl.bwd if s.kind == "allreduce")
 
     def n_launches(self, shape):
         pl = self.plan_for(shape)["plan"]

@@ -78,9 +78,12 @@ def run_step(st):
         partial.zero_()
         partial[:c] = xf.sum(0)
         partial[c:2 * c] = (xf * xf).sum(0)
-    elif kind == "bn_finalize":
+    elif kind in ("bn_finalize", "bn_finalize_sync"):
         c, cnt, st_ = i["c"], i["count"], i["st"]
         p = i["partial"].view(i["slabs"], 2, c).double().sum(0)
+        if kind == "bn_finalize_sync":              # the kernel's peer-memory exchange == a SUM over ranks of the local [2][c] sums
+            p = p.contiguous()
+            i["dist"].all_reduce(p)
         m = p[0] / cnt
         var = (p[1] / cnt - m * m).clamp(min=0)
         inv = 1.0 / torch.sqrt(var + i["eps"])
@@ -132,17 +135,20 @@ def run_step(st):
                 else:
                     o = g * st_["scale"] if st_.get("scale") is not None else g
                 i["dy"].copy_(o.to(i["dy"].dtype))
-    elif kind == "bn_bwd_finalize":
+    elif kind in ("bn_bwd_finalize", "bn_bwd_finalize_sync"):
         st_, c = i["st"], i["c"]
         p = st_["partial"].view(st_["slabs"], 2, c).double().sum(0)
         mean = st_["mean"].double() if st_.get("mean") is not None else 0.0
         inv = st_["invstd"].double() if st_.get("invstd") is not None else 1.0
         p = torch.stack([p[0], inv * (p[1] - mean * p[0])])
-        st_["sums"][0] = p[0].to(CD); st_["sums"][1] = p[1].to(CD)
-        if i["dgamma"] is not None:
+        if i["dgamma"] is not None:                 # LOCAL sums (DDP averages the parameter gradients)
             i["dgamma"].add_(p[1].to(i["dgamma"].dtype))
         if i["dbeta"] is not None:
             i["dbeta"].add_(p[0].to(i["dbeta"].dtype))
+        if kind == "bn_bwd_finalize_sync":
+            p = p.contiguous()
+            i["dist"].all_reduce(p)
+        st_["sums"][0] = p[0].to(CD); st_["sums"][1] = p[1].to(CD)
     elif kind == "reduce_partials":
         K, c, slabs = i["K"], i["c"], i["slabs"]
         # partial[(slab*K + k)*cc + ch] with cc = the channel count the producer used

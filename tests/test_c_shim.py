@@ -41,8 +41,8 @@ def _rt(shape, seed, dtype):
     return t.to(dtype).float()                          # representable in the kernel dtype
 
 
-def _close(a, b, tol, what):
-    err = float((a.float().cpu() - b).abs().max() / (b.abs().max() + 1e-30))
+def _close(a, b, tol, what, floor=0.0):
+    err = float((a.float().cpu() - b).abs().max() / max(float(b.abs().max()), floor, 1e-30))
     assert err <= tol, (what, err, tol)
     return err
 
@@ -113,12 +113,20 @@ def test_reference_autograd_functions_on_the_shim():
     sd = {k[len("cca."):]: v.detach() for k, v in P.t.items() if k.startswith("cca.")}
     m.load_state_dict(sd, strict=True)
     xr = x.cuda().requires_grad_()
-    yr = m(xr)
-    yr.backward(dy.cuda())
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # the module's own 1x1 convs run in cuDNN
+    try:
+        yr = m(xr)
+        yr.backward(dy.cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
     _close(yr.detach(), yo.detach(), 2e-5, "CrissCrossAttention forward")
     _close(xr.grad, xo.grad, 2e-4, "dx")
+    wscale = float(P.t["cca.value_conv.weight"].grad.abs().max())
     for name, p in m.named_parameters():
-        _close(p.grad, P.t["cca." + name].grad.reshape(p.shape), 2e-4, "d" + name)
+        # key_conv.bias: adding a constant to every key shifts all energies of a query equally -> the softmax, hence the loss, does not
+        # depend on it; its gradient is pure rounding noise (1e-5) on both sides, so it is measured against the weight-gradient scale
+        _close(p.grad, P.t["cca." + name].grad.reshape(p.shape), 2e-4, "d" + name, floor=1e-3 * wscale if name == "key_conv.bias" else 0.0)
 
 
 @pytest.mark.gpu

@@ -29,7 +29,20 @@ def _data(rank):
     return x, t, m
 
 
-def _worker(rank, world, port, out):
+class _FakeExchange:
+    """stand-in for parallel.SyncExchange (needs CUDA symmetric memory): lets the plan builder emit the FUSED exchange steps
+    (bn_finalize_sync / bn_bwd_finalize_sync), which the CPU interpreter executes as local sums + all_reduce(SUM) + finalize"""
+
+    def __init__(self, world, rank):
+        self.world, self.rank, self.cmax, self.peers_dev, self.n = world, rank, 2048, 0, 0
+        self.epoch = torch.zeros(1, dtype=torch.int32)
+
+    def new_slot(self):
+        self.n += 1
+        return (self.n - 1) * self.world * 2 * self.cmax, 10 ** 9 + (self.n - 1) * self.world * 32
+
+
+def _worker(rank, world, port, out, fused=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(4)
     sys.path.insert(0, os.path.dirname(__file__))
@@ -44,10 +57,17 @@ def _worker(rank, world, port, out):
     P = R.build_params(MODEL, SEED)
     tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.float64, device="cpu", lr=0.02, bucket_mb=20)
     assert tr.world == 2 and tr.dist is not None
+    if fused:
+        tr.xchg = _FakeExchange(world, rank)
     x, t, m = _data(rank)
     st = tr.plan_for(x.shape)
     pl, S = st["plan"], tr.store
-    assert sum(1 for s in pl.fwd + pl.bwd if s.kind == "allreduce") > 200          # SyncBN collectives are in the list
+    kinds = [s.kind for s in pl.fwd + pl.bwd]
+    if fused:                                                                       # no collective left on the compute path
+        assert kinds.count("allreduce") == 0 and kinds.count("bn_finalize_sync") > 100 and kinds.count("bn_bwd_finalize_sync") > 100
+        assert tr.xchg.n == kinds.count("bn_finalize_sync") + kinds.count("bn_bwd_finalize_sync")
+    else:
+        assert kinds.count("allreduce") > 200                                      # SyncBN collectives are in the list
     pl.x_in.copy_(x); pl.target.copy_(t)
     pl.masks["head.aspp.dropout"].copy_(m.reshape(SHAPE[0], 256))
     S.grad.zero_()
@@ -71,12 +91,16 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_training_step_matches_oracle_on_the_joint_batch():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl_form", "fused_exchange_form"])
+def test_two_rank_training_step_matches_oracle_on_the_joint_batch(fused):
     import torch.nn.functional as F
     from oracle import segref as R
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, fused), nprocs=2, join=True)
     assert out[0]["nb"] >= 3
     # oracle: joint batch, DDP loss
     P = R.build_params(MODEL, SEED).to(dtype=torch.float64)

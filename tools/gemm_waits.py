@@ -18,7 +18,7 @@ try:
 except AttributeError:
     HAS_DBG = False
 cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
-NAMES = ["prod:slot_free", "mma:acc_free", "mma:operands", "epi0:acc_ready", "epi1:acc_ready", "epi0:store", "epi1:store", "total"]
+NAMES = ["prod:slot_free", "mma:acc_free", "mma:operands", "epi:acc_ready", "epi:busy", "-", "tiles", "total"]
 
 
 def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
@@ -47,16 +47,17 @@ def run(name, n, h, w, cin, cout, k=1, res=False, pad=0):
     flops = 2.0 * n * h * w * cin * cout * k * k
     byts = 2.0 * (n * h * w * (cin + cout * (2 if res else 1)))
     print(f"{name}: {us:.1f} us  {flops / us / 1e6:.0f} TFLOP/s  {byts / us / 1e3:.0f} GB/s   cycles/CTA {tot:.0f}")
-    print("    " + "  ".join(f"{nm}={100.0 * v / 148.0 / max(tot, 1):.0f}%" for nm, v in zip(NAMES[:7], c[:7])))
-    print("    epi0 leader: " + "  ".join(f"{nm}={100.0 * v / 148.0 / max(tot, 1):.0f}%" for nm, v in
-                                          zip(["bar1", "res_wait", "ld+math+sts", "fence+bar2"], c[8:12])))
+    print("    " + "  ".join(f"{nm}={100.0 * v / 148.0 / max(tot, 1):.0f}%" for nm, v in zip(NAMES[:5], c[:5])) +
+          f"   tiles/CTA {c[6] / 148.0:.2f}  cycles/tile {tot / max(c[6] / 148.0, 1e-9):.0f}  epi busy cycles/tile {c[4] / max(c[6], 1):.0f}")
 
 
 modes = [int(m) for m in sys.argv[1:]] or [0]
 for mode in modes:
-    print(f"##### debug mode {mode}")
+    print(f"##### debug mode {mode}  (0 normal, 1 no MMA, 2 no TMA loads, 3 no epilogue work)")
+    L.segb200_set_option(b"gemm_dbg_mode", mode)
     run("pw 128->128 @8x513x1025", 8, 513, 1025, 128, 128)
     run("pw 728->728 @8x65x129", 8, 65, 129, 728, 728)
+    run("pw 1024->1024 @8x65x129", 8, 65, 129, 1024, 1024)
     run("pw 1536->2048", 8, 65, 129, 1536, 2048)
     if mode == 0:
         run("pw 64->128 @8x513x1025", 8, 513, 1025, 64, 128)
