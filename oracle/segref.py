@@ -577,6 +577,31 @@ def ccnet(P, x, nclass=19, output_stride=16, recurrence=2):
     return F.interpolate(out, size, mode="bilinear", align_corners=True)
 
 
+def fcn_head(P, x, prefix, nclass):
+    """_FCNHead.forward (modules/module.py:13-27): conv3x3(C -> C/4, no bias) + BN + ReLU + Dropout(0.1) (identity in eval) +
+    conv1x1(C/4 -> nclass, bias)."""
+    y = conv_bn_act(P, x, prefix + ".block", x.shape[1] // 4, 3, 1, 1, conv="0", bn="1")
+    return conv2d(P, y, prefix + ".block.4", nclass, 1, bias=True, gain=4.0)
+
+
+def pspnet(P, x, nclass=19, output_stride=8, aux=True, all=False):
+    """PSPNet.forward (models/pspnet.py:30-43) with _PSPHead (:46-61): ResNet101 (OS8, cityscapes_pspnet_resnet.yaml:25) ->
+    PyramidPooling(2048) -> conv3x3(4096 -> 512, no bias) + BN + ReLU + Dropout(0.1) (identity in eval) -> conv1x1(512 -> nclass)
+    -> bilinear(align_corners=True); the auxiliary _FCNHead(1024) on c3 (SOLVER.AUX True in the YAML) is the second output.
+    Inference only (nn.Dropout, not Dropout2d, sits in both heads)."""
+    assert not P.training, "the PSPNet oracle is inference-only"
+    size = x.shape[2:]
+    _, _, c3, c4 = resnet_v1(P, x, "encoder", (3, 4, 23, 3), output_stride)
+    y = pyramid_pooling(P, c4, "head.psp")
+    y = conv_bn_act(P, y, "head.block", 512, 3, 1, 1, conv="0", bn="1")
+    y = conv2d(P, y, "head.block.4", nclass, 1, bias=True, gain=4.0)
+    out = F.interpolate(y, size, mode="bilinear", align_corners=True)
+    if not aux:
+        return out
+    auxout = F.interpolate(fcn_head(P, c3, "auxlayer", nclass), size, mode="bilinear", align_corners=True)
+    return (out, auxout) if all else out
+
+
 def danet_head(P, x, nclass, prefix="head"):
     """DANetHead.forward (models/danet.py:70-88).  Each classifier is nn.Sequential(Dropout2d(0.1), Conv2d) (:64-68): the three
     dropouts are identity in eval and, in training, draw their masks in the order conv6, conv7, conv8."""
@@ -622,6 +647,8 @@ def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
             danet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
         elif model == "ccnet_resnet101":
             ccnet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
+        elif model == "pspnet_resnet101":
+            pspnet(P, torch.zeros(1, 3, 49, 49), nclass=nclass)
         elif model == "hrnet_w18_small_v1":
             hrnet_seg(P, torch.zeros(1, 3, 64, 64), nclass=nclass)
         else:
@@ -681,6 +708,8 @@ def forward(model: str, P: Params, x, nclass: int = 19, **kw):
             return outs if kw.get("all") else outs[0]
         if model == "ccnet_resnet101":
             return ccnet(P, x, nclass=nclass)
+        if model == "pspnet_resnet101":
+            return pspnet(P, x, nclass=nclass, all=bool(kw.get("all")))
         if model == "hrnet_w18_small_v1":
             return hrnet_seg(P, x, nclass=nclass)
         return deeplabv3plus(P, x, nclass=nclass, **MODELS[model], **kw)

@@ -736,6 +736,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_epi2_maxk")) { g_epi2_maxk = value > 0 ? value : 512; return 0; }
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
+  if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "gemm_dbg_mode")) { g_dbg_mode = value; return 0; }     // effective in -DSEGB200_DBG builds only
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }

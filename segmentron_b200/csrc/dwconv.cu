@@ -215,8 +215,10 @@ struct DwRingParams {
 
 static int g_dw_ring_slots = 0;
 static int g_dw_v8 = 0;           // 1: the round-1 8-channel ring kernel (A/B knob "dw_v8")
+static int g_dw_persistent = 0;   // 1: grid = 3 CTAs / SM walking the tiles through one continuous ring (A/B knob "dw_persistent")
 int set_dw_ring_slots(int n) { g_dw_ring_slots = n; return 0; }
 int set_dw_v8(int v) { g_dw_v8 = v ? 1 : 0; return 0; }
+int set_dw_persistent(int v) { g_dw_persistent = v ? 1 : 0; return 0; }
 
 constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = t >> 3); +1 producer warp = 256 threads
 constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
@@ -422,10 +424,11 @@ __device__ __forceinline__ void store_out4(void* dst, const float2 (&o)[2]) {
 template <bool kBF16, int kStride, bool kPreRelu, int kAct, bool kD1>
 __global__ void __launch_bounds__(kDwConsumers + 32, 3)
 dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
-  // PERSISTENT: the grid is (at most) 3 CTAs per SM; a CTA walks work items  item = blockIdx.x + k * gridDim.x  with
-  //   item -> (channel block | image | row segment | column block)   (column block fastest: concurrently running CTAs share halos in L2)
-  // and streams their input rows through ONE continuous ring: the producer runs ahead across item boundaries, so the pipeline
-  // fills once per CTA instead of once per (tiny) tile -- at 65x129 a 14-column x 22-row tile is ~3 us of work against ~1.5 us of fill.
+  // Work items (tiles):  item -> (image | row segment | column block | channel block), channel block fastest.  Default grid: one
+  // item per CTA.  Optional persistent mode (segb200_set_option("dw_persistent", 1)): the grid is 3 CTAs per SM, a CTA walks
+  // item = blockIdx.x + k * gridDim.x and streams the rows of successive items through ONE continuous ring (the producer runs
+  // ahead across item boundaries).  Measured on B200 (profiles/r2_dw_sweep.jsonl): not faster -- the hardware scheduler balances
+  // one-tile CTAs better than a static round-robin, and 3 resident CTAs already overlap one tile's fill with another's drain.
   using H = Half2<kBF16>;
   using T = typename H::T;
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -443,8 +446,10 @@ dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPara
   }
   __syncthreads();
   auto decode = [&](int item, int& cblk, int& n, int& h_begin, int& h_end, int& w0) {
-    cblk = item / per_cblk;
-    int r = item - cblk * per_cblk;
+    // channel block fastest: CTAs that run together read neighbouring 128-byte chunks of the SAME pixels (DRAM page / L2 sector
+    // locality: a pixel's 2*C bytes are touched once, not cblocks times at different moments)
+    cblk = item % p.cblocks;
+    int r = item / p.cblocks;
     n = r / (wblocks * segs); r -= n * (wblocks * segs);
     const int seg = r / wblocks;
     w0 = (r - seg * wblocks) * kDw4Cols;
@@ -594,7 +599,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     // persistent kernel: no need to over-decompose for occupancy; balanced segments (65 rows -> 3 x 22, not 32 + 32 + 1)
     rows = a->stride == 1 ? 32 * a->dilation : 32;
     if (rows > a->ho) rows = a->ho;
-    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 3 * 2) rows = (rows + 1) / 2;
+    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 3 * (g_dw_persistent ? 2 : 4)) rows = (rows + 1) / 2;
     const int nseg = (a->ho + rows - 1) / rows;
     rows = (a->ho + nseg - 1) / nseg;
   }
@@ -639,7 +644,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
       rp.wblocks = wblocks; rp.segs = (int)grid.y;
       const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
       if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
-      long long pgrid = (long long)num_sms() * 3;
+      long long pgrid = g_dw_persistent ? (long long)num_sms() * 3 : total;     // non-persistent: one tile per CTA, same kernel
       if (pgrid > total) pgrid = total;
       fns4[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)pgrid, threads, smem, stream>>>(tmX, rp);
       return check_launch("dwconv3x3(ring4)");

@@ -5,6 +5,9 @@
 // main loop of conv_gemm independently of L2 / TMA / epilogue effects (profiles/r2_gemm_decomposition.md):
 //   variant 0: cta_group::1, M = 128, N = n      (A 4 KB + B n*32 B read from smem per MMA)
 //   variant 1: cta_group::2, M = 256, N = n      (per SM: A 4 KB + B/2)
+// mode (variant 0): 0 = back-to-back issue; 1 = + one tcgen05.commit per 4 MMAs; 2 = + mbarrier try_wait on a completed phase and
+// tcgen05.fence before each group of 4; 3 = conv_gemm's full main-loop protocol (4-stage full/empty ring, a second warp standing in
+// for the TMA producer, operands read from the ring's rotating stages) -- each step isolates what one element of the protocol costs.
 #include "common.cuh"
 
 namespace segb200 {
@@ -16,14 +19,19 @@ __device__ __forceinline__ uint32_t probe_ctarank() {
 }
 
 template <int kPair>
-__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int mode, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t done;
+  __shared__ uint64_t sfull[4], sempty[4], sdummy;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? probe_ctarank() : 0;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // finite values
-  if (threadIdx.x == 0) { mbar_init(&done, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) {
+    mbar_init(&done, 1); mbar_init(&sdummy, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
+    fence_mbar_init();
+  }
   if (warp == 1) {
     if (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
@@ -46,15 +54,29 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, uns
     const uint32_t fmt = 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)n >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
     const long long t0 = clock64();
+    int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
+      uint32_t soff = 0;
+      if (!kPair && mode == 3) {                       // the conv_gemm main-loop protocol: wait full[stage], MMAs on THAT stage, commit empty[stage]
+        mbar_wait(&sfull[stage], phase);
+        tc_fence_after();
+        soff = (uint32_t)stage * 49152u;               // 4 stages of {A 16 KB, B 32 KB}
+      } else if (!kPair && mode == 2) {
+        mbar_wait(&sdummy, 1);                         // a barrier whose awaited phase already completed: pure try_wait + fence cost
+        tc_fence_after();
+      }
+      const uint64_t ad = make_kmajor_desc(smem_u32(smem) + soff, 128), bd = make_kmajor_desc(smem_u32(smem) + soff + 16384, 128);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (kPair)
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                        ::"r"(tmem + (uint32_t)((it & 1) * 256)), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(1u) : "memory");
         else
-          umma_f16(tmem + (uint32_t)((it & 1) * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          umma_f16(tmem + (uint32_t)(((it >> 3) & 1) * 256), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it & 7) | k));
       }
+      if (!kPair && mode == 1) umma_commit(&sdummy);   // commit nobody waits for
+      if (!kPair && mode == 2) umma_commit(&sempty[it & 3]);
+      if (!kPair && mode == 3) { umma_commit(&sempty[stage]); if (++stage == 4) { stage = 0; phase ^= 1; } }
     }
     if (kPair)
       asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -67,6 +89,13 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, uns
     atomicAdd(out + 1, 1ull);
   } else if (kPair && warp == 0 && lane == 0) {
     mbar_wait(&done, 0);          // the peer may not exit (its smem / TMEM are in use) before the pair's MMAs retire
+  } else if (!kPair && mode == 3 && warp == 2 && lane == 0) {
+    int stage = 0; uint32_t phase = 0;               // stand-in for the TMA producer: a slot becomes "full" as soon as it is empty
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&sempty[stage], phase ^ 1);
+      mbar_arrive(&sfull[stage]);
+      if (++stage == 4) { stage = 0; phase ^= 1; }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -83,14 +112,14 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, uns
 using namespace segb200;
 
 // out: 2 device u64 {sum of cycles over the issuing CTAs, number of issuing CTAs}.  Returns 0 / cudaError.
-extern "C" int segb200_debug_mma_probe(int variant, int n, int iters, void* out2_u64, void* stream_) {
+extern "C" int segb200_debug_mma_probe(int variant, int n, int iters, int mode, void* out2_u64, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!out2_u64 || n < 16 || n > 256 || (n & 15) || iters < 1) return set_error(-4, "mma_probe: bad arguments");
   const int smem = 200 * 1024;          // whole-SM shared memory: exactly one CTA per SM (each allocates all 512 TMEM columns)
   unsigned long long* out = reinterpret_cast<unsigned long long*>(out2_u64);
   if (variant == 0) {
     cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    mma_probe_kernel<0><<<num_sms(), 128, smem, stream>>>(n, iters, out);
+    mma_probe_kernel<0><<<num_sms(), 128, smem, stream>>>(n, iters, mode, out);
   } else {
     cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg;
@@ -99,7 +128,7 @@ extern "C" int segb200_debug_mma_probe(int variant, int n, int iters, void* out2
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_probe_kernel<1>, n, iters, out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_probe_kernel<1>, n, iters, mode, out);
     if (e != cudaSuccess) return set_error((int)e, "mma_probe: %s", cudaGetErrorString(e));
   }
   return check_launch("mma_probe");

@@ -575,6 +575,39 @@ def build_ccnet(pl, x_shape, holder, nclass, output_stride, recurrence, out_dtyp
     return [(o, am)]
 
 
+def build_pspnet(pl, x_shape, holder, nclass=19, output_stride=8, out_dtype=None, want_argmax=False):
+    """PSPNet.forward + _PSPHead.forward (models/pspnet.py:30-61; `forward()[0]`, the output SegBaseModel.evaluate uses).  The
+    backbone's last block writes channels [0, 2048) of the 4096-channel pyramid buffer and every pooled branch (adaptive average pool
+    -> 1x1 conv + BN + ReLU GEMM -> bilinear, PyramidPooling, modules/module.py:82-97) writes its 512-channel slice: no torch.cat.
+    Then the 3x3 4096 -> 512 conv + BN + ReLU (the head's dominant GEMM, K = 36 864), Dropout(0.1) = identity in eval, the 1x1
+    classifier and the fused bilinear NCHW output (+ argmax)."""
+    n, _, H, W = x_shape
+    hh, ww = H, W
+    for s in ([2, 2, 2] + ([2] if output_stride >= 16 else []) + ([2] if output_stride == 32 else [])):
+        hh, ww = (hh - 1) // s + 1, (ww - 1) // s + 1
+    sizes = (1, 2, 3, 6)
+    cat = pl.new(n, hh, ww, 2048 + 512 * len(sizes))
+    _, _, _, c4 = _resnet(pl, x_shape, holder, (3, 4, 23, 3), output_stride, 1e-5, c4_out=cat[..., :2048])
+    assert tuple(c4.shape[1:3]) == (hh, ww), (c4.shape, hh, ww)
+    for i, s in enumerate(sizes):
+        pooled = pl.new(n, s, s, 2048)
+        pl.call("segb200_adaptive_avgpool", ops._ptr(c4), ops._ptr(pooled), n, hh, ww, 2048, c4.stride(2), s, pooled.stride(2),
+                ops.dt_code(pl.dtype), nbytes=2.0 * c4.numel())
+        f = pl.conv_bn_act(pooled, f"head.psp.convs.{i}", 512, 1, act="relu")
+        pl.call("segb200_bilinear_nhwc", ops._ptr(f), ops._ptr(cat[..., 2048 + 512 * i:2560 + 512 * i]), n, s, s, 512, f.stride(2), hh, ww,
+                cat.stride(2), 1, ops.dt_code(pl.dtype), nbytes=2.0 * n * hh * ww * 512)
+    y = pl.conv_bn_act(cat, "head.block", 512, 3, pad=1, act="relu", conv="0", bn="1")
+    logits = pl.new(n, hh, ww, fold.round_up(nclass, 8), ld=32)
+    pl.conv_bn_act(y, "head.block.4", nclass, 1, act=None, conv=None, bn=None, bias=True, out=logits)
+    out_dtype = out_dtype or pl.dtype
+    o = torch.empty(n, nclass, H, W, dtype=out_dtype, device=pl.device)
+    am = torch.empty(n, H, W, dtype=torch.uint8, device=pl.device) if want_argmax else None
+    pl.call("segb200_bilinear_nchw_out", ops._ptr(logits), ops._ptr(o), ops._ptr(am), n, hh, ww, nclass, logits.stride(2), H, W, 1,
+            ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
+    pl.keep += [o] + ([am] if am is not None else [])
+    return [(o, am)]
+
+
 class DeepLabV3PlusB200:
     """Inference engine: ``engine(x_nchw) -> logits [N, nclass, H, W]`` (same contract as
     ``DeepLabV3Plus.forward(x)[0]``, models/deeplabv3_plus.py:33-46)."""
@@ -688,6 +721,22 @@ class CCNetB200(DANetB200):
         pl = Plan(self.sd, self.dtype, self.device)
         outs = build_ccnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.recurrence, self.out_dtype,
                            self.want_argmax)
+        return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)
+
+
+class PSPNetB200(DANetB200):
+    """``engine(x) -> logits`` (``PSPNet.forward(x)[0]``, models/pspnet.py:30-43): ResNet101 OS8 + PyramidPooling + _PSPHead.  The
+    auxiliary _FCNHead is a training-time output (``forward()[1]``) and is not computed."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=8, dtype=torch.bfloat16, out_dtype=None, device="cuda", cuda_graph=False,
+                 want_argmax=False):
+        DeepLabV3PlusB200.__init__(self, state_dict, backbone="resnet101", nclass=nclass, output_stride=output_stride,
+                                   dtype=dtype, out_dtype=out_dtype, device=device, cuda_graph=cuda_graph, want_argmax=want_argmax)
+
+    def _build(self, shape, in_dtype):
+        holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
+        pl = Plan(self.sd, self.dtype, self.device)
+        outs = build_pspnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.out_dtype, self.want_argmax)
         return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)
 
 

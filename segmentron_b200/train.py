@@ -22,6 +22,7 @@ Design (B200-first, not an autograd port):
 There is no CPU or PyTorch fallback: everything below calls the C ABI (lib.py) and raises RuntimeError otherwise.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -1321,6 +1322,8 @@ class DeepLabV3PlusTrainerB200:
         # SyncBatchNorm exchange over NVLink peer memory (csrc/syncbn.cu); falls back -- loudly -- to per-layer NCCL all-reduces when
         # symmetric memory cannot be set up (and always under gloo: the CPU tests interpret the all_reduce form)
         self.xchg = None
+        if os.environ.get("SEGB200_NO_FUSED_SYNCBN"):                # A/B switch: per-layer NCCL all-reduces (round-1 form)
+            fused_sync_bn = False
         if self.dist is not None and sync_bn and fused_sync_bn and self.device.type == "cuda" and self.dist.get_backend() == "nccl":
             try:
                 from .parallel import SyncExchange

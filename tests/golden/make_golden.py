@@ -28,6 +28,7 @@ MODEL_CASES = {
     "danet_resnet101_64x96": ("danet_resnet101", "cityscapes_danet_resnet.yaml", (1, 3, 64, 96), 5),
     "ccnet_resnet101_65x97": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (1, 3, 65, 97), 6),
     "hrnet_w18s_128x192": ("hrnet_w18_small_v1", "cityscapes_hrnet_w18_small_v1.yaml", (2, 3, 128, 192), 7),
+    "pspnet_resnet101_65x97": ("pspnet_resnet101", "cityscapes_pspnet_resnet.yaml", (1, 3, 65, 97), 8),
 }
 
 
@@ -52,6 +53,17 @@ def run_model_case(case):
         sys.modules["segmentron._C"] = fake
         segmentron._C = fake
         import segmentron.models.ccnet  # noqa: F401  (registers "CCNet")
+    if name == "pspnet_resnet101":
+        # The reference's PSPNet() cannot be constructed as shipped: _PSPHead passes norm_kwargs=None down to _ConvBNReLU, which has
+        # no such parameter (pspnet.py:47 -> module.py:90 -> basic.py:66).  Harness-side workaround, outside the
+        # reference tree: drop that one keyword in PyramidPooling's constructor.  No forward code is touched.
+        import segmentron.modules.module as _mm
+        _orig_init = _mm.PyramidPooling.__init__
+
+        def _init(self, in_channels, sizes=(1, 2, 3, 6), norm_layer=torch.nn.BatchNorm2d, **kwargs):
+            kwargs.pop("norm_kwargs", None)
+            _orig_init(self, in_channels, sizes=sizes, norm_layer=norm_layer, **kwargs)
+        _mm.PyramidPooling.__init__ = _init
     from segmentron.config import cfg
     from segmentron.models.model_zoo import get_segmentation_model
     cfg.update_from_file(os.path.join(REF, "configs", yaml_file))
@@ -65,6 +77,14 @@ def run_model_case(case):
                 m.eps = cfg.MODEL.BN_EPS_FOR_ENCODER
     P = R.build_params(name, seed)
     missing = model.load_state_dict(P.state_dict(), strict=True)
+    if name == "pspnet_resnet101":                      # two outputs (main, aux): check both, store the first
+        g_ = torch.Generator().manual_seed(1000 + seed)
+        x_ = torch.randn(*shape, generator=g_)
+        with torch.no_grad():
+            yr, yo = model(x_), R.forward(name, P, x_, all=True)
+        assert len(yr) == 2
+        for a_, b_ in zip(yr, yo):
+            assert float((a_ - b_).abs().max() / a_.abs().max()) < 1e-5
     if name == "danet_resnet101":                       # three outputs (sasc, sa, sc): check all, store the first
         g_ = torch.Generator().manual_seed(1000 + seed)
         x_ = torch.randn(*shape, generator=g_)
@@ -141,6 +161,17 @@ def run_train_case(case):
         sys.modules["segmentron._C"] = fake
         segmentron._C = fake
         import segmentron.models.ccnet  # noqa: F401  (registers "CCNet")
+    if name == "pspnet_resnet101":
+        # The reference's PSPNet() cannot be constructed as shipped: _PSPHead passes norm_kwargs=None down to _ConvBNReLU, which has
+        # no such parameter (pspnet.py:47 -> module.py:90 -> basic.py:66).  Harness-side workaround, outside the
+        # reference tree: drop that one keyword in PyramidPooling's constructor.  No forward code is touched.
+        import segmentron.modules.module as _mm
+        _orig_init = _mm.PyramidPooling.__init__
+
+        def _init(self, in_channels, sizes=(1, 2, 3, 6), norm_layer=torch.nn.BatchNorm2d, **kwargs):
+            kwargs.pop("norm_kwargs", None)
+            _orig_init(self, in_channels, sizes=sizes, norm_layer=norm_layer, **kwargs)
+        _mm.PyramidPooling.__init__ = _init
     from segmentron.config import cfg
     from segmentron.models.model_zoo import get_segmentation_model
     cfg.update_from_file(os.path.join(REF, "configs", yaml_file))

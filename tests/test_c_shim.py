@@ -120,13 +120,16 @@ def test_reference_autograd_functions_on_the_shim():
         yr.backward(dy.cuda())
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
-    _close(yr.detach(), yo.detach(), 2e-5, "CrissCrossAttention forward")
-    _close(xr.grad, xo.grad, 2e-4, "dx")
+    # fp32 on both sides, but cuDNN / cuBLAS and the CPU sum in different orders and the softmax sits on energies of O(10):
+    # forward to 2e-5, gradients to 1e-3 of their max
+    errs = {"y": _close(yr.detach(), yo.detach(), 2e-5, "CrissCrossAttention forward"), "dx": _close(xr.grad, xo.grad, 1e-3, "dx")}
     wscale = float(P.t["cca.value_conv.weight"].grad.abs().max())
     for name, p in m.named_parameters():
         # key_conv.bias: adding a constant to every key shifts all energies of a query equally -> the softmax, hence the loss, does not
         # depend on it; its gradient is pure rounding noise (1e-5) on both sides, so it is measured against the weight-gradient scale
-        _close(p.grad, P.t["cca." + name].grad.reshape(p.shape), 2e-4, "d" + name, floor=1e-3 * wscale if name == "key_conv.bias" else 0.0)
+        errs[name] = _close(p.grad, P.t["cca." + name].grad.reshape(p.shape), 1e-3, "d" + name,
+                            floor=1e-3 * wscale if name == "key_conv.bias" else 0.0)
+    print("\n[reference CrissCrossAttention on the segb200 _C shim] max-rel errors vs the CPU oracle:", {k: f"{v:.1e}" for k, v in errs.items()})
 
 
 @pytest.mark.gpu

@@ -149,6 +149,8 @@ def main():
                "tensor_core_tflops": {k: v["flops"] / (v["ms"] * 1e-3) / 1e12 for k, v in mm.items()},
                "activation_GB": pl.act_bytes / 1e9, "grad_pool_GB": pl.pool_bytes / 1e9,
                "sync_bn": bool(world > 1), "allreduce_buckets": len(tr.plan_for(shape)["buckets"]) if world > 1 else 0,
+               "fused_syncbn_exchange": bool(getattr(tr, "xchg", None) is not None),
+               "nccl_collectives_per_step": tr.collectives_per_step(shape),
                "param_digest": float(tr.store.master.double().abs().sum())}
     if not args.no_ref and world == 1:
         del tr

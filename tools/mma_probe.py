@@ -10,19 +10,19 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = C.CDLL(os.path.join(ROOT, "segmentron_b200", "libsegb200_dbg.so"))
-lib.segb200_debug_mma_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.segb200_debug_mma_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.segb200_last_error.restype = C.c_char_p
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 iters = 4096
 rows = []
-for variant in (0, 1):
-    for n in (256, 192, 128, 64):
+for variant, n, mode in [(0, 256, 0), (0, 256, 1), (0, 256, 2), (0, 256, 3), (0, 224, 3), (0, 128, 0), (0, 64, 0), (1, 256, 0), (1, 128, 0)]:
+    if True:
         best = None
         for rep in range(3):
             out.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc = lib.segb200_debug_mma_probe(variant, n, iters, C.c_void_p(out.data_ptr()), None)
+            rc = lib.segb200_debug_mma_probe(variant, n, iters, mode, C.c_void_p(out.data_ptr()), None)
             e1.record()
             torch.cuda.synchronize()
             if rc:
@@ -32,7 +32,7 @@ for variant in (0, 1):
             ms = e0.elapsed_time(e1)
             m = 256 if variant else 128
             flop = 2.0 * m * n * 16 * iters * 4 * ctas
-            r = dict(variant="cta_group::%d" % (variant + 1), m=m, n=n, cycles_per_mma=round(per, 1), issuing_ctas=int(ctas),
+            r = dict(variant="cta_group::%d" % (variant + 1), mode=mode, m=m, n=n, cycles_per_mma=round(per, 1), issuing_ctas=int(ctas),
                      tflops=round(flop / (ms * 1e-3) / 1e12, 1), flop_per_clk_per_sm=round(2.0 * m * n * 16 / per / (2 if variant else 1), 0),
                      mhz=round(cyc / ctas / (ms * 1e-3) / 1e6, 0))
             if best is None or r["cycles_per_mma"] < best["cycles_per_mma"]:
