@@ -125,6 +125,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking poll (mbarrier.test_wait): true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Spin with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -145,6 +155,21 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar_addr, uint32_t parit
       "@p bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}"
+      ::"r"(bar_addr), "r"(parity) : "memory");
+}
+// lean spin whose RETRY path carries the watchdog (fast path = one try_wait + one branch): a protocol bug traps instead of hanging
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "GW_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GW_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.gt.u32 q, n, 67108864;\n\t"
+      "@q trap;\n\t"
+      "bra GW_WAIT;\n\t"
+      "GW_DONE:\n\t}"
       ::"r"(bar_addr), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {

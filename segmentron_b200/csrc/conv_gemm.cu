@@ -175,10 +175,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    // tcgen05.mma issue is nearly synchronous: the tensor pipe queues about one instruction ahead of the one it executes
+    // (tools/mma_probe.py: every instruction this thread executes between two MMAs beyond ~128 cycles of slack is a cycle the pipe
+    // idles).  A single thread runs at one dependent instruction per ~4-6 cycles, so the k-block boundary (commit, barrier wait,
+    // fence, descriptors, loop control) is written for minimum instruction count: every kernel parameter is hoisted into registers,
+    // the descriptors' low words advance by one multiply-add per k-block (the high words are constants), the channel-block counter
+    // replaces a modulo, and barrier addresses are 32-bit shared addresses computed once.
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      uint32_t stage = 0, phase = 0; int acc = 0; uint32_t acc_phase = 0;
       const int kmma = p.bk_bytes >> 5;          // K=16 elements (32 B) per instruction
-      const uint32_t b_res = smem_u32(smem + p.num_stages * stage_bytes);
+      const int kmma_tail = p.kmma_tail, cblocks = p.cblocks;
+      const uint32_t nstages = (uint32_t)p.num_stages;
+      const bool b_res_mode = p.b_resident != 0;
+      const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+      // descriptor = {lo: start>>4 | LBO(1)<<16, hi: SBO | version<<14 | layout<<29}  (make_kmajor_desc)
+      const uint64_t d0 = make_kmajor_desc(smem_u32(smem), (uint32_t)p.bk_bytes);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4, b_off = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t bres_lo0 = a_lo0 + nstages * stage_step, bres_step = (uint32_t)p.b_stage_bytes >> 4;
       if (p.b_resident) mbar_wait(&ctl->b_full, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
@@ -189,21 +203,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         TIMED_WAIT(&ctl->tmem_empty[acc], acc_phase ^ 1, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        int cb = 0;
+        // (Consuming k-blocks in pairs -- two barrier observations, then 8 MMAs back to back -- runs at 162 instead of 235 cycles per MMA
+        // in the stand-alone probe (tools/mma_probe.py mode 6 vs 3) but LOSES in this kernel: with 48 KB stages only 3-4 fit, and a
+        // pair-granular ring halves the TMA prefetch distance (operand starvation 21 % -> 29 %, +res shapes 29 % -> 46 %;
+        // profiles/r2_gemm_decomposition.md).  One k-block per observation it stays.)
         for (int kb = 0; kb < num_kb; ++kb) {
+#ifdef SEGB200_DBG
           TIMED_WAIT(&ctl->full[stage], phase, 2);
+#else
+          mbar_wait_guarded(full0 + stage * 8, phase);
+#endif
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
-          const uint64_t bdesc = make_kmajor_desc(p.b_resident ? b_res + (uint32_t)(kb * p.b_stage_bytes) : sa + (uint32_t)p.a_stage_bytes,
-                                                  (uint32_t)p.bk_bytes);
-          const int kcnt = (kb % p.cblocks == p.cblocks - 1) ? p.kmma_tail : kmma;
+          const uint32_t a_lo = a_lo0 + stage * stage_step;
+          const uint32_t b_lo = b_res_mode ? bres_lo0 + (uint32_t)kb * bres_step : a_lo + b_off;
+          int kcnt = kmma;
+          if (++cb == cblocks) { cb = 0; kcnt = kmma_tail; }
 #ifdef SEGB200_DBG
           if (p.dbg_mode != 1)
 #endif
           for (int k = 0; k < kcnt; ++k)
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit(&ctl->empty[stage]);           // frees the smem slot when these MMAs retire
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            umma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * (uint32_t)k), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)k),
+                     idesc, (uint32_t)(kb | k));
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + stage * 8) : "memory");
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&ctl->tmem_full[acc]);            // accumulator ready for the epilogue
         acc ^= 1; if (acc == 0) acc_phase ^= 1;

@@ -64,6 +64,28 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
       } else if (!kPair && mode == 2) {
         mbar_wait(&sdummy, 1);                         // a barrier whose awaited phase already completed: pure try_wait + fence cost
         tc_fence_after();
+      } else if (!kPair && mode == 4) {
+        mbar_wait(&sdummy, 1);                         // wait only, no tcgen05.fence
+      } else if (!kPair && mode == 5) {
+        tc_fence_after();                              // fence only
+      } else if (!kPair && mode == 7) {
+        mbar_wait_lean(smem_u32(&sdummy), 1);          // lean wait (no watchdog loop) + fence
+        tc_fence_after();
+      } else if (!kPair && mode == 6) {                // ring protocol consumed in PAIRS of stages: 2 waits, one fence, 8 MMAs
+        mbar_wait(&sfull[stage], phase);
+        mbar_wait(&sfull[stage + 1], phase);
+        tc_fence_after();
+        const uint64_t a0 = make_kmajor_desc(smem_u32(smem) + (uint32_t)stage * 49152u, 128), b0 = a0 + (16384 >> 4);
+        const uint64_t a1 = a0 + (49152 >> 4), b1 = b0 + (49152 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + (uint32_t)(((it >> 3) & 1) * 256), a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (uint32_t)((it & 7) | k));
+        umma_commit(&sempty[stage]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + (uint32_t)(((it >> 3) & 1) * 256), a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, 1u);
+        umma_commit(&sempty[stage + 1]);
+        stage += 2; if (stage == 4) { stage = 0; phase ^= 1; }
+        ++it;                                          // this iteration consumed two k-blocks
+        continue;
       }
       const uint64_t ad = make_kmajor_desc(smem_u32(smem) + soff, 128), bd = make_kmajor_desc(smem_u32(smem) + soff + 16384, 128);
 #pragma unroll
@@ -75,7 +97,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
           umma_f16(tmem + (uint32_t)(((it >> 3) & 1) * 256), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it & 7) | k));
       }
       if (!kPair && mode == 1) umma_commit(&sdummy);   // commit nobody waits for
-      if (!kPair && mode == 2) umma_commit(&sempty[it & 3]);
+      if (!kPair && (mode == 2 || mode == 4 || mode == 5 || mode == 7)) umma_commit(&sempty[it & 3]);
       if (!kPair && mode == 3) { umma_commit(&sempty[stage]); if (++stage == 4) { stage = 0; phase ^= 1; } }
     }
     if (kPair)
@@ -89,7 +111,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
     atomicAdd(out + 1, 1ull);
   } else if (kPair && warp == 0 && lane == 0) {
     mbar_wait(&done, 0);          // the peer may not exit (its smem / TMEM are in use) before the pair's MMAs retire
-  } else if (!kPair && mode == 3 && warp == 2 && lane == 0) {
+  } else if (!kPair && (mode == 3 || mode == 6) && warp == 2 && lane == 0) {
     int stage = 0; uint32_t phase = 0;               // stand-in for the TMA producer: a slot becomes "full" as soon as it is empty
     for (int it = 0; it < iters; ++it) {
       mbar_wait(&sempty[stage], phase ^ 1);

@@ -63,14 +63,15 @@ def _check(model, P, x, y32, dtype, tol):
     print(f"\n[{model} {dtype}] rel-L2 ours={e_ours:.3e} ref16={e_ref:.3e}; argmax mismatches {int(mism.sum())}/"
           f"{mism.numel()} (beyond-resolution: {hard}); ref16 mismatches {int((y16.argmax(1) != y32.argmax(1)).sum())}")
     assert torch.equal(am, y.argmax(1)), "fused argmax disagrees with argmax of the engine's own logits"
-    # DANet: CAM's softmax(rowmax(E) - E) runs on UNNORMALISED Gram energies (|E| ~ 1e2..1e3 with these synthetic weights),
-    # which amplifies the 16-bit rounding of its input by |E| -- the reference's own fp16 forward overflows to NaN on this
-    # fixture and its bf16 forward is at 3e-2.  The whole-model comparison is ill-conditioned there, so DANet gets a 2x
-    # band and a small beyond-resolution allowance; PAM / CAM are held to tight bounds in tests/test_modules_gpu.py.
+    # DANet: CAM's softmax(rowmax(E) - E) runs on UNNORMALISED Gram energies (|E| ~ 1e2..1e3 with these synthetic weights), which
+    # amplifies any 16-bit rounding upstream of it by |E|: on ONE fixture the engine and the reference's own 16-bit forward are two
+    # noisy samples of the same error distribution (tools/danet_diag.py: per-seed ratios 0.5 .. 1.5).  The comparison against the
+    # reference's 16-bit forward is therefore made on the MEAN over seeds (test_danet_error_vs_reference_16bit_over_seeds below);
+    # here DANet only has to stay under the absolute cap (fp16: 2e-2 -- the reference's own fp16 forward is NaN on this fixture).
     ill = model == "danet_resnet101"
-    assert e_ours < (3.0 if ill else 1.0) * tol, (e_ours, tol)                                    # absolute sanity cap
-    if e_ref == e_ref:                                                                              # reference 16-bit forward finite
-        assert e_ours < (2.0 if ill else 1.05) * e_ref + 1e-4, (e_ours, e_ref)                    # vs the reference's own 16-bit forward
+    assert e_ours < (2e-2 if (ill and dtype == torch.float16) else tol), (e_ours, tol)            # absolute sanity cap
+    if e_ref == e_ref and not ill:                                                                  # reference 16-bit forward finite
+        assert e_ours < 1.05 * e_ref + 1e-4, (e_ours, e_ref)                                       # vs the reference's own 16-bit forward
     if e_ref != e_ref:
         # The reference's OWN 16-bit forward overflows to NaN on this fixture (CCNet / DANet in fp16: activations beyond 65504), i.e.
         # the network is outside the dtype's range for the reference itself.  The engine stays finite (fp32 epilogues), but in that
@@ -78,6 +79,28 @@ def _check(model, P, x, y32, dtype, tol):
         # folding, tools/fold_diff.py): there is no 16-bit reference to be faithful to, so only the absolute cap above applies.
         return
     assert hard <= (mism.numel() // 500 if ill else 0), hard
+
+
+def test_danet_error_vs_reference_16bit_over_seeds():
+    """DANet (PAM + CAM head): mean rel-L2 error against the fp32 oracle over 6 seeded (weights, input) pairs, bf16, 64x96 and
+    128x192 -- the engine's mean error must not exceed the mean error of the reference's own bf16 forward (same torch ops, oracle
+    port in bf16) by more than 5 %.  Measured on B200: 2.3e-2 vs 2.8e-2 (64x96), 2.4e-2 vs 2.7e-2 (128x192)."""
+    from segmentron_b200.engine import DANetB200
+    model, dtype = "danet_resnet101", torch.bfloat16
+    for shape in ((1, 3, 64, 96), (1, 3, 128, 192)):
+        ours, ref = [], []
+        for seed in range(6):
+            P = R.build_params(model, 100 + seed)
+            x = torch.randn(*shape, generator=torch.Generator().manual_seed(200 + seed)).cuda()
+            with torch.no_grad():
+                y32 = R.forward(model, P.to("cuda"), x).float()
+                y16 = R.forward(model, P.to("cuda", dtype), x.to(dtype)).float()
+            y = DANetB200(P.state_dict(), dtype=dtype)(x).float()
+            ours.append(_rel(y, y32)); ref.append(_rel(y16, y32))
+        mo, mr = sum(ours) / len(ours), sum(ref) / len(ref)
+        print(f"\n[danet bf16 {shape[2]}x{shape[3]}] mean rel-L2 over 6 seeds: ours {mo:.3e}, reference-bf16 {mr:.3e}  (per seed ours "
+              f"{[round(v, 4) for v in ours]}, ref {[round(v, 4) for v in ref]})")
+        assert mo <= 1.05 * mr, (mo, mr)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)], ids=["f16", "bf16"])

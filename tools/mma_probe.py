@@ -15,7 +15,7 @@ lib.segb200_last_error.restype = C.c_char_p
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 iters = 4096
 rows = []
-for variant, n, mode in [(0, 256, 0), (0, 256, 1), (0, 256, 2), (0, 256, 3), (0, 224, 3), (0, 128, 0), (0, 64, 0), (1, 256, 0), (1, 128, 0)]:
+for variant, n, mode in [(0, 256, 0), (0, 256, 0), (0, 256, 2), (0, 256, 4), (0, 256, 5), (0, 256, 7), (0, 256, 3), (0, 256, 6), (0, 128, 3), (0, 128, 6)]:
     if True:
         best = None
         for rep in range(3):
