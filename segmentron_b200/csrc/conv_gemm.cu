@@ -59,6 +59,7 @@ struct ConvGemmParams {
   int n_tiles, total_tiles;
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
+  int mma_pairs;        // CTA-pair kernel: consume k-blocks two at a time (needs a deep ring)
   int kmma_tail;        // K=16 MMA steps of the LAST channel block of a tap (the zero-filled K tail beyond it is skipped)
   int a_stage_bytes, b_stage_bytes;
   int b_resident;       // 1: all K blocks of the (single) N tile stay in smem for the whole kernel; the ring holds A only
@@ -567,30 +568,49 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    // Same lean loop as the single-CTA kernel.  Here one barrier observation feeds 4 MMAs of M = 256 (twice the FLOPs), and the
+    // 32 KB stages leave 5-6 ring slots, so k-blocks can be consumed in PAIRS (two observations, then 8 MMAs back to back:
+    // tools/mma_probe.py mode 6) without starving the TMA prefetch -- p.mma_pairs, set by the host when num_stages >= 5.
     if (lane == 0 && leader) {
-      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      uint32_t stage = 0, phase = 0; int acc = 0; uint32_t acc_phase = 0;
       const int kmma = p.bk_bytes >> 5;
+      const int kmma_tail = p.kmma_tail, cblocks = p.cblocks;
+      const uint32_t nstages = (uint32_t)p.num_stages;
+      const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+      const uint64_t d0 = make_kmajor_desc(smem_u32(smem), (uint32_t)p.bk_bytes);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4, b_off = (uint32_t)p.a_stage_bytes >> 4;
+      const int group = p.mma_pairs ? 2 : 1;
+      // the instruction's N spans both halves: CTA r supplies columns [r*half_n, r*half_n + N/2); keep the split at half_n
+      const uint32_t idesc = make_idesc_m256(kBF16, (uint32_t)p.bn);
       for (int tile = cluster_id; tile < pair_tiles; tile += n_clusters) {
-        const int n_tile = tile % p.n_tiles;
-        const int n0 = n_tile * p.bn;
-        int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
-        // the instruction's N spans both halves: CTA r supplies columns [r*half_n, r*half_n + N/2); keep the split at half_n
-        const uint32_t idesc = make_idesc_m256(kBF16, (uint32_t)p.bn);
-        (void)nvalid;
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&ctl->full[stage], phase);
+        int cb = 0;
+        for (int kb = 0; kb < num_kb; kb += group) {
+          const bool two = group == 2 && kb + 1 < num_kb;
+          uint32_t s1 = stage + 1, ph1 = phase;
+          if (s1 == nstages) { s1 = 0; ph1 ^= 1; }
+          mbar_wait_guarded(full0 + stage * 8, phase);
+          if (two) mbar_wait_guarded(full0 + s1 * 8, ph1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t adesc = make_kmajor_desc(sa, (uint32_t)p.bk_bytes);
-          const uint64_t bdesc = make_kmajor_desc(sa + (uint32_t)p.a_stage_bytes, (uint32_t)p.bk_bytes);
-          const int kcnt = (kb % p.cblocks == p.cblocks - 1) ? p.kmma_tail : kmma;
-          for (int k = 0; k < kcnt; ++k)
-            umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma2_commit_both(&ctl->empty[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const uint32_t st = h == 0 ? stage : s1;
+            const int kbb = kb + h;
+            const uint32_t a_lo = a_lo0 + st * stage_step, b_lo = a_lo + b_off;
+            int kcnt = kmma;
+            if (++cb == cblocks) { cb = 0; kcnt = kmma_tail; }
+            for (int k = 0; k < kcnt; ++k)
+              umma2_f16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * (uint32_t)k), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)k),
+                        idesc, (uint32_t)(kbb | k));
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(empty0 + st * 8), "h"((uint16_t)3) : "memory");
+          }
+          if (two) { stage = s1 + 1; phase = ph1; if (stage == nstages) { stage = 0; phase ^= 1; } }
+          else { stage = s1; phase = ph1; }
         }
         umma2_commit_both(&ctl->tmem_full[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -744,6 +764,7 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 using namespace segb200;
 
 static int g_dbg_mode = 0;
+static int g_mma_pairs = 1;    // CTA-pair kernel: pair-wise k-block consumption when the ring has >= 5 stages ("gemm_mma_pairs")
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
 static int g_no_img_tiles = 0;
@@ -760,6 +781,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_ring_slots")) return segb200::set_dw_ring_slots(value);
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
+  if (name && !strcmp(name, "gemm_mma_pairs")) { g_mma_pairs = value; return 0; }
   if (name && !strcmp(name, "gemm_dbg_mode")) { g_dbg_mode = value; return 0; }     // effective in -DSEGB200_DBG builds only
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -879,6 +901,7 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.dbg = g_dbg_counters;
   p.dbg_mode = g_dbg_mode;
+  p.mma_pairs = (use2 && g_mma_pairs && p.num_stages >= 5) ? 1 : 0;
   p.out_f32 = a->y_f32 ? 1 : 0;
   p.act = a->act; p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.res_ld = a->res_ld;
 

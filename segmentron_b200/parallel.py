@@ -63,11 +63,14 @@ class SyncExchange:
         self.flags_base = self.max_slots * self.slot_floats                       # in 4-byte words from the buffer base
         nwords = self.max_slots * (self.slot_floats + self.slot_flags)
         group = dist.group.WORLD
-        if hasattr(symm, "enable_symm_mem_for_group"):
-            try:
-                symm.enable_symm_mem_for_group(group.group_name)
-            except Exception:                                                       # newer torch: implicit
-                pass
+        if hasattr(symm, "enable_symm_mem_for_group"):                             # needed by torch < 2.8, a deprecated no-op since
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    symm.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass
         self.buf = symm.empty(nwords, dtype=torch.float32, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
