@@ -59,6 +59,7 @@ struct ConvGemmParams {
   int n_tiles, total_tiles;
   int cout, bn;
   int cblocks, ntaps, bk_bytes, num_stages;
+  int group;            // single-CTA kernel: k-blocks per ring stage (one full/empty hand-shake per `group` k-blocks)
   int mma_pairs;        // CTA-pair kernel: consume k-blocks two at a time (needs a deep ring)
   int kmma_tail;        // K=16 MMA steps of the LAST channel block of a tap (the zero-filled K tail beyond it is skipped)
   int a_stage_bytes, b_stage_bytes;
@@ -107,7 +108,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   Control* ctl = reinterpret_cast<Control*>(smem + p.ring_bytes + 2 * kEpiBufBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
+  const int sub_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);    // one k-block: A 128 x bk (+ B bn x bk)
+  const int stage_bytes = p.group * sub_bytes;                                      // a ring stage holds `group` k-blocks
   const int num_kb = p.ntaps * p.cblocks;
   const int bk_elems = p.bk_bytes >> 1;
 
@@ -157,19 +159,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int hb = m_tile % p.htiles;
         const int img = m_tile / p.htiles;
         const int w0 = wb * p.bw, h0 = hb * p.bh, n0 = n_tile * p.bn;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const uint32_t t = p.taps[tap];
-          const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
+        int tap = 0, cb = 0;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.group) {
+          const int gn = num_kb - kb0 < p.group ? num_kb - kb0 : p.group;
           TIMED_WAIT(&ctl->empty[stage], phase ^ 1, 0);
 #ifdef SEGB200_DBG
-          if (p.dbg_mode == 2) { mbar_arrive(&ctl->full[stage]); if (++stage == p.num_stages) { stage = 0; phase ^= 1; } continue; }
+          if (p.dbg_mode == 2) {
+            tap += (cb + gn) / p.cblocks; cb = (cb + gn) % p.cblocks;
+            mbar_arrive(&ctl->full[stage]); if (++stage == p.num_stages) { stage = 0; phase ^= 1; } continue;
+          }
 #endif
-          mbar_expect_tx(&ctl->full[stage], tx);
+          mbar_expect_tx(&ctl->full[stage], tx * (uint32_t)gn);
           uint8_t* sa = smem + stage * stage_bytes;
-          tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
-          if (!p.b_resident) tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, kb * bk_elems, n0);
+          for (int g = 0; g < gn; ++g, sa += sub_bytes) {
+            const uint32_t t = p.taps[tap];
+            const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
+            tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
+            if (!p.b_resident) tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, (kb0 + g) * bk_elems, n0);
+            if (++cb == p.cblocks) { cb = 0; ++tap; }
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -206,26 +214,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         int cb = 0;
         // (Consuming k-blocks in pairs -- two barrier observations, then 8 MMAs back to back -- runs at 162 instead of 235 cycles per MMA
-        // in the stand-alone probe (tools/mma_probe.py mode 6 vs 3) but LOSES in this kernel: with 48 KB stages only 3-4 fit, and a
+        // in the stand-alone probe (tools/mma_probe.py mode 6 vs 3) but LOSES in this kernel when a k-block is 48 KB: only 3-4 fit, and a
         // pair-granular ring halves the TMA prefetch distance (operand starvation 21 % -> 29 %, +res shapes 29 % -> 46 %;
-        // profiles/r2_gemm_decomposition.md).  One k-block per observation it stays.)
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // profiles/r2_gemm_decomposition.md).  Small k-blocks are different: the host packs `group` of them into one ring stage
+        // (<= 32 KB, so the ring stays >= 5 stages deep) and the whole group rides on ONE full/empty hand-shake.)
+        const uint32_t sub_step = (uint32_t)sub_bytes >> 4;
+        const int group = p.group;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += group) {
+          const int gn = num_kb - kb0 < group ? num_kb - kb0 : group;
 #ifdef SEGB200_DBG
           TIMED_WAIT(&ctl->full[stage], phase, 2);
 #else
           mbar_wait_guarded(full0 + stage * 8, phase);
 #endif
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + stage * stage_step;
-          const uint32_t b_lo = b_res_mode ? bres_lo0 + (uint32_t)kb * bres_step : a_lo + b_off;
-          int kcnt = kmma;
-          if (++cb == cblocks) { cb = 0; kcnt = kmma_tail; }
+          uint32_t a_lo = a_lo0 + stage * stage_step;
+          for (int g = 0; g < gn; ++g, a_lo += sub_step) {
+            const int kb = kb0 + g;
+            const uint32_t b_lo = b_res_mode ? bres_lo0 + (uint32_t)kb * bres_step : a_lo + b_off;
+            int kcnt = kmma;
+            if (++cb == cblocks) { cb = 0; kcnt = kmma_tail; }
 #ifdef SEGB200_DBG
-          if (p.dbg_mode != 1)
+            if (p.dbg_mode != 1)
 #endif
-          for (int k = 0; k < kcnt; ++k)
-            umma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * (uint32_t)k), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)k),
-                     idesc, (uint32_t)(kb | k));
+            for (int k = 0; k < kcnt; ++k)
+              umma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * (uint32_t)k), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)k),
+                       idesc, (uint32_t)(kb | k));
+          }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + stage * 8) : "memory");
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
@@ -764,6 +779,8 @@ static inline int floordiv2(int o, int* parity) {   // o = 2*a + p, p in {0,1}
 using namespace segb200;
 
 static int g_dbg_mode = 0;
+static int g_kgroup_kb = 40;   // largest ring stage a group of k-blocks may fill, in KB ("gemm_kgroup_kb"; measured: 40 KB / 9 best)
+static int g_kgroup = 0;       // k-blocks per ring stage: 0 = auto (<= 32 KB, <= 4), 1 = off, n = cap ("gemm_kgroup")
 static int g_mma_pairs = 1;    // CTA-pair kernel: pair-wise k-block consumption when the ring has >= 5 stages ("gemm_mma_pairs")
 static int g_ring_kb = 0;
 static int g_no_b_resident = 0;
@@ -782,6 +799,8 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "gemm_mma_pairs")) { g_mma_pairs = value; return 0; }
+  if (name && !strcmp(name, "gemm_kgroup")) { g_kgroup = value; return 0; }
+  if (name && !strcmp(name, "gemm_kgroup_kb")) { g_kgroup_kb = value > 0 ? value : 32; return 0; }
   if (name && !strcmp(name, "gemm_dbg_mode")) { g_dbg_mode = value; return 0; }     // effective in -DSEGB200_DBG builds only
   return set_error(-30, "segb200_set_option: unknown option '%s'", name ? name : "(null)");
 }
@@ -896,9 +915,23 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   const long long b_total = (long long)nkb * p.b_stage_bytes;
   const int avail = ring - (a->residual ? kResRegion : 0);
   p.b_resident = (!use2 && p.n_tiles == 1 && b_total <= 72 * 1024 && avail - b_total >= 4 * p.a_stage_bytes && !g_no_b_resident) ? 1 : 0;
-  if (p.b_resident) p.num_stages = (int)((avail - b_total) / p.a_stage_bytes);
-  else p.num_stages = avail / (p.a_stage_bytes + p.b_stage_bytes);
+  // k-blocks per ring stage: every full/empty hand-shake costs the single MMA-issuing thread several hundred cycles whatever the
+  // size of the MMAs behind it (profiles/r2_gemm_decomposition.md), so small k-blocks (small Cin: stems, 3x3 convs on 16-64
+  // channels) share one: as many as fit in 40 KB, at most 9 (a whole 3x3 kernel), never more than the conv has.  Measured on B200
+  // (profiles/r2_call12_kgroup_sweep.log): HRNet-w18-small fp16 16x1024x2048 1 224 -> 1 706 img/s, ResNet101-DLv3+ forward 481 -> 501
+  const int sub = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
+  p.group = 1;
+  if (!use2 && g_kgroup != 1) {
+    int g = (g_kgroup_kb * 1024) / sub;
+    const int cap = g_kgroup > 1 ? g_kgroup : 9;
+    if (g > cap) g = cap;
+    if (g > nkb) g = nkb;
+    if (g > 1) p.group = g;
+  }
+  const int stage_sz = p.group * sub;
+  p.num_stages = (int)((avail - (p.b_resident ? b_total : 0)) / stage_sz);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (p.num_stages < 2) return set_error(-8, "conv_gemm: shared-memory ring too small for this shape");
   p.dbg = g_dbg_counters;
   p.dbg_mode = g_dbg_mode;
   p.mma_pairs = (use2 && g_mma_pairs && p.num_stages >= 5) ? 1 : 0;

@@ -43,7 +43,14 @@ def time_it(fn, iters):
 
 
 def main():
-    names = sys.argv[1:] or ["c3", "c4", "c5", "c1"]
+    no_ref = "--no-ref" in sys.argv
+    kinds = "--kinds" in sys.argv                    # also print the per-kernel-kind time table of each plan
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3", "c4", "c5", "c1"]
+    for a in sys.argv[1:]:                          # e.g. --opt:gemm_kgroup=9 --opt:gemm_kgroup_kb=48  (segb200_set_option knobs)
+        if a.startswith("--opt:"):
+            k, v = a[6:].split("=")
+            from segmentron_b200 import lib as L
+            L.check(L.load().segb200_set_option(k.encode(), int(v)), "set_option")
     torch.backends.cudnn.benchmark = True
     for name in names:
         model, factory, shape, dt, what = CONFIGS[name]
@@ -53,10 +60,19 @@ def main():
         eng(x)
         ms = time_it(lambda: eng(x, copy_input=False), 10)
         ours = shape[0] / (ms * 1e-3)
+        per_kind = None
+        if kinds:
+            pl = eng.plan_for(x)["plan"]
+            pl.run_timed()
+            agg = {}
+            for m, t in pl.run_timed():
+                a = agg.setdefault(m["kind"], [0.0, 0])
+                a[0] += t; a[1] += 1
+            per_kind = {k: [round(v[0], 3), v[1]] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
         del eng
         torch.cuda.empty_cache()
         ref = {}
-        for fmt in ("nchw", "channels_last"):
+        for fmt in (() if no_ref else ("nchw", "channels_last")):
             try:
                 Pg = P.to("cuda", dt)
                 xb = x.to(dt)
@@ -74,7 +90,7 @@ def main():
         best = max(nums) if nums else None
         print(json.dumps({"config": name, "what": what, "shape": shape, "dtype": str(dt).split(".")[-1], "segb200_img_s": ours,
                           "segb200_ms": ms, "ref_cudnn_img_s": best, "ref_by_layout": ref,
-                          "speedup": (ours / best) if best else None}), flush=True)
+                          "speedup": (ours / best) if best else None, "per_kind_ms": per_kind}), flush=True)
 
 
 if __name__ == "__main__":
