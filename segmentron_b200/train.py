@@ -1291,7 +1291,7 @@ class DeepLabV3PlusTrainerB200:
     def __init__(self, state_dict, backbone="resnet101", nclass=19, output_stride=16, eps_encoder=None, use_aspp=None,
                  use_decoder=None, dtype=torch.bfloat16, device="cuda",
                  lr=0.02, momentum=0.9, weight_decay=1e-4, decoder_lr_factor=10.0, bn_momentum=0.1, dropout=True,
-                 bucket_mb=25, cuda_graph=False, sync_bn=True, fused_sync_bn=True):
+                 bucket_mb=25, cuda_graph=False, sync_bn=True, fused_sync_bn=True, grad_comm_dtype=torch.float32):
         if not ops._PLAN_DRY_RUN and not torch.cuda.is_available():
             raise RuntimeError("segb200: a CUDA device (sm_100a) is required; there is no CPU fallback")
         self.device = torch.device(device)
@@ -1308,6 +1308,11 @@ class DeepLabV3PlusTrainerB200:
         self.bucket_bytes = int(bucket_mb * 2 ** 20)
         self.cuda_graph = cuda_graph
         self.sync_bn = sync_bn                  # cfg.TRAIN.SYNC_BATCH_NORM (config/settings.py:59): only matters when world > 1
+        # dtype of the gradient all-reduce payload: fp32 = what the reference's DDP moves (tools/train.py:108-111, 191 MB per step);
+        # bf16 halves the NVLink bytes at the price of one rounding of every summand (opt-in: the sums differ from DDP's in the last bits)
+        if grad_comm_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("segb200: grad_comm_dtype must be torch.float32 or torch.bfloat16")
+        self.grad_comm_dtype = grad_comm_dtype
         stem = "encoder.conv1.conv.weight" if backbone == "mobilenet_v2" else "encoder.conv1.weight"
         self.store = ParamStore({k: v.detach() for k, v in state_dict.items()}, self.device, dtype, stem=stem)
         self.plans = {}
@@ -1401,10 +1406,17 @@ class DeepLabV3PlusTrainerB200:
             for pos, lo, hi in st["buckets"]:
                 pl.run(pl.bwd[pos0:pos])
                 pos0 = pos
-                works.append(self.dist.all_reduce(self.store.grad[lo:hi], async_op=True))
+                g = self.store.grad[lo:hi]
+                if self.grad_comm_dtype == torch.float32:
+                    works.append((self.dist.all_reduce(g, async_op=True), None, None))
+                else:                                # bf16 payload: cast -> all-reduce -> copy back (after the wait)
+                    t = g.to(self.grad_comm_dtype)
+                    works.append((self.dist.all_reduce(t, async_op=True), g, t))
             pl.run(pl.bwd[pos0:])
-            for w in works:
+            for w, g, t in works:
                 w.wait()
+                if t is not None:
+                    g.copy_(t)
         return pl.out3[0]
 
     def optimizer_step(self, lr=None):
