@@ -9,9 +9,11 @@
 //   pass 2 (kPass = 2): per (128-query tile, 256-column half of d_v): S again, P = exp(S - m_i) / l_i in bf16/fp16
 //                       -> shared memory (A operand), O[128 x 256] += P V accumulates in TMEM over all key tiles,
 //                       epilogue y = gamma * (O + b_v) + x.
-// Warp roles (192 threads): warp 0 = TMA producer (Q tile once; K tile [64 keys x 64] and V^T tile [256 x 64 keys] per
+// Warp roles (320 threads): warp 0 = TMA producer (Q tile once; K tile [64 keys x 64] and V^T tile [256 x 64 keys] per
 // key tile), warp 1 = tcgen05.mma issuer (S_j is issued before P_{j-1} V_{j-1} so the softmax of tile j overlaps the
-// PV MMAs of tile j-1), warps 2..5 = softmax / epilogue (one query row per thread = one TMEM lane).
+// PV MMAs of tile j-1), warps 2..9 = softmax / epilogue: TWO warps per TMEM lane quadrant, each thread owns one query row (= TMEM
+// lane) and HALF of the tile's 64 keys (round 2: with one warp per scheduler the exp / pack chain of a tile ran without any
+// latency hiding and paced the kernel; the row statistics of pass 1 are combined across the two halves at the end).
 // TMEM: O = columns [0,256), S double buffer = columns [256,384).  Smem: Q 16 KB, K 2 x 8 KB, P 2 x 16 KB, V 3 x 32 KB.
 // V is consumed as V^T [d_v][N] (K-major along keys); the caller produces it with the same GEMM kernel (roles swapped),
 // the value bias b_v is added in the epilogue (sum_j attention_ij = 1).
@@ -46,7 +48,7 @@ struct PamParams {
 };
 
 template <bool kBF16, int kPass>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
            const __grid_constant__ CUtensorMap tmV, const PamParams p) {
   using H = Half2<kBF16>;
@@ -64,8 +66,8 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       mbar_init(&ctl->q_full, 1); mbar_init(&ctl->o_full, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&ctl->k_full[i], 1); mbar_init(&ctl->k_empty[i], 1);
-        mbar_init(&ctl->s_full[i], 1); mbar_init(&ctl->s_empty[i], 128);
-        mbar_init(&ctl->p_full[i], 128); mbar_init(&ctl->p_empty[i], 1);
+        mbar_init(&ctl->s_full[i], 1); mbar_init(&ctl->s_empty[i], 256);
+        mbar_init(&ctl->p_full[i], 256); mbar_init(&ctl->p_empty[i], 1);
       }
       for (int i = 0; i < 3; ++i) { mbar_init(&ctl->v_full[i], 1); mbar_init(&ctl->v_empty[i], 1); }
       fence_mbar_init();
@@ -104,14 +106,20 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const uint32_t idesc_s = make_idesc(kBF16, kPamK);
       const uint32_t idesc_o = make_idesc(kBF16, kPamDV);
       const uint64_t qdesc = make_kmajor_desc(smem_u32(smem + kPamSmemQ), 128);
+      // descriptors of every buffer, built once (the issuing thread's instruction count between MMAs is what the pipe waits for)
+      const uint64_t pdescs[2] = {make_kmajor_desc(smem_u32(smem + kPamSmemP), 128), make_kmajor_desc(smem_u32(smem + kPamSmemP + 16384), 128)};
+      const uint64_t kdescs[2] = {make_kmajor_desc(smem_u32(smem + kPamSmemK), 128), make_kmajor_desc(smem_u32(smem + kPamSmemK + 8192), 128)};
+      const uint64_t vdesc0 = make_kmajor_desc(smem_u32(smem + kPamSmemV), 128);
+      int vb_pv = 0; uint32_t vph_pv = 0;              // V ring cursor of the PV side (3 slots)
       auto do_pv = [&](int t) {
         const int pb = t & 1; const uint32_t pph = (t >> 1) & 1;
-        const int vb = t % 3; const uint32_t vph = (t / 3) & 1;
+        const int vb = vb_pv; const uint32_t vph = vph_pv;
+        if (++vb_pv == 3) { vb_pv = 0; vph_pv ^= 1; }
         mbar_wait(&ctl->p_full[pb], pph);
         mbar_wait(&ctl->v_full[vb], vph);
         tc_fence_after();
-        const uint64_t pdesc = make_kmajor_desc(smem_u32(smem + kPamSmemP + pb * 16384), 128);
-        const uint64_t vdesc = make_kmajor_desc(smem_u32(smem + kPamSmemV + vb * 32768), 128);
+        const uint64_t pdesc = pdescs[pb];
+        const uint64_t vdesc = vdesc0 + (uint64_t)(vb * (32768 >> 4));
 #pragma unroll
         for (int k = 0; k < kPamK / 16; ++k)
           umma_f16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (uint32_t)((t | k) != 0));
@@ -124,7 +132,7 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         mbar_wait(&ctl->k_full[kb], kph);
         mbar_wait(&ctl->s_empty[kb], kph ^ 1);
         tc_fence_after();
-        const uint64_t kdesc = make_kmajor_desc(smem_u32(smem + kPamSmemK + kb * 8192), 128);
+        const uint64_t kdesc = kdescs[kb];
 #pragma unroll
         for (int k = 0; k < kPamD / 16; ++k)
           umma_f16(tmem_s + (uint32_t)(kb * kPamK), qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
@@ -136,8 +144,9 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     }
     __syncwarp();
   } else {
-    // ------------------------------ softmax / epilogue warps ------------------------------
-    const int quad = warp & 3;
+    // ------------------------------ softmax / epilogue warps (2..9) ------------------------------
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int hk = (warp - 2) >> 2;                  // which half of the tile's 64 keys (and of the output columns) this warp owns
     const int row = quad * 32 + lane;
     const int qi = q0 + row;
     const bool row_ok = qi < p.n_tok;
@@ -153,55 +162,57 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const int sb = j & 1; const uint32_t sph = (j >> 1) & 1;
       mbar_wait(&ctl->s_full[sb], sph);
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_s + (uint32_t)(sb * kPamK) + lane_off, v0);
-      tmem_ld_32x32(tmem_s + (uint32_t)(sb * kPamK + 32) + lane_off, v1);
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_s + (uint32_t)(sb * kPamK + hk * 32) + lane_off, v);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&ctl->s_empty[sb]);
-      const int nkeys = p.n_tok - j * kPamK;        // keys >= nkeys in this tile are padding (zero-filled by TMA)
+      const int nkeys = p.n_tok - j * kPamK - hk * 32;   // keys >= nkeys of this half-tile are padding (zero-filled by TMA)
       if (kPass == 1) {
         float tmax = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c < nkeys) tmax = fmaxf(tmax, __uint_as_float(v0[c]));
-          if (c + 32 < nkeys) tmax = fmaxf(tmax, __uint_as_float(v1[c]));
-        }
+        for (int c = 0; c < 32; ++c)
+          if (c < nkeys) tmax = fmaxf(tmax, __uint_as_float(v[c]));
         const float m_new = fmaxf(m, tmax);
-        float sum = 0.f;
-        const float mn2 = m_new * kLog2e;
+        if (m_new > -INFINITY) {
+          float sum = 0.f;
+          const float mn2 = m_new * kLog2e;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c < nkeys) sum += exp2f(fmaf(__uint_as_float(v0[c]), kLog2e, -mn2));
-          if (c + 32 < nkeys) sum += exp2f(fmaf(__uint_as_float(v1[c]), kLog2e, -mn2));
+          for (int c = 0; c < 32; ++c)
+            if (c < nkeys) sum += exp2f(fmaf(__uint_as_float(v[c]), kLog2e, -mn2));
+          l = l * exp2f((m - m_new) * kLog2e) + sum;
+          m = m_new;
         }
-        l = l * exp2f((m - m_new) * kLog2e) + sum;
-        m = m_new;
       } else {
         mbar_wait(&ctl->p_empty[sb], sph ^ 1);
         uint8_t* pbuf = smem + kPamSmemP + sb * 16384 + row * 128;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {              // 8 x 16 B = 64 keys of this row, 128B-swizzled (A operand, K-major)
+        for (int g = 0; g < 4; ++g) {              // 4 x 16 B = this thread's 32 keys of the row, 128B-swizzled (A operand, K-major)
           uint32_t pk[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int c = g * 8 + jj * 2;
-            const float s0 = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
-            const float s1 = __uint_as_float(c + 1 < 32 ? v0[(c + 1) & 31] : v1[(c + 1) & 31]);
-            const float p0 = c < nkeys ? exp2f(fmaf(s0, kLog2e, -m2)) * inv_l : 0.f;
-            const float p1 = c + 1 < nkeys ? exp2f(fmaf(s1, kLog2e, -m2)) * inv_l : 0.f;
+            const float p0 = c < nkeys ? exp2f(fmaf(__uint_as_float(v[c]), kLog2e, -m2)) * inv_l : 0.f;
+            const float p1 = c + 1 < nkeys ? exp2f(fmaf(__uint_as_float(v[c + 1]), kLog2e, -m2)) * inv_l : 0.f;
             pk[jj] = H::pack(p0, p1);
           }
-          *reinterpret_cast<uint4*>(pbuf + ((g ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(pbuf + (((hk * 4 + g) ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         fence_proxy_async();
         mbar_arrive(&ctl->p_full[sb]);
       }
     }
     if (kPass == 1) {
-      if (row_ok) {
-        p.stat_m[(long long)b * p.n_tok + qi] = m;
-        p.stat_l[(long long)b * p.n_tok + qi] = l;
+      // combine the two half-rows' (max, sum): stats live in the (idle in pass 1) P region of shared memory
+      float2* xch = reinterpret_cast<float2*>(smem + kPamSmemP);
+      if (hk == 1) xch[row] = make_float2(m, l);
+      named_bar_sync(1, 256);
+      if (hk == 0 && row_ok) {
+        const float2 o = xch[row];
+        const float mm = fmaxf(m, o.x);
+        const float ll = (m > -INFINITY ? l * exp2f((m - mm) * kLog2e) : 0.f) + (o.x > -INFINITY ? o.y * exp2f((o.x - mm) * kLog2e) : 0.f);
+        p.stat_m[(long long)b * p.n_tok + qi] = mm;
+        p.stat_l[(long long)b * p.n_tok + qi] = ll;
       }
     } else {
       mbar_wait(&ctl->o_full, 0);
@@ -209,7 +220,7 @@ pam_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       const float gamma = __ldg(p.gamma);
       const T* xr = reinterpret_cast<const T*>(p.x) + ((long long)b * p.n_tok + qi) * p.x_ld + half * kPamDV;
       T* yr = reinterpret_cast<T*>(p.y) + ((long long)b * p.n_tok + qi) * p.y_ld + half * kPamDV;
-      for (int c0 = 0; c0 < kPamDV; c0 += 32) {
+      for (int c0 = hk * (kPamDV / 2); c0 < (hk + 1) * (kPamDV / 2); c0 += 32) {     // each warp of the pair: half of the 256 output columns
         uint32_t o[32];
         tmem_ld_32x32(tmem_o + (uint32_t)c0 + lane_off, o);
         tmem_ld_wait();
@@ -285,11 +296,11 @@ extern "C" int segb200_pam_attention(const void* q, const void* k, const void* v
   const int qtiles = (n_tok + kPamQ - 1) / kPamQ;
   dim3 g1((unsigned)qtiles, 1, (unsigned)batch), g2((unsigned)qtiles, (unsigned)(dv / kPamDV), (unsigned)batch);
   if (dtype == DT_BF16) {
-    pam_kernel<true, 1><<<g1, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
-    pam_kernel<true, 2><<<g2, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<true, 1><<<g1, 320, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<true, 2><<<g2, 320, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   } else {
-    pam_kernel<false, 1><<<g1, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
-    pam_kernel<false, 2><<<g2, 192, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<false, 1><<<g1, 320, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+    pam_kernel<false, 2><<<g2, 320, kPamSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   }
   return check_launch("pam_attention");
 }
