@@ -79,17 +79,39 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_step(R, P, x):
+def _cpu_reference_forward():
+    """-> (forward(x) -> logits, kind, params): the reference's CPU implementation of the path.  The unmodified reference package
+    staged under baseline/_ref when present ("reference"), else the oracle port ("port"); same weights either way."""
     import torch
+    from oracle import segref as R
+    P = R.build_params(MODEL, 0)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import ref_harness as H
+        if H.available():
+            model = H.build_model("cityscapes_deeplabv3_plus.yaml")
+            model.load_state_dict(P.state_dict(), strict=True)
+
+            def fwd(x):
+                with torch.no_grad():
+                    return model(x)[0]
+            return fwd, "reference", P
+    except Exception as e:                                   # noqa: BLE001
+        print(f"[bench] staged reference unusable on the CPU ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+
+    def fwd_port(x):
+        with torch.no_grad():
+            return R.forward(MODEL, P, x)
+    return fwd_port, "port", P
+
+
+def _time_cpu(fwd, x):
     t = time.perf_counter()
-    with torch.no_grad():
-        R.forward(MODEL, P, x)
+    fwd(x)
     return time.perf_counter() - t
 
 
-def pick_threads(R, P, x):
-    """Choose the torch CPU thread count that is fastest on a small probe (oversubscribing a shared host with
-    all logical cores is often slower); returns the count used."""
+def _pick_threads_fn(fwd, x):
     import torch
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (ncpu, ncpu // 2, 32, 16) if 1 <= c <= ncpu})
@@ -97,8 +119,8 @@ def pick_threads(R, P, x):
     best, best_t = cands[-1], None
     for c in cands:
         torch.set_num_threads(c)
-        cpu_reference_step(R, P, probe)
-        t = min(cpu_reference_step(R, P, probe) for _ in range(2))
+        _time_cpu(fwd, probe)
+        t = min(_time_cpu(fwd, probe) for _ in range(2))
         if best_t is None or t < best_t:
             best, best_t = c, t
     torch.set_num_threads(best)
@@ -106,28 +128,29 @@ def pick_threads(R, P, x):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, rank 0 only: the unmodified
+    reference package (baseline/_ref, `get_segmentation_model()`) when it is staged, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import segref as R
-    P = R.build_params(MODEL, 0)
+    fwd, kind, _ = _cpu_reference_forward()
     x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(1024))
-    cores = pick_threads(R, P, x)
+    cores = _pick_threads_fn(fwd, x)
     for _ in range(args.warmup):
-        cpu_reference_step(R, P, x)
+        _time_cpu(fwd, x)
     t = 0.0
     for _ in range(args.steps):
-        t += cpu_reference_step(R, P, x)
+        t += _time_cpu(fwd, x)
     val = args.steps / t
-    sample = f"1 image (1x3x{H}x{W} fp32) per step, {args.steps} steps, torch CPU {torch.get_num_threads()} threads"
+    what = "the reference package (baseline/_ref)" if kind == "reference" else "the CPU oracle port of the reference forward"
+    sample = f"1 image (1x3x{H}x{W} fp32) per step, {args.steps} steps, torch CPU {torch.get_num_threads()} threads, {what}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference forward; one image per step"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "note": f"{what} on the host cores; one image per step"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -465,10 +488,12 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             xc = x_host[:1].clone()
-            cores = pick_threads(R, P, xc)
-            t = cpu_reference_step(R, P, xc)
-            cpu = {"value": 1.0 / t, "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": f"1 image 1x3x{hh}x{ww} fp32, 1 forward of the oracle port, {torch.get_num_threads()} threads"}
+            cfwd, ckind, _ = _cpu_reference_forward()
+            cores = _pick_threads_fn(cfwd, xc)
+            t = _time_cpu(cfwd, xc)
+            cpu = {"value": 1.0 / t, "unit": "images/s", "cores": cores, "kind": ckind,
+                   "sample": f"1 image 1x3x{hh}x{ww} fp32, 1 forward of "
+                             f"{'the reference package (baseline/_ref)' if ckind == 'reference' else 'the oracle port'}, {torch.get_num_threads()} threads"}
         cudnn = None
         if not args.no_cudnn_ref:
             cudnn = cudnn_reference(P, x_dev, eng, bsz)
