@@ -2,6 +2,7 @@
 weight packing is exact, and the product refuses to run without CUDA (no fallback)."""
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -351,3 +352,36 @@ def test_input_normalize_is_torchvision_bit_for_bit(built):
         assert got.dtype == np.float32 and np.array_equal(got.transpose(2, 0, 1), ref.numpy())
     with pytest.raises(RuntimeError, match="not implemented on the CPU"):
         D.normalize(img[None], [0.5] * 3, [0.5] * 3)
+
+
+def test_launcher_local_rank_shim_keeps_the_command_line_parseable(monkeypatch):
+    """under torchrun the launcher injects --local_rank=N.  It must not split an option from its value
+    nor land in the reference's `opts` REMAINDER (utils/options.py:25-26): the result is parsed with the reference's own parser when
+    the staged copy is present, else with the same argparse definition."""
+    import argparse
+    import importlib
+    from segmentron_b200 import launch
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    argv = ["tools/eval.py", "--config-file", "configs/x.yaml", "--log-iter", "5", "TEST.BATCH_SIZE", "2"]
+    monkeypatch.setattr(sys, "argv", list(argv))
+    launch._shims()
+    assert sys.argv[0] == "tools/eval.py" and sys.argv[1] == "--local_rank=3"
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "segmentron")):
+        spec = importlib.util.spec_from_file_location("ref_options", os.path.join(ref, "segmentron", "utils", "options.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        args = mod.parse_args()
+    else:
+        p = argparse.ArgumentParser()
+        p.add_argument("--config-file")
+        p.add_argument("--local_rank", type=int, default=0)
+        p.add_argument("--log-iter", type=int, default=10)
+        p.add_argument("opts", nargs=argparse.REMAINDER)
+        args = p.parse_args()
+    assert args.local_rank == 3 and args.config_file == "configs/x.yaml" and args.log_iter == 5
+    assert args.opts == ["TEST.BATCH_SIZE", "2"]
+    # an explicit --local-rank (what torch.distributed.run passes) is rewritten, not duplicated
+    monkeypatch.setattr(sys, "argv", ["tools/train.py", "--local-rank=1", "--config-file", "c.yaml"])
+    launch._shims()
+    assert sys.argv == ["tools/train.py", "--local_rank=1", "--config-file", "c.yaml"]

@@ -238,3 +238,20 @@ def test_sgd_steps_reduce_the_loss():
     assert losses[-1] < 0.8 * losses[0], losses          # fp32 oracle with the same recipe: 5.54 -> 3.32
     sd = tr.state_dict()
     assert set(sd) == set(P.state_dict()) and all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
+def test_cuda_graph_step_is_bit_identical_to_eager():
+    """cuda_graph=True (single GPU): the step replayed as one CUDA graph -- same kernels, same order -- must reproduce the eager
+    trainer's losses and parameters bit for bit over several SGD steps (first call eager, second captured, later ones replayed)."""
+    from segmentron_b200.train import DeepLabV3PlusTrainerB200
+    P, x, target, _ = _case(seed=7, shape=(4, 3, 65, 97))
+    xs, ts = x.cuda(), target.cuda()
+    out = []
+    for graph in (False, True):
+        tr = DeepLabV3PlusTrainerB200(P.state_dict(), dtype=torch.bfloat16, lr=0.01, dropout=False, cuda_graph=graph)
+        losses = [float(tr.step(xs, ts)) for _ in range(5)]
+        out.append((losses, tr.store.master.clone()))
+        if graph:
+            assert tr.plan_for(xs.shape)["graph"] is not None
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])

@@ -77,6 +77,7 @@ def main():
     ap.add_argument("--backbone", default="resnet101", choices=["resnet101", "xception65", "mobilenet_v2", "hrnet", "danet", "ccnet"])
     ap.add_argument("--same-data", action="store_true", help="every rank trains on rank 0's batch (N-GPU result must equal the 1-GPU one)")
     ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="single GPU: replay the step as one CUDA graph")
     ap.add_argument("--bf16-grads", action="store_true", help="all-reduce the gradient buckets in bf16 (opt-in; the reference's DDP moves fp32)")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time ONE training iteration of the oracle port on the host cores (batch 1)")
     args = ap.parse_args()
@@ -106,7 +107,7 @@ def main():
                                                                                  dropout=not args.no_dropout)
     else:
         tr = DeepLabV3PlusTrainerB200(P.state_dict(), backbone=args.backbone, dtype=torch.bfloat16, lr=0.02, dropout=not args.no_dropout,
-                                      grad_comm_dtype=torch.bfloat16 if args.bf16_grads else torch.float32)
+                                      grad_comm_dtype=torch.bfloat16 if args.bf16_grads else torch.float32, cuda_graph=args.graph)
     losses = [float(tr.step(x, target)) for _ in range(max(args.warmup, 3))]
     parallel.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
