@@ -219,6 +219,8 @@ static int g_dw_persistent = 0;   // 1: grid = 3 CTAs / SM walking the tiles thr
 int set_dw_ring_slots(int n) { g_dw_ring_slots = n; return 0; }
 int set_dw_v8(int v) { g_dw_v8 = v ? 1 : 0; return 0; }
 int set_dw_persistent(int v) { g_dw_persistent = v ? 1 : 0; return 0; }
+static int g_dw_cols2 = 1;        // 1: two output columns per thread for stride 1 / dilation 1 (A/B knob "dw_cols2")
+int set_dw_cols2(int v) { g_dw_cols2 = v ? 1 : 0; return 0; }
 
 constexpr int kDwConsumers = 224;   // 7 warps: thread -> (c8 = t & 7, column = t >> 3); +1 producer warp = 256 threads
 constexpr int kDwTW = kDwConsumers / 8;   // 28 output columns per CTA (128 regs x 256 threads -> 2 CTAs / SM)
@@ -565,6 +567,146 @@ dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPara
 #undef DW4_ROW
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-column variant of the lean ring kernel for stride 1, dilation 1 (59 of the 68 depthwise launches of the headline step):
+// a thread owns FOUR channels of TWO adjacent output columns.  The two outputs share two of their three taps, so a ring row costs
+// 4 shared-memory loads + 8 unpacks per 8 outputs instead of 3 + 6 per 4, and the per-row ring hand-shake (wait, arrive, slot
+// advance) is paid once per 8 outputs: ~10.5 issued instructions per output element against ~15.5 (the one-column kernel is bound by
+// instruction issue, profiles/r2_ncu_full_summary.md).  28 output columns per CTA, slot = 30 input columns x 128 B.  The first two
+// rows of a segment (accumulate only) are peeled, so the steady-state loop has no row-index test.  Same producer protocol, same
+// fp32 operation order per output -> bit-identical to the one-column kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDw2Cols = 2 * kDw4Cols;   // 28 output columns per CTA
+
+template <bool kBF16, bool kPreRelu>
+__device__ __forceinline__ void ring_row_sums4x2(uint32_t row_addr, const float2 (&wt)[9][2], float2 (&sa)[3][2], float2 (&sb)[3][2],
+                                                 uint32_t empty_bar) {
+  using H = Half2<kBF16>;
+  uint2 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[k].x), "=r"(v[k].y) : "r"(row_addr + k * 128));
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive_addr(empty_bar);
+  float2 f[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t u[2] = {v[k].x, v[k].y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (kPreRelu) u[j] = H::relu2(u[j]);
+      f[k][j] = H::unpack(u[j]);
+    }
+  }
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        sa[ky][j] = ffma2(f[kx][j], wt[ky * 3 + kx][j], sa[ky][j]);
+        sb[ky][j] = ffma2(f[kx + 1][j], wt[ky * 3 + kx][j], sb[ky][j]);
+      }
+}
+
+template <bool kBF16, bool kPreRelu, int kAct>
+__global__ void __launch_bounds__(kDwConsumers + 32, 2)
+dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
+  using H = Half2<kBF16>;
+  using T = typename H::T;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const DwParams& p = rp.b;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + rp.nslots * rp.slot_bytes);
+  uint64_t* empty = full + rp.nslots;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kDwConsumers / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // one tile per CTA; channel block fastest (see dwconv3x3_ring4_kernel)
+  const int item = blockIdx.x;
+  const int cblk = item % p.cblocks;
+  int r = item / p.cblocks;
+  const int n = r / (rp.wblocks * rp.segs); r -= n * (rp.wblocks * rp.segs);
+  const int seg = r / rp.wblocks;
+  const int w0 = (r - seg * rp.wblocks) * kDw2Cols;
+  const int h_begin = seg * p.rows_per_block;
+  const int h_end = h_begin + p.rows_per_block < p.ho ? h_begin + p.rows_per_block : p.ho;
+  const int n_out = h_end - h_begin;
+
+  if (warp == kDwConsumers / 32) {                     // ---- producer warp: input rows h_begin - 1 .. h_end ----
+    if ((threadIdx.x & 31) == 0) {
+      int slot = 0; uint32_t phase = 0;
+      for (int k = 0; k < n_out + 2; ++k) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_expect_tx(&full[slot], (uint32_t)rp.slot_bytes);
+        tma_load_4d(&tmX, &full[slot], dsm + slot * rp.slot_bytes, cblk * 64, w0 - 1, h_begin - 1 + k, n);
+        if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  const int c4 = threadIdx.x & 15, wl = threadIdx.x >> 4;
+  const long long yrow_bytes = (long long)p.wo * p.y_ld * (long long)sizeof(T);
+  const uint32_t ring0 = smem_u32(dsm) + (uint32_t)(wl * 256 + c4 * 8);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  const uint32_t slot_bytes = (uint32_t)rp.slot_bytes;
+  const uint32_t bar_end = full0 + (uint32_t)rp.nslots * 8;
+  uint32_t ring = ring0, fbar = full0, ebar = empty0, phase = 0;
+#define DW2_ROW(SA, SB) do { \
+    mbar_wait_lean(fbar, phase); \
+    ring_row_sums4x2<kBF16, kPreRelu>(ring, wt, SA, SB, ebar); \
+    ring += slot_bytes; fbar += 8; ebar += 8; \
+    if (fbar == bar_end) { ring = ring0; fbar = full0; ebar = empty0; phase ^= 1; } } while (0)
+
+  const int cq = cblk * 16 + c4;                       // channel quad
+  const int wo = w0 + 2 * wl;
+  const bool act_a = cq * 4 < p.c && wo < p.wo, act_b = cq * 4 < p.c && wo + 1 < p.wo;
+  const int c0 = (cq * 4 < p.c ? cq : 0) * 4;
+  float2 wt[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.wgt + t * p.c + c0));
+    wt[t][0] = make_float2(a.x, a.y); wt[t][1] = make_float2(a.z, a.w);
+  }
+  float2 sh[2];
+  if (p.shift != nullptr) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    sh[0] = make_float2(a.x, a.y); sh[1] = make_float2(a.z, a.w);
+  } else {
+    sh[0] = sh[1] = make_float2(0.f, 0.f);
+  }
+  const long long ypix = (long long)p.y_ld * (long long)sizeof(T);
+  uint8_t* yp = reinterpret_cast<uint8_t*>(reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0) +
+                (long long)h_begin * yrow_bytes;
+
+  // rolling partial sums per column: a0 = kernel row 0 of the newest input row, a1 = rows 0..1 of the two newest
+  float2 a0a[2], a1a[2], a0b[2], a1b[2];
+  {                                                    // input row h_begin - 1: only its ky = 0 sum survives
+    float2 sa[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}};
+    DW2_ROW(sa, sb);
+    a0a[0] = sa[0][0]; a0a[1] = sa[0][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+  }
+  {                                                    // input row h_begin
+    float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {sh[0], sh[1]}};
+    DW2_ROW(sa, sb);
+    a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
+    a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+  }
+  for (int k = 0; k < n_out; ++k) {                    // input row h_begin + 1 + k completes output row h_begin + k
+    float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {a1a[0], a1a[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {a1b[0], a1b[1]}};
+    DW2_ROW(sa, sb);
+    if (act_a) store_out4<kBF16, kAct>(yp, sa[2]);
+    if (act_b) store_out4<kBF16, kAct>(yp + ypix, sb[2]);
+    yp += yrow_bytes;
+    a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
+    a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+  }
+#undef DW2_ROW
+}
+
 }  // namespace segb200
 
 using namespace segb200;
@@ -587,7 +729,8 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   p.cv = a->c / 8;
   const bool ring = a->c >= 64 && (a->stride == 1 || a->dilation == 1) && a->dilation <= 64;
   int lw;
-  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : kDw4Cols; }
+  const bool cols2 = ring && !g_dw_v8 && !g_dw_persistent && g_dw_cols2 && a->stride == 1 && a->dilation == 1;
+  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols; }
   else { p.lc = p.cv <= 8 ? 8 : 16; p.cblocks = (p.cv + p.lc - 1) / p.lc; lw = 128 / p.lc; }
   const int wblocks = (a->wo + lw - 1) / lw;
   // rows per block: long enough to amortise the 2-row halo of each chain, short enough to fill the GPU
@@ -599,7 +742,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     // persistent kernel: no need to over-decompose for occupancy; balanced segments (65 rows -> 3 x 22, not 32 + 32 + 1)
     rows = a->stride == 1 ? 32 * a->dilation : 32;
     if (rows > a->ho) rows = a->ho;
-    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * 3 * (g_dw_persistent ? 2 : 4)) rows = (rows + 1) / 2;
+    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * (cols2 ? 2 : 3) * (g_dw_persistent ? 2 : 4)) rows = (rows + 1) / 2;
     const int nseg = (a->ho + rows - 1) / rows;
     rows = (a->ho + nseg - 1) / nseg;
   }
@@ -610,7 +753,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   if (ring) {
     DwRingParams rp;
     rp.b = p;
-    const int tw = g_dw_v8 ? kDwTW : kDw4Cols;
+    const int tw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols;
     rp.twin = (tw - 1) * a->stride + 2 * a->dilation + 1;
     rp.slot_bytes = rp.twin * 128;
     rp.nslots = 49152 / rp.slot_bytes;
@@ -626,6 +769,24 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     if (rc) return rc;
     typedef void (*RingFn)(const CUtensorMap, const DwRingParams);
     const int threads = kDwConsumers + 32;
+    if (cols2) {
+      // [dtype][pre_relu][act]
+      static const RingFn fns2[2][2][3] = {
+          {{dwconv3x3_ring4x2_kernel<false, false, 0>, dwconv3x3_ring4x2_kernel<false, false, 1>, dwconv3x3_ring4x2_kernel<false, false, 2>},
+           {dwconv3x3_ring4x2_kernel<false, true, 0>, dwconv3x3_ring4x2_kernel<false, true, 1>, dwconv3x3_ring4x2_kernel<false, true, 2>}},
+          {{dwconv3x3_ring4x2_kernel<true, false, 0>, dwconv3x3_ring4x2_kernel<true, false, 1>, dwconv3x3_ring4x2_kernel<true, false, 2>},
+           {dwconv3x3_ring4x2_kernel<true, true, 0>, dwconv3x3_ring4x2_kernel<true, true, 1>, dwconv3x3_ring4x2_kernel<true, true, 2>}}};
+      static std::once_flag once2;
+      std::call_once(once2, [] {
+        for (int i = 0; i < 12; ++i) cudaFuncSetAttribute(fns2[i / 6][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      });
+      if (a->act < 0 || a->act > 2) return set_error(-3, "dwconv3x3: bad activation code");
+      rp.wblocks = wblocks; rp.segs = (int)grid.y;
+      const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
+      if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
+      fns2[a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)total, threads, smem, stream>>>(tmX, rp);
+      return check_launch("dwconv3x3(ring4x2)");
+    }
     if (!g_dw_v8) {
       // [dtype][stride-1][pre_relu][act]
       // [dilation == 1][dtype][stride-1][pre_relu][act]

@@ -174,6 +174,46 @@ def test_dwconv(case, dtype):
     _close(_to_nchw(y), ref, "dwconv")
 
 
+DW2_CASES = [(2, 33, 65, 728, True, None), (1, 40, 29, 64, False, "relu"), (1, 7, 28, 304, True, "relu6"), (2, 70, 57, 128, False, None),
+             (1, 1, 31, 72, False, None), (1, 65, 129, 1536, True, None)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", DW2_CASES, ids=[f"dw2_{i}" for i in range(len(DW2_CASES))])
+def test_dwconv_two_column_kernel(case, dtype):
+    """stride 1 / dilation 1 runs the two-columns-per-thread ring kernel (csrc/dwconv.cu dwconv3x3_ring4x2_kernel): against the fp32
+    torch reference, BIT-identical to the one-column kernel (segb200_set_option("dw_cols2", 0); same fp32 operation order per output),
+    into a channel slice of a wider buffer (y_ld > c) with the neighbouring channels untouched, from a channel slice (x_ld > c)."""
+    from segmentron_b200 import fold, lib as L, ops
+    lib = L.load()
+    n, h, w, c, pre_relu, act = case
+    xbuf = _rand(n, h, w, c + 24, dtype=dtype, seed=11)
+    x = xbuf[..., 8:8 + c]
+    wt = _rand(c, 1, 3, 3, dtype=torch.float32, seed=12, scale=0.4)
+    scale = (0.5 + torch.rand(c, generator=torch.Generator().manual_seed(13))).cuda()
+    shift = (0.2 * torch.randn(c, generator=torch.Generator().manual_seed(14))).cuda()
+    outs = []
+    for cols2 in (1, 0):
+        L.check(lib.segb200_set_option(b"dw_cols2", cols2))
+        try:
+            ybuf = torch.full((n, h, w, c + 16), 7.0, dtype=dtype, device="cuda")
+            ybuf[..., 8:8 + c] = float("nan")
+            ops.dwconv3x3(x, fold.pack_dw_weight(wt, scale), ybuf[..., 8:8 + c], stride=1, dilation=1, shift=shift, pre_relu=pre_relu, act=act)
+            torch.cuda.synchronize()
+        finally:
+            L.check(lib.segb200_set_option(b"dw_cols2", 1))
+        assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + c:] == 7.0).all(), "wrote outside its channel slice"
+        outs.append(ybuf[..., 8:8 + c].clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), "two-column kernel differs from the one-column kernel"
+    xin = _to_nchw(x)
+    if pre_relu:
+        xin = F.relu(xin)
+    ref = F.conv2d(xin, wt, None, 1, 1, 1, groups=c) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = F.relu(ref) if act == "relu" else (F.relu6(ref) if act == "relu6" else ref)
+    _close(_to_nchw(outs[0]), ref, "dwconv two-column")
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 def test_pool_and_resize(dtype):
     from segmentron_b200 import ops

@@ -24,7 +24,11 @@ SHAPES = [(8, 65, 129, 728, 1, 1), (8, 513, 1025, 128, 1, 1), (8, 257, 513, 256,
           (8, 513, 1025, 64, 1, 1), (8, 513, 1025, 128, 2, 1), (8, 65, 129, 2048, 1, 12), (8, 65, 129, 1536, 1, 2)]
 if "--quick" in sys.argv:
     SHAPES = SHAPES[:3]
-CONFIGS = [dict(dw_v8=1), dict(), dict(dw_ring_slots=8), dict(dw_ring_slots=12), dict(dw_persistent=1), dict(dw_persistent=1, dw_ring_slots=12)]
+CONFIGS = [dict(dw_v8=1, dw_cols2=0), dict(dw_cols2=0), dict(), dict(dw_ring_slots=8), dict(dw_ring_slots=6), dict(dw_persistent=1, dw_cols2=0)]
+if "--cols2" in sys.argv:                      # round-2 A/B of the two-column kernel only
+    CONFIGS = [dict(dw_cols2=0), dict(), dict(dw_ring_slots=8), dict(dw_ring_slots=6)]
+    SHAPES = SHAPES[:6]
+KNOBS = {"dw_v8": 0, "dw_persistent": 0, "dw_ring_slots": 0, "dw_cols2": 1}
 
 
 def bench(n, h, w, c, stride, dil, reps=30):
@@ -50,10 +54,10 @@ def bench(n, h, w, c, stride, dil, reps=30):
 
 for shp in SHAPES:
     for cfg in CONFIGS:
-        for k in ("dw_v8", "dw_persistent", "dw_ring_slots"):
-            L.segb200_set_option(k.encode(), int(cfg.get(k, 0)))
+        for k, dflt in KNOBS.items():
+            L.segb200_set_option(k.encode(), int(cfg.get(k, dflt)))
         us, gbs = bench(*shp)
-        print(json.dumps(dict(shape="dw3x3 s%dd%d c%d @%dx%dx%d" % (shp[4], shp[5], shp[3], shp[0], shp[1], shp[2]), cfg=cfg or "default (ring4)",
+        print(json.dumps(dict(shape="dw3x3 s%dd%d c%d @%dx%dx%d" % (shp[4], shp[5], shp[3], shp[0], shp[1], shp[2]), cfg=cfg or "default",
                               us=round(us, 1), GBps=round(gbs), frac_of_measured_hbm=round(gbs / peak, 3))), flush=True)
-for k in ("dw_v8", "dw_persistent", "dw_ring_slots"):
-    L.segb200_set_option(k.encode(), 0)
+for k, dflt in KNOBS.items():
+    L.segb200_set_option(k.encode(), dflt)
