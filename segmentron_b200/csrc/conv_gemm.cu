@@ -799,6 +799,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "dw_cols2")) return segb200::set_dw_cols2(value);
+  if (name && !strcmp(name, "bilinear_out_v1")) return segb200::set_bilinear_out_v1(value);
   if (name && !strcmp(name, "gemm_mma_pairs")) { g_mma_pairs = value; return 0; }
   if (name && !strcmp(name, "gemm_kgroup")) { g_kgroup = value; return 0; }
   if (name && !strcmp(name, "gemm_kgroup_kb")) { g_kgroup_kb = value > 0 ? value : 32; return 0; }

@@ -578,19 +578,25 @@ dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPara
 // ---------------------------------------------------------------------------------------------
 constexpr int kDw2Cols = 2 * kDw4Cols;   // 28 output columns per CTA
 
-template <bool kBF16, bool kPreRelu>
-__device__ __forceinline__ void ring_row_sums4x2(uint32_t row_addr, const float2 (&wt)[9][2], float2 (&sa)[3][2], float2 (&sb)[3][2],
-                                                 uint32_t empty_bar) {
+// One ring row -> the three kernel-row partial sums of both columns.  kD1: the columns share two of their three taps (4 loads);
+// dilated: taps are d columns apart and nothing is shared (6 loads), the gain is the per-row hand-shake paid once per 8 outputs.
+template <bool kBF16, bool kPreRelu, bool kD1>
+__device__ __forceinline__ void ring_row_sums4x2(uint32_t row_addr, uint32_t tap_step, const float2 (&wt)[9][2], float2 (&sa)[3][2],
+                                                 float2 (&sb)[3][2], uint32_t empty_bar) {
   using H = Half2<kBF16>;
-  uint2 v[4];
+  constexpr int kLoads = kD1 ? 4 : 6;
+  uint2 v[kLoads];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[k].x), "=r"(v[k].y) : "r"(row_addr + k * 128));
+  for (int k = 0; k < kLoads; ++k) {
+    // kD1: slot columns 2wl + k.  dilated: k = 2 * kx + e -> slot column 2wl + e + kx * d
+    const uint32_t off = kD1 ? (uint32_t)(k * 128) : (uint32_t)((k & 1) * 128) + (uint32_t)(k >> 1) * tap_step;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[k].x), "=r"(v[k].y) : "r"(row_addr + off));
+  }
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive_addr(empty_bar);
-  float2 f[4][2];
+  float2 f[kLoads][2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < kLoads; ++k) {
     uint32_t u[2] = {v[k].x, v[k].y};
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -604,12 +610,12 @@ __device__ __forceinline__ void ring_row_sums4x2(uint32_t row_addr, const float2
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        sa[ky][j] = ffma2(f[kx][j], wt[ky * 3 + kx][j], sa[ky][j]);
-        sb[ky][j] = ffma2(f[kx + 1][j], wt[ky * 3 + kx][j], sb[ky][j]);
+        sa[ky][j] = ffma2(f[kD1 ? kx : 2 * kx][j], wt[ky * 3 + kx][j], sa[ky][j]);
+        sb[ky][j] = ffma2(f[kD1 ? kx + 1 : 2 * kx + 1][j], wt[ky * 3 + kx][j], sb[ky][j]);
       }
 }
 
-template <bool kBF16, bool kPreRelu, int kAct>
+template <bool kBF16, bool kPreRelu, int kAct, bool kD1>
 __global__ void __launch_bounds__(kDwConsumers + 32, 2)
 dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
   using H = Half2<kBF16>;
@@ -619,6 +625,7 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
   uint64_t* full = reinterpret_cast<uint64_t*>(dsm + rp.nslots * rp.slot_bytes);
   uint64_t* empty = full + rp.nslots;
   const int warp = threadIdx.x >> 5;
+  const int d = kD1 ? 1 : p.dil;
   if (threadIdx.x == 0) {
     for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kDwConsumers / 32); }
     fence_mbar_init();
@@ -633,16 +640,21 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
   const int w0 = (r - seg * rp.wblocks) * kDw2Cols;
   const int h_begin = seg * p.rows_per_block;
   const int h_end = h_begin + p.rows_per_block < p.ho ? h_begin + p.rows_per_block : p.ho;
-  const int n_out = h_end - h_begin;
+  // d interleaved row chains (output rows h0, h0 + d, ...): a chain streams input rows h0 - d, h0, ..., one ring slot each
+  const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
 
-  if (warp == kDwConsumers / 32) {                     // ---- producer warp: input rows h_begin - 1 .. h_end ----
+  if (warp == kDwConsumers / 32) {                     // ---- producer warp ----
     if ((threadIdx.x & 31) == 0) {
       int slot = 0; uint32_t phase = 0;
-      for (int k = 0; k < n_out + 2; ++k) {
-        mbar_wait(&empty[slot], phase ^ 1);
-        mbar_expect_tx(&full[slot], (uint32_t)rp.slot_bytes);
-        tma_load_4d(&tmX, &full[slot], dsm + slot * rp.slot_bytes, cblk * 64, w0 - 1, h_begin - 1 + k, n);
-        if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+      for (int ch = 0; ch < nchains; ++ch) {
+        const int h0 = h_begin + ch;
+        const int n_out = (h_end - h0 + d - 1) / d;
+        for (int k = 0; k < n_out + 2; ++k) {
+          mbar_wait(&empty[slot], phase ^ 1);
+          mbar_expect_tx(&full[slot], (uint32_t)rp.slot_bytes);
+          tma_load_4d(&tmX, &full[slot], dsm + slot * rp.slot_bytes, cblk * 64, w0 - d, h0 + (k - 1) * d, n);
+          if (++slot == rp.nslots) { slot = 0; phase ^= 1; }
+        }
       }
     }
     return;
@@ -651,13 +663,14 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
   const int c4 = threadIdx.x & 15, wl = threadIdx.x >> 4;
   const long long yrow_bytes = (long long)p.wo * p.y_ld * (long long)sizeof(T);
   const uint32_t ring0 = smem_u32(dsm) + (uint32_t)(wl * 256 + c4 * 8);
+  const uint32_t tap_step = (uint32_t)(d * 128);
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
   const uint32_t slot_bytes = (uint32_t)rp.slot_bytes;
   const uint32_t bar_end = full0 + (uint32_t)rp.nslots * 8;
   uint32_t ring = ring0, fbar = full0, ebar = empty0, phase = 0;
 #define DW2_ROW(SA, SB) do { \
     mbar_wait_lean(fbar, phase); \
-    ring_row_sums4x2<kBF16, kPreRelu>(ring, wt, SA, SB, ebar); \
+    ring_row_sums4x2<kBF16, kPreRelu, kD1>(ring, tap_step, wt, SA, SB, ebar); \
     ring += slot_bytes; fbar += 8; ebar += 8; \
     if (fbar == bar_end) { ring = ring0; fbar = full0; ebar = empty0; phase ^= 1; } } while (0)
 
@@ -679,30 +692,35 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
     sh[0] = sh[1] = make_float2(0.f, 0.f);
   }
   const long long ypix = (long long)p.y_ld * (long long)sizeof(T);
-  uint8_t* yp = reinterpret_cast<uint8_t*>(reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0) +
-                (long long)h_begin * yrow_bytes;
+  const long long ystep = yrow_bytes * d;
+  uint8_t* ybase = reinterpret_cast<uint8_t*>(reinterpret_cast<T*>(p.y) + ((long long)n * p.ho * p.wo + (wo < p.wo ? wo : 0)) * p.y_ld + c0);
 
-  // rolling partial sums per column: a0 = kernel row 0 of the newest input row, a1 = rows 0..1 of the two newest
-  float2 a0a[2], a1a[2], a0b[2], a1b[2];
-  {                                                    // input row h_begin - 1: only its ky = 0 sum survives
-    float2 sa[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}};
-    DW2_ROW(sa, sb);
-    a0a[0] = sa[0][0]; a0a[1] = sa[0][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
-  }
-  {                                                    // input row h_begin
-    float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {sh[0], sh[1]}};
-    DW2_ROW(sa, sb);
-    a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
-    a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
-  }
-  for (int k = 0; k < n_out; ++k) {                    // input row h_begin + 1 + k completes output row h_begin + k
-    float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {a1a[0], a1a[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {a1b[0], a1b[1]}};
-    DW2_ROW(sa, sb);
-    if (act_a) store_out4<kBF16, kAct>(yp, sa[2]);
-    if (act_b) store_out4<kBF16, kAct>(yp + ypix, sb[2]);
-    yp += yrow_bytes;
-    a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
-    a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+  for (int ch = 0; ch < nchains; ++ch) {
+    const int h0 = h_begin + ch;
+    const int n_out = (h_end - h0 + d - 1) / d;
+    uint8_t* yp = ybase + (long long)h0 * yrow_bytes;
+    // rolling partial sums per column: a0 = kernel row 0 of the newest input row, a1 = rows 0..1 of the two newest
+    float2 a0a[2], a1a[2], a0b[2], a1b[2];
+    {                                                  // input row h0 - d: only its ky = 0 sum survives
+      float2 sa[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {sh[0], sh[1]}, {sh[0], sh[1]}};
+      DW2_ROW(sa, sb);
+      a0a[0] = sa[0][0]; a0a[1] = sa[0][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+    }
+    {                                                  // input row h0
+      float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {sh[0], sh[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {sh[0], sh[1]}};
+      DW2_ROW(sa, sb);
+      a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
+      a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+    }
+    for (int k = 0; k < n_out; ++k) {                  // input row h0 + (k + 1) d completes output row h0 + k d
+      float2 sa[3][2] = {{sh[0], sh[1]}, {a0a[0], a0a[1]}, {a1a[0], a1a[1]}}, sb[3][2] = {{sh[0], sh[1]}, {a0b[0], a0b[1]}, {a1b[0], a1b[1]}};
+      DW2_ROW(sa, sb);
+      if (act_a) store_out4<kBF16, kAct>(yp, sa[2]);
+      if (act_b) store_out4<kBF16, kAct>(yp + ypix, sb[2]);
+      yp += ystep;
+      a1a[0] = sa[1][0]; a1a[1] = sa[1][1]; a0a[0] = sa[0][0]; a0a[1] = sa[0][1];
+      a1b[0] = sb[1][0]; a1b[1] = sb[1][1]; a0b[0] = sb[0][0]; a0b[1] = sb[0][1];
+    }
   }
 #undef DW2_ROW
 }
@@ -729,7 +747,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   p.cv = a->c / 8;
   const bool ring = a->c >= 64 && (a->stride == 1 || a->dilation == 1) && a->dilation <= 64;
   int lw;
-  const bool cols2 = ring && !g_dw_v8 && !g_dw_persistent && g_dw_cols2 && a->stride == 1 && a->dilation == 1;
+  const bool cols2 = ring && !g_dw_v8 && !g_dw_persistent && g_dw_cols2 && a->stride == 1;
   if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols; }
   else { p.lc = p.cv <= 8 ? 8 : 16; p.cblocks = (p.cv + p.lc - 1) / p.lc; lw = 128 / p.lc; }
   const int wblocks = (a->wo + lw - 1) / lw;
@@ -756,7 +774,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     const int tw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols;
     rp.twin = (tw - 1) * a->stride + 2 * a->dilation + 1;
     rp.slot_bytes = rp.twin * 128;
-    rp.nslots = 49152 / rp.slot_bytes;
+    rp.nslots = (cols2 && a->dilation > 1 ? 65536 : 49152) / rp.slot_bytes;
     if (rp.nslots > (g_dw_v8 ? 12 : 24)) rp.nslots = g_dw_v8 ? 12 : 24;
     if (g_dw_ring_slots > 0 && rp.nslots > g_dw_ring_slots) rp.nslots = g_dw_ring_slots;
     if (rp.nslots < 3) rp.nslots = 3;
@@ -770,21 +788,20 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     typedef void (*RingFn)(const CUtensorMap, const DwRingParams);
     const int threads = kDwConsumers + 32;
     if (cols2) {
-      // [dtype][pre_relu][act]
-      static const RingFn fns2[2][2][3] = {
-          {{dwconv3x3_ring4x2_kernel<false, false, 0>, dwconv3x3_ring4x2_kernel<false, false, 1>, dwconv3x3_ring4x2_kernel<false, false, 2>},
-           {dwconv3x3_ring4x2_kernel<false, true, 0>, dwconv3x3_ring4x2_kernel<false, true, 1>, dwconv3x3_ring4x2_kernel<false, true, 2>}},
-          {{dwconv3x3_ring4x2_kernel<true, false, 0>, dwconv3x3_ring4x2_kernel<true, false, 1>, dwconv3x3_ring4x2_kernel<true, false, 2>},
-           {dwconv3x3_ring4x2_kernel<true, true, 0>, dwconv3x3_ring4x2_kernel<true, true, 1>, dwconv3x3_ring4x2_kernel<true, true, 2>}}};
+      // [dilation == 1][dtype][pre_relu][act]
+#define DW2_ACTS(BF, PR, D1) {dwconv3x3_ring4x2_kernel<BF, PR, 0, D1>, dwconv3x3_ring4x2_kernel<BF, PR, 1, D1>, dwconv3x3_ring4x2_kernel<BF, PR, 2, D1>}
+      static const RingFn fns2[2][2][2][3] = {{{DW2_ACTS(false, false, false), DW2_ACTS(false, true, false)}, {DW2_ACTS(true, false, false), DW2_ACTS(true, true, false)}},
+                                              {{DW2_ACTS(false, false, true), DW2_ACTS(false, true, true)}, {DW2_ACTS(true, false, true), DW2_ACTS(true, true, true)}}};
+#undef DW2_ACTS
       static std::once_flag once2;
       std::call_once(once2, [] {
-        for (int i = 0; i < 12; ++i) cudaFuncSetAttribute(fns2[i / 6][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        for (int i = 0; i < 24; ++i) cudaFuncSetAttribute(fns2[i / 12][(i / 6) & 1][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       });
       if (a->act < 0 || a->act > 2) return set_error(-3, "dwconv3x3: bad activation code");
       rp.wblocks = wblocks; rp.segs = (int)grid.y;
       const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
       if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
-      fns2[a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)total, threads, smem, stream>>>(tmX, rp);
+      fns2[a->dilation == 1 ? 1 : 0][a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)total, threads, smem, stream>>>(tmX, rp);
       return check_launch("dwconv3x3(ring4x2)");
     }
     if (!g_dw_v8) {

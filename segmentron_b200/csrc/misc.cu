@@ -272,6 +272,80 @@ bilinear_nchw_out_kernel(const void* __restrict__ x, void* __restrict__ y, uint8
   }
 }
 
+// Strip variant (default for c <= 32): a thread owns ONE output column and kRows consecutive output rows.  With the 4x up-sampling
+// of the segmentation heads the rows of a strip share their two source rows, so the four neighbours are loaded and unpacked, and
+// the horizontal interpolation is done, once per strip instead of once per pixel; data types are template parameters (the
+// one-pixel kernel above dispatches on them per element).  The arithmetic is spelled with explicit mul / fma in exactly the
+// contraction nvcc applies to `ly.l0 * (lx.l0 * f00 + lx.l1 * f01) + ly.l1 * (lx.l0 * f10 + lx.l1 * f11)` -- bit-identical
+// to bilinear_nchw_out_kernel and to the fused consumers (metric.cu, evaluate.cu, train.cu upsample_ce).
+template <int kCV, bool kInBF16, int kOut, int kRows>
+__global__ void __launch_bounds__(128)
+bilinear_nchw_strip_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ amax, int n, int hi, int wi, int c,
+                           int x_ld, int ho, int wo, int align, int groups) {
+  using H = Half2<kInBF16>;
+  const int ox = blockIdx.x * 128 + threadIdx.x;
+  if (ox >= wo) return;
+  const int b = blockIdx.y / groups, g = blockIdx.y - b * groups;
+  const long long plane = (long long)ho * wo;
+  const Lerp lx = lerp_coord(ox, wi, wo, align);
+  const char* base = reinterpret_cast<const char*>(x) + (long long)b * hi * wi * x_ld * 2;
+  float A[kCV * 8], B[kCV * 8];
+  int ci0 = -1, ci1 = -1;
+  char* yb = reinterpret_cast<char*>(y);
+#pragma unroll 1
+  for (int r = 0; r < kRows; ++r) {
+    const int oy = g * kRows + r;
+    if (oy >= ho) break;
+    const Lerp ly = lerp_coord(oy, hi, ho, align);
+    if (ly.i0 != ci0 || ly.i1 != ci1) {                // new pair of source rows: horizontal interpolation of both
+      ci0 = ly.i0; ci1 = ly.i1;
+      const char* p00 = base + ((long long)ly.i0 * wi + lx.i0) * x_ld * 2;
+      const char* p01 = base + ((long long)ly.i0 * wi + lx.i1) * x_ld * 2;
+      const char* p10 = base + ((long long)ly.i1 * wi + lx.i0) * x_ld * 2;
+      const char* p11 = base + ((long long)ly.i1 * wi + lx.i1) * x_ld * 2;
+#pragma unroll
+      for (int cv = 0; cv < kCV; ++cv) {
+        const uint4 v00 = ldg_v4(p00 + cv * 16), v01 = ldg_v4(p01 + cv * 16), v10 = ldg_v4(p10 + cv * 16), v11 = ldg_v4(p11 + cv * 16);
+        const uint32_t u00[4] = {v00.x, v00.y, v00.z, v00.w}, u01[4] = {v01.x, v01.y, v01.z, v01.w};
+        const uint32_t u10[4] = {v10.x, v10.y, v10.z, v10.w}, u11[4] = {v11.x, v11.y, v11.z, v11.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f00 = H::unpack(u00[j]), f01 = H::unpack(u01[j]), f10 = H::unpack(u10[j]), f11 = H::unpack(u11[j]);
+          A[cv * 8 + 2 * j] = __fmaf_rn(lx.l0, f00.x, __fmul_rn(lx.l1, f01.x));
+          A[cv * 8 + 2 * j + 1] = __fmaf_rn(lx.l0, f00.y, __fmul_rn(lx.l1, f01.y));
+          B[cv * 8 + 2 * j] = __fmaf_rn(lx.l0, f10.x, __fmul_rn(lx.l1, f11.x));
+          B[cv * 8 + 2 * j + 1] = __fmaf_rn(lx.l0, f10.y, __fmul_rn(lx.l1, f11.y));
+        }
+      }
+    }
+    float best = -INFINITY; int besti = 0;
+    const long long pix = (long long)oy * wo + ox;
+#pragma unroll
+    for (int ch = 0; ch < kCV * 8; ++ch) {
+      if (ch < c) {
+        float o = __fmaf_rn(ly.l0, A[ch], __fmul_rn(ly.l1, B[ch]));
+        const long long oi = ((long long)b * c + ch) * plane + pix;
+        if (kOut == DT_F32) {
+          reinterpret_cast<float*>(yb)[oi] = o;
+        } else if (kOut == DT_BF16) {
+          const __nv_bfloat16 q = __float2bfloat16_rn(o);
+          reinterpret_cast<__nv_bfloat16*>(yb)[oi] = q;
+          o = __bfloat162float(q);
+        } else {
+          const __half q = __float2half_rn(o);
+          reinterpret_cast<__half*>(yb)[oi] = q;
+          o = __half2float(q);
+        }
+        if (o > best) { best = o; besti = ch; }
+      }
+    }
+    if (amax != nullptr) amax[(long long)b * plane + pix] = (uint8_t)besti;
+  }
+}
+
+static int g_bilinear_out_v1 = 0;   // 1: the one-pixel-per-thread kernel for every c (A/B knob "bilinear_out_v1")
+int set_bilinear_out_v1(int v) { g_bilinear_out_v1 = v ? 1 : 0; return 0; }
+
 // -------------------------------------------------------------------------------------------
 // layout converters: [n][c][hw] <-> [n][hw][ld]   (32x32 smem tile transpose)
 // -------------------------------------------------------------------------------------------
@@ -393,6 +467,20 @@ extern "C" int segb200_bilinear_nchw_out(const void* x, void* y, uint8_t* argmax
   if (!half_dt(dtype) || out_dtype < 0 || out_dtype > 2) return set_error(-2, "bilinear_nchw_out: bad dtype");
   if ((x_ld & 7) || c < 1 || c > 256 || ((c + 7) & ~7) > x_ld) return set_error(-4, "bilinear_nchw_out: bad c/x_ld");
   const long long total = (long long)n * ho * wo;
+  if (c <= 32 && !g_bilinear_out_v1) {
+    constexpr int kRows = 4;
+    const int groups = (ho + kRows - 1) / kRows;
+    if ((long long)n * groups > 65535) return set_error(-6, "bilinear_nchw_out: too many row groups");
+    const dim3 grid((unsigned)((wo + 127) / 128), (unsigned)(n * groups));
+    const int cv = (c + 7) / 8;
+    typedef void (*Fn)(const void*, void*, uint8_t*, int, int, int, int, int, int, int, int, int);
+#define BL_OUT(CV, BF) {bilinear_nchw_strip_kernel<CV, BF, DT_BF16, kRows>, bilinear_nchw_strip_kernel<CV, BF, DT_F16, kRows>, bilinear_nchw_strip_kernel<CV, BF, DT_F32, kRows>}
+    static const Fn fns[4][2][3] = {{BL_OUT(1, false), BL_OUT(1, true)}, {BL_OUT(2, false), BL_OUT(2, true)}, {BL_OUT(3, false), BL_OUT(3, true)},
+                                    {BL_OUT(4, false), BL_OUT(4, true)}};
+#undef BL_OUT
+    fns[cv - 1][dtype == DT_BF16 ? 1 : 0][out_dtype]<<<grid, 128, 0, STREAM(stream)>>>(x, y, argmax_out, n, hi, wi, c, x_ld, ho, wo, align_corners, groups);
+    return check_launch("bilinear_nchw_out(strip)");
+  }
   const int g = grid_for(total, 256);
   if (c <= 32)
     bilinear_nchw_out_kernel<32><<<g, 256, 0, STREAM(stream)>>>(x, y, argmax_out, n, hi, wi, c, x_ld, ho, wo,

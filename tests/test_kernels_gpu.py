@@ -174,19 +174,21 @@ def test_dwconv(case, dtype):
     _close(_to_nchw(y), ref, "dwconv")
 
 
-DW2_CASES = [(2, 33, 65, 728, True, None), (1, 40, 29, 64, False, "relu"), (1, 7, 28, 304, True, "relu6"), (2, 70, 57, 128, False, None),
-             (1, 1, 31, 72, False, None), (1, 65, 129, 1536, True, None)]
+DW2_CASES = [(2, 33, 65, 728, 1, True, None), (1, 40, 29, 64, 1, False, "relu"), (1, 7, 28, 304, 1, True, "relu6"), (2, 70, 57, 128, 1, False, None),
+             (1, 1, 31, 72, 1, False, None), (1, 65, 129, 1536, 1, True, None),
+             (1, 65, 129, 1536, 2, True, None), (1, 33, 65, 2048, 6, False, "relu"), (2, 33, 65, 256, 18, False, "relu"), (1, 16, 32, 96, 2, False, "relu6"),
+             (1, 9, 29, 64, 12, True, None), (1, 65, 129, 128, 36, False, "relu"), (1, 70, 30, 64, 64, False, None)]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", DW2_CASES, ids=[f"dw2_{i}" for i in range(len(DW2_CASES))])
 def test_dwconv_two_column_kernel(case, dtype):
-    """stride 1 / dilation 1 runs the two-columns-per-thread ring kernel (csrc/dwconv.cu dwconv3x3_ring4x2_kernel): against the fp32
+    """stride 1 (any dilation) runs the two-columns-per-thread ring kernel (csrc/dwconv.cu dwconv3x3_ring4x2_kernel): against the fp32
     torch reference, BIT-identical to the one-column kernel (segb200_set_option("dw_cols2", 0); same fp32 operation order per output),
     into a channel slice of a wider buffer (y_ld > c) with the neighbouring channels untouched, from a channel slice (x_ld > c)."""
     from segmentron_b200 import fold, lib as L, ops
     lib = L.load()
-    n, h, w, c, pre_relu, act = case
+    n, h, w, c, dil, pre_relu, act = case
     xbuf = _rand(n, h, w, c + 24, dtype=dtype, seed=11)
     x = xbuf[..., 8:8 + c]
     wt = _rand(c, 1, 3, 3, dtype=torch.float32, seed=12, scale=0.4)
@@ -198,7 +200,7 @@ def test_dwconv_two_column_kernel(case, dtype):
         try:
             ybuf = torch.full((n, h, w, c + 16), 7.0, dtype=dtype, device="cuda")
             ybuf[..., 8:8 + c] = float("nan")
-            ops.dwconv3x3(x, fold.pack_dw_weight(wt, scale), ybuf[..., 8:8 + c], stride=1, dilation=1, shift=shift, pre_relu=pre_relu, act=act)
+            ops.dwconv3x3(x, fold.pack_dw_weight(wt, scale), ybuf[..., 8:8 + c], stride=1, dilation=dil, shift=shift, pre_relu=pre_relu, act=act)
             torch.cuda.synchronize()
         finally:
             L.check(lib.segb200_set_option(b"dw_cols2", 1))
@@ -209,7 +211,7 @@ def test_dwconv_two_column_kernel(case, dtype):
     xin = _to_nchw(x)
     if pre_relu:
         xin = F.relu(xin)
-    ref = F.conv2d(xin, wt, None, 1, 1, 1, groups=c) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = F.conv2d(xin, wt, None, 1, dil, dil, groups=c) * scale[None, :, None, None] + shift[None, :, None, None]
     ref = F.relu(ref) if act == "relu" else (F.relu6(ref) if act == "relu6" else ref)
     _close(_to_nchw(outs[0]), ref, "dwconv two-column")
 
@@ -247,6 +249,38 @@ def test_pool_and_resize(dtype):
         ref = F.interpolate(_to_nchw(lg)[:, :19], (4 * h - 3, 4 * w - 3), mode="bilinear", align_corners=True)
         _close(yo, ref, "logits_up")
         assert (am.long() == yo.float().argmax(1)).all(), "fused argmax != torch.argmax of the same output"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", [(2, 17, 33, 19, 24, 65, 129, True), (1, 33, 65, 19, 32, 129, 257, True), (2, 9, 13, 21, 24, 70, 59, False),
+                                  (1, 16, 16, 2, 8, 64, 64, False), (1, 5, 7, 32, 32, 5, 7, True), (1, 12, 20, 11, 16, 45, 131, True)],
+                         ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_logits_upsample_strip_kernel(case, dtype):
+    """segb200_bilinear_nchw_out for c <= 32 runs the strip kernel (misc.cu bilinear_nchw_strip_kernel: one column x 4 rows per
+    thread, compile-time dtypes): logits and fused argmax BIT-identical to the one-pixel-per-thread kernel
+    (segb200_set_option("bilinear_out_v1", 1)) for every output dtype, both align_corners modes, integer and non-integer scales;
+    and against torch's bilinear interpolation."""
+    from segmentron_b200 import lib as L, ops
+    lib = L.load()
+    n, hi, wi, c, ld, ho, wo, align = case
+    lg = _rand(n, hi, wi, ld, dtype=dtype, seed=21)
+    for od in (dtype, torch.float32):
+        res = []
+        for v1 in (0, 1):
+            L.check(lib.segb200_set_option(b"bilinear_out_v1", v1))
+            try:
+                yo = torch.full((n, c, ho, wo), float("nan"), dtype=od, device="cuda")
+                am = torch.full((n, ho, wo), 255, dtype=torch.uint8, device="cuda")
+                ops.bilinear_nchw_out(lg, yo, c, align, am)
+                torch.cuda.synchronize()
+            finally:
+                L.check(lib.segb200_set_option(b"bilinear_out_v1", 0))
+            res.append((yo, am))
+        assert torch.isfinite(res[0][0]).all()
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        assert (res[0][1].long() == res[0][0].float().argmax(1)).all(), "fused argmax != torch.argmax of the same output"
+        ref = F.interpolate(_to_nchw(lg)[:, :c], (ho, wo), mode="bilinear", align_corners=align)
+        _close(res[0][0], ref, "logits_up(strip)")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
