@@ -98,8 +98,13 @@ struct ConvGemmParams {
 #define DBG_COUNT(slot, v) do {} while (0)
 #endif
 
-template <bool kBF16, int kEpiGroups>
-__global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1)
+// kDual: TWO tile streams per CTA.  Stream s owns the CTA's tiles j = s (mod 2) -- hence accumulator stage s --, half of the ring
+// stages, and its own producer warp and MMA-issuing warp (two extra warps after the epilogue warps).  The tensor pipe interleaves
+// the two instruction streams, so the several hundred cycles one issuing thread spends on a full/empty hand-shake are covered by
+// the other stream's MMAs (tools/mma_probe.py mode 8: 128 cycles per 128x256x16 MMA with two issuers against 239 with one, both
+// running this kernel's ring protocol).  The epilogue is unchanged: it drains tile j from accumulator j & 1 in tile order.
+template <bool kBF16, int kEpiGroups, bool kDual>
+__global__ void __launch_bounds__(64 + 128 * kEpiGroups + (kDual ? 64 : 0), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -112,6 +117,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int stage_bytes = p.group * sub_bytes;                                      // a ring stage holds `group` k-blocks
   const int num_kb = p.ntaps * p.cblocks;
   const int bk_elems = p.bk_bytes >> 1;
+  constexpr int kStreams = kDual ? 2 : 1;
+  constexpr int kWarp2 = 2 + 4 * kEpiGroups;                  // dual: producer of stream 1 (kWarp2) and its MMA issuer (kWarp2 + 1)
+  const int strm = (kDual && warp >= kWarp2) ? 1 : 0;
+  const int st_n = kDual ? (p.num_stages >> 1) : p.num_stages;   // ring stages of one stream
+  const int st_base = strm * st_n;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("segb200: dynamic smem base not 1024B aligned\n");
@@ -141,18 +151,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const long long dbg_kernel_t0 = clock64();
 #endif
 
-  if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
+  if (warp == 0 || (kDual && warp == kWarp2)) {
+    // ------------------------------ TMA producer (of stream `strm`) ------------------------------
     if (lane == 0) {
       const CUtensorMap* amaps[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(128 * p.bk_bytes + (p.b_resident ? 0 : p.bn * p.bk_bytes));
-      if (p.b_resident) {          // weights: loaded once, [num_kb] tiles of {bk, bn} behind the A ring
+      if (p.b_resident && strm == 0) {          // weights: loaded once, [num_kb] tiles of {bk, bn} behind the A ring
         mbar_expect_tx(&ctl->b_full, (uint32_t)(num_kb * p.bn * p.bk_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
           tma_load_2d(&tmB, &ctl->b_full, smem + p.num_stages * stage_bytes + kb * p.b_stage_bytes, kb * bk_elems, 0);
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x + strm * gridDim.x; tile < p.total_tiles; tile += kStreams * gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int m_tile = tile / p.n_tiles;
         const int wb = m_tile % p.wtiles; m_tile /= p.wtiles;
@@ -162,27 +172,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int tap = 0, cb = 0;
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.group) {
           const int gn = num_kb - kb0 < p.group ? num_kb - kb0 : p.group;
-          TIMED_WAIT(&ctl->empty[stage], phase ^ 1, 0);
+          TIMED_WAIT(&ctl->empty[st_base + stage], phase ^ 1, 0);
 #ifdef SEGB200_DBG
           if (p.dbg_mode == 2) {
             tap += (cb + gn) / p.cblocks; cb = (cb + gn) % p.cblocks;
-            mbar_arrive(&ctl->full[stage]); if (++stage == p.num_stages) { stage = 0; phase ^= 1; } continue;
+            mbar_arrive(&ctl->full[st_base + stage]); if (++stage == st_n) { stage = 0; phase ^= 1; } continue;
           }
 #endif
-          mbar_expect_tx(&ctl->full[stage], tx * (uint32_t)gn);
-          uint8_t* sa = smem + stage * stage_bytes;
+          uint64_t* fullb = &ctl->full[st_base + stage];
+          mbar_expect_tx(fullb, tx * (uint32_t)gn);
+          uint8_t* sa = smem + (st_base + stage) * stage_bytes;
           for (int g = 0; g < gn; ++g, sa += sub_bytes) {
             const uint32_t t = p.taps[tap];
             const int ow = (int)((t >> 8) & 0xff) - 128, oh = (int)((t >> 16) & 0xff) - 128;
-            tma_load_4d(amaps[t & 3], &ctl->full[stage], sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
-            if (!p.b_resident) tma_load_2d(&tmB, &ctl->full[stage], sa + p.a_stage_bytes, (kb0 + g) * bk_elems, n0);
+            tma_load_4d(amaps[t & 3], fullb, sa, cb * bk_elems, w0 + ow, h0 + oh, img * p.bi);
+            if (!p.b_resident) tma_load_2d(&tmB, fullb, sa + p.a_stage_bytes, (kb0 + g) * bk_elems, n0);
             if (++cb == p.cblocks) { cb = 0; ++tap; }
           }
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          if (++stage == st_n) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (kDual && warp == kWarp2 + 1)) {
     // ------------------------------ MMA issuer ------------------------------
     // tcgen05.mma issue is nearly synchronous: the tensor pipe queues about one instruction ahead of the one it executes
     // (tools/mma_probe.py: every instruction this thread executes between two MMAs beyond ~128 cycles of slack is a cycle the pipe
@@ -191,19 +202,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // the descriptors' low words advance by one multiply-add per k-block (the high words are constants), the channel-block counter
     // replaces a modulo, and barrier addresses are 32-bit shared addresses computed once.
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      uint32_t stage = 0, phase = 0;
       const int kmma = p.bk_bytes >> 5;          // K=16 elements (32 B) per instruction
       const int kmma_tail = p.kmma_tail, cblocks = p.cblocks;
-      const uint32_t nstages = (uint32_t)p.num_stages;
+      const uint32_t nstages = (uint32_t)st_n, sbase = (uint32_t)st_base;
       const bool b_res_mode = p.b_resident != 0;
       const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
       // descriptor = {lo: start>>4 | LBO(1)<<16, hi: SBO | version<<14 | layout<<29}  (make_kmajor_desc)
       const uint64_t d0 = make_kmajor_desc(smem_u32(smem), (uint32_t)p.bk_bytes);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
       const uint32_t stage_step = (uint32_t)stage_bytes >> 4, b_off = (uint32_t)p.a_stage_bytes >> 4;
-      const uint32_t bres_lo0 = a_lo0 + nstages * stage_step, bres_step = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t bres_lo0 = a_lo0 + (uint32_t)p.num_stages * stage_step, bres_step = (uint32_t)p.b_stage_bytes >> 4;
       if (p.b_resident) mbar_wait(&ctl->b_full, 0);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // tile j of this CTA uses accumulator stage j & 1 in its (j >> 1)-th use; a dual stream walks j = strm, strm + 2, ...
+      for (int j = strm, tile = blockIdx.x + strm * gridDim.x; tile < p.total_tiles; j += kStreams, tile += kStreams * gridDim.x) {
+        const int acc = j & 1; const uint32_t acc_phase = (uint32_t)(j >> 1) & 1u;
         const int n_tile = tile % p.n_tiles;
         const int n0 = n_tile * p.bn;
         int nvalid = p.cout - n0; if (nvalid > p.bn) nvalid = p.bn;
@@ -223,12 +236,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kb0 = 0; kb0 < num_kb; kb0 += group) {
           const int gn = num_kb - kb0 < group ? num_kb - kb0 : group;
 #ifdef SEGB200_DBG
-          TIMED_WAIT(&ctl->full[stage], phase, 2);
+          TIMED_WAIT(&ctl->full[sbase + stage], phase, 2);
 #else
-          mbar_wait_guarded(full0 + stage * 8, phase);
+          mbar_wait_guarded(full0 + (sbase + stage) * 8, phase);
 #endif
           tc_fence_after();
-          uint32_t a_lo = a_lo0 + stage * stage_step;
+          uint32_t a_lo = a_lo0 + (sbase + stage) * stage_step;
           for (int g = 0; g < gn; ++g, a_lo += sub_step) {
             const int kb = kb0 + g;
             const uint32_t b_lo = b_res_mode ? bres_lo0 + (uint32_t)kb * bres_step : a_lo + b_off;
@@ -241,15 +254,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               umma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * (uint32_t)k), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)k),
                        idesc, (uint32_t)(kb | k));
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + stage * 8) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + (sbase + stage) * 8) : "memory");
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&ctl->tmem_full[acc]);            // accumulator ready for the epilogue
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
     __syncwarp();
-  } else {
+  } else if (!kDual || warp < kWarp2) {
     // ------------------------------ epilogue (warps 2..5 [, 6..9]) ------------------------------
     // kEpiGroups groups of 4 warps walk the same (tile, 64-column chunk) sequence; with two groups, group g owns the chunks
     // whose running index is g (mod 2), plus its own staging buffer, residual buffer, named barrier and bulk-store group.
@@ -787,6 +799,13 @@ static int g_no_b_resident = 0;
 static int g_no_img_tiles = 0;
 static int g_epi2_maxk = 512;  // K (taps x padded cin) up to which the two-epilogue-group variant is used
 static int g_2cta = 0;        // opt-in: CTA-pair kernel for the tensor-bound shapes
+// Two tile streams per CTA (opt-in, "gemm_dual": 0 off (default), 1 auto, 2 wherever the ring allows).  Measured on B200
+// (profiles/r2_gemm_decomposition.md section 5): the bare issue loops reach 128 cycles per MMA with two issuers against 239 with one,
+// but in this kernel two streams halve each stream's ring -- 2 x 48 KB slots: 728->728 85 -> 96 us, 1536->2048 318 -> 355 us -- and
+// half k-blocks (4 x 24 KB slots per stream, 64-byte rows) are slower still (conv_gemm 9.4 -> 11.3 ms per step).
+static int g_dual = 0;
+static int g_dual_subk = 0;   // dual streams walk half k-blocks (32 channels) so that each keeps >= 3 ring slots ("gemm_dual_subk")
+static int g_dual_min_kb = 3; // auto: at least this many ring hand-shakes per tile ("gemm_dual_min_kb")
 static int g_no_bn128 = 1;   // measured: 128-wide tiles lose 45 % on the 3x3 256->256 layers (operand traffic per FLOP up 33 %)
 extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_ring_kb")) { g_ring_kb = value; return 0; }
@@ -799,6 +818,9 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "dw_cols2")) return segb200::set_dw_cols2(value);
+  if (name && !strcmp(name, "gemm_dual")) { g_dual = value; return 0; }
+  if (name && !strcmp(name, "gemm_dual_min_kb")) { g_dual_min_kb = value; return 0; }
+  if (name && !strcmp(name, "gemm_dual_subk")) { g_dual_subk = value; return 0; }
   if (name && !strcmp(name, "bilinear_out_v1")) return segb200::set_bilinear_out_v1(value);
   if (name && !strcmp(name, "gemm_mma_pairs")) { g_mma_pairs = value; return 0; }
   if (name && !strcmp(name, "gemm_kgroup")) { g_kgroup = value; return 0; }
@@ -836,9 +858,9 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   if (((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15) || ((uintptr_t)a->wgt & 15) || ((uintptr_t)a->residual & 15))
     return set_error(-7, "conv_gemm: pointers must be 16-byte aligned");
 
-  const int bk = segb200_conv_kblock(a->cin);
-  const int bk_bytes = bk * 2;
-  const int cblocks = (a->cin + bk - 1) / bk;
+  int bk = segb200_conv_kblock(a->cin);            // k-block of the weight PACKING (cin is padded to a multiple of it per tap)
+  int bk_bytes = bk * 2;
+  int cblocks = (a->cin + bk - 1) / bk;
   const int cin_pad = cblocks * bk;
   const long long ktot = (long long)ntaps * cin_pad;
 
@@ -895,6 +917,18 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   const long long total = (long long)p.wtiles * p.htiles * p.n_img * p.n_tiles;
   if (total > 0x7fffffffLL) return set_error(-8, "conv_gemm: too many tiles");
   p.total_tiles = (int)total;
+  // Two tile streams per CTA (kDual) split the ring in two: with 48 KB k-blocks (64 channels x (128 + 256) rows) a stream would
+  // be left with two slots, too shallow to cover the TMA latency.  The streams therefore walk HALF k-blocks -- 32 channels, 64-byte
+  // swizzled rows, 24 KB -- over the same packed weights (legal whenever the linear k-block index still addresses them: one tap, or
+  // cin a multiple of 64); their extra hand-shakes are what the second issuer hides.
+  int grid0 = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  if (grid0 > p.total_tiles) grid0 = p.total_tiles;
+  const bool use2_early = g_2cta != 0 && !a->y_f32 && (p.bn % 32) == 0 && p.bn >= 64 && (long long)p.wtiles * p.htiles * p.n_img >= 2 &&
+                          (g_2cta == 1 || ktot >= 1024);
+  const bool want_dual = g_dual != 0 && !use2_early && p.total_tiles >= 2 * grid0;
+  if (want_dual && g_dual_subk && bk == 64 && p.bn > 128 && (ntaps == 1 || (a->cin & 63) == 0)) {
+    bk = 32; bk_bytes = 64; cblocks = (a->cin + 31) / 32;
+  }
   p.cblocks = cblocks; p.ntaps = ntaps; p.bk_bytes = bk_bytes;
   p.kmma_tail = (a->cin - (cblocks - 1) * bk + 15) / 16;
   p.a_stage_bytes = 128 * bk_bytes;
@@ -1006,12 +1040,16 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
 
   int grid = a->max_ctas > 0 ? a->max_ctas : num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
+  typedef void (*GemmFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                         const CUtensorMap, const ConvGemmParams);
+  // [bf16][two epilogue groups][dual streams]
+  static const GemmFn gemm_fns[2][2][2] = {{{conv_gemm_kernel<false, 1, false>, conv_gemm_kernel<false, 1, true>},
+                                            {conv_gemm_kernel<false, 2, false>, conv_gemm_kernel<false, 2, true>}},
+                                           {{conv_gemm_kernel<true, 1, false>, conv_gemm_kernel<true, 1, true>},
+                                            {conv_gemm_kernel<true, 2, false>, conv_gemm_kernel<true, 2, true>}}};
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(conv_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(conv_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(conv_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 8; ++i) cudaFuncSetAttribute(gemm_fns[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
   const int smem_bytes = p.ring_bytes + 2 * kEpiBufBytes + 2432;
   // HBM-bound shapes (short K loop: the epilogue paces the tile) get two epilogue groups, tensor-bound ones a single group
@@ -1054,12 +1092,12 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
     }
     return check_launch("conv_gemm(2cta)");
   }
-  if (a->dtype == DT_BF16) {
-    if (two_groups) conv_gemm_kernel<true, 2><<<grid, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-    else conv_gemm_kernel<true, 1><<<grid, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-  } else {
-    if (two_groups) conv_gemm_kernel<false, 2><<<grid, 320, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-    else conv_gemm_kernel<false, 1><<<grid, 192, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
-  }
-  return check_launch("conv_gemm");
+  // two tile streams per CTA: each needs >= 2 ring stages of its own and its own tiles; auto mode asks for a K loop of at least
+  // g_dual_min_kb hand-shakes per tile (below that the tile is paced by its epilogue, not by the issuing thread)
+  const int shakes = (nkb + p.group - 1) / p.group;
+  const bool dual = want_dual && p.num_stages >= 4 && p.total_tiles >= 2 * grid && (g_dual == 2 || shakes >= g_dual_min_kb);
+  if (dual) p.num_stages &= ~1;
+  gemm_fns[a->dtype == DT_BF16 ? 1 : 0][two_groups ? 1 : 0][dual ? 1 : 0]<<<grid, (two_groups ? 320 : 192) + (dual ? 64 : 0), smem_bytes, stream>>>(
+      tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  return check_launch(dual ? "conv_gemm(dual)" : "conv_gemm");
 }

@@ -8,6 +8,8 @@
 // mode (variant 0): 0 = back-to-back issue; 1 = + one tcgen05.commit per 4 MMAs; 2 = + mbarrier try_wait on a completed phase and
 // tcgen05.fence before each group of 4; 3 = conv_gemm's full main-loop protocol (4-stage full/empty ring, a second warp standing in
 // for the TMA producer, operands read from the ring's rotating stages) -- each step isolates what one element of the protocol costs.
+// mode 8: TWO issuing warps, each running the mode-3 protocol on its own 2-stage ring and its own 256-column accumulator (two tiles
+// in flight per CTA): does the tensor pipe interleave two instruction streams, hiding each issuer's hand-shake behind the other's MMAs?
 #include "common.cuh"
 
 namespace segb200 {
@@ -19,17 +21,20 @@ __device__ __forceinline__ uint32_t probe_ctarank() {
 }
 
 template <int kPair>
-__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int mode, unsigned long long* out) {
+__global__ void __launch_bounds__(256, 1) mma_probe_kernel(int n, int iters, int mode, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t done;
   __shared__ uint64_t sfull[4], sempty[4], sdummy;
+  __shared__ uint64_t dfull[2][2], dempty[2][2], ddone[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? probe_ctarank() : 0;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // finite values
+  for (int i = threadIdx.x; i < (mode == 8 ? 4 : 1) * (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // finite values
   if (threadIdx.x == 0) {
     mbar_init(&done, 1); mbar_init(&sdummy, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&dfull[i >> 1][i & 1], 1); mbar_init(&dempty[i >> 1][i & 1], 1); }
+    mbar_init(&ddone[0], 1); mbar_init(&ddone[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -48,7 +53,40 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   long long cycles = 0;
-  if (warp == 0 && lane == 0 && rank == 0) {
+  if (!kPair && mode == 8) {
+    // warps 0 / 3: issuers of streams 0 / 1;  warps 2 / 4: their stand-in producers
+    if ((warp == 0 || warp == 3) && lane == 0) {
+      const int sidx = warp == 0 ? 0 : 1;
+      const uint32_t fmt = 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t acc = tmem + (uint32_t)(sidx * 256);
+      const long long t0 = clock64();
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&dfull[sidx][stage], phase);
+        tc_fence_after();
+        const uint32_t soff = (uint32_t)(sidx * 2 + stage) * 49152u;
+        const uint64_t ad = make_kmajor_desc(smem_u32(smem) + soff, 128), bd = make_kmajor_desc(smem_u32(smem) + soff + 16384, 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it & 7) | k));
+        umma_commit(&dempty[sidx][stage]);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&ddone[sidx]);
+      mbar_wait(&ddone[sidx], 0);
+      cycles = clock64() - t0;
+      atomicMax(out, (unsigned long long)cycles);      // slowest issuer of the slowest CTA
+      if (sidx == 0) atomicAdd(out + 1, 1ull);
+    } else if ((warp == 2 || warp == 4) && lane == 0) {
+      const int sidx = warp == 2 ? 0 : 1;
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&dempty[sidx][stage], phase ^ 1);
+        mbar_arrive(&dfull[sidx][stage]);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0 && lane == 0 && rank == 0) {
     const uint64_t adesc = make_kmajor_desc(smem_u32(smem), 128);
     const uint64_t bdesc = make_kmajor_desc(smem_u32(smem + 16384), 128);
     const uint32_t fmt = 1u;
@@ -141,7 +179,7 @@ extern "C" int segb200_debug_mma_probe(int variant, int n, int iters, int mode, 
   unsigned long long* out = reinterpret_cast<unsigned long long*>(out2_u64);
   if (variant == 0) {
     cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    mma_probe_kernel<0><<<num_sms(), 128, smem, stream>>>(n, iters, mode, out);
+    mma_probe_kernel<0><<<num_sms(), mode == 8 ? 160 : 128, smem, stream>>>(n, iters, mode, out);
   } else {
     cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg;

@@ -144,6 +144,11 @@ def load():
                     continue
                 raise
             fn.restype, fn.argtypes = res, args
+        # A/B measurements only: SEGB200_OPTS="gemm_dual=0,dw_cols2=0" applies segb200_set_option knobs at load time
+        for kv in filter(None, os.environ.get("SEGB200_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            if lib.segb200_set_option(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError(f"segb200: unknown option in SEGB200_OPTS: {kv}")
         _lib = lib
     return _lib
 

@@ -70,7 +70,7 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_gemm(case, dtype):
+def test_conv_gemm(case, dtype, max_ctas=0):
     from segmentron_b200 import fold, ops
     name, n, h, w, cin, cout, k, stride, dil, pad, act, use_res, sl = case
     x = _rand(n, h, w, cin, dtype=dtype, seed=1)
@@ -89,7 +89,7 @@ def test_conv_gemm(case, dtype):
         y = buf[..., off:off + cout]
     wpk = fold.pack_conv_weight(wt, dtype)
     ops.conv_gemm(x, wpk, y, cin=cin, cout=cout, kh=k, kw=k, stride=stride, dilation=dil, pad_t=pad, pad_l=pad,
-                  scale=scale, shift=shift, act=act, residual=res)
+                  scale=scale, shift=shift, act=act, residual=res, max_ctas=max_ctas)
     torch.cuda.synchronize()
     ref = F.conv2d(_to_nchw(x), wt.float(), None, stride, pad, dil)
     ref = ref * scale[None, :, None, None] + shift[None, :, None, None]
@@ -101,6 +101,29 @@ def test_conv_gemm(case, dtype):
         ld, off = sl
         mask = torch.ones(ld, dtype=torch.bool); mask[off:off + cout] = False
         assert (buf[..., mask.cuda()] == 7.0).all(), f"{name}: wrote outside its channel slice"
+    return y.clone()  # (used by the A/B tests below)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("max_ctas,subk", [(1, 0), (3, 0), (3, 1)])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_dual_streams(case, max_ctas, subk, dtype):
+    """The opt-in two-tile-streams-per-CTA kernel (two producer warps + two MMA-issuing warps, conv_gemm_kernel<..., kDual = true>;
+    segb200_set_option("gemm_dual", 2), optionally walking half k-blocks, "gemm_dual_subk") with a 1- or 3-CTA persistent grid so
+    that every CTA walks several tiles, odd and even counts; against the torch reference and BIT-identical to the single-stream
+    kernel (a tile's MMA order does not change).  Slower than the default on B200, kept as a measured experiment."""
+    from segmentron_b200 import lib as L
+    lib = L.load()
+    outs = []
+    for dual in (2, 0):
+        L.check(lib.segb200_set_option(b"gemm_dual", dual))
+        L.check(lib.segb200_set_option(b"gemm_dual_subk", subk))
+        try:
+            outs.append(test_conv_gemm(case, dtype, max_ctas=max_ctas))
+        finally:
+            L.check(lib.segb200_set_option(b"gemm_dual", 0))
+            L.check(lib.segb200_set_option(b"gemm_dual_subk", 0))
+    assert torch.equal(outs[0], outs[1]), "dual-stream result differs from the single-stream kernel"
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
