@@ -160,6 +160,15 @@ int segb200_pam_attention(const void* q, const void* k, const void* vt, const fl
                           const void* x, void* y, float* stat_m, float* stat_l, int batch, int n_tok, int dv, int q_ld,
                           int k_ld, int vt_ld, int x_ld, int y_ld, int dtype, void* stream);
 
+/* The same kernel for the non-local / self-attention blocks of the other heads -- OCNet BaseAttentionBlock.forward
+ * (models/ocnet.py:95-113: two torch.bmm around F.softmax, sim_map scaled by key_channels^-0.5):
+ *   dk   : query/key depth, 64 or 256 (OCNet: key_channels = 256); q and k may be the same tensor (OCNet's f_query IS f_key) or q a
+ *          pre-scaled copy -- the softmax scale is folded into q by the caller (256^-0.5 = 2^-4 is exact in 16-bit floats)
+ *   gamma: device pointer to one float, or NULL (= 1);   x: residual, or NULL (none):  y = gamma * (softmax(q k^T) v + bias_v) + x */
+int segb200_nonlocal_attention(const void* q, const void* k, const void* vt, const float* bias_v, const float* gamma,
+                               const void* x, void* y, float* stat_m, float* stat_l, int batch, int n_tok, int dk, int dv,
+                               int q_ld, int k_ld, int vt_ld, int x_ld, int y_ld, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Channel attention (CAM_Module, modules/module.py:142-162).  The two matrix products run on segb200_conv_gemm
  * (E = X^T X with y_f32 = 1 on a [C][N] transposed copy; y = gamma*(A X) + x with scale = gamma, residual = x);

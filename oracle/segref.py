@@ -626,6 +626,41 @@ def danet(P, x, nclass=19, output_stride=8, multi_grid=True, multi_dilation=(4, 
     return tuple(F.interpolate(o, size, mode="bilinear", align_corners=True) for o in outs)
 
 
+def base_attention_block(P, x, prefix, key_ch, value_ch, out_ch):
+    """BaseAttentionBlock.forward (models/ocnet.py:95-113) at scale 1: value = conv1x1(bias); key = query = ReLU(BN(conv1x1(bias)))
+    -- ONE module registered under both names (`self.f_query = self.f_key`, :88), so the state dict carries each of its tensors
+    twice --; sim = softmax(Q K^T * key_ch^-0.5) over the keys; context = sim V; W = conv1x1(bias).  ``W`` is non-zero on creation
+    so that the branch is not vacuous (the reference initialises it to 0, :90-91)."""
+    b, c, h, w = x.shape
+    value = conv2d(P, x, prefix + ".f_value", value_ch, 1, bias=True).view(b, value_ch, -1).permute(0, 2, 1)
+    kq = F.relu(batchnorm(P, conv2d(P, x, prefix + ".f_key.0", key_ch, 1, bias=True), prefix + ".f_key.1"))
+    for suffix in ("0.weight", "0.bias", "1.weight", "1.bias", "1.running_mean", "1.running_var", "1.num_batches_tracked"):
+        if f"{prefix}.f_query.{suffix}" not in P.t and not P.frozen:
+            P.t[f"{prefix}.f_query.{suffix}"] = P.t[f"{prefix}.f_key.{suffix}"]          # shared module: same tensors
+    query = kq.view(b, key_ch, -1).permute(0, 2, 1)
+    key = kq.view(b, key_ch, -1)
+    sim = torch.softmax(torch.bmm(query, key) * (key_ch ** -0.5), dim=-1)
+    ctx = torch.bmm(sim, value).permute(0, 2, 1).contiguous().view(b, value_ch, h, w)
+    return conv2d(P, ctx, prefix + ".W", out_ch, 1, bias=True)
+
+
+def ocnet(P, x, nclass=19, output_stride=16, layers=(3, 4, 6, 3)):
+    """OCNet.forward (models/ocnet.py:30-43) with _OCHead 'base' (:47-54, cfg.MODEL.OCNet.OC_ARCH = 'base', settings.py:162):
+    ResNet50 OS16 (configs/cityscapes_ocnet.yaml) -> conv3x3(2048 -> 512, no bias) + BN + ReLU -> BaseOCModule(512, 512, 256, 256,
+    scales [1]) (:116-141: one BaseAttentionBlock, cat[context, x], project = conv1x1(1024 -> 512, bias) + BN + ReLU + Dropout2d(0.05),
+    identity in eval) -> conv1x1(512 -> nclass, bias) -> bilinear(align_corners=True).  SOLVER.AUX is off in the YAML.
+    Inference only."""
+    assert not P.training, "the OCNet oracle is inference-only"
+    size = x.shape[2:]
+    _, _, _, c4 = resnet_v1(P, x, "encoder", layers, output_stride)
+    f = conv_bn_act(P, c4, "head.context", 512, 3, 1, 1, conv="0", bn="1")
+    ctx = base_attention_block(P, f, "head.context.3.stages.0", 256, 256, 512)
+    y = torch.cat([ctx, f], dim=1)                                                  # ocnet.py:138-139
+    y = F.relu(batchnorm(P, conv2d(P, y, "head.context.3.project.0", 512, 1, bias=True), "head.context.3.project.1"))
+    y = conv2d(P, y, "head.out", nclass, 1, bias=True, gain=4.0)
+    return F.interpolate(y, size, mode="bilinear", align_corners=True)
+
+
 # ----------------------------------------------------------------------------------------
 # convenience
 # ----------------------------------------------------------------------------------------
@@ -649,6 +684,8 @@ def build_params(model: str, seed: int = 0, nclass: int = 19) -> Params:
             ccnet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
         elif model == "pspnet_resnet101":
             pspnet(P, torch.zeros(1, 3, 49, 49), nclass=nclass)
+        elif model == "ocnet_resnet50":
+            ocnet(P, torch.zeros(1, 3, 33, 33), nclass=nclass)
         elif model == "hrnet_w18_small_v1":
             hrnet_seg(P, torch.zeros(1, 3, 64, 64), nclass=nclass)
         else:
@@ -710,6 +747,8 @@ def forward(model: str, P: Params, x, nclass: int = 19, **kw):
             return ccnet(P, x, nclass=nclass)
         if model == "pspnet_resnet101":
             return pspnet(P, x, nclass=nclass, all=bool(kw.get("all")))
+        if model == "ocnet_resnet50":
+            return ocnet(P, x, nclass=nclass)
         if model == "hrnet_w18_small_v1":
             return hrnet_seg(P, x, nclass=nclass)
         return deeplabv3plus(P, x, nclass=nclass, **MODELS[model], **kw)

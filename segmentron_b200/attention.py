@@ -252,6 +252,38 @@ def pam_nhwc(x, wq, bq, wk, bk, wv, bv, gamma, out=None):
     return y
 
 
+def nonlocal_nhwc(x, wqk, scale_qk, shift_qk, wv, bv, key_ch, out):
+    """OCNet BaseAttentionBlock (models/ocnet.py:95-113, scale 1) up to, not including, its output conv W, on a contiguous NHWC
+    x [n,h,w,c]:  out[n,h,w,dv] = softmax(Q K^T * key_ch^-0.5) V + b_v.
+      wqk / scale_qk / shift_qk : the shared f_key = f_query 1x1 conv (+ bias + folded BN + ReLU) packed TWICE into one
+                                  2*key_ch-channel GEMM -- channels [0, key_ch) pre-multiplied by key_ch^-0.5 (the query copy; exact
+                                  for key_ch = 256 = 2^8), channels [key_ch, 2 key_ch) plain (the keys)
+      wv, bv                    : f_value weights packed [dv][1][c] and bias
+    Q K^T, the softmax and P V run in segb200_nonlocal_attention (csrc/pam.cu, query/key depth 256): the N x N similarity map of the
+    reference's two torch.bmm is never materialised."""
+    n, h, w, c, x_ld = ops._nhwc(x, "x")
+    if x_ld != c or c % 64 != 0:
+        raise RuntimeError("segb200 nonlocal: x must be a contiguous NHWC tensor with channels % 64 == 0")
+    dt = x.dtype
+    ntok = h * w
+    dv = wv.shape[0]
+    lib = L.load()
+    qk = torch.empty(n, h, w, 2 * key_ch, dtype=dt, device=x.device)
+    ops.conv_gemm(x, wqk, qk, cin=c, cout=2 * key_ch, scale=scale_qk, shift=shift_qk, act="relu")
+    pitch = fold.round_up(ntok, 8)
+    vt = torch.empty(n, dv, pitch, dtype=dt, device=x.device)
+    wv_as_x = wv.view(1, 1, dv, wv.shape[-1])
+    for b in range(n):                                   # V^T[b] = W_v . X_b^T (the conv GEMM with the operand roles swapped)
+        ops.conv_gemm(wv_as_x, x[b], vt[b].view(1, 1, dv, pitch)[..., :ntok], cin=c, cout=ntok)
+    sm = torch.empty(n * ntok, dtype=torch.float32, device=x.device)
+    sl = torch.empty(n * ntok, dtype=torch.float32, device=x.device)
+    q, k = qk[..., :key_ch], qk[..., key_ch:]
+    L.check(lib.segb200_nonlocal_attention(ops._ptr(q), ops._ptr(k), ops._ptr(vt), ops._ptr(bv), None, None, ops._ptr(out),
+                                           ops._ptr(sm), ops._ptr(sl), n, ntok, key_ch, dv, 2 * key_ch, 2 * key_ch, pitch, 0,
+                                           out.stride(2), ops.dt_code(dt), ops._stream()), "nonlocal_attention")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # criss-cross attention with a backward pass (training): torch.autograd.Function over the C-ABI kernels
 # ------------------------------------------------------------------------------------------------------------

@@ -608,6 +608,57 @@ def build_pspnet(pl, x_shape, holder, nclass=19, output_stride=8, out_dtype=None
     return [(o, am)]
 
 
+def build_ocnet(pl, x_shape, holder, nclass=19, output_stride=16, layers=(3, 4, 6, 3), out_dtype=None, want_argmax=False):
+    """OCNet.forward + _OCHead 'base' (models/ocnet.py:30-54; cfg.MODEL.OCNet.OC_ARCH = 'base', configs/cityscapes_ocnet.yaml:
+    ResNet50, OS16): conv3x3(2048 -> 512) + BN + ReLU -> BaseOCModule (:116-141) = BaseAttentionBlock (:72-113) on the tensor-core
+    attention kernel + its output conv W, then project(cat[context, feats]) -- evaluated as two GEMMs, the feats half (pre-multiplied by
+    the folded BN scale) being the residual operand of the context half (the 1x1 conv is linear; no concat buffer, and feats stays
+    contiguous for the V^T GEMM) -- + BN + ReLU (Dropout2d(0.05) = identity in eval) -> 1x1 classifier -> fused bilinear NCHW output."""
+    from . import attention as A
+    n, _, H, W = x_shape
+    _, _, _, c4 = _resnet(pl, x_shape, holder, layers, output_stride, 1e-5)
+    hh, ww = c4.shape[1], c4.shape[2]
+    feats = pl.conv_bn_act(c4, "head.context", 512, 3, pad=1, act="relu", conv="0", bn="1")
+    bp = "head.context.3.stages.0"
+    key_ch, val_ch = pl.w(bp + ".f_key.0.weight").shape[0], pl.w(bp + ".f_value.weight").shape[0]
+    s = float(key_ch) ** -0.5
+    ksc, ksh = pl.bn(bp + ".f_key.1", 1e-5)
+    ksh = ksh + ksc * pl.w(bp + ".f_key.0.bias").float()                            # conv bias through the folded BN
+    wk = pl.w(bp + ".f_key.0.weight")
+    wqk = pl.dev(fold.pack_conv_weight(torch.cat([wk, wk], 0), pl.dtype))
+    scale_qk = pl.dev(torch.cat([ksc * s, ksc]).float())                            # ReLU(s z) = s ReLU(z), s > 0
+    shift_qk = pl.dev(torch.cat([ksh * s, ksh]).float())
+    wv = pl.dev(fold.pack_conv_weight(pl.w(bp + ".f_value.weight"), pl.dtype))
+    bv = pl.dev(pl.w(bp + ".f_value.bias").float())
+    pl.keep += [wqk, scale_qk, shift_qk, wv, bv]
+    ctx = pl.new(n, hh, ww, val_ch)
+    ntok = hh * ww
+    pl.steps.append((lambda s_: A.nonlocal_nhwc(feats, wqk, scale_qk, shift_qk, wv, bv, key_ch, ctx),
+                     dict(kind="nonlocal", flops=2.0 * n * ntok * ntok * (key_ch + val_ch), bytes=2.0 * n * ntok * (512 + 2 * key_ch + 2 * val_ch),
+                          desc=f"non-local attention N={ntok} d={key_ch} dv={val_ch} b={n}")))
+    pl.n_launch += 3 + n
+    cw = pl.conv_bn_act(ctx, bp + ".W", 512, 1, act=None, conv=None, bn=None, bias=True)
+    # project: BN(W_p [context | feats] + b_p) = scale (W_a context) + [scale (W_b feats)] + (scale b_p + shift)
+    pp = "head.context.3.project"
+    psc, psh = pl.bn(pp + ".1", 1e-5)
+    psh = psh + psc * pl.w(pp + ".0.bias").float()
+    wp = pl.w(pp + ".0.weight")
+    t = pl.new(n, hh, ww, 512)
+    pl.conv(feats, fold.pack_conv_weight(wp[:, 512:].contiguous(), pl.dtype), t, cin=512, cout=512, scale=psc.float())
+    y = pl.new(n, hh, ww, 512)
+    pl.conv(cw, fold.pack_conv_weight(wp[:, :512].contiguous(), pl.dtype), y, cin=512, cout=512, scale=psc.float(), shift=psh.float(),
+            act="relu", residual=t)
+    logits = pl.new(n, hh, ww, fold.round_up(nclass, 8), ld=32)
+    pl.conv_bn_act(y, "head.out", nclass, 1, act=None, conv=None, bn=None, bias=True, out=logits)
+    out_dtype = out_dtype or pl.dtype
+    o = torch.empty(n, nclass, H, W, dtype=out_dtype, device=pl.device)
+    am = torch.empty(n, H, W, dtype=torch.uint8, device=pl.device) if want_argmax else None
+    pl.call("segb200_bilinear_nchw_out", ops._ptr(logits), ops._ptr(o), ops._ptr(am), n, hh, ww, nclass, logits.stride(2), H, W, 1,
+            ops.dt_code(pl.dtype), ops.dt_code(out_dtype))
+    pl.keep += [o] + ([am] if am is not None else [])
+    return [(o, am)]
+
+
 class DeepLabV3PlusB200:
     """Inference engine: ``engine(x_nchw) -> logits [N, nclass, H, W]`` (same contract as
     ``DeepLabV3Plus.forward(x)[0]``, models/deeplabv3_plus.py:33-46)."""
@@ -737,6 +788,23 @@ class PSPNetB200(DANetB200):
         holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
         pl = Plan(self.sd, self.dtype, self.device)
         outs = build_pspnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.out_dtype, self.want_argmax)
+        return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)
+
+
+class OCNetB200(DANetB200):
+    """``engine(x) -> logits`` (``OCNet.forward(x)[0]``, models/ocnet.py:30-43) for the 'base' object-context head on ResNet50 at
+    output stride 16 (configs/cityscapes_ocnet.yaml); the 'pyramid' and 'asp' variants are not built."""
+
+    def __init__(self, state_dict, nclass=19, output_stride=16, layers=(3, 4, 6, 3), dtype=torch.bfloat16, out_dtype=None, device="cuda",
+                 cuda_graph=False, want_argmax=False):
+        DeepLabV3PlusB200.__init__(self, state_dict, backbone="resnet50", nclass=nclass, output_stride=output_stride,
+                                   dtype=dtype, out_dtype=out_dtype, device=device, cuda_graph=cuda_graph, want_argmax=want_argmax)
+        self.layers = tuple(layers)
+
+    def _build(self, shape, in_dtype):
+        holder = {"x": torch.empty(shape, dtype=in_dtype, device=self.device)}
+        pl = Plan(self.sd, self.dtype, self.device)
+        outs = build_ocnet(pl, shape, holder, self.cfg["nclass"], self.cfg["output_stride"], self.layers, self.out_dtype, self.want_argmax)
         return dict(plan=pl, holder=holder, out=outs[0][0], amax=outs[0][1], all=[o for o, _ in outs], graph=None, logits=None)
 
 

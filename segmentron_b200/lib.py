@@ -62,6 +62,7 @@ SYMBOLS = {
     "segb200_bilinear_nhwc": (C.c_int, [vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_bilinear_nchw_out": (C.c_int, [vp, vp, vp] + [C.c_int] * 10 + [vp]),
     "segb200_pam_attention": (C.c_int, [vp] * 9 + [C.c_int] * 9 + [vp]),
+    "segb200_nonlocal_attention": (C.c_int, [vp] * 9 + [C.c_int] * 10 + [vp]),
     "segb200_cam_softmax": (C.c_int, [vp, vp] + [C.c_int] * 5 + [vp]),
     "segb200_cca_weight_softmax": (C.c_int, [vp, vp, vp] + [C.c_int] * 8 + [vp]),
     "segb200_cca_map": (C.c_int, [vp, vp, vp, vp, vp] + [C.c_int] * 9 + [vp]),

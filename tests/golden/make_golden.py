@@ -29,6 +29,7 @@ MODEL_CASES = {
     "ccnet_resnet101_65x97": ("ccnet_resnet101", "cityscapes_ccnet_resnet.yaml", (1, 3, 65, 97), 6),
     "hrnet_w18s_128x192": ("hrnet_w18_small_v1", "cityscapes_hrnet_w18_small_v1.yaml", (2, 3, 128, 192), 7),
     "pspnet_resnet101_65x97": ("pspnet_resnet101", "cityscapes_pspnet_resnet.yaml", (1, 3, 65, 97), 8),
+    "ocnet_resnet50_65x97": ("ocnet_resnet50", "cityscapes_ocnet.yaml", (1, 3, 65, 97), 9),
 }
 
 

@@ -335,3 +335,44 @@ def test_errors_are_loud():
     xc = torch.zeros(1, 4, 4, 60, dtype=torch.bfloat16, device="cuda")   # 60 channels: not a multiple of 8
     with pytest.raises(RuntimeError):
         ops.dwconv3x3(xc, torch.zeros(9, 60, device="cuda"), torch.empty_like(xc))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", [(1, 300, 256, 256, False), (2, 1000, 256, 512, True), (1, 64, 256, 256, False), (2, 129, 64, 256, True),
+                                  (1, 8192, 256, 256, False)],
+                         ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_nonlocal_attention(case, dtype):
+    """segb200_nonlocal_attention (csrc/pam.cu, query/key depth 64 or 256): y = gamma * (softmax(q k^T) v + b_v) + x against the
+    fp32 torch evaluation of the same formula on the same 16-bit inputs, with and without the residual / gamma, ragged query and key
+    tiles (n_tok not a multiple of 128 / 64), q and k as channel slices of one tensor (OCNet: shared key/query transform), and
+    N = 8192 = a 1024x2048 image at output stride 16."""
+    import ctypes as C
+    from segmentron_b200 import lib as L, ops
+    lib = L.load()
+    b, n, dk, dv, with_x = case
+    g = torch.Generator().manual_seed(n + dk)
+    qk = (torch.randn(b, n, 2 * dk, generator=g) * (2.0 / dk ** 0.5)).to(dtype).cuda()          # energies O(4)
+    q, k = qk[..., :dk], qk[..., dk:]
+    v = torch.randn(b, n, dv, generator=g).to(dtype).cuda()
+    pitch = (n + 7) // 8 * 8
+    vt = torch.zeros(b, dv, pitch, dtype=dtype, device="cuda")
+    vt[..., :n] = v.transpose(1, 2)
+    bv = (0.1 * torch.randn(dv, generator=g)).cuda()
+    x = torch.randn(b, n, dv, generator=g).to(dtype).cuda() if with_x else None
+    gamma = torch.tensor([0.7], device="cuda") if with_x else None
+    y = torch.full((b, n, dv), float("nan"), dtype=dtype, device="cuda")
+    sm = torch.empty(b * n, device="cuda"); sl = torch.empty(b * n, device="cuda")
+    L.check(lib.segb200_nonlocal_attention(ops._ptr(q), ops._ptr(k), ops._ptr(vt), ops._ptr(bv), ops._ptr(gamma), ops._ptr(x), ops._ptr(y),
+                                           ops._ptr(sm), ops._ptr(sl), b, n, dk, dv, 2 * dk, 2 * dk, pitch, dv if with_x else 0, dv,
+                                           ops.dt_code(dtype), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "nonlocal_attention")
+    torch.cuda.synchronize()
+    att = torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)), dim=-1)
+    ref = torch.bmm(att, v.float()) + bv
+    if with_x:
+        ref = 0.7 * ref + x.float()
+    got = y.float()
+    assert torch.isfinite(got).all()
+    # P is rounded to 16 bits before the P V product (as the reference's 16-bit bmm would): 2^-7 / 2^-9 of the output scale
+    tol = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -9
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < tol, (err, tol)

@@ -12,7 +12,8 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 
 @pytest.mark.parametrize("case", ["dlv3p_xception65_65x129", "dlv3p_xception65_97x161_b2",
                                   "dlv3p_mobilenetv2_64x128", "dlv3p_resnet101_65x129",
-                                  "danet_resnet101_64x96", "ccnet_resnet101_65x97", "hrnet_w18s_128x192"])
+                                  "danet_resnet101_64x96", "ccnet_resnet101_65x97", "hrnet_w18s_128x192", "pspnet_resnet101_65x97",
+                                  "ocnet_resnet50_65x97"])
 def test_model_matches_reference_fixture(case):
     fx = torch.load(os.path.join(G, case + ".pt"))
     P = R.build_params(fx["model"], fx["seed"])
