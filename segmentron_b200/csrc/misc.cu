@@ -38,6 +38,31 @@ pack_s2d_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ out,
   }
 }
 
+// One thread per (output pixel, 8-channel group) on a 2-D grid (x: pixel-of-row x group, y: image x row): same loads and stores as
+// pack_s2d_kernel without its 64-bit index divisions and grid-stride loop (196 -> measured in profiles/ for the 8x3x1025x2049 input).
+__global__ void __launch_bounds__(256)
+pack_s2d_rows_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ out, int out_dtype, int c, int h, int w, int hs,
+                     int ws, int out_ld) {
+  const int groups = out_ld / 8;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= ws * groups) return;
+  const int j = t / groups, g = t - j * groups;
+  const int b = blockIdx.y / hs, i = blockIdx.y - b * hs;
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch4 = g * 8 + k;
+    float v = 0.f;
+    if (ch4 < 4 * c) {
+      const int par = ch4 / c, ch = ch4 - par * c;
+      const int yy = 2 * i + (par >> 1), xx = 2 * j + (par & 1);
+      if (yy < h && xx < w) v = load_any(x, (((long long)b * c + ch) * h + yy) * w + xx, x_dtype);
+    }
+    f[k] = v;
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (((long long)b * hs + i) * ws + j) * out_ld * 2 + g * 16) = pack8(f, out_dtype);
+}
+
 // -------------------------------------------------------------------------------------------
 // global average pool: one block per (image, 16 channel vectors); 16 pixel lanes x 16 channel lanes,
 // fixed-order accumulation and a fixed-order shared-memory reduction => bit-reproducible (no atomics)
@@ -82,6 +107,55 @@ gap_kernel(const void* __restrict__ x, void* __restrict__ out, int hw, int c, in
     const float inv = 1.f / (float)hw;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] *= inv;
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + ((long long)n * c + cv * 8) * 2) = pack8(t, dtype);
+  }
+}
+
+// Wide variant (default): 1024 threads = 8 channel-vector lanes x 128 pixel lanes per block, one block per (image, 8 channel
+// vectors): twice the blocks and 8x the loads in flight per SM of gap_kernel (which leaves 20 of 148 SMs idle at c = 2048, batch 8).
+// Fixed-order accumulation per lane, fixed-order shared-memory tree => bit-reproducible.
+__global__ void __launch_bounds__(1024)
+gap_wide_kernel(const void* __restrict__ x, void* __restrict__ out, int hw, int c, int x_ld, int dtype) {
+  __shared__ float red[128][8][8];                 // 32 KB
+  const int n = blockIdx.y;
+  const int lc = threadIdx.x & 7, lp = threadIdx.x >> 3;
+  const int cv = blockIdx.x * 8 + lc;
+  const int cvn = c / 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cv < cvn) {
+    const char* base = reinterpret_cast<const char*>(x) + ((long long)n * hw * x_ld + cv * 8) * 2;
+    int p = lp;
+    for (; p + 384 < hw; p += 512) {                 // 4 independent 128-bit loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(ldg_nc_v4(base + (long long)p * x_ld * 2), dtype, f0);
+      unpack8(ldg_nc_v4(base + (long long)(p + 128) * x_ld * 2), dtype, f1);
+      unpack8(ldg_nc_v4(base + (long long)(p + 256) * x_ld * 2), dtype, f2);
+      unpack8(ldg_nc_v4(base + (long long)(p + 384) * x_ld * 2), dtype, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; p < hw; p += 128) {
+      float f[8];
+      unpack8(ldg_nc_v4(base + (long long)p * x_ld * 2), dtype, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lp][lc][j] = acc[j];
+  __syncthreads();
+  for (int half = 64; half >= 1; half >>= 1) {       // fixed-order tree over the 128 pixel lanes
+    if (lp < half) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[lp][lc][j] += red[lp + half][lc][j];
+    }
+    __syncthreads();
+  }
+  if (lp == 0 && cv < cvn) {
+    float t[8];
+    const float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = red[0][lc][j] * inv;
     *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + ((long long)n * c + cv * 8) * 2) = pack8(t, dtype);
   }
 }
@@ -222,6 +296,53 @@ bilinear_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, int n, in
       o[j] = ly.l0 * (lx.l0 * f00[j] + lx.l1 * f01[j]) + ly.l1 * (lx.l0 * f10[j] + lx.l1 * f11[j]);
     *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + ((((long long)b * ho + oy) * wo + ox) * y_ld + cv * 8) * 2) =
         pack8(o, dtype);
+  }
+}
+
+// Strip variant (default): a thread owns one (output column, 8-channel vector) and kRows consecutive output rows; rows that share
+// their two source rows (4x up-sampling: all four) reuse the loaded neighbours and the horizontal interpolation.  2-D grid, 32-bit
+// index math, compile-time dtype.  Explicit mul / fma in the contraction nvcc applies to bilinear_nhwc_kernel's expression:
+// bit-identical results.
+template <bool kBF16, int kRows>
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_strip_kernel(const void* __restrict__ x, void* __restrict__ y, int hi, int wi, int c, int x_ld, int ho, int wo, int y_ld,
+                           int align, int groups) {
+  using H = Half2<kBF16>;
+  const int cvn = c / 8;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= wo * cvn) return;
+  const int ox = t / cvn, cv = t - ox * cvn;
+  const int b = blockIdx.y / groups, g = blockIdx.y - b * groups;
+  const Lerp lx = lerp_coord(ox, wi, wo, align);
+  const char* base = reinterpret_cast<const char*>(x) + ((long long)b * hi * wi * x_ld + cv * 8) * 2;
+  float A[8], B[8];
+  int ci0 = -1, ci1 = -1;
+#pragma unroll 1
+  for (int r = 0; r < kRows; ++r) {
+    const int oy = g * kRows + r;
+    if (oy >= ho) break;
+    const Lerp ly = lerp_coord(oy, hi, ho, align);
+    if (ly.i0 != ci0 || ly.i1 != ci1) {
+      ci0 = ly.i0; ci1 = ly.i1;
+      const uint4 v00 = ldg_v4(base + ((long long)ly.i0 * wi + lx.i0) * x_ld * 2), v01 = ldg_v4(base + ((long long)ly.i0 * wi + lx.i1) * x_ld * 2);
+      const uint4 v10 = ldg_v4(base + ((long long)ly.i1 * wi + lx.i0) * x_ld * 2), v11 = ldg_v4(base + ((long long)ly.i1 * wi + lx.i1) * x_ld * 2);
+      const uint32_t u00[4] = {v00.x, v00.y, v00.z, v00.w}, u01[4] = {v01.x, v01.y, v01.z, v01.w};
+      const uint32_t u10[4] = {v10.x, v10.y, v10.z, v10.w}, u11[4] = {v11.x, v11.y, v11.z, v11.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f00 = H::unpack(u00[j]), f01 = H::unpack(u01[j]), f10 = H::unpack(u10[j]), f11 = H::unpack(u11[j]);
+        A[2 * j] = __fmaf_rn(lx.l0, f00.x, __fmul_rn(lx.l1, f01.x));
+        A[2 * j + 1] = __fmaf_rn(lx.l0, f00.y, __fmul_rn(lx.l1, f01.y));
+        B[2 * j] = __fmaf_rn(lx.l0, f10.x, __fmul_rn(lx.l1, f11.x));
+        B[2 * j + 1] = __fmaf_rn(lx.l0, f10.y, __fmul_rn(lx.l1, f11.y));
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      pk[j] = H::pack(__fmaf_rn(ly.l0, A[2 * j], __fmul_rn(ly.l1, B[2 * j])), __fmaf_rn(ly.l0, A[2 * j + 1], __fmul_rn(ly.l1, B[2 * j + 1])));
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + ((((long long)b * ho + oy) * wo + ox) * y_ld + cv * 8) * 2) =
+        make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -397,6 +518,11 @@ extern "C" int segb200_pack_s2d(const void* x, int x_dtype, void* out, int out_d
   if ((out_ld & 7) || out_ld < 4 * c) return set_error(-4, "pack_s2d: out_ld must be a multiple of 8 and >= 4*c");
   const int hs = (h + 1) / 2, ws = (w + 1) / 2;
   const long long total = (long long)n * hs * ws * (out_ld / 8);
+  if ((long long)n * hs <= 65535) {
+    pack_s2d_rows_kernel<<<dim3((unsigned)((ws * (out_ld / 8) + 255) / 256), (unsigned)(n * hs)), 256, 0, STREAM(stream)>>>(
+        x, x_dtype, out, out_dtype, c, h, w, hs, ws, out_ld);
+    return check_launch("pack_s2d(rows)");
+  }
   pack_s2d_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, x_dtype, out, out_dtype, n, c, h, w, hs, ws, out_ld);
   return check_launch("pack_s2d");
 }
@@ -407,6 +533,10 @@ extern "C" int segb200_global_avgpool(const void* x, void* out, int n, int h, in
   if (!half_dt(dtype)) return set_error(-2, "global_avgpool: bad dtype");
   if ((c & 7) || (x_ld & 7)) return set_error(-4, "global_avgpool: c and x_ld must be multiples of 8");
   if (((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return set_error(-7, "global_avgpool: pointers must be 16-byte aligned");
+  if (h * w >= 2048) {
+    gap_wide_kernel<<<dim3((c / 8 + 7) / 8, n), 1024, 0, STREAM(stream)>>>(x, out, h * w, c, x_ld, dtype);
+    return check_launch("global_avgpool(wide)");
+  }
   gap_kernel<<<dim3((c / 8 + 15) / 16, n), 256, 0, STREAM(stream)>>>(x, out, h * w, c, x_ld, dtype);
   return check_launch("global_avgpool");
 }
@@ -455,6 +585,14 @@ extern "C" int segb200_bilinear_nhwc(const void* x, void* y, int n, int hi, int 
   if (!half_dt(dtype)) return set_error(-2, "bilinear_nhwc: bad dtype");
   if ((c & 7) || (x_ld & 7) || (y_ld & 7)) return set_error(-4, "bilinear_nhwc: c/pitches must be multiples of 8");
   const long long total = (long long)n * ho * wo * (c / 8);
+  constexpr int kRows = 4;
+  const int groups = (ho + kRows - 1) / kRows;
+  if (!g_bilinear_out_v1 && (long long)n * groups <= 65535 && (long long)wo * (c / 8) < 0x7fffffffLL) {
+    const dim3 grid((unsigned)((wo * (c / 8) + 255) / 256), (unsigned)(n * groups));
+    if (dtype == DT_BF16) bilinear_nhwc_strip_kernel<true, kRows><<<grid, 256, 0, STREAM(stream)>>>(x, y, hi, wi, c, x_ld, ho, wo, y_ld, align_corners, groups);
+    else bilinear_nhwc_strip_kernel<false, kRows><<<grid, 256, 0, STREAM(stream)>>>(x, y, hi, wi, c, x_ld, ho, wo, y_ld, align_corners, groups);
+    return check_launch("bilinear_nhwc(strip)");
+  }
   bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, n, hi, wi, c, x_ld, ho, wo, y_ld,
                                                                          align_corners, dtype);
   return check_launch("bilinear_nhwc");

@@ -307,6 +307,33 @@ def test_logits_upsample_strip_kernel(case, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", [(2, 17, 33, 256, 65, 129, True), (1, 9, 13, 48, 70, 59, False), (2, 1, 1, 256, 33, 65, True),
+                                  (1, 33, 65, 512, 17, 33, True), (1, 6, 6, 64, 33, 33, False)],
+                         ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_bilinear_nhwc_strip_kernel(case, dtype):
+    """segb200_bilinear_nhwc runs the strip kernel (one column x 8 channels x 4 rows per thread): BIT-identical to the one-output-
+    per-thread kernel (segb200_set_option("bilinear_out_v1", 1)) for up- and down-sampling, broadcast from 1x1, both align_corners
+    modes, into a channel slice; and against torch."""
+    from segmentron_b200 import lib as L, ops
+    lib = L.load()
+    n, hi, wi, c, ho, wo, align = case
+    x = _rand(n, hi, wi, c, dtype=dtype, seed=31)
+    res = []
+    for v1 in (0, 1):
+        L.check(lib.segb200_set_option(b"bilinear_out_v1", v1))
+        try:
+            buf = torch.full((n, ho, wo, c + 16), 3.0, dtype=dtype, device="cuda")
+            ops.bilinear_nhwc(x, buf[..., 8:8 + c], align_corners=align)
+            torch.cuda.synchronize()
+        finally:
+            L.check(lib.segb200_set_option(b"bilinear_out_v1", 0))
+        assert (buf[..., :8] == 3.0).all() and (buf[..., 8 + c:] == 3.0).all()
+        res.append(buf[..., 8:8 + c].clone())
+    assert torch.equal(res[0], res[1])
+    _close(_to_nchw(res[0]), F.interpolate(_to_nchw(x), (ho, wo), mode="bilinear", align_corners=align), "bilinear_nhwc(strip)")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 def test_maxpool(dtype):
     from segmentron_b200 import ops
     for (n, h, w, c) in [(2, 33, 65, 64), (1, 34, 66, 128)]:
