@@ -373,8 +373,8 @@ def main():
         cur.wait_event(ev_in[i & 1])
         st["holder"]["x"].copy_(stage[i & 1], non_blocking=True)
         ev_free[i & 1].record(cur)
-        cur.wait_event(ev_read)                          # previous result has left amax_dev
         graph.replay()
+        cur.wait_event(ev_read)                          # previous result has left amax_dev (its D2H overlapped this step's compute)
         amax_dev.copy_(st["amax"], non_blocking=True)
         ev_done.record(cur)
         with torch.cuda.stream(s_out):
@@ -412,8 +412,8 @@ def main():
         cur.wait_event(ev_in[i & 1])
         st["holder"]["x"].copy_(stage[i & 1], non_blocking=True)
         ev_free[i & 1].record(cur)
-        cur.wait_event(ev_read)
         graph.replay()
+        cur.wait_event(ev_read)                          # the previous step's logits have left logits_dev: their 0.64 GB D2H ran under this step
         logits_dev.copy_(st["out"], non_blocking=True)
         ev_done.record(cur)
         with torch.cuda.stream(s_out):
@@ -512,7 +512,7 @@ def main():
                     "result": "uint8 argmax class maps"},
             "e2e_logits": {"value": e2e_logits_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_logits,
                            "ms_per_step": ms_e2e_logits / k_log, "steps": k_log,
-                           "result": "bf16 logits [B,19,H,W], what forward()[0] returns (PCIe-bound: 0.64 GB per step)"},
+                           "result": "bf16 logits [B,19,H,W], what forward()[0] returns (0.64 GB per step over PCIe, overlapped with the next step's compute)"},
             "gpu_launches": plan.n_launch * args.steps, "launches_per_step": plan.n_launch,
             "roofline": roofline, "roofline_all_gemm": roofline_all, "roofline_dw": roofline_dw, "cpu_baseline": cpu, "clocks": clocks,
             "per_kind_ms": {k: round(v["ms"], 3) for k, v in agg.items()},

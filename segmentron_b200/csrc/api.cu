@@ -62,6 +62,14 @@ int encode_map(CUtensorMap* m, int dtype, int rank, const void* base, const uint
   return 0;
 }
 
+// Programmatic dependent launch of conv_gemm / dwconv3x3 (common.cuh): opt-in.  Measured on B200 (gpurun call 28, same box, back to
+// back): headline step 15.82 ms without, 16.21 ms with; training step 46.6 / 46.4 ms -- the persistent GEMM and the two-CTA-per-SM
+// depthwise kernel each fill the SM's shared memory, so a dependent CTA can only take an SM that has fully drained and the overlap
+// is limited to the last CTAs' tail, which does not pay for the extra scheduling.
+static int g_pdl = 0;
+int pdl_enabled() { return g_pdl; }
+int set_pdl(int v) { g_pdl = v ? 1 : 0; return 0; }
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {

@@ -21,6 +21,8 @@ int check_launch(const char* what);
 int encode_map(CUtensorMap* m, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, int swizzle_bytes, const char* what);
 int num_sms();
+int pdl_enabled();              // 1 = launch the persistent kernels with programmatic dependent launch (api.cu; knob "pdl")
+int set_pdl(int v);
 int set_dw_ring_slots(int n);   // tuning knob (dwconv.cu): 0 = default
 int set_dw_v8(int v);           // 1 = round-1 8-channel depthwise ring kernel (A/B)
 int set_dw_cols2(int v);        // 1 = two output columns per thread for stride-1 / dilation-1 depthwise (default; A/B)
@@ -29,6 +31,30 @@ int set_dw_persistent(int v);   // 1 = persistent grid for the 4-channel depthwi
 
 enum : int { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still running, as soon as every CTA of the predecessor has executed
+// pdl_launch_dependents() (or exited) and an SM has room; it must execute pdl_wait() before it reads anything the predecessor wrote
+// or writes anything the predecessor may still read.  Everything before pdl_wait() -- barrier initialisation, TMEM allocation,
+// tensor-map prefetch -- then overlaps the predecessor's tail and the launch latency.  Both instructions are no-ops in a kernel
+// launched without the attribute.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------
 // small device utilities

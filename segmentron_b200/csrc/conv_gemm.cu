@@ -147,6 +147,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // set-up done (barriers, TMEM, tensor-map prefetch): let the next kernel of the stream be scheduled onto SMs as they free up, and
+  // only now wait for the previous kernel's results (programmatic dependent launch; no-ops without the launch attribute)
+  pdl_launch_dependents();
+  pdl_wait();
 #ifdef SEGB200_DBG
   const long long dbg_kernel_t0 = clock64();
 #endif
@@ -818,6 +822,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "dw_cols2")) return segb200::set_dw_cols2(value);
+  if (name && !strcmp(name, "pdl")) return segb200::set_pdl(value);
   if (name && !strcmp(name, "gemm_dual")) { g_dual = value; return 0; }
   if (name && !strcmp(name, "gemm_dual_min_kb")) { g_dual_min_kb = value; return 0; }
   if (name && !strcmp(name, "gemm_dual_subk")) { g_dual_subk = value; return 0; }
@@ -1097,7 +1102,9 @@ extern "C" int segb200_conv_gemm(const segb200_conv_args* a, void* stream_) {
   const int shakes = (nkb + p.group - 1) / p.group;
   const bool dual = want_dual && p.num_stages >= 4 && p.total_tiles >= 2 * grid && (g_dual == 2 || shakes >= g_dual_min_kb);
   if (dual) p.num_stages &= ~1;
-  gemm_fns[a->dtype == DT_BF16 ? 1 : 0][two_groups ? 1 : 0][dual ? 1 : 0]<<<grid, (two_groups ? 320 : 192) + (dual ? 64 : 0), smem_bytes, stream>>>(
-      tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  cudaError_t le = launch_kernel(gemm_fns[a->dtype == DT_BF16 ? 1 : 0][two_groups ? 1 : 0][dual ? 1 : 0], dim3((unsigned)grid),
+                                 dim3((unsigned)((two_groups ? 320 : 192) + (dual ? 64 : 0))), (size_t)smem_bytes, stream, pdl_enabled() != 0,
+                                 tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmC, tmR, p);
+  if (le != cudaSuccess) return set_error((int)le, "conv_gemm: launch failed: %s", cudaGetErrorString(le));
   return check_launch(dual ? "conv_gemm(dual)" : "conv_gemm");
 }

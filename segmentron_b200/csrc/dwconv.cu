@@ -447,6 +447,8 @@ dwconv3x3_ring4_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPara
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   auto decode = [&](int item, int& cblk, int& n, int& h_begin, int& h_end, int& w0) {
     // channel block fastest: CTAs that run together read neighbouring 128-byte chunks of the SAME pixels (DRAM page / L2 sector
     // locality: a pixel's 2*C bytes are touched once, not cblocks times at different moments)
@@ -631,6 +633,8 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();                             // programmatic dependent launch (common.cuh): the barrier set-up above overlapped
+  pdl_wait();                                          // the previous kernel's tail; its results are visible from here on
   // one tile per CTA; channel block fastest (see dwconv3x3_ring4_kernel)
   const int item = blockIdx.x;
   const int cblk = item % p.cblocks;
@@ -801,7 +805,9 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
       rp.wblocks = wblocks; rp.segs = (int)grid.y;
       const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
       if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
-      fns2[a->dilation == 1 ? 1 : 0][a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)total, threads, smem, stream>>>(tmX, rp);
+      cudaError_t le = launch_kernel(fns2[a->dilation == 1 ? 1 : 0][a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act], dim3((unsigned)total),
+                                     dim3((unsigned)threads), (size_t)smem, stream, pdl_enabled() != 0, tmX, rp);
+      if (le != cudaSuccess) return set_error((int)le, "dwconv3x3: launch failed: %s", cudaGetErrorString(le));
       return check_launch("dwconv3x3(ring4x2)");
     }
     if (!g_dw_v8) {
@@ -824,7 +830,9 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
       if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
       long long pgrid = g_dw_persistent ? (long long)num_sms() * 3 : total;     // non-persistent: one tile per CTA, same kernel
       if (pgrid > total) pgrid = total;
-      fns4[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0][a->act]<<<(unsigned)pgrid, threads, smem, stream>>>(tmX, rp);
+      cudaError_t le = launch_kernel(fns4[a->dtype == DT_BF16 ? 1 : 0][a->stride - 1][a->pre_relu ? 1 : 0][a->act], dim3((unsigned)pgrid),
+                                     dim3((unsigned)threads), (size_t)smem, stream, pdl_enabled() != 0, tmX, rp);
+      if (le != cudaSuccess) return set_error((int)le, "dwconv3x3: launch failed: %s", cudaGetErrorString(le));
       return check_launch("dwconv3x3(ring4)");
     }
     static const RingFn fns[2][2][2] = {
