@@ -1,6 +1,6 @@
 """Launch a few representative hot-path kernels once each (after a warm-up launch) so that ncu can capture them:
 
-    ncu --set full --clock-control none --import-source on -k regex:'dwconv|conv_gemm' -o gpurun_out/prof python tools/prof_kernels.py
+    ncu --set full --clock-control none --import-source on -k regex:'dwconv|conv_gemm|bilinear' -o gpurun_out/prof python tools/prof_kernels.py
 
 Shapes are the BASELINE config-2 layer shapes (batch reduced to 2 for the big early layers to keep replays short)."""
 import math
@@ -41,6 +41,21 @@ if which in ("all", "dw"):
     dw(8, 65, 129, 728)
     dw(2, 513, 1025, 128)
     dw(2, 513, 1025, 128, stride=2)
+def up(n, hi, wi, c, k):
+    lg = torch.randn(n, hi, wi, 24, device="cuda").to(dt)
+    o = torch.empty(n, c, (hi - 1) * k + 1, (wi - 1) * k + 1, device="cuda", dtype=dt)
+    am = torch.empty(n, (hi - 1) * k + 1, (wi - 1) * k + 1, device="cuda", dtype=torch.uint8)
+    for _ in range(2):
+        ops.bilinear_nchw_out(lg, o, c, True, am)
+    x = torch.randn(n, 65, 129, 256, device="cuda").to(dt)
+    y = torch.empty(n, 257, 513, 256, device="cuda", dtype=dt)
+    for _ in range(2):
+        ops.bilinear_nhwc(x, y, align_corners=True)
+    torch.cuda.synchronize()
+
+
+if which in ("all", "up"):
+    up(8, 257, 513, 19, 4)
 if which in ("all", "gemm"):
     pw(8, 65, 129, 728, 728, res=True)
     pw(8, 65, 129, 1536, 2048)
