@@ -25,6 +25,7 @@ int pdl_enabled();              // 1 = launch the persistent kernels with progra
 int set_pdl(int v);
 int set_dw_ring_slots(int n);   // tuning knob (dwconv.cu): 0 = default
 int set_dw_v8(int v);           // 1 = round-1 8-channel depthwise ring kernel (A/B)
+int set_dw_cw5(int v);          // 1 = 5-consumer-warp (3 CTAs / SM) two-column depthwise kernel for dilation 1 (A/B)
 int set_dw_cols2(int v);        // 1 = two output columns per thread for stride-1 / dilation-1 depthwise (default; A/B)
 int set_bilinear_out_v1(int v); // 1 = one-pixel-per-thread logits up-sampling kernel (A/B; misc.cu)
 int set_dw_persistent(int v);   // 1 = persistent grid for the 4-channel depthwise kernel (A/B)

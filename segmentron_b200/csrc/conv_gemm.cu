@@ -822,6 +822,7 @@ extern "C" int segb200_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dw_v8")) return segb200::set_dw_v8(value);
   if (name && !strcmp(name, "dw_persistent")) return segb200::set_dw_persistent(value);
   if (name && !strcmp(name, "dw_cols2")) return segb200::set_dw_cols2(value);
+  if (name && !strcmp(name, "dw_cw5")) return segb200::set_dw_cw5(value);
   if (name && !strcmp(name, "pdl")) return segb200::set_pdl(value);
   if (name && !strcmp(name, "gemm_dual")) { g_dual = value; return 0; }
   if (name && !strcmp(name, "gemm_dual_min_kb")) { g_dual_min_kb = value; return 0; }

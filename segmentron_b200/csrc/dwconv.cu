@@ -219,6 +219,11 @@ static int g_dw_persistent = 0;   // 1: grid = 3 CTAs / SM walking the tiles thr
 int set_dw_ring_slots(int n) { g_dw_ring_slots = n; return 0; }
 int set_dw_v8(int v) { g_dw_v8 = v ? 1 : 0; return 0; }
 int set_dw_persistent(int v) { g_dw_persistent = v ? 1 : 0; return 0; }
+// 1: two-column kernel with 5 consumer warps (20 columns, 192 threads, 3 CTAs / SM) for dilation 1 (A/B knob "dw_cw5").  Measured on
+// B200 (profiles/r2_dw_sweep_cw5.jsonl): within +-2 % of the 7-warp / 2-CTA form on five of six shapes (c728 @129x257 +4.5 %, c128
+// @513x1025 -3 %), step 16.34 vs 16.37 ms: no gain, off by default.
+static int g_dw_cw5 = 0;
+int set_dw_cw5(int v) { g_dw_cw5 = v ? 1 : 0; return 0; }
 static int g_dw_cols2 = 1;        // 1: two output columns per thread for stride 1 / dilation 1 (A/B knob "dw_cols2")
 int set_dw_cols2(int v) { g_dw_cols2 = v ? 1 : 0; return 0; }
 
@@ -617,8 +622,10 @@ __device__ __forceinline__ void ring_row_sums4x2(uint32_t row_addr, uint32_t tap
       }
 }
 
-template <bool kBF16, bool kPreRelu, int kAct, bool kD1>
-__global__ void __launch_bounds__(kDwConsumers + 32, 2)
+// kCW = consumer warps: 7 (28 output columns, 256 threads, 2 CTAs / SM) or 5 (20 columns, 192 threads, 3 CTAs / SM when the kernel
+// stays within 113 registers: 18 warps per SM instead of 16, and while one CTA fills its ring two others compute).
+template <bool kBF16, bool kPreRelu, int kAct, bool kD1, int kCW>
+__global__ void __launch_bounds__(kCW * 32 + 32, kCW == 7 ? 2 : 3)
 dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingParams rp) {
   using H = Half2<kBF16>;
   using T = typename H::T;
@@ -629,7 +636,7 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
   const int warp = threadIdx.x >> 5;
   const int d = kD1 ? 1 : p.dil;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kDwConsumers / 32); }
+    for (int i = 0; i < rp.nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kCW); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -641,13 +648,13 @@ dwconv3x3_ring4x2_kernel(const __grid_constant__ CUtensorMap tmX, const DwRingPa
   int r = item / p.cblocks;
   const int n = r / (rp.wblocks * rp.segs); r -= n * (rp.wblocks * rp.segs);
   const int seg = r / rp.wblocks;
-  const int w0 = (r - seg * rp.wblocks) * kDw2Cols;
+  const int w0 = (r - seg * rp.wblocks) * (4 * kCW);
   const int h_begin = seg * p.rows_per_block;
   const int h_end = h_begin + p.rows_per_block < p.ho ? h_begin + p.rows_per_block : p.ho;
   // d interleaved row chains (output rows h0, h0 + d, ...): a chain streams input rows h0 - d, h0, ..., one ring slot each
   const int nchains = d < (h_end - h_begin) ? d : (h_end - h_begin);
 
-  if (warp == kDwConsumers / 32) {                     // ---- producer warp ----
+  if (warp == kCW) {                     // ---- producer warp ----
     if ((threadIdx.x & 31) == 0) {
       int slot = 0; uint32_t phase = 0;
       for (int ch = 0; ch < nchains; ++ch) {
@@ -752,7 +759,8 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   const bool ring = a->c >= 64 && (a->stride == 1 || a->dilation == 1) && a->dilation <= 64;
   int lw;
   const bool cols2 = ring && !g_dw_v8 && !g_dw_persistent && g_dw_cols2 && a->stride == 1;
-  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols; }
+  const int cw2 = (cols2 && g_dw_cw5 && a->dilation == 1) ? 5 : 7;          // consumer warps of the two-column kernel
+  if (ring) { p.lc = 8; p.cblocks = (a->c + 63) / 64; lw = g_dw_v8 ? kDwTW : cols2 ? 4 * cw2 : kDw4Cols; }
   else { p.lc = p.cv <= 8 ? 8 : 16; p.cblocks = (p.cv + p.lc - 1) / p.lc; lw = 128 / p.lc; }
   const int wblocks = (a->wo + lw - 1) / lw;
   // rows per block: long enough to amortise the 2-row halo of each chain, short enough to fill the GPU
@@ -764,7 +772,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     // persistent kernel: no need to over-decompose for occupancy; balanced segments (65 rows -> 3 x 22, not 32 + 32 + 1)
     rows = a->stride == 1 ? 32 * a->dilation : 32;
     if (rows > a->ho) rows = a->ho;
-    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * (cols2 ? 2 : 3) * (g_dw_persistent ? 2 : 4)) rows = (rows + 1) / 2;
+    while (rows > 8 * a->dilation && blocks_xy * ((a->ho + rows - 1) / rows) < 148LL * ((cols2 && cw2 == 7) ? 2 : 3) * (g_dw_persistent ? 2 : 4)) rows = (rows + 1) / 2;
     const int nseg = (a->ho + rows - 1) / rows;
     rows = (a->ho + nseg - 1) / nseg;
   }
@@ -775,7 +783,7 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
   if (ring) {
     DwRingParams rp;
     rp.b = p;
-    const int tw = g_dw_v8 ? kDwTW : cols2 ? kDw2Cols : kDw4Cols;
+    const int tw = g_dw_v8 ? kDwTW : cols2 ? 4 * cw2 : kDw4Cols;
     rp.twin = (tw - 1) * a->stride + 2 * a->dilation + 1;
     rp.slot_bytes = rp.twin * 128;
     rp.nslots = (cols2 && a->dilation > 1 ? 65536 : 49152) / rp.slot_bytes;
@@ -793,20 +801,26 @@ extern "C" int segb200_dwconv3x3(const segb200_dwconv_args* a, void* stream_) {
     const int threads = kDwConsumers + 32;
     if (cols2) {
       // [dilation == 1][dtype][pre_relu][act]
-#define DW2_ACTS(BF, PR, D1) {dwconv3x3_ring4x2_kernel<BF, PR, 0, D1>, dwconv3x3_ring4x2_kernel<BF, PR, 1, D1>, dwconv3x3_ring4x2_kernel<BF, PR, 2, D1>}
+#define DW2_ACTS(BF, PR, D1) {dwconv3x3_ring4x2_kernel<BF, PR, 0, D1, 7>, dwconv3x3_ring4x2_kernel<BF, PR, 1, D1, 7>, dwconv3x3_ring4x2_kernel<BF, PR, 2, D1, 7>}
       static const RingFn fns2[2][2][2][3] = {{{DW2_ACTS(false, false, false), DW2_ACTS(false, true, false)}, {DW2_ACTS(true, false, false), DW2_ACTS(true, true, false)}},
                                               {{DW2_ACTS(false, false, true), DW2_ACTS(false, true, true)}, {DW2_ACTS(true, false, true), DW2_ACTS(true, true, true)}}};
 #undef DW2_ACTS
+      // 5 consumer warps, dilation 1 only: [dtype][pre_relu][act]
+#define DW2_ACTS5(BF, PR) {dwconv3x3_ring4x2_kernel<BF, PR, 0, true, 5>, dwconv3x3_ring4x2_kernel<BF, PR, 1, true, 5>, dwconv3x3_ring4x2_kernel<BF, PR, 2, true, 5>}
+      static const RingFn fns25[2][2][3] = {{DW2_ACTS5(false, false), DW2_ACTS5(false, true)}, {DW2_ACTS5(true, false), DW2_ACTS5(true, true)}};
+#undef DW2_ACTS5
       static std::once_flag once2;
       std::call_once(once2, [] {
         for (int i = 0; i < 24; ++i) cudaFuncSetAttribute(fns2[i / 12][(i / 6) & 1][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        for (int i = 0; i < 12; ++i) cudaFuncSetAttribute(fns25[i / 6][(i / 3) & 1][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       });
       if (a->act < 0 || a->act > 2) return set_error(-3, "dwconv3x3: bad activation code");
       rp.wblocks = wblocks; rp.segs = (int)grid.y;
       const long long total = (long long)p.cblocks * wblocks * grid.y * a->n;
       if (total > 0x7fffffffLL) return set_error(-6, "dwconv3x3: too many tiles");
-      cudaError_t le = launch_kernel(fns2[a->dilation == 1 ? 1 : 0][a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act], dim3((unsigned)total),
-                                     dim3((unsigned)threads), (size_t)smem, stream, pdl_enabled() != 0, tmX, rp);
+      const RingFn fn2 = cw2 == 5 ? fns25[a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act]
+                                  : fns2[a->dilation == 1 ? 1 : 0][a->dtype == DT_BF16 ? 1 : 0][a->pre_relu ? 1 : 0][a->act];
+      cudaError_t le = launch_kernel(fn2, dim3((unsigned)total), dim3((unsigned)(cw2 * 32 + 32)), (size_t)smem, stream, pdl_enabled() != 0, tmX, rp);
       if (le != cudaSuccess) return set_error((int)le, "dwconv3x3: launch failed: %s", cudaGetErrorString(le));
       return check_launch("dwconv3x3(ring4x2)");
     }

@@ -218,8 +218,11 @@ def test_dwconv_two_column_kernel(case, dtype):
     scale = (0.5 + torch.rand(c, generator=torch.Generator().manual_seed(13))).cuda()
     shift = (0.2 * torch.randn(c, generator=torch.Generator().manual_seed(14))).cuda()
     outs = []
-    for cols2 in (1, 0):
+    # (dw_cols2, dw_cw5): two-column kernel with 5 consumer warps / 3 CTAs per SM (opt-in, dilation 1), with 7 warps / 2 CTAs (default),
+    # and the one-column kernel
+    for cols2, cw5 in ((1, 1), (1, 0), (0, 1)):
         L.check(lib.segb200_set_option(b"dw_cols2", cols2))
+        L.check(lib.segb200_set_option(b"dw_cw5", cw5))
         try:
             ybuf = torch.full((n, h, w, c + 16), 7.0, dtype=dtype, device="cuda")
             ybuf[..., 8:8 + c] = float("nan")
@@ -227,10 +230,11 @@ def test_dwconv_two_column_kernel(case, dtype):
             torch.cuda.synchronize()
         finally:
             L.check(lib.segb200_set_option(b"dw_cols2", 1))
+            L.check(lib.segb200_set_option(b"dw_cw5", 0))
         assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + c:] == 7.0).all(), "wrote outside its channel slice"
         outs.append(ybuf[..., 8:8 + c].clone())
     assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1]), "two-column kernel differs from the one-column kernel"
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2]), "two-column kernel differs from the one-column kernel"
     xin = _to_nchw(x)
     if pre_relu:
         xin = F.relu(xin)

@@ -26,9 +26,9 @@ if "--quick" in sys.argv:
     SHAPES = SHAPES[:3]
 CONFIGS = [dict(dw_v8=1, dw_cols2=0), dict(dw_cols2=0), dict(), dict(dw_ring_slots=8), dict(dw_ring_slots=6), dict(dw_persistent=1, dw_cols2=0)]
 if "--cols2" in sys.argv:                      # round-2 A/B of the two-column kernel only
-    CONFIGS = [dict(dw_cols2=0), dict(), dict(dw_ring_slots=8), dict(dw_ring_slots=6)]
-    SHAPES = SHAPES[:1] + SHAPES[7:] + [(8, 65, 129, 2048, 1, 36)]
-KNOBS = {"dw_v8": 0, "dw_persistent": 0, "dw_ring_slots": 0, "dw_cols2": 1}
+    CONFIGS = [dict(dw_cols2=0), dict(), dict(dw_cw5=1), dict(dw_ring_slots=8)]
+    SHAPES = SHAPES[:6]
+KNOBS = {"dw_v8": 0, "dw_persistent": 0, "dw_ring_slots": 0, "dw_cols2": 1, "dw_cw5": 0}
 
 
 def bench(n, h, w, c, stride, dil, reps=30):
